@@ -1,0 +1,186 @@
+// extern "C" surface of libbezk.so (declared in include/bezk.h): argument validation + launches.
+// Plain pointers and sizes only; no torch types; no allocation; no synchronisation.
+#include "bezk_internal.h"
+#include <stdio.h>
+#include <string.h>
+
+
+
+static thread_local char g_err[256] = "";
+
+static int fail(int code, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s", what);
+    return code;
+}
+static int cuda_rc(cudaError_t e, const char* where) {
+    if (e == cudaSuccess) return 0;
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return (int)e;
+}
+static int check_cfg(const BezkTaskCfg* c) {
+    if (!c) return fail(BEZK_E_BADARG, "cfg is NULL");
+    const int span = (c->flags & BEZK_F_CLEATS) ? 4 : 1;
+    if (c->num_bodies <= 0 || c->imu_body < 0 || c->imu_body >= c->num_bodies || c->left_foot_body < 0 ||
+        c->right_foot_body < 0 || c->left_foot_body + span > c->num_bodies || c->right_foot_body + span > c->num_bodies)
+        return fail(BEZK_E_CONFIG, "body index outside num_bodies");
+    if (!(c->dt > 0.0f) || c->max_episode_length <= 0) return fail(BEZK_E_CONFIG, "dt / max_episode_length must be positive");
+    return 0;
+}
+#define REQUIRE(cond, msg) do { if (!(cond)) return fail(BEZK_E_BADARG, msg); } while (0)
+#define ALIGNED(p, a) ((reinterpret_cast<uintptr_t>(p) & ((a) - 1)) == 0)
+
+extern "C" {
+
+int bezk_version(void) { return BEZK_VERSION; }
+const char* bezk_last_error(void) { return g_err; }
+
+int bezk_pre_physics(const float* actions, float* actions_out, float* targets, const BezkTaskCfg* cfg, int64_t n, void* stream) {
+    if (int rc = check_cfg(cfg)) return rc;
+    REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return 0;
+    REQUIRE(actions && targets, "actions/targets NULL");
+    return cuda_rc(bezk::launch_pre_physics(actions, actions_out, targets, *cfg, n, (cudaStream_t)stream), "bezk_pre_physics");
+}
+
+static int run_task(int parts, bezk::TaskArgs& a, const BezkTaskCfg* cfg, void* stream, const char* where) {
+    if (int rc = check_cfg(cfg)) return rc;
+    REQUIRE(a.n >= 0, "n < 0");
+    if (a.n == 0) return 0;
+    REQUIRE(a.dof_state && a.rigid_body && a.root_states && a.goal && a.ball_init, "state tensor NULL");
+    if (!ALIGNED(a.goal, 8) || !ALIGNED(a.ball_init, 8)) return fail(BEZK_E_ALIGN, "goal / ball_init must be 8-byte aligned");
+    if (parts & BEZK_PART_OBS) REQUIRE(a.net_contact && a.obs, "net_contact/obs NULL");
+    if (parts & BEZK_PART_REWARD) REQUIRE(a.rew && a.reset_in && a.reset_out && a.progress_in, "reward buffers NULL");
+    if (parts & BEZK_PART_BOOKKEEP) {
+        REQUIRE(a.reset_in && a.reset_out && a.progress_in && a.progress_out && a.timeout_buf, "bookkeeping buffers NULL");
+        if (cfg->flags & BEZK_F_RESET_ROOT_STATES) REQUIRE(a.initial_root, "initial_root_states NULL");
+    }
+    bezk::fill_alignment(a, *cfg);
+    return cuda_rc(bezk::launch_task(parts, a, *cfg, (cudaStream_t)stream), where);
+}
+
+int bezk_compute_observations(const float* dof_state, const float* rigid_body, const float* root_states, float* net_contact,
+                              float* prev_lin_vel, const float* goal, const float* ball_init, const BezkTaskCfg* cfg,
+                              float* obs, float* obs_clipped, int64_t n, void* stream) {
+    bezk::TaskArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dof_state = const_cast<float*>(dof_state); a.rigid_body = rigid_body; a.root_states = const_cast<float*>(root_states);
+    a.net_contact = net_contact; a.prev_lin_vel = prev_lin_vel; a.goal = goal; a.ball_init = ball_init;
+    a.obs = obs; a.obs_clipped = obs_clipped; a.n = n;
+    return run_task(BEZK_PART_OBS, a, cfg, stream, "bezk_compute_observations");
+}
+
+int bezk_compute_reward(const float* dof_state, const float* rigid_body, const float* root_states, const float* goal,
+                        const float* ball_init, const int64_t* reset_in, const int64_t* progress, const BezkTaskCfg* cfg,
+                        float* rew, int64_t* reset_out, int64_t n, void* stream) {
+    bezk::TaskArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dof_state = const_cast<float*>(dof_state); a.rigid_body = rigid_body; a.root_states = const_cast<float*>(root_states);
+    a.goal = goal; a.ball_init = ball_init; a.reset_in = reset_in; a.reset_out = reset_out; a.progress_in = progress;
+    a.rew = rew; a.n = n;
+    return run_task(BEZK_PART_REWARD, a, cfg, stream, "bezk_compute_reward");
+}
+
+int bezk_reset_idx(const int64_t* env_ids, int64_t k, const float* uniforms, uint64_t seed, uint64_t step, float* dof_state,
+                   float* root_states, const float* initial_root_states, int64_t* progress, int64_t* reset,
+                   const BezkTaskCfg* cfg, int64_t n, void* stream) {
+    if (int rc = check_cfg(cfg)) return rc;
+    REQUIRE(k >= 0 && n >= 0, "k/n < 0");
+    if (k == 0) return 0;
+    REQUIRE(env_ids && dof_state && progress && reset, "reset_idx buffers NULL");
+    if (cfg->flags & BEZK_F_RESET_ROOT_STATES) REQUIRE(root_states && initial_root_states, "root state buffers NULL");
+    return cuda_rc(bezk::launch_reset_idx(env_ids, k, uniforms, seed, step, dof_state, root_states, initial_root_states, progress,
+                                          reset, *cfg, n, (cudaStream_t)stream), "bezk_reset_idx");
+}
+
+int bezk_post_physics(float* dof_state, const float* rigid_body, float* root_states, float* net_contact, float* prev_lin_vel,
+                      const float* goal, const float* ball_init, const float* initial_root_states, const float* uniforms,
+                      uint64_t seed, uint64_t step, int64_t* reset_buf, int64_t* progress_buf, int64_t* timeout_buf,
+                      int64_t* randomize_buf, const BezkTaskCfg* cfg, float* obs, float* obs_clipped, float* rew, int parts,
+                      int64_t n, void* stream) {
+    REQUIRE(parts >= 1 && parts <= 7, "parts must be a non-empty subset of {1,2,4}");
+    bezk::TaskArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dof_state = dof_state; a.rigid_body = rigid_body; a.root_states = root_states; a.net_contact = net_contact;
+    a.prev_lin_vel = prev_lin_vel; a.goal = goal; a.ball_init = ball_init; a.initial_root = initial_root_states;
+    a.uniforms = uniforms; a.seed = seed; a.step = step;
+    a.reset_in = reset_buf; a.reset_out = reset_buf; a.progress_in = progress_buf; a.progress_out = progress_buf;
+    a.timeout_buf = timeout_buf; a.randomize_buf = randomize_buf;
+    a.obs = obs; a.obs_clipped = obs_clipped; a.rew = rew; a.n = n;
+    return run_task(parts, a, cfg, stream, "bezk_post_physics");
+}
+
+int bezk_philox_uniforms(uint64_t seed, uint64_t step, float* out, int64_t n, void* stream) {
+    REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return 0;
+    REQUIRE(out, "out NULL");
+    return cuda_rc(bezk::launch_philox_uniforms(seed, step, out, n, (cudaStream_t)stream), "bezk_philox_uniforms");
+}
+
+int bezk_gae(const float* rewards, const float* values, const void* dones, const float* last_values, const void* last_dones,
+             int dones_kind, double gamma, double tau, float* advs, float* returns, int32_t horizon, int64_t n, void* stream) {
+    REQUIRE(horizon >= 0 && n >= 0, "horizon/n < 0");
+    REQUIRE(dones_kind == 0 || dones_kind == 1, "dones_kind must be 0 (uint8) or 1 (float32)");
+    if (horizon == 0 || n == 0) return 0;
+    REQUIRE(rewards && values && dones && last_values && last_dones && advs && returns, "gae buffers NULL");
+    return cuda_rc(bezk::launch_gae(rewards, values, dones, last_values, last_dones, dones_kind, gamma, tau, advs, returns,
+                                    horizon, n, (cudaStream_t)stream), "bezk_gae");
+}
+
+int64_t bezk_rms_scratch_doubles(int32_t c) { return bezk::rms_scratch_doubles(c); }
+
+int bezk_rms_moments(const float* x, const double* pivot, double* acc, double* partials, int64_t m, int32_t c, void* stream) {
+    REQUIRE(m > 0 && c > 0, "m/c must be positive");
+    REQUIRE(x && acc && partials, "rms buffers NULL");
+    return cuda_rc(bezk::launch_rms_moments(x, pivot, acc, partials, m, c, (cudaStream_t)stream), "bezk_rms_moments");
+}
+
+int bezk_rms_merge(const double* acc, const double* pivot, double* running_mean, double* running_var, double* count, int32_t c,
+                   void* stream) {
+    REQUIRE(c > 0, "c must be positive");
+    REQUIRE(acc && running_mean && running_var && count, "rms buffers NULL");
+    return cuda_rc(bezk::launch_rms_merge(acc, pivot, running_mean, running_var, count, c, (cudaStream_t)stream), "bezk_rms_merge");
+}
+
+int bezk_rms_normalize(const float* x, const double* running_mean, const double* running_var, float eps, int unnorm, float* y,
+                       int64_t m, int32_t c, void* stream) {
+    REQUIRE(m >= 0 && c > 0 && c <= 4096, "bad m/c");
+    if (m == 0) return 0;
+    REQUIRE(x && y && running_mean && running_var, "rms buffers NULL");
+    return cuda_rc(bezk::launch_rms_normalize(x, running_mean, running_var, eps, unnorm, y, m, c, (cudaStream_t)stream),
+                   "bezk_rms_normalize");
+}
+
+int bezk_adv_moments(const float* returns, const float* values, double* acc, double* partials, int64_t m, void* stream) {
+    REQUIRE(m > 0, "m must be positive");
+    REQUIRE(returns && values && acc && partials, "adv buffers NULL");
+    return cuda_rc(bezk::launch_adv_moments(returns, values, acc, partials, m, (cudaStream_t)stream), "bezk_adv_moments");
+}
+
+int bezk_adv_normalize(const float* returns, const float* values, const double* acc, float* adv_out, int normalize, int64_t m,
+                       void* stream) {
+    REQUIRE(m >= 0, "m < 0");
+    if (m == 0) return 0;
+    REQUIRE(returns && values && adv_out && (acc || !normalize), "adv buffers NULL");
+    return cuda_rc(bezk::launch_adv_normalize(returns, values, acc, adv_out, normalize, m, (cudaStream_t)stream), "bezk_adv_normalize");
+}
+
+int64_t bezk_ppo_scratch_doubles(void) { return bezk::ppo_scratch_doubles(); }
+
+int bezk_ppo_loss(const float* actions, const float* mu, const float* logstd, const float* old_mu, const float* old_sigma,
+                  const float* values, const float* old_values, const float* returns, const float* old_neglogp,
+                  const float* advantages, const BezkPpoCfg* cfg, double* stats, float* grad_mu, float* grad_values,
+                  float* grad_logstd, float* neglogp_out, double* partials, int64_t m, void* stream) {
+    REQUIRE(cfg, "cfg NULL");
+    REQUIRE(m > 0, "m must be positive");
+    REQUIRE(actions && mu && logstd && old_mu && old_sigma && values && old_values && returns && old_neglogp && advantages &&
+            stats && partials, "ppo buffers NULL");
+    REQUIRE(cfg->bound_form == 0 || cfg->bound_form == 1, "bound_form must be 0 or 1");
+    REQUIRE(ALIGNED(actions, 8) && ALIGNED(mu, 8) && ALIGNED(old_mu, 8) && ALIGNED(old_sigma, 8), "row arrays must be 8-byte aligned");
+    bezk::PpoArgs a;
+    a.actions = actions; a.mu = mu; a.logstd = logstd; a.old_mu = old_mu; a.old_sigma = old_sigma; a.values = values;
+    a.old_values = old_values; a.returns = returns; a.old_neglogp = old_neglogp; a.advantages = advantages;
+    a.grad_mu = grad_mu; a.grad_values = grad_values; a.neglogp_out = neglogp_out; a.partials = partials; a.m = m; a.use_tma = 0;
+    return cuda_rc(bezk::launch_ppo_loss(a, *cfg, stats, grad_logstd, (cudaStream_t)stream), "bezk_ppo_loss");
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+// Internal launcher interface shared by the .cu translation units of libbezk.so (not installed).
+#pragma once
+#include "../../include/bezk.h"
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bezk {
+struct TaskArgs {
+    float* dof_state;            // (n*18, 2)
+    const float* rigid_body;     // (n*NB, 13)
+    float* root_states;          // (n*2, 13)
+    float* net_contact;          // (n*NB, 3)
+    float* prev_lin_vel;         // (n, 3) or nullptr (aliasing mode)
+    const float* goal;           // (n, 2)
+    const float* ball_init;      // (n, 2)
+    const float* initial_root;   // (n*2, 13)
+    const float* uniforms;       // (n, 36) or nullptr (Philox)
+    uint64_t seed, step;
+    const int64_t* reset_in;
+    int64_t* reset_out;
+    const int64_t* progress_in;
+    int64_t* progress_out;
+    int64_t* timeout_buf;
+    int64_t* randomize_buf;
+    float* obs;
+    float* obs_clipped;
+    float* rew;
+    int64_t n;
+    int use_tma;      // all dense bases 16 B aligned
+    int rb_vec2;      // IMU-link slice of every env is 8 B aligned
+};
+struct PpoArgs {
+    const float *actions, *mu, *logstd, *old_mu, *old_sigma, *values, *old_values, *returns, *old_neglogp, *advantages;
+    float *grad_mu, *grad_values, *neglogp_out;
+    double* partials;
+    int64_t m;
+    int use_tma;
+};
+cudaError_t launch_task(int parts, const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st);
+void fill_alignment(TaskArgs& a, const BezkTaskCfg& cfg);
+cudaError_t launch_pre_physics(const float*, float*, float*, const BezkTaskCfg&, int64_t, cudaStream_t);
+cudaError_t launch_reset_idx(const int64_t*, int64_t, const float*, uint64_t, uint64_t, float*, float*, const float*, int64_t*,
+                             int64_t*, const BezkTaskCfg&, int64_t, cudaStream_t);
+cudaError_t launch_philox_uniforms(uint64_t, uint64_t, float*, int64_t, cudaStream_t);
+cudaError_t launch_gae(const float*, const float*, const void*, const float*, const void*, int, double, double, float*, float*,
+                       int, int64_t, cudaStream_t);
+int64_t rms_scratch_doubles(int c);
+cudaError_t launch_rms_moments(const float*, const double*, double*, double*, int64_t, int, cudaStream_t);
+cudaError_t launch_rms_merge(const double*, const double*, double*, double*, double*, int, cudaStream_t);
+cudaError_t launch_rms_normalize(const float*, const double*, const double*, float, int, float*, int64_t, int, cudaStream_t);
+cudaError_t launch_adv_moments(const float*, const float*, double*, double*, int64_t, cudaStream_t);
+cudaError_t launch_adv_normalize(const float*, const float*, const double*, float*, int, int64_t, cudaStream_t);
+int64_t ppo_scratch_doubles();
+cudaError_t launch_ppo_loss(const PpoArgs&, const BezkPpoCfg&, double*, float*, cudaStream_t);
+}  // namespace bezk

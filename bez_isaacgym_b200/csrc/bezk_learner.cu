@@ -1,0 +1,543 @@
+// rl_games rollout / learner math for B200 (sm_100a): GAE reverse scan, RunningMeanStd moments /
+// merge / normalise, advantage statistics, fused PPO loss forward + backward.
+// All HBM-bound streaming or reduction kernels; statistics are accumulated in fp64 with a fixed
+// reduction order (thread -> fixed-order shared-memory fold -> per-block partial -> single-block
+// finalize), so results are run-to-run deterministic and additive across ranks.
+#include "bezk_common.cuh"
+#include "bezk_internal.h"
+#include <math.h>
+
+namespace bezk {
+
+// ------------------------------------------------------------------------------------------------
+// K6: GAE.  One thread per env keeps (lastgaelam, next value, next non-terminal) in registers and
+// walks the horizon backwards; for a fixed t a warp touches 32 consecutive floats of every array.
+// rl_games a2c_common.py discount_values:
+//   delta = r[t] + gamma * nextvalues * nextnonterminal - v[t]
+//   adv[t] = lastgaelam = delta + gamma * tau * nextnonterminal * lastgaelam ;  ret = adv + v
+// ------------------------------------------------------------------------------------------------
+template <typename DoneT, int UNROLL>
+__global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
+                                                  const DoneT* __restrict__ dones, const float* __restrict__ last_values,
+                                                  const DoneT* __restrict__ last_dones, float gamma, float gamma_tau,
+                                                  float* __restrict__ advs, float* __restrict__ returns, int horizon, int64_t n) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float next_v = last_values[e];
+    float next_nt = 1.0f - (float)last_dones[e];
+    float lam = 0.0f;
+    int t = horizon - 1;
+    for (; t >= UNROLL - 1; t -= UNROLL) {
+        float r[UNROLL], v[UNROLL], d[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {               // all loads of the chunk first (memory-level parallelism)
+            const int64_t idx = (int64_t)(t - k) * n + e;
+            r[k] = ldg_stream(rewards + idx);
+            v[k] = ldg_stream(values + idx);
+            d[k] = (float)dones[idx];
+        }
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            const int64_t idx = (int64_t)(t - k) * n + e;
+            const float delta = (r[k] + (gamma * next_v) * next_nt) - v[k];
+            lam = delta + ((gamma_tau * next_nt) * lam);
+            __stcs(advs + idx, lam);
+            __stcs(returns + idx, lam + v[k]);
+            next_v = v[k];
+            next_nt = 1.0f - d[k];
+        }
+    }
+    for (; t >= 0; --t) {
+        const int64_t idx = (int64_t)t * n + e;
+        const float r = rewards[idx], v = values[idx], d = (float)dones[idx];
+        const float delta = (r + (gamma * next_v) * next_nt) - v;
+        lam = delta + ((gamma_tau * next_nt) * lam);
+        advs[idx] = lam;
+        returns[idx] = lam + v;
+        next_v = v;
+        next_nt = 1.0f - d;
+    }
+}
+
+cudaError_t launch_gae(const float* rewards, const float* values, const void* dones, const float* last_values,
+                       const void* last_dones, int dones_kind, double gamma, double tau, float* advs, float* returns,
+                       int horizon, int64_t n, cudaStream_t st) {
+    if (n == 0 || horizon == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    const float g = (float)gamma, gt = (float)(gamma * tau);
+    if (dones_kind == 0)
+        gae_kernel<uint8_t, 8><<<blocks, 256, 0, st>>>(rewards, values, (const uint8_t*)dones, last_values,
+                                                       (const uint8_t*)last_dones, g, gt, advs, returns, horizon, n);
+    else
+        gae_kernel<float, 8><<<blocks, 256, 0, st>>>(rewards, values, (const float*)dones, last_values,
+                                                     (const float*)last_dones, g, gt, advs, returns, horizon, n);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: RunningMeanStd batch moments, pivoted: acc = [m, sum_j (x-p_j), sum_j (x-p_j)^2].
+// Block of RMS_THREADS threads covers `rpi = RMS_THREADS / cg` consecutive rows per iteration
+// (cg = column groups of VEC floats), so every thread keeps the same column(s) and every warp load
+// is a contiguous 128 B * VEC segment.
+// ------------------------------------------------------------------------------------------------
+constexpr int RMS_THREADS = 256;
+constexpr int RMS_MAX_BLOCKS = 148 * 4;
+constexpr int RMS_MAX_C = 256;                  // columns supported by the multi-column kernel
+
+template <int VEC>
+__global__ void __launch_bounds__(RMS_THREADS) rms_partials_kernel(const float* __restrict__ x, const double* __restrict__ pivot,
+                                                                   double* __restrict__ partials, int64_t m, int c) {
+    extern __shared__ double s_red[];           // [2][rpi][c]
+    const int cg = c / VEC;
+    const int rpi = RMS_THREADS / cg;           // rows per iteration (>= 1 because c <= RMS_MAX_C)
+    const int tid = threadIdx.x;
+    const int rsub = tid / cg, g = tid - rsub * cg;
+    const bool active = rsub < rpi;
+    double s[VEC], ss[VEC], pv[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) { s[k] = 0.0; ss[k] = 0.0; pv[k] = (pivot && active) ? pivot[g * VEC + k] : 0.0; }
+    if (active) {
+        const int64_t row_stride = (int64_t)gridDim.x * rpi;
+        int64_t r = (int64_t)blockIdx.x * rpi + rsub;
+        // 4 independent loads in flight per thread
+        for (; r + 3 * row_stride < m; r += 4 * row_stride) {
+            float xv[4][VEC];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float* p = x + (r + u * row_stride) * c + g * VEC;
+                if (VEC == 2) { const float2 t = *reinterpret_cast<const float2*>(p); xv[u][0] = t.x; xv[u][VEC - 1] = t.y; }
+                else xv[u][0] = *p;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) { const double d = (double)xv[u][k] - pv[k]; s[k] += d; ss[k] += d * d; }
+        }
+        for (; r < m; r += row_stride) {
+            const float* p = x + r * c + g * VEC;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) { const double d = (double)p[k] - pv[k]; s[k] += d; ss[k] += d * d; }
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            s_red[(0 * rpi + rsub) * c + g * VEC + k] = s[k];
+            s_red[(1 * rpi + rsub) * c + g * VEC + k] = ss[k];
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < 2 * c; j += RMS_THREADS) {        // fixed-order fold over the rpi row slots
+        const int stat = j / c, col = j - stat * c;
+        double acc = 0.0;
+        for (int q = 0; q < rpi; ++q) acc += s_red[(stat * rpi + q) * c + col];
+        partials[(int64_t)blockIdx.x * 2 * c + j] = acc;
+    }
+}
+
+// flat (c == 1) moments of x, or of (a - b) when b != nullptr (advantage = returns - values in fp32)
+__global__ void __launch_bounds__(RMS_THREADS) flat_partials_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                    const double* __restrict__ pivot, double* __restrict__ partials,
+                                                                    int64_t m, int vec4) {
+    __shared__ double s_w[2][RMS_THREADS / 32];
+    const double pv = pivot ? pivot[0] : 0.0;
+    double s = 0.0, ss = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nvec = vec4 ? (m >> 2) : 0;
+    for (int64_t i = tid; i < nvec; i += stride) {
+        float4 t = ldg_stream4(reinterpret_cast<const float4*>(a) + i);
+        if (b) { const float4 u = ldg_stream4(reinterpret_cast<const float4*>(b) + i); t.x -= u.x; t.y -= u.y; t.z -= u.z; t.w -= u.w; }
+        const double d0 = (double)t.x - pv, d1 = (double)t.y - pv, d2 = (double)t.z - pv, d3 = (double)t.w - pv;
+        s += (d0 + d1) + (d2 + d3);
+        ss += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+    for (int64_t i = nvec * 4 + tid; i < m; i += stride) {
+        float t = a[i];
+        if (b) t -= b[i];
+        const double d = (double)t - pv;
+        s += d; ss += d * d;
+    }
+    s = warp_sum(s); ss = warp_sum(ss);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { s_w[0][wid] = s; s_w[1][wid] = ss; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double acc = 0.0;
+        for (int q = 0; q < RMS_THREADS / 32; ++q) acc += s_w[threadIdx.x][q];
+        partials[(int64_t)blockIdx.x * 2 + threadIdx.x] = acc;
+    }
+}
+
+// fold the per-block partials in block order -> acc = [m, sums(c), sumsqs(c)]
+__global__ void moments_finalize_kernel(const double* __restrict__ partials, int nblocks, int c, int64_t m, double* __restrict__ acc) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0) acc[0] = (double)m;
+    if (j >= 2 * c) return;
+    double t = 0.0;
+    for (int b = 0; b < nblocks; ++b) t += partials[(int64_t)b * 2 * c + j];
+    acc[1 + j] = t;
+}
+
+// K4b: merge (reference running_mean_std.py training branch, fp64):
+//   batch mean = p + S/B, batch var (unbiased) = (SS - S*S/B)/(B-1)
+//   delta = mean_b - mean; tot = count + B; new_mean = mean + delta*B/tot
+//   M2 = var*count + var_b*B + delta^2*count*B/tot ; new_var = M2/tot ; count = tot
+__global__ void rms_merge_kernel(const double* __restrict__ acc, const double* __restrict__ pivot, double* running_mean,
+                                 double* running_var, double* count, int c) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const double B = acc[0];
+    const double cnt = count[0];
+    const double tot = cnt + B;
+    if (j < c && B > 0.0) {
+        const double p = pivot ? pivot[j] : 0.0;
+        const double S = acc[1 + j], SS = acc[1 + c + j];
+        const double mean_b = p + S / B;
+        const double var_b = (SS - S * S / B) / (B - 1.0);          // NaN for B == 1, like torch.var
+        const double mean = running_mean[j], var = running_var[j];
+        const double delta = mean_b - mean;
+        running_mean[j] = mean + delta * B / tot;
+        running_var[j] = (var * cnt + var_b * B + delta * delta * cnt * B / tot) / tot;
+    }
+    __syncthreads();
+    // count is read by every thread of every block above; a single trailing kernel-ordered write
+    // would race across blocks, so the launcher uses ONE block (c <= 1024).
+    if (j == 0 && B > 0.0) count[0] = tot;
+}
+
+// K5: normalise / un-normalise
+__global__ void __launch_bounds__(256) rms_normalize_kernel(const float* __restrict__ x, const double* __restrict__ running_mean,
+                                                            const double* __restrict__ running_var, float eps, int unnorm,
+                                                            float* __restrict__ y, int64_t total, int c, int vec4) {
+    extern __shared__ float s_stat[];       // [2][c]: mean.float(), sqrt(var.float() + eps)
+    for (int j = threadIdx.x; j < c; j += blockDim.x) {
+        s_stat[j] = (float)running_mean[j];
+        s_stat[c + j] = sqrtf((float)running_var[j] + eps);
+    }
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nvec = vec4 ? (total >> 2) : 0;
+    for (int64_t i = tid; i < nvec; i += stride) {
+        const float4 t = ldg_stream4(reinterpret_cast<const float4*>(x) + i);
+        const float in[4] = {t.x, t.y, t.z, t.w};
+        float out[4];
+        int col = (int)((i * 4) % c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float mean = s_stat[col], den = s_stat[c + col];
+            out[k] = unnorm ? (den * clamp_nan(in[k], -5.0f, 5.0f) + mean) : clamp_nan((in[k] - mean) / den, -5.0f, 5.0f);
+            col = (col + 1 == c) ? 0 : col + 1;
+        }
+        __stcs(reinterpret_cast<float4*>(y) + i, make_float4(out[0], out[1], out[2], out[3]));
+    }
+    for (int64_t i = nvec * 4 + tid; i < total; i += stride) {
+        const int col = (int)(i % c);
+        const float mean = s_stat[col], den = s_stat[c + col];
+        y[i] = unnorm ? (den * clamp_nan(x[i], -5.0f, 5.0f) + mean) : clamp_nan((x[i] - mean) / den, -5.0f, 5.0f);
+    }
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
+
+static inline int stream_blocks(int64_t work_items, int threads, int per_sm) {
+    int64_t b = (work_items + threads - 1) / threads;
+    if (b < 1) b = 1;
+    const int64_t cap = 148LL * per_sm;
+    return (int)(b > cap ? cap : b);
+}
+
+int64_t rms_scratch_doubles(int c) { return (int64_t)RMS_MAX_BLOCKS * 2 * (c > 0 ? c : 1); }
+
+cudaError_t launch_rms_moments(const float* x, const double* pivot, double* acc, double* partials, int64_t m, int c,
+                               cudaStream_t st) {
+    int nblocks;
+    if (c == 1) {
+        const int vec4 = aligned16(x);
+        nblocks = stream_blocks(vec4 ? m / 4 : m, RMS_THREADS, 4);
+        flat_partials_kernel<<<nblocks, RMS_THREADS, 0, st>>>(x, nullptr, pivot, partials, m, vec4);
+    } else {
+        if (c > RMS_MAX_C) return cudaErrorInvalidValue;
+        const bool v2 = (c % 2 == 0) && aligned8(x);
+        const int cg = v2 ? c / 2 : c;
+        const int rpi = RMS_THREADS / cg;
+        int64_t b = (m + rpi - 1) / rpi;
+        b = (b + 3) / 4;                               // >= 4 row slots per thread where possible
+        if (b < 1) b = 1;
+        nblocks = (int)(b > RMS_MAX_BLOCKS ? RMS_MAX_BLOCKS : b);
+        const size_t smem = (size_t)2 * rpi * c * sizeof(double);
+        if (v2) rms_partials_kernel<2><<<nblocks, RMS_THREADS, smem, st>>>(x, pivot, partials, m, c);
+        else rms_partials_kernel<1><<<nblocks, RMS_THREADS, smem, st>>>(x, pivot, partials, m, c);
+    }
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    moments_finalize_kernel<<<(2 * c + 127) / 128, 128, 0, st>>>(partials, nblocks, c, m, acc);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rms_merge(const double* acc, const double* pivot, double* running_mean, double* running_var,
+                             double* count, int c, cudaStream_t st) {
+    if (c > 1024) return cudaErrorInvalidValue;
+    rms_merge_kernel<<<1, ((c + 31) / 32) * 32, 0, st>>>(acc, pivot, running_mean, running_var, count, c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rms_normalize(const float* x, const double* running_mean, const double* running_var, float eps,
+                                 int unnorm, float* y, int64_t m, int c, cudaStream_t st) {
+    const int64_t total = m * c;
+    if (total == 0) return cudaSuccess;
+    const int vec4 = aligned16(x) && aligned16(y);
+    const int blocks = stream_blocks(vec4 ? total / 4 : total, 256, 8);
+    rms_normalize_kernel<<<blocks, 256, 2 * c * sizeof(float), st>>>(x, running_mean, running_var, eps, unnorm, y, total, c, vec4);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: advantage statistics / normalisation (a2c_common.py prepare_dataset)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adv_normalize_kernel(const float* __restrict__ returns, const float* __restrict__ values,
+                                                            const double* __restrict__ acc, float* __restrict__ adv, int normalize,
+                                                            int64_t m, int vec4) {
+    float mean = 0.0f, den = 1.0f;
+    if (normalize) {
+        const double B = acc[0], S = acc[1], SS = acc[2];
+        const double mu = S / B;
+        const double var = (SS - S * mu) / (B - 1.0);              // unbiased, torch.std default
+        mean = (float)mu;
+        den = (float)sqrt(var > 0.0 ? var : 0.0) + 1e-8f;
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nvec = vec4 ? (m >> 2) : 0;
+    for (int64_t i = tid; i < nvec; i += stride) {
+        const float4 r = ldg_stream4(reinterpret_cast<const float4*>(returns) + i);
+        const float4 v = ldg_stream4(reinterpret_cast<const float4*>(values) + i);
+        float4 o = make_float4(r.x - v.x, r.y - v.y, r.z - v.z, r.w - v.w);
+        if (normalize) { o.x = (o.x - mean) / den; o.y = (o.y - mean) / den; o.z = (o.z - mean) / den; o.w = (o.w - mean) / den; }
+        __stcs(reinterpret_cast<float4*>(adv) + i, o);
+    }
+    for (int64_t i = nvec * 4 + tid; i < m; i += stride) {
+        float o = returns[i] - values[i];
+        if (normalize) o = (o - mean) / den;
+        adv[i] = o;
+    }
+}
+
+cudaError_t launch_adv_moments(const float* returns, const float* values, double* acc, double* partials, int64_t m,
+                               cudaStream_t st) {
+    const int vec4 = aligned16(returns) && aligned16(values);
+    const int nblocks = stream_blocks(vec4 ? m / 4 : m, RMS_THREADS, 4);
+    flat_partials_kernel<<<nblocks, RMS_THREADS, 0, st>>>(returns, values, nullptr, partials, m, vec4);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    moments_finalize_kernel<<<1, 128, 0, st>>>(partials, nblocks, 1, m, acc);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_adv_normalize(const float* returns, const float* values, const double* acc, float* adv, int normalize,
+                                 int64_t m, cudaStream_t st) {
+    if (m == 0) return cudaSuccess;
+    const int vec4 = aligned16(returns) && aligned16(values) && aligned16(adv);
+    const int blocks = stream_blocks(vec4 ? m / 4 : m, 256, 8);
+    adv_normalize_kernel<<<blocks, 256, 0, st>>>(returns, values, acc, adv, normalize, m, vec4);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8: fused PPO loss forward + backward.  One thread per sample; the four (m,18) row arrays of a
+// 128-sample tile arrive as four cp.async.bulk copies (9216 contiguous bytes each) and grad_mu leaves
+// as one bulk store.  Per-block partial sums (fp64) of the five loss terms, clip fraction and the 18
+// logstd gradients are folded in block order by a finalize kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int PPO_TILE = 128;
+constexpr int PPO_NSTAT = 7;                    // a, c, b, kl, clipped, (spare), (spare)
+constexpr int PPO_PART = PPO_NSTAT + 18;        // doubles per block
+constexpr int PPO_MAX_BLOCKS = 1 << 16;
+
+
+__global__ void __launch_bounds__(PPO_TILE) ppo_loss_kernel(const PpoArgs a, const __grid_constant__ BezkPpoCfg cfg) {
+    __shared__ __align__(128) float s_act[PPO_TILE * 18];
+    __shared__ __align__(128) float s_mu[PPO_TILE * 18];
+    __shared__ __align__(128) float s_omu[PPO_TILE * 18];
+    __shared__ __align__(128) float s_osig[PPO_TILE * 18];
+    __shared__ __align__(128) float s_gmu[PPO_TILE * 18];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ float s_sigma[18], s_logstd[18];
+    __shared__ double s_red[PPO_TILE / 32][PPO_PART];
+
+    const int tid = threadIdx.x;
+    const int64_t i0 = (int64_t)blockIdx.x * PPO_TILE;
+    const int nv = (int)((a.m - i0) < (int64_t)PPO_TILE ? (a.m - i0) : (int64_t)PPO_TILE);
+    const bool full = (nv == PPO_TILE) && a.use_tma;
+    const int64_t i = i0 + tid;
+    const bool valid = tid < nv;
+    constexpr uint32_t TILE_BYTES = PPO_TILE * 18 * 4;
+
+    if (full) {
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            fence_mbar_init();
+            mbar_arrive_expect_tx(&s_bar, 4 * TILE_BYTES);
+            bulk_g2s(s_act, a.actions + i0 * 18, TILE_BYTES, &s_bar);
+            bulk_g2s(s_mu, a.mu + i0 * 18, TILE_BYTES, &s_bar);
+            bulk_g2s(s_omu, a.old_mu + i0 * 18, TILE_BYTES, &s_bar);
+            bulk_g2s(s_osig, a.old_sigma + i0 * 18, TILE_BYTES, &s_bar);
+        }
+    } else {
+        for (int k = tid; k < nv * 18; k += PPO_TILE) {
+            s_act[k] = a.actions[i0 * 18 + k]; s_mu[k] = a.mu[i0 * 18 + k];
+            s_omu[k] = a.old_mu[i0 * 18 + k]; s_osig[k] = a.old_sigma[i0 * 18 + k];
+        }
+    }
+    if (tid < 18) { const float ls = a.logstd[tid]; s_logstd[tid] = ls; s_sigma[tid] = expf(ls); }
+    float val = 0.f, oval = 0.f, ret = 0.f, onlp = 0.f, adv = 0.f;
+    if (valid) { val = a.values[i]; oval = a.old_values[i]; ret = a.returns[i]; onlp = a.old_neglogp[i]; adv = a.advantages[i]; }
+    __syncthreads();
+    if (full) mbar_wait(&s_bar, 0);
+
+    double part[PPO_PART];
+#pragma unroll
+    for (int k = 0; k < PPO_PART; ++k) part[k] = 0.0;
+
+    if (valid) {
+        const float inv_m = 1.0f / (float)a.m;
+        // ---- neglogp (models.py), bound loss, KL: one sweep over the 18 action dims ----
+        float z[18];
+        float sq = 0.0f, lsum = 0.0f, bsum = 0.0f, kl = 0.0f;
+        float dbound[18];
+        const float2* act2 = reinterpret_cast<const float2*>(s_act + tid * 18);
+        const float2* mu2 = reinterpret_cast<const float2*>(s_mu + tid * 18);
+        const float2* omu2 = reinterpret_cast<const float2*>(s_omu + tid * 18);
+        const float2* osig2 = reinterpret_cast<const float2*>(s_osig + tid * 18);
+#pragma unroll
+        for (int h = 0; h < 9; ++h) {
+            const float2 A2 = act2[h], M2 = mu2[h], OM2 = omu2[h], OS2 = osig2[h];
+            const float av[2] = {A2.x, A2.y}, mv[2] = {M2.x, M2.y}, omv[2] = {OM2.x, OM2.y}, osv[2] = {OS2.x, OS2.y};
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int j = 2 * h + q;
+                const float sig = s_sigma[j];
+                const float zz = (av[q] - mv[q]) / sig;
+                z[j] = zz;
+                sq += zz * zz;
+                lsum += s_logstd[j];
+                float hi, lo, dh, dl;
+                if (cfg.bound_form == 0) {          // rl_games 1.1.3 as recalled
+                    hi = fminf(mv[q] - cfg.soft_bound, 0.0f); lo = fminf(-mv[q] + cfg.soft_bound, 0.0f);
+                    dh = 2.0f * hi; dl = -2.0f * lo;
+                } else {                            // later releases
+                    hi = fmaxf(mv[q] - cfg.soft_bound, 0.0f); lo = fminf(mv[q] + cfg.soft_bound, 0.0f);
+                    dh = 2.0f * hi; dl = 2.0f * lo;
+                }
+                bsum += lo * lo + hi * hi;
+                dbound[j] = dh + dl;
+                const float c1 = logf(osv[q] / sig + 1e-5f);
+                const float dm = omv[q] - mv[q];
+                const float c2 = (sig * sig + dm * dm) / (2.0f * (osv[q] * osv[q] + 1e-5f));
+                kl += (c1 + c2) + (-0.5f);
+            }
+        }
+        const float nlp = (0.5f * sq + (float)(0.5 * 1.8378770664093453 * 18.0)) + lsum;   // log(2*pi) = 1.83787706...
+        if (a.neglogp_out) a.neglogp_out[i] = nlp;
+        // ---- actor loss (common_losses.actor_loss) ----
+        const float ratio = expf(onlp - nlp);
+        const float lo_r = 1.0f - cfg.e_clip, hi_r = 1.0f + cfg.e_clip;
+        const float s1 = adv * ratio, s2 = adv * clamp_nan(ratio, lo_r, hi_r);
+        const float a_loss = max_nan(-s1, -s2);
+        const bool inside = (ratio >= lo_r) && (ratio <= hi_r);
+        const bool through = inside || (-s1 > -s2);
+        const float dnlp = through ? (adv * ratio) : 0.0f;            // d a_loss / d neglogp
+        // ---- critic loss (common_losses.critic_loss) ----
+        float c_loss, dval;
+        const float t1 = (val - ret) * (val - ret);
+        if (cfg.clip_value) {
+            const float dv = val - oval;
+            const float vpc = oval + clamp_nan(dv, -cfg.e_clip, cfg.e_clip);
+            const float t2 = (vpc - ret) * (vpc - ret);
+            c_loss = max_nan(t1, t2);
+            const float g1 = 2.0f * (val - ret);
+            const float g2 = (dv >= -cfg.e_clip && dv <= cfg.e_clip) ? 2.0f * (vpc - ret) : 0.0f;
+            dval = (t1 > t2) ? g1 : ((t2 > t1) ? g2 : 0.5f * (g1 + g2));
+        } else {
+            c_loss = t1;
+            dval = 2.0f * (val - ret);
+        }
+        if (a.grad_values) a.grad_values[i] = (0.5f * cfg.critic_coef) * dval * inv_m;
+        // ---- gradients wrt mu (row) and partials for logstd ----
+        float* g = s_gmu + tid * 18;
+#pragma unroll
+        for (int j = 0; j < 18; ++j) {
+            const float sig = s_sigma[j];
+            g[j] = (dnlp * (-z[j] / sig) + cfg.bounds_loss_coef * dbound[j]) * inv_m;
+            part[PPO_NSTAT + j] = (double)(dnlp * (1.0f - z[j] * z[j]));
+        }
+        part[0] = (double)a_loss; part[1] = (double)c_loss; part[2] = (double)bsum; part[3] = (double)kl;
+        part[4] = inside ? 0.0 : 1.0;
+    }
+
+    // ---- grad_mu tile out ----
+    if (a.grad_mu) {
+        if (full) {
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (tid == 0) { bulk_s2g(a.grad_mu + i0 * 18, s_gmu, TILE_BYTES); bulk_commit(); }
+        } else {
+            __syncthreads();
+            for (int k = tid; k < nv * 18; k += PPO_TILE) a.grad_mu[i0 * 18 + k] = s_gmu[k];
+        }
+    }
+
+    // ---- block reduction of the partial sums (warp shuffle, then fixed-order fold over 4 warps) ----
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < PPO_PART; ++k) {
+        const double t = warp_sum(part[k]);
+        if (lane == 0) s_red[wid][k] = t;
+    }
+    __syncthreads();
+    if (tid < PPO_PART) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < PPO_TILE / 32; ++q) t += s_red[q][tid];
+        a.partials[(int64_t)blockIdx.x * PPO_PART + tid] = t;
+    }
+    if (a.grad_mu && full && tid == 0) bulk_wait_read0();
+}
+
+__global__ void ppo_finalize_kernel(const double* __restrict__ partials, int nblocks, int64_t m, const float* __restrict__ logstd,
+                                    const __grid_constant__ BezkPpoCfg cfg, double* __restrict__ stats, float* __restrict__ grad_logstd) {
+    __shared__ double s_tot[PPO_PART];
+    const int j = threadIdx.x;
+    if (j < PPO_PART) {
+        double t = 0.0;
+        for (int b = 0; b < nblocks; ++b) t += partials[(int64_t)b * PPO_PART + j];
+        s_tot[j] = t;
+    }
+    __syncthreads();
+    const double inv_m = 1.0 / (double)m;
+    if (j == 0) {
+        double ent = 0.0;
+        for (int k = 0; k < 18; ++k) ent += (double)((0.5f + 0.9189385332046727f) + logstd[k]);   // 0.5*log(2*pi)
+        const double a_m = s_tot[0] * inv_m, c_m = s_tot[1] * inv_m, b_m = s_tot[2] * inv_m, kl_m = s_tot[3] * inv_m;
+        stats[1] = a_m; stats[2] = c_m; stats[3] = ent; stats[4] = b_m; stats[5] = kl_m; stats[6] = s_tot[4] * inv_m; stats[7] = 0.0;
+        stats[0] = a_m + 0.5 * c_m * (double)cfg.critic_coef - ent * (double)cfg.entropy_coef + b_m * (double)cfg.bounds_loss_coef;
+    }
+    if (grad_logstd && j < 18) grad_logstd[j] = (float)(s_tot[PPO_NSTAT + j] * inv_m - (double)cfg.entropy_coef);
+}
+
+int64_t ppo_scratch_doubles() { return (int64_t)PPO_MAX_BLOCKS * PPO_PART; }
+
+cudaError_t launch_ppo_loss(const PpoArgs& args, const BezkPpoCfg& cfg, double* stats, float* grad_logstd, cudaStream_t st) {
+    PpoArgs a = args;
+    if (a.m <= 0) return cudaErrorInvalidValue;
+    const int64_t nblocks = (a.m + PPO_TILE - 1) / PPO_TILE;
+    if (nblocks > PPO_MAX_BLOCKS) return cudaErrorInvalidValue;
+    a.use_tma = aligned16(a.actions) && aligned16(a.mu) && aligned16(a.old_mu) && aligned16(a.old_sigma) &&
+                (a.grad_mu == nullptr || aligned16(a.grad_mu));
+    ppo_loss_kernel<<<(unsigned)nblocks, PPO_TILE, 0, st>>>(a, cfg);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    ppo_finalize_kernel<<<1, 32, 0, st>>>(a.partials, (int)nblocks, a.m, a.logstd, cfg, stats, grad_logstd);
+    return cudaGetLastError();
+}
+
+}  // namespace bezk

@@ -1,0 +1,550 @@
+// BezKick task-side kernels for B200 (sm_100a): K0 pre-physics, the fused post-physics tile kernel
+// (bookkeeping + masked reset + observations + reward/termination; also instantiated as the separate
+// observation / reward kernels), explicit-id reset, and the Philox uniform dump.
+//
+// Layout facts (Isaac Gym AoS): per env, dof_state is 36 contiguous floats, root_states
+// 26 contiguous floats (2 actors x 13); rigid_body / net_contact are sparse (10 of 286 resp. 6 of 66
+// floats used).  One CTA owns a tile of TILE consecutive envs, one thread per env:
+//   * the two dense inputs of the tile are contiguous byte ranges -> two cp.async.bulk (TMA 1-D)
+//     copies into shared memory, completion on one mbarrier;
+//   * the sparse rows are gathered with per-thread sector-aligned vector loads issued BEFORE the
+//     barrier wait, so they fly together with the bulk copies;
+//   * each thread reads its rows out of shared memory with bank-conflict-free 128-bit loads (row stride
+//     36 words), computes everything in registers, then the 54-float observation rows are written
+//     back into the SAME shared region (after a CTA barrier) and leave as one cp.async.bulk store of
+//     TILE*216 contiguous bytes.
+// HBM-bound: 656-680 algorithmic B/env-step, no tensor cores.
+#include "bezk_common.cuh"
+#include "bezk_internal.h"
+#include <math.h>
+
+namespace bezk {
+
+constexpr int TILE = 128;            // envs per CTA = threads per CTA
+constexpr int DOF_ROW = 36;          // floats per env in dof_state
+constexpr int ROOT_ROW = 26;         // floats per env in root_states
+constexpr int OBS_ROW = 54;
+constexpr int SMEM_IN_FLOATS = TILE * (DOF_ROW + ROOT_ROW);   // 7936 floats = 31744 B >= TILE*54*4
+constexpr int SMEM_OBS_FLOATS = TILE * OBS_ROW;               // 6912 floats = 27648 B
+
+
+// ------------------------------------------------------------------------------------------------
+// K0: pre-physics.  Pure streaming elementwise pass over (n,18): 72 B read + 72 B written per env.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pre_physics_kernel(const float* __restrict__ actions, float* __restrict__ actions_out,
+                                                          float* __restrict__ targets, const __grid_constant__ BezkTaskCfg cfg,
+                                                          int64_t total, int vec4) {
+    __shared__ float s_def[18], s_lo[18], s_hi[18];
+    if (threadIdx.x < 18) {
+        s_def[threadIdx.x] = cfg.default_dof_pos[threadIdx.x];
+        s_lo[threadIdx.x] = cfg.dof_lower[threadIdx.x];
+        s_hi[threadIdx.x] = cfg.dof_upper[threadIdx.x];
+    }
+    __syncthreads();
+    const float clip = cfg.clip_actions;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nvec = vec4 ? (total >> 2) : 0;
+    for (int64_t i = tid; i < nvec; i += stride) {
+        const float4 a = ldg_stream4(reinterpret_cast<const float4*>(actions) + i);
+        const float in[4] = {a.x, a.y, a.z, a.w};
+        float st[4], tg[4];
+        int col = (int)((i * 4) % 18);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float v = clamp_nan(in[k], -clip, clip);
+            if (col < 2) v = 0.0f;
+            st[k] = v;
+            tg[k] = tensor_clamp(v + s_def[col], s_lo[col], s_hi[col]);
+            col = (col == 17) ? 0 : col + 1;
+        }
+        __stcs(reinterpret_cast<float4*>(targets) + i, make_float4(tg[0], tg[1], tg[2], tg[3]));
+        if (actions_out) __stcs(reinterpret_cast<float4*>(actions_out) + i, make_float4(st[0], st[1], st[2], st[3]));
+    }
+    for (int64_t i = nvec * 4 + tid; i < total; i += stride) {      // scalar tail / unaligned path
+        const int col = (int)(i % 18);
+        float v = clamp_nan(actions[i], -clip, clip);
+        if (col < 2) v = 0.0f;
+        targets[i] = tensor_clamp(v + s_def[col], s_lo[col], s_hi[col]);
+        if (actions_out) actions_out[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-env math (device functions; arithmetic order follows the reference op by op)
+// ------------------------------------------------------------------------------------------------
+
+// compute_imu, kick_env.py:918-930, with quaternion_to_matrix (:857-885) applied to the xyzw
+// quaternion as if it were real-first: (r,i,j,k) = (x,y,z,w).
+__device__ __forceinline__ void imu_term(const float (&q)[4], const float (&v)[3], const float (&w)[3],
+                                         const float (&prev)[3], const BezkTaskCfg& c, float (&out)[6]) {
+    float a[3];
+    a[0] = (v[0] - prev[0]) / c.dt - 0.0f;
+    a[1] = (v[1] - prev[1]) / c.dt - 0.0f;
+    a[2] = (v[2] - prev[2]) / c.dt - (-1.0f);            // gravity_vec = (0,0,-1), :217
+    const float r = q[0], i = q[1], j = q[2], k = q[3];
+    const float two_s = 2.0f / (((r * r + i * i) + j * j) + k * k);
+    const float m00 = 1.0f - two_s * (j * j + k * k), m01 = two_s * (i * j - k * r), m02 = two_s * (i * k + j * r);
+    const float m10 = two_s * (i * j + k * r), m11 = 1.0f - two_s * (i * i + k * k), m12 = two_s * (j * k - i * r);
+    const float m20 = two_s * (i * k - j * r), m21 = two_s * (j * k + i * r), m22 = 1.0f - two_s * (i * i + j * j);
+    const float t0 = (m00 * a[0] + m01 * a[1]) + m02 * a[2];
+    const float t1 = (m10 * a[0] + m11 * a[1]) + m12 * a[2];
+    const float t2 = (m20 * a[0] + m21 * a[1]) + m22 * a[2];
+    out[0] = clamp_nan(t0, -c.imu_max_lin_acc, c.imu_max_lin_acc);
+    out[1] = clamp_nan(t1, -c.imu_max_lin_acc, c.imu_max_lin_acc);
+    out[2] = clamp_nan(t2, -c.imu_max_lin_acc, c.imu_max_lin_acc);
+    out[3] = clamp_nan(w[0], -c.imu_max_ang_vel, c.imu_max_ang_vel);
+    out[4] = clamp_nan(w[1], -c.imu_max_ang_vel, c.imu_max_ang_vel);
+    out[5] = clamp_nan(w[2], -c.imu_max_ang_vel, c.imu_max_ang_vel);
+}
+
+// python-style remainder by a positive modulus (torch.remainder / Tensor.__mod__)
+__device__ __forceinline__ float py_mod(float x, float m) {
+    float r = fmodf(x, m);
+    if (r != 0.0f && r < 0.0f) r += m;
+    return r;
+}
+
+// compute_off_orn, kick_env.py:941-960 (+ yaw of get_euler_xyz)
+__device__ __forceinline__ void off_orn_term(float px, float py, const float (&q)[4], float gx, float gy, float (&out)[2]) {
+    const float dx = gx - px, dy = gy - py;
+    const float nrm = sqrtf(dx * dx + dy * dy);
+    const float ux = dx / nrm, uy = dy / nrm;
+    const float x = q[0], y = q[1], z = q[2], w = q[3];
+    const float siny = 2.0f * (w * z + x * y);
+    const float cosy = ((w * w + x * x) - y * y) - z * z;
+    const float yaw = py_mod(atan2f(siny, cosy), 6.283185307179586f);
+    const float hx = cosf(yaw), hy = sinf(yaw);
+    const float c = hx * ux + hy * uy;
+    const float cz = ux * hy - uy * hx;                  // only non-zero component of the 3-D cross
+    out[0] = sqrtf((0.0f + 0.0f) + cz * cz);             // linalg.norm of (0, 0, cz)
+    out[1] = -c;
+}
+
+// compute_feet_sensors_no_cleats, kick_env.py:987-1038: returns the 4 bits of one foot and filters f.
+__device__ __forceinline__ void foot_bits(float (&f)[3], float (&bits)[4]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) f[k] = (fabsf(f[k]) > 0.01f) ? f[k] : 0.0f;     // NaN -> 0 as in torch.where
+    const bool x0 = (f[0] == 0.0f), y0 = (f[1] == 0.0f);
+    // (x!=0,y!=0)->case 1, (x!=0,y==0)->3, (x==0,y!=0)->9, (x==0,y==0)->11   (SURVEY a9 truth table)
+    float b0 = 1.0f, b1 = x0 ? 1.0f : -1.0f, b2 = y0 ? 1.0f : -1.0f, b3 = (x0 && y0) ? 1.0f : -1.0f;
+    if (f[2] < 1.0f) { b0 = b1 = b2 = b3 = -1.0f; }
+    bits[0] = b0; bits[1] = b1; bits[2] = b2; bits[3] = b3;
+}
+
+struct RewardIn {
+    float bez[3];          // torso root position
+    float ball_xy[2];
+    float ball_vxy[2];
+    float goal[2];
+    float ball_init[2];
+    float v[3], w[3];      // IMU-link linear / angular velocity
+    float pos_sq;          // sum_j (default_j - dof_pos_j)^2, sequential
+};
+
+// compute_bez_reward, kick_env.py:1224-1395.  `progress` is the post-increment value.
+__device__ __forceinline__ void reward_term(const RewardIn& s, const BezkTaskCfg& c, int64_t progress,
+                                            int64_t reset_cur, float* rew_out, int64_t* reset_out) {
+    const float dbx = s.ball_xy[0] - s.bez[0], dby = s.ball_xy[1] - s.bez[1];
+    const float nbb = sqrtf(dbx * dbx + dby * dby);
+    const float vel_fwd = (dbx / nbb) * s.v[0] + (dby / nbb) * s.v[1];
+
+    const float dgx = s.goal[0] - s.ball_xy[0], dgy = s.goal[1] - s.ball_xy[1];
+    const float n_goal = sqrtf(dgx * dgx + dgy * dgy);
+    const float ugx = dgx / n_goal, ugy = dgy / n_goal;
+    const float ball_fwd = ugx * s.ball_vxy[0] + ugy * s.ball_vxy[1];
+
+    const float dix = s.goal[0] - s.ball_init[0], diy = s.goal[1] - s.ball_init[1];
+    const float n_init = sqrtf(dix * dix + diy * diy);
+    const float ang_now = atan2f(ugy, ugx);
+    const float ang_init = atan2f(diy / n_init, dix / n_init);
+    const float angle_diff = fabsf(ang_init - ang_now);
+
+    float vs = s.v[0] * s.v[0];
+    vs += s.v[1] * s.v[1]; vs += s.v[2] * s.v[2];
+    vs += s.w[0] * s.w[0]; vs += s.w[1] * s.w[1]; vs += s.w[2] * s.w[2];
+    const float vel_r = sqrtf(vs) * 0.05f;
+    const float pos_r = sqrtf(s.pos_sq) * 0.05f;
+    const float height = fabsf(0.325f - s.bez[2]) * 1.0f;
+    const float kx = s.ball_xy[0] - s.ball_init[0], ky = s.ball_xy[1] - s.ball_init[1];
+    const float kicked = sqrtf(kx * kx + ky * ky);
+
+    const float far_r = ball_fwd * 0.1f - (height + (vel_r + pos_r));
+    const float near_r = ball_fwd * 0.1f + (vel_fwd * 0.05f - height);
+    float rew = (kicked > 0.3f) ? far_r : near_r;
+    int64_t reset = reset_cur;
+
+    if (s.bez[2] < 0.275f) { reset = 1; rew = -1.0f; }                                    // rule 1
+    const float tx = s.bez[0] - c.bez_init_xy[0], ty = s.bez[1] - c.bez_init_xy[1];
+    if (sqrtf(tx * tx + ty * ty) > 0.5f) { reset = 1; rew = -1.0f; }                      // rule 2
+    if (angle_diff > 1.5708f) { reset = 1; rew = -1.0f; }                                 // rule 3
+    if (n_goal < 0.05f) {                                                                 // rule 4
+        reset = 1;
+        rew = 1.0f * (100.0f - 100.0f * ((float)progress / (float)c.max_episode_length));
+    }
+    if (progress >= (int64_t)c.max_episode_length) { reset = 1; rew = 0.0f; }             // rule 5
+    *rew_out = rew;
+    *reset_out = reset;
+}
+
+// reset_idx DOF part, kick_env.py:786-791
+__device__ __forceinline__ void reset_dof_row(const float (&u)[36], const BezkTaskCfg& c, float (&row)[36]) {
+#pragma unroll
+    for (int j = 0; j < 18; ++j) {
+        const float off = c.reset_pos_span * u[j] + c.reset_pos_lo;
+        row[2 * j] = tensor_clamp(c.default_dof_pos[j] + off, c.dof_lower[j], c.dof_upper[j]);
+        row[2 * j + 1] = c.reset_vel_span * u[18 + j] + c.reset_vel_lo;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The fused tile kernel.  PARTS: 1 bookkeeping+masked reset, 2 observations, 4 reward/termination.
+// ------------------------------------------------------------------------------------------------
+template <int PARTS>
+__global__ void __launch_bounds__(TILE) task_tile_kernel(const TaskArgs a, const __grid_constant__ BezkTaskCfg cfg) {
+    constexpr bool BOOK = (PARTS & BEZK_PART_BOOKKEEP) != 0;
+    constexpr bool OBS = (PARTS & BEZK_PART_OBS) != 0;
+    constexpr bool REW = (PARTS & BEZK_PART_REWARD) != 0;
+
+    extern __shared__ __align__(128) float smem[];
+    float* s_dof = smem;                              // [TILE][36]
+    float* s_root = smem + TILE * DOF_ROW;            // [TILE][26]
+    float* s_obs = smem;                              // [TILE][54], aliases the two input tiles
+    float* s_obs_clip = smem + SMEM_IN_FLOATS;        // [TILE][54], only when a.obs_clipped
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int tid = threadIdx.x;
+    const int64_t e0 = (int64_t)blockIdx.x * TILE;
+    const int nv = (int)((a.n - e0) < (int64_t)TILE ? (a.n - e0) : (int64_t)TILE);
+    const bool full = (nv == TILE) && a.use_tma;
+    const int64_t e = e0 + tid;
+    const bool valid = tid < nv;
+
+    // ---- 1. dense tiles: TMA bulk copies (full tiles) or cooperative coalesced loads (tail tile) ----
+    if (full) {
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            fence_mbar_init();
+            mbar_arrive_expect_tx(&s_bar, TILE * (DOF_ROW + ROOT_ROW) * 4);
+            bulk_g2s(s_dof, a.dof_state + e0 * DOF_ROW, TILE * DOF_ROW * 4, &s_bar);
+            bulk_g2s(s_root, a.root_states + e0 * ROOT_ROW, TILE * ROOT_ROW * 4, &s_bar);
+        }
+    } else {
+        for (int i = tid; i < nv * DOF_ROW; i += TILE) s_dof[i] = a.dof_state[e0 * DOF_ROW + i];
+        for (int i = tid; i < nv * ROOT_ROW; i += TILE) s_root[i] = a.root_states[e0 * ROOT_ROW + i];
+    }
+
+    // ---- 2. sparse gathers, issued before anyone waits ----
+    float q[4] = {0.f, 0.f, 0.f, 1.f}, v[3] = {0.f, 0.f, 0.f}, w[3] = {0.f, 0.f, 0.f};
+    float fl[12], fr[12];
+    float goal[2] = {0.f, 0.f}, binit[2] = {0.f, 0.f}, prev[3] = {0.f, 0.f, 0.f};
+    int64_t reset_prev = 0, progress = 0;
+    const bool cleats = (cfg.flags & BEZK_F_CLEATS) != 0;
+    const int nforce = cleats ? 12 : 3;
+    float* cf_l = nullptr;
+    float* cf_r = nullptr;
+    if (valid) {
+        const float* rb = a.rigid_body + ((e * cfg.num_bodies + cfg.imu_body) * 13 + 3);
+        if (a.rb_vec2) {
+            const float2* rb2 = reinterpret_cast<const float2*>(rb);
+            const float2 t0 = __ldg(rb2), t1 = __ldg(rb2 + 1), t2 = __ldg(rb2 + 2), t3 = __ldg(rb2 + 3), t4 = __ldg(rb2 + 4);
+            q[0] = t0.x; q[1] = t0.y; q[2] = t1.x; q[3] = t1.y;
+            v[0] = t2.x; v[1] = t2.y; v[2] = t3.x; w[0] = t3.y; w[1] = t4.x; w[2] = t4.y;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[k] = __ldg(rb + k);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { v[k] = __ldg(rb + 4 + k); w[k] = __ldg(rb + 7 + k); }
+        }
+        if (OBS) {
+            cf_l = a.net_contact + (e * cfg.num_bodies + cfg.left_foot_body) * 3;
+            cf_r = a.net_contact + (e * cfg.num_bodies + cfg.right_foot_body) * 3;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                if (k < nforce) { fl[k] = cf_l[k]; fr[k] = cf_r[k]; }
+            }
+            if (a.prev_lin_vel) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) prev[k] = a.prev_lin_vel[e * 3 + k];
+            }
+        }
+        const float2 g2 = __ldg(reinterpret_cast<const float2*>(a.goal) + e);
+        const float2 b2 = __ldg(reinterpret_cast<const float2*>(a.ball_init) + e);
+        goal[0] = g2.x; goal[1] = g2.y; binit[0] = b2.x; binit[1] = b2.y;
+        if (BOOK || REW) {
+            reset_prev = a.reset_in[e];
+            progress = a.progress_in[e];
+        }
+    }
+
+    // ---- 3. wait for the dense tiles, pull this env's rows into registers ----
+    __syncthreads();                       // mbarrier init / cooperative stores visible
+    if (full) mbar_wait(&s_bar, 0);
+
+    float row[36];
+    float rt[ROOT_ROW];
+    if (valid) {
+        const float4* r4 = reinterpret_cast<const float4*>(s_dof + tid * DOF_ROW);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const float4 t = r4[k];
+            row[4 * k] = t.x; row[4 * k + 1] = t.y; row[4 * k + 2] = t.z; row[4 * k + 3] = t.w;
+        }
+        const float2* r2 = reinterpret_cast<const float2*>(s_root + tid * ROOT_ROW);
+#pragma unroll
+        for (int k = 0; k < 13; ++k) {
+            const float2 t = r2[k];
+            rt[2 * k] = t.x; rt[2 * k + 1] = t.y;
+        }
+    }
+
+    // ---- 4. bookkeeping + masked reset (vec_task.py:331-332, kick_env.py:429-435, 779-850) ----
+    int64_t timeout = 0, reset_cur = reset_prev;
+    if (BOOK && valid) {
+        timeout = (progress >= (int64_t)cfg.max_episode_length - 1) ? 1 : 0;
+        progress += 1;
+        if (a.randomize_buf) a.randomize_buf[e] += 1;
+        if (reset_prev != 0) {
+            float u[36];
+            if (a.uniforms) {
+#pragma unroll
+                for (int k = 0; k < 36; ++k) u[k] = a.uniforms[e * 36 + k];
+            } else {
+                philox_reset_uniforms(a.seed, a.step, e, u);
+            }
+            reset_dof_row(u, cfg, row);
+            float4* g4 = reinterpret_cast<float4*>(a.dof_state + e * DOF_ROW);
+            if (a.use_tma) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) g4[k] = make_float4(row[4 * k], row[4 * k + 1], row[4 * k + 2], row[4 * k + 3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 36; ++k) a.dof_state[e * DOF_ROW + k] = row[k];
+            }
+            if (cfg.flags & BEZK_F_RESET_ROOT_STATES) {
+#pragma unroll
+                for (int k = 0; k < ROOT_ROW; ++k) {
+                    rt[k] = a.initial_root[e * ROOT_ROW + k];
+                    a.root_states[e * ROOT_ROW + k] = rt[k];
+                }
+            }
+            progress = 0;
+            reset_cur = 0;
+        }
+        a.timeout_buf[e] = timeout;
+        if (!REW) { a.progress_out[e] = progress; a.reset_out[e] = reset_cur; }
+    }
+
+    // ---- 5. observations (kick_env.py:749-777) ----
+    float imu6[6], orn2[2], feet[8];
+    if (OBS && valid) {
+        float pv[3];
+        if (a.prev_lin_vel) { pv[0] = prev[0]; pv[1] = prev[1]; pv[2] = prev[2]; }
+        else { pv[0] = v[0]; pv[1] = v[1]; pv[2] = v[2]; }                  // aliasing, kick_env.py:930
+        imu_term(q, v, w, pv, cfg, imu6);
+        if (a.prev_lin_vel) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) a.prev_lin_vel[e * 3 + k] = v[k];
+        }
+        off_orn_term(rt[0], rt[1], q, goal[0], goal[1], orn2);
+        if (cleats) {                                                      // kick_env.py:1053-1061
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float nl = sqrtf((fl[3 * k] * fl[3 * k] + fl[3 * k + 1] * fl[3 * k + 1]) + fl[3 * k + 2] * fl[3 * k + 2]);
+                const float nr = sqrtf((fr[3 * k] * fr[3 * k] + fr[3 * k + 1] * fr[3 * k + 1]) + fr[3 * k + 2] * fr[3 * k + 2]);
+                feet[k] = (nl > 1.0f) ? 1.0f : -1.0f;
+                feet[4 + k] = (nr > 1.0f) ? 1.0f : -1.0f;
+            }
+        } else {
+            float l3[3] = {fl[0], fl[1], fl[2]}, r3[3] = {fr[0], fr[1], fr[2]};
+            float lb[4], rbits[4];
+            foot_bits(l3, lb);
+            foot_bits(r3, rbits);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { feet[k] = lb[k]; feet[4 + k] = rbits[k]; }
+            if (cfg.flags & BEZK_F_WRITE_CONTACT_FILTER) {                 // in-place filter, :987-990
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (__float_as_uint(l3[k]) != __float_as_uint(fl[k])) cf_l[k] = l3[k];
+                    if (__float_as_uint(r3[k]) != __float_as_uint(fr[k])) cf_r[k] = r3[k];
+                }
+            }
+        }
+    }
+
+    // ---- 6. observation rows -> shared (aliasing the input tiles) -> one bulk store ----
+    if (OBS) {
+        __syncthreads();                   // every thread has finished reading s_dof / s_root
+        if (valid) {
+            float2* o2 = reinterpret_cast<float2*>(s_obs + tid * OBS_ROW);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {  // dof_pos 0:18, dof_vel 18:36 (de-interleave of [pos, vel] pairs)
+                o2[k] = make_float2(row[4 * k], row[4 * k + 2]);
+                o2[9 + k] = make_float2(row[4 * k + 1], row[4 * k + 3]);
+            }
+            o2[18] = make_float2(imu6[0], imu6[1]); o2[19] = make_float2(imu6[2], imu6[3]); o2[20] = make_float2(imu6[4], imu6[5]);
+            o2[21] = make_float2(orn2[0], orn2[1]);
+            o2[22] = make_float2(feet[0], feet[1]); o2[23] = make_float2(feet[2], feet[3]);
+            o2[24] = make_float2(feet[4], feet[5]); o2[25] = make_float2(feet[6], feet[7]);
+            o2[26] = make_float2(binit[0], binit[1]);
+            if (a.obs_clipped) {           // vec_task.py:343 clamp(obs_buf, -clip_obs, clip_obs)
+                float2* c2 = reinterpret_cast<float2*>(s_obs_clip + tid * OBS_ROW);
+                const float lim = cfg.clip_obs;
+#pragma unroll
+                for (int k = 0; k < 27; ++k) {
+                    const float2 t = o2[k];
+                    c2[k] = make_float2(clamp_nan(t.x, -lim, lim), clamp_nan(t.y, -lim, lim));
+                }
+            }
+        }
+        if (full) {
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                bulk_s2g(a.obs + e0 * OBS_ROW, s_obs, TILE * OBS_ROW * 4);
+                if (a.obs_clipped) bulk_s2g(a.obs_clipped + e0 * OBS_ROW, s_obs_clip, TILE * OBS_ROW * 4);
+                bulk_commit();
+            }
+        } else {
+            __syncthreads();
+            for (int i = tid; i < nv * OBS_ROW; i += TILE) a.obs[e0 * OBS_ROW + i] = s_obs[i];
+            if (a.obs_clipped)
+                for (int i = tid; i < nv * OBS_ROW; i += TILE) a.obs_clipped[e0 * OBS_ROW + i] = s_obs_clip[i];
+        }
+    }
+
+    // ---- 7. reward / termination (overlaps the bulk store) ----
+    if (REW && valid) {
+        RewardIn s;
+        s.bez[0] = rt[0]; s.bez[1] = rt[1]; s.bez[2] = rt[2];
+        s.ball_xy[0] = rt[13]; s.ball_xy[1] = rt[14];
+        s.ball_vxy[0] = rt[20]; s.ball_vxy[1] = rt[21];
+        s.goal[0] = goal[0]; s.goal[1] = goal[1];
+        s.ball_init[0] = binit[0]; s.ball_init[1] = binit[1];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { s.v[k] = v[k]; s.w[k] = w[k]; }
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 18; ++j) {
+            const float d = cfg.default_dof_pos[j] - row[2 * j];
+            acc += d * d;
+        }
+        s.pos_sq = acc;
+        float rew;
+        int64_t reset;
+        reward_term(s, cfg, progress, reset_cur, &rew, &reset);
+        a.rew[e] = rew;
+        a.reset_out[e] = reset;
+        if (BOOK) a.progress_out[e] = progress;
+    }
+
+    if (OBS && full && tid == 0) bulk_wait_read0();   // shared memory must outlive the bulk store's reads
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 (function level): reset_idx over an explicit id list; one thread per (id, dof) pair + root rows.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) reset_idx_kernel(const int64_t* __restrict__ env_ids, int64_t k, const float* __restrict__ uniforms,
+                                                        uint64_t seed, uint64_t step, float* dof_state, float* root_states,
+                                                        const float* __restrict__ initial_root, int64_t* progress, int64_t* reset,
+                                                        const __grid_constant__ BezkTaskCfg cfg, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    const int64_t e = env_ids[i];
+    if (e < 0 || e >= n) return;
+    float u[36], row[36];
+    if (uniforms) {
+#pragma unroll
+        for (int c = 0; c < 36; ++c) u[c] = uniforms[i * 36 + c];
+    } else {
+        philox_reset_uniforms(seed, step, e, u);
+    }
+    reset_dof_row(u, cfg, row);
+#pragma unroll
+    for (int c = 0; c < 36; ++c) dof_state[e * DOF_ROW + c] = row[c];
+    if (cfg.flags & BEZK_F_RESET_ROOT_STATES) {
+#pragma unroll
+        for (int c = 0; c < ROOT_ROW; ++c) root_states[e * ROOT_ROW + c] = initial_root[e * ROOT_ROW + c];
+    }
+    progress[e] = 0;
+    reset[e] = 0;
+}
+
+__global__ void philox_uniforms_kernel(uint64_t seed, uint64_t step, float* out, int64_t n) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float u[36];
+    philox_reset_uniforms(seed, step, e, u);
+#pragma unroll
+    for (int c = 0; c < 36; ++c) out[e * 36 + c] = u[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
+
+template <int PARTS>
+static cudaError_t launch_parts(const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st) {
+    const size_t smem = (size_t)(SMEM_IN_FLOATS + (a.obs_clipped ? SMEM_OBS_FLOATS : 0)) * sizeof(float);
+    static bool attr_set = false;          // per instantiation; opt in to > 48 KB dynamic shared memory once
+    if (!attr_set) {
+        cudaError_t err = cudaFuncSetAttribute(task_tile_kernel<PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)((SMEM_IN_FLOATS + SMEM_OBS_FLOATS) * sizeof(float)));
+        if (err != cudaSuccess) return err;
+        attr_set = true;
+    }
+    const int64_t tiles = (a.n + TILE - 1) / TILE;
+    task_tile_kernel<PARTS><<<(unsigned)tiles, TILE, smem, st>>>(a, cfg);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_task(int parts, const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st) {
+    switch (parts) {
+        case 1: return launch_parts<1>(a, cfg, st);
+        case 2: return launch_parts<2>(a, cfg, st);
+        case 3: return launch_parts<3>(a, cfg, st);
+        case 4: return launch_parts<4>(a, cfg, st);
+        case 5: return launch_parts<5>(a, cfg, st);
+        case 6: return launch_parts<6>(a, cfg, st);
+        case 7: return launch_parts<7>(a, cfg, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+void fill_alignment(TaskArgs& a, const BezkTaskCfg& cfg) {
+    a.use_tma = aligned16(a.dof_state) && aligned16(a.root_states) && (a.obs == nullptr || aligned16(a.obs)) &&
+                (a.obs_clipped == nullptr || aligned16(a.obs_clipped));
+    a.rb_vec2 = aligned8(a.rigid_body) && (cfg.num_bodies % 2 == 0) && ((cfg.imu_body * 13 + 3) % 2 == 0);
+}
+
+cudaError_t launch_pre_physics(const float* actions, float* actions_out, float* targets, const BezkTaskCfg& cfg,
+                               int64_t n, cudaStream_t st) {
+    const int64_t total = n * 18;
+    const int vec4 = aligned16(actions) && aligned16(targets) && (actions_out == nullptr || aligned16(actions_out));
+    const int threads = 256;
+    int64_t blocks = ((vec4 ? total / 4 : total) + threads - 1) / threads;
+    if (blocks < 1) blocks = 1;
+    const int64_t cap = 148LL * 16;
+    if (blocks > cap) blocks = cap;
+    pre_physics_kernel<<<(unsigned)blocks, threads, 0, st>>>(actions, actions_out, targets, cfg, total, vec4);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reset_idx(const int64_t* env_ids, int64_t k, const float* uniforms, uint64_t seed, uint64_t step,
+                             float* dof_state, float* root_states, const float* initial_root, int64_t* progress,
+                             int64_t* reset, const BezkTaskCfg& cfg, int64_t n, cudaStream_t st) {
+    if (k == 0) return cudaSuccess;
+    reset_idx_kernel<<<(unsigned)((k + 127) / 128), 128, 0, st>>>(env_ids, k, uniforms, seed, step, dof_state, root_states,
+                                                                  initial_root, progress, reset, cfg, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_philox_uniforms(uint64_t seed, uint64_t step, float* out, int64_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    philox_uniforms_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seed, step, out, n);
+    return cudaGetLastError();
+}
+
+}  // namespace bezk

@@ -1,0 +1,246 @@
+"""torch-facing shims over the C ABI: validate dtype / device / contiguity, pass raw device pointers and the
+current CUDA stream to libbezk.so.  Every function launches hand-written sm_100a kernels; none has a
+CPU or torch fallback (CPU tensors raise)."""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from . import bez_model as bm
+from ._lib import BezkPpoCfg, BezkTaskCfg, BezkError
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _p(t, dtype, name, numel=None, allow_none=False):
+    if t is None:
+        if allow_none:
+            return None
+        raise BezkError(f"{name} is None")
+    if not isinstance(t, torch.Tensor):
+        raise BezkError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise BezkError(f"{name} is on {t.device}: bez_isaacgym_b200 ops run on CUDA only (no CPU fallback)")
+    if t.dtype != dtype:
+        raise BezkError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise BezkError(f"{name} must be contiguous")
+    if numel is not None and t.numel() != numel:
+        raise BezkError(f"{name} has {t.numel()} elements, expected {numel}")
+    return C.c_void_p(t.data_ptr())
+
+
+def make_task_cfg(num_bodies=bm.BODIES_NO_CLEATS, cleats=False, dt=0.01667, max_episode_length=900,
+                  clip_actions=3.9, clip_obs=math.inf, default_dof_pos=None, dof_lower=bm.DOF_LOWER,
+                  dof_upper=bm.DOF_UPPER, bez_init_xy=(0.0, 0.0), write_contact_filter=True,
+                  reset_root_states=True, imu_body=bm.IMU_BODY, left_foot_body=None, right_foot_body=None,
+                  imu_max_lin_acc=bm.IMU_MAX_LIN_ACC, imu_max_ang_vel=bm.IMU_MAX_ANG_VEL,
+                  reset_pos_noise=0.15, reset_vel_noise=0.1) -> BezkTaskCfg:
+    """Build the by-value kernel constant block from the quantities ``KickEnv.__init__`` derives
+    (reference ``bez_isaacgym/tasks/kick_env.py:46-238``)."""
+    if default_dof_pos is None:
+        from .synthetic_gym import READY_POSE
+        default_dof_pos = READY_POSE
+    c = BezkTaskCfg()
+    c.num_bodies = int(num_bodies)
+    c.imu_body = int(imu_body)
+    if left_foot_body is None:
+        left_foot_body = bm.LEFT_CLEATS[0] if cleats else bm.LEFT_FOOT_BODY
+    if right_foot_body is None:
+        right_foot_body = bm.RIGHT_CLEATS[0] if cleats else bm.RIGHT_FOOT_BODY
+    c.left_foot_body, c.right_foot_body = int(left_foot_body), int(right_foot_body)
+    c.max_episode_length = int(max_episode_length)
+    c.flags = ((_lib.F_CLEATS if cleats else 0) | (_lib.F_WRITE_CONTACT_FILTER if write_contact_filter else 0)
+               | (_lib.F_RESET_ROOT_STATES if reset_root_states else 0))
+    c.dt = dt
+    c.imu_max_lin_acc, c.imu_max_ang_vel = imu_max_lin_acc, imu_max_ang_vel
+    c.clip_obs, c.clip_actions = clip_obs, clip_actions
+    c.bez_init_xy[0], c.bez_init_xy[1] = bez_init_xy
+    # torch_rand_float(lo, hi): (hi - lo) is formed in double, then multiplies an fp32 tensor
+    c.reset_pos_lo, c.reset_pos_span = -reset_pos_noise, reset_pos_noise - (-reset_pos_noise)
+    c.reset_vel_lo, c.reset_vel_span = -reset_vel_noise, reset_vel_noise - (-reset_vel_noise)
+    lo, hi = list(dof_lower), list(dof_upper)
+    for j in range(bm.NUM_DOF):
+        if lo[j] > hi[j]:                         # kick_env.py:395-397
+            lo[j], hi[j] = hi[j], lo[j]
+        c.default_dof_pos[j] = float(default_dof_pos[j])
+        c.dof_lower[j], c.dof_upper[j] = float(lo[j]), float(hi[j])
+    return c
+
+
+F32, F64, I64, U8 = torch.float32, torch.float64, torch.int64, torch.uint8
+
+
+# ------------------------------------------------------------------------------------------- task
+def pre_physics(actions, targets, cfg: BezkTaskCfg, actions_out=None):
+    n = actions.shape[0]
+    lib = _lib.load()
+    _lib.check(lib.bezk_pre_physics(_p(actions, F32, "actions", n * 18), _p(actions_out, F32, "actions_out", n * 18, True),
+                                    _p(targets, F32, "targets", n * 18), C.byref(cfg), n, _stream(actions)),
+               "bezk_pre_physics")
+    return targets
+
+
+def compute_observations(dof_state, rigid_body, root_states, net_contact, goal, ball_init, cfg, obs,
+                         prev_lin_vel=None, obs_clipped=None):
+    n = obs.shape[0]
+    nb = cfg.num_bodies
+    lib = _lib.load()
+    _lib.check(lib.bezk_compute_observations(
+        _p(dof_state, F32, "dof_state", n * 36), _p(rigid_body, F32, "rigid_body", n * nb * 13),
+        _p(root_states, F32, "root_states", n * 26), _p(net_contact, F32, "net_contact", n * nb * 3),
+        _p(prev_lin_vel, F32, "prev_lin_vel", n * 3, True), _p(goal, F32, "goal", n * 2),
+        _p(ball_init, F32, "ball_init", n * 2), C.byref(cfg), _p(obs, F32, "obs", n * 54),
+        _p(obs_clipped, F32, "obs_clipped", n * 54, True), n, _stream(obs)), "bezk_compute_observations")
+    return obs
+
+
+def compute_reward(dof_state, rigid_body, root_states, goal, ball_init, reset_in, progress, cfg, rew, reset_out):
+    n = rew.shape[0]
+    nb = cfg.num_bodies
+    lib = _lib.load()
+    _lib.check(lib.bezk_compute_reward(
+        _p(dof_state, F32, "dof_state", n * 36), _p(rigid_body, F32, "rigid_body", n * nb * 13),
+        _p(root_states, F32, "root_states", n * 26), _p(goal, F32, "goal", n * 2),
+        _p(ball_init, F32, "ball_init", n * 2), _p(reset_in, I64, "reset_in", n), _p(progress, I64, "progress", n),
+        C.byref(cfg), _p(rew, F32, "rew", n), _p(reset_out, I64, "reset_out", n), n, _stream(rew)),
+        "bezk_compute_reward")
+    return rew, reset_out
+
+
+def reset_idx(env_ids, dof_state, root_states, initial_root_states, progress, reset, cfg, uniforms=None,
+              seed=0, step=0):
+    k = int(env_ids.numel())
+    n = progress.shape[0]
+    lib = _lib.load()
+    _lib.check(lib.bezk_reset_idx(
+        _p(env_ids, I64, "env_ids"), k, _p(uniforms, F32, "uniforms", k * 36, True), seed, step,
+        _p(dof_state, F32, "dof_state", n * 36), _p(root_states, F32, "root_states", n * 26, True),
+        _p(initial_root_states, F32, "initial_root_states", n * 26, True), _p(progress, I64, "progress", n),
+        _p(reset, I64, "reset", n), C.byref(cfg), n, _stream(progress)), "bezk_reset_idx")
+
+
+def post_physics(dof_state, rigid_body, root_states, net_contact, goal, ball_init, initial_root_states,
+                 reset_buf, progress_buf, timeout_buf, cfg, obs, rew, prev_lin_vel=None, uniforms=None,
+                 seed=0, step=0, randomize_buf=None, obs_clipped=None, parts=_lib.PART_ALL):
+    n = progress_buf.shape[0]
+    nb = cfg.num_bodies
+    lib = _lib.load()
+    _lib.check(lib.bezk_post_physics(
+        _p(dof_state, F32, "dof_state", n * 36), _p(rigid_body, F32, "rigid_body", n * nb * 13),
+        _p(root_states, F32, "root_states", n * 26), _p(net_contact, F32, "net_contact", n * nb * 3, True),
+        _p(prev_lin_vel, F32, "prev_lin_vel", n * 3, True), _p(goal, F32, "goal", n * 2),
+        _p(ball_init, F32, "ball_init", n * 2), _p(initial_root_states, F32, "initial_root_states", n * 26, True),
+        _p(uniforms, F32, "uniforms", n * 36, True), seed, step, _p(reset_buf, I64, "reset_buf", n),
+        _p(progress_buf, I64, "progress_buf", n), _p(timeout_buf, I64, "timeout_buf", n, True),
+        _p(randomize_buf, I64, "randomize_buf", n, True), C.byref(cfg), _p(obs, F32, "obs", n * 54, True),
+        _p(obs_clipped, F32, "obs_clipped", n * 54, True), _p(rew, F32, "rew", n, True), int(parts), n,
+        _stream(progress_buf)), "bezk_post_physics")
+
+
+def philox_uniforms(seed, step, out):
+    n = out.shape[0]
+    lib = _lib.load()
+    _lib.check(lib.bezk_philox_uniforms(seed, step, _p(out, F32, "out", n * 36), n, _stream(out)), "bezk_philox_uniforms")
+    return out
+
+
+# ------------------------------------------------------------------------------------------- learner
+def gae(rewards, values, dones, last_values, last_dones, gamma, tau, advs, returns):
+    horizon = rewards.shape[0]
+    n = rewards.numel() // max(horizon, 1)
+    if dones.dtype == U8:
+        kind, dt = 0, U8
+    elif dones.dtype == F32:
+        kind, dt = 1, F32
+    else:
+        raise BezkError(f"dones must be uint8 or float32, got {dones.dtype}")
+    lib = _lib.load()
+    _lib.check(lib.bezk_gae(_p(rewards, F32, "rewards", horizon * n), _p(values, F32, "values", horizon * n),
+                            _p(dones, dt, "dones", horizon * n), _p(last_values, F32, "last_values", n),
+                            _p(last_dones, dt, "last_dones", n), kind, float(gamma), float(tau),
+                            _p(advs, F32, "advs", horizon * n), _p(returns, F32, "returns", horizon * n), horizon, n,
+                            _stream(rewards)), "bezk_gae")
+    return advs, returns
+
+
+def rms_scratch_doubles(c):
+    return int(_lib.load().bezk_rms_scratch_doubles(int(c)))
+
+
+def rms_moments(x, pivot, acc, partials):
+    c = x.shape[-1] if x.dim() > 1 else 1
+    m = x.numel() // c
+    lib = _lib.load()
+    _lib.check(lib.bezk_rms_moments(_p(x, F32, "x"), _p(pivot, F64, "pivot", c, True), _p(acc, F64, "acc", 1 + 2 * c),
+                                    _p(partials, F64, "partials"), m, c, _stream(x)), "bezk_rms_moments")
+    if partials.numel() < rms_scratch_doubles(c):
+        raise BezkError("partials scratch too small")
+    return acc
+
+
+def rms_merge(acc, pivot, running_mean, running_var, count):
+    c = running_mean.numel()
+    lib = _lib.load()
+    _lib.check(lib.bezk_rms_merge(_p(acc, F64, "acc", 1 + 2 * c), _p(pivot, F64, "pivot", c, True),
+                                  _p(running_mean, F64, "running_mean", c), _p(running_var, F64, "running_var", c),
+                                  _p(count, F64, "count", 1), c, _stream(acc)), "bezk_rms_merge")
+
+
+def rms_normalize(x, running_mean, running_var, y, eps=1e-5, unnorm=False):
+    c = running_mean.numel()
+    m = x.numel() // c
+    lib = _lib.load()
+    _lib.check(lib.bezk_rms_normalize(_p(x, F32, "x", m * c), _p(running_mean, F64, "running_mean", c),
+                                      _p(running_var, F64, "running_var", c), eps, int(bool(unnorm)),
+                                      _p(y, F32, "y", m * c), m, c, _stream(x)), "bezk_rms_normalize")
+    return y
+
+
+def adv_moments(returns, values, acc, partials):
+    m = returns.numel()
+    lib = _lib.load()
+    _lib.check(lib.bezk_adv_moments(_p(returns, F32, "returns", m), _p(values, F32, "values", m), _p(acc, F64, "acc", 3),
+                                    _p(partials, F64, "partials"), m, _stream(returns)), "bezk_adv_moments")
+    return acc
+
+
+def adv_normalize(returns, values, acc, adv_out, normalize=True):
+    m = returns.numel()
+    lib = _lib.load()
+    _lib.check(lib.bezk_adv_normalize(_p(returns, F32, "returns", m), _p(values, F32, "values", m),
+                                      _p(acc, F64, "acc", 3, not normalize), _p(adv_out, F32, "adv_out", m),
+                                      int(bool(normalize)), m, _stream(returns)), "bezk_adv_normalize")
+    return adv_out
+
+
+def make_ppo_cfg(e_clip=0.2, critic_coef=2.0, entropy_coef=0.0, bounds_loss_coef=0.001, soft_bound=1.1,
+                 clip_value=True, bound_form="v1.1.3") -> BezkPpoCfg:
+    c = BezkPpoCfg()
+    c.e_clip, c.critic_coef, c.entropy_coef = e_clip, critic_coef, entropy_coef
+    c.bounds_loss_coef, c.soft_bound = bounds_loss_coef, soft_bound
+    c.clip_value = int(bool(clip_value))
+    c.bound_form = {"v1.1.3": 0, "outside": 1}[bound_form]
+    return c
+
+
+def ppo_scratch_doubles():
+    return int(_lib.load().bezk_ppo_scratch_doubles())
+
+
+def ppo_loss(actions, mu, logstd, old_mu, old_sigma, values, old_values, returns, old_neglogp, advantages, cfg,
+             stats, partials, grad_mu=None, grad_values=None, grad_logstd=None, neglogp_out=None):
+    m = mu.shape[0]
+    lib = _lib.load()
+    _lib.check(lib.bezk_ppo_loss(
+        _p(actions, F32, "actions", m * 18), _p(mu, F32, "mu", m * 18), _p(logstd, F32, "logstd", 18),
+        _p(old_mu, F32, "old_mu", m * 18), _p(old_sigma, F32, "old_sigma", m * 18), _p(values, F32, "values", m),
+        _p(old_values, F32, "old_values", m), _p(returns, F32, "returns", m), _p(old_neglogp, F32, "old_neglogp", m),
+        _p(advantages, F32, "advantages", m), C.byref(cfg), _p(stats, F64, "stats", 8),
+        _p(grad_mu, F32, "grad_mu", m * 18, True), _p(grad_values, F32, "grad_values", m, True),
+        _p(grad_logstd, F32, "grad_logstd", 18, True), _p(neglogp_out, F32, "neglogp_out", m, True),
+        _p(partials, F64, "partials"), m, _stream(mu)), "bezk_ppo_loss")
+    return stats

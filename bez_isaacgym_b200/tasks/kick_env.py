@@ -1,0 +1,300 @@
+"""``KickEnv`` -- drop-in for the reference's BezKick task (``bez_isaacgym/tasks/kick_env.py:44-850``) on B200.
+
+Same constructor (``cfg, sim_device, graphics_device_id, headless``), public attributes and
+``step`` / ``reset`` / ``reset_idx`` / ``pre_physics_step`` / ``post_physics_step`` / ``compute_observations`` /
+``compute_reward`` methods; underneath, ``step`` is TWO launches of hand-written sm_100a kernels through the C ABI
+(``libbezk.so``):
+
+    K0  ``bezk_pre_physics``    action clip, head zeroing, PD targets        (before the simulator)
+    K*  ``bezk_post_physics``   timeout, progress, masked reset of the envs flagged by the previous step,
+                                54-wide observation, reward / termination / new reset mask   (after it)
+
+``fusion="split"`` launches the north-star's two kernels instead of the fused one (observation kernel =
+bookkeeping + reset + observations, then the reward / termination kernel).  There is no CPU path: with
+``use_gpu_pipeline: False`` the simulator tensors stay in pinned host memory and are staged to the GPU each step.
+
+Reference behaviours kept bug-for-bug (SURVEY 7 "hard parts"): xyzw quaternion fed to the real-first matrix
+formula; unit gravity vector; ``prev_lin_vel`` aliasing the velocity view after the first observation (so
+``lin_acc == R(q)(0,0,1)`` from the second step on; ``env.imuPrevVelAliasing: False`` keeps a real buffer);
+in-place contact noise filter; resets applied at the start of the NEXT step; ``reset_buf`` starting at ones.
+Documented deviations: reset noise comes from Philox4x32-10 keyed by (seed, step, env id) instead of torch's
+global generator (invariant to sharding and to how many envs reset); ``default_dof_pos`` / joint limits are
+kernel constants (the ``(N,18)`` tensor attributes are kept for API compatibility); ``obs_dict['obs']``
+aliases ``obs_buf`` when ``clip_obs`` is infinite (the reference's clamp is then a plain copy).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from .. import _lib, bez_model as bm, ops
+from ..synthetic_sim import SimBackend, SyntheticGym
+from .base.vec_task import VecTask
+
+_P = C.c_void_p
+
+
+def _ptr(t):
+    return _P(t.data_ptr()) if t is not None else None
+
+
+class KickEnv(VecTask):
+
+    def __init__(self, cfg, sim_device, graphics_device_id, headless, sim: SimBackend = None, fusion="fused"):
+        self.cfg = cfg
+        env_cfg = cfg["env"]
+        self.randomize = cfg["task"]["randomize"]
+        self.randomization_params = cfg["task"].get("randomization_params", {})
+        if self.randomize:
+            raise NotImplementedError("domain randomisation drives PhysX property setters: out of scope (SURVEY 8)")
+        if fusion not in ("fused", "split"):
+            raise ValueError(fusion)
+        self.fusion = fusion
+
+        def state13(key):
+            s = env_cfg[key]
+            return list(s["pos"]) + list(s["rot"]) + list(s["vLinear"]) + list(s["vAngular"])
+
+        self.bez_init_state = state13("bezInitState")
+        self.ball_init_state = state13("ballInitState")
+        goal = env_cfg["goalState"]["goal"]
+        self.cleats = env_cfg["asset"]["cleats"]
+        self.debug_rewards = env_cfg.get("debug", {}).get("rewards", False)
+        self.named_default_joint_angles = env_cfg["readyJointAngles"]
+        self.max_episode_length_s = env_cfg["learn"]["episodeLength_s"]
+        self.Kp = env_cfg["control"]["stiffness"]
+        self.Kd = env_cfg["control"]["damping"]
+        self.orn_dim, self.imu_dim, self.feet_dim, self.dof_dim, self.rnn_dim, self.ball_dim = 2, 6, 8, 18, 1, 2
+        self.imu_max_ang_vel = bm.IMU_MAX_ANG_VEL
+        self.imu_max_lin_acc = bm.IMU_MAX_LIN_ACC
+        env_cfg["numObservations"] = bm.NUM_OBS
+        env_cfg["numActions"] = bm.NUM_ACTIONS
+        self._sim_arg = sim
+        self._seed = int(cfg.get("seed", 42))
+        self._alias_prev = bool(env_cfg.get("imuPrevVelAliasing", True))
+
+        super().__init__(config=cfg, sim_device=sim_device, graphics_device_id=graphics_device_id, headless=headless)
+
+        self.dt = cfg["sim"]["dt"]
+        self.max_episode_length = int(self.max_episode_length_s / self.dt + 0.5)
+        dev, n = self.compute_device, self.num_envs
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        # simulator tensors (borrowed) and their device images
+        self.root_states, self.dof_state = self.sim.root_states, self.sim.dof_state
+        self.rigid_body, self.net_contact = self.sim.rigid_body, self.sim.net_contact
+        if self.host_staged:
+            self._d_root, self._d_dof = (torch.empty_like(t, device=dev) for t in (self.root_states, self.dof_state))
+            self._d_rb, self._d_cf = (torch.empty_like(t, device=dev) for t in (self.rigid_body, self.net_contact))
+        else:
+            self._d_root, self._d_dof, self._d_rb, self._d_cf = self.root_states, self.dof_state, self.rigid_body, self.net_contact
+        for name, t, width in (("root_states", self.root_states, 26), ("dof_state", self.dof_state, 36),
+                               ("rigid_body", self.rigid_body, 13 * self.sim.num_bodies),
+                               ("net_contact", self.net_contact, 3 * self.sim.num_bodies)):
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n * width:
+                raise ValueError(f"simulator tensor {name} must be contiguous float32 with {n * width} elements")
+
+        self.goal = torch.tensor([goal], **f32).repeat((n, 1))
+        self.bez_init_xy = torch.tensor(self.bez_init_state[0:2], **f32)
+        self.ball_init = torch.tensor([self.ball_init_state[0:2]], **f32).repeat((n, 1))
+        self.initial_root_states = torch.tensor([self.bez_init_state, self.ball_init_state], **f32).repeat((n, 1))
+        self.initial_root_states[:, 7:13] = 0
+        self.num_dof = bm.NUM_DOF
+        self.num_dofs = bm.NUM_DOF
+        self.dof_names = list(bm.DOF_NAMES)
+
+        # strided views with the reference's names (kick_env.py:168-196)
+        self.dof_pos_bez = self.dof_state.view(n, 18, -1)[..., 0]
+        self.dof_vel_bez = self.dof_state.view(n, 18, -1)[..., 1]
+        self.root_pos_bez = self.root_states.view(n, -1, 13)[..., 0, 0:3]
+        self.root_orient_bez = self.rigid_body.view(n, -1, 13)[..., bm.IMU_BODY, 3:7]
+        self.root_vel_bez = self.rigid_body.view(n, -1, 13)[..., bm.IMU_BODY, 7:10]
+        self.root_ang_bez = self.rigid_body.view(n, -1, 13)[..., bm.IMU_BODY, 10:13]
+        self.root_pos_ball = self.root_states.view(n, -1, 13)[..., 1, 0:3]
+        self.root_orient_ball = self.root_states.view(n, -1, 13)[..., 1, 3:7]
+        self.root_vel_ball = self.root_states.view(n, -1, 13)[..., 1, 7:10]
+
+        ready = [float(self.named_default_joint_angles[name]) for name in bm.DOF_NAMES]
+        self.default_dof_pos = torch.tensor(ready, **f32).repeat((n, 1))
+        self.dof_pos_limits_lower = torch.tensor(bm.DOF_LOWER, **f32)
+        self.dof_pos_limits_upper = torch.tensor(bm.DOF_UPPER, **f32)
+        self.gravity_vec = torch.tensor([[0.0, 0.0, -1.0]], **f32).repeat((n, 1))
+        self.up_vec = torch.tensor([[0.0, 0.0, 1.0]], **f32).repeat((n, 1))
+
+        self._kcfg = ops.make_task_cfg(
+            num_bodies=self.sim.num_bodies, cleats=self.cleats, dt=self.dt, max_episode_length=self.max_episode_length,
+            clip_actions=float(self.clip_actions), clip_obs=float(self.clip_obs), default_dof_pos=ready,
+            bez_init_xy=tuple(self.bez_init_state[0:2]),
+            write_contact_filter=bool(env_cfg.get("writeContactFilter", not self.host_staged)),
+            reset_root_states=not self.sim.owns_root_reset)
+
+        # persistent task state
+        self._prev_buf = torch.zeros(n, 3, **f32)       # the reference's int64 zeros, promoted (kick_env.py:183)
+        self._prev_is_view = False
+        self.targets = torch.zeros(n, 18, **f32)
+        self._actions_in = torch.zeros(n, 18, **f32)      # staging buffer for actions arriving from another device
+        self._actions_src = self._actions_in
+        self._actions_cache = None
+        self.obs_clipped_buf = torch.zeros(n, 54, **f32) if math.isfinite(float(self.clip_obs)) else None
+        self._rng_step = 0
+        self._lib = _lib.load()
+        if self.host_staged:
+            pin = dict(pin_memory=True)
+            self._h_obs = torch.empty(n, 54, **pin); self._h_rew = torch.empty(n, **pin)
+            self._h_reset = torch.empty(n, dtype=torch.long, **pin); self._h_timeout = torch.empty(n, dtype=torch.long, **pin)
+            self._h_actions = torch.empty(n, 18, **pin)
+        self._bind()
+        self.reset_idx(torch.arange(n, device=dev))       # kick_env.py:238
+
+    # ------------------------------------------------------------------ construction helpers
+    def create_sim(self):
+        """The reference builds the PhysX scene here (kick_env.py:240-408, out of scope); this attaches the
+        simulator backend that owns the state tensors."""
+        self.up_axis_idx = 2
+        if self._sim_arg is not None:
+            self.sim = self._sim_arg
+        else:
+            host = self.device == "cpu"
+            self.sim = SyntheticGym(self.num_environments, device=f"cuda:{self.device_id}", cleats=self.cfg["env"]["asset"]["cleats"],
+                                    seed=int(self.cfg.get("seed", 42)), host=host)
+        if self.sim.root_states.is_cuda != (self.device != "cpu"):
+            raise ValueError("simulator tensors must live on the pipeline device "
+                             f"({'cuda' if self.device != 'cpu' else 'pinned host'})")
+
+    def _bind(self):
+        """Pre-convert every pointer argument once: buffers are persistent, so a step costs two ctypes calls."""
+        n = self.num_envs
+        kc = C.byref(self._kcfg)
+        self._pre_args = [_ptr(self._actions_in), None, _ptr(self.targets), kc, n]
+        self._post_fixed = dict(
+            head=[_ptr(self._d_dof), _ptr(self._d_rb), _ptr(self._d_root), _ptr(self._d_cf)],
+            mid=[_ptr(self.goal), _ptr(self.ball_init), _ptr(self.initial_root_states), None],
+            tail=[_ptr(self.reset_buf), _ptr(self.progress_buf), _ptr(self.timeout_buf), _ptr(self.randomize_buf), kc,
+                  _ptr(self.obs_buf), _ptr(self.obs_clipped_buf), _ptr(self.rew_buf)])
+
+    def _stream(self):
+        return _P(torch.cuda.current_stream(self.compute_device).cuda_stream)
+
+    def _launch_post(self, parts):
+        f = self._post_fixed
+        prev = None if self._prev_is_view else _ptr(self._prev_buf)
+        rc = self._lib.bezk_post_physics(*f["head"], prev, *f["mid"], self._seed, self._rng_step, *f["tail"], parts,
+                                         self.num_envs, self._stream())
+        if rc:
+            _lib.check(rc, "bezk_post_physics")
+
+    # ------------------------------------------------------------------ reference-named attributes
+    @property
+    def actions(self):
+        """``self.actions`` of the reference (clipped, head zeroed, kick_env.py:413-414), materialised on demand."""
+        if self._actions_cache is None:
+            a = torch.clamp(self._actions_src, -self.clip_actions, self.clip_actions)
+            a[..., 0:2] = 0.0
+            self._actions_cache = a
+        return self._actions_cache
+
+    @property
+    def prev_lin_vel(self):
+        return self.root_vel_bez if self._prev_is_view else self._prev_buf
+
+    @property
+    def feet(self):
+        return self.obs_buf[:, bm.OBS_FEET]
+
+    # ------------------------------------------------------------------ the step
+    def _stage_in(self):
+        if self.host_staged:
+            for d, h in ((self._d_root, self.root_states), (self._d_dof, self.dof_state), (self._d_rb, self.rigid_body),
+                         (self._d_cf, self.net_contact)):
+                d.copy_(h, non_blocking=True)
+
+    def pre_physics_step(self, actions):
+        """kick_env.py:410-419 (+ the clamp of vec_task.py:317): one K0 launch."""
+        if actions.shape != (self.num_envs, 18) or actions.dtype != torch.float32:
+            raise ValueError(f"actions must be float32 of shape ({self.num_envs}, 18)")
+        if actions.device != self.compute_device:
+            if self.host_staged and actions.device.type == "cpu" and not actions.is_pinned():
+                self._h_actions.copy_(actions)
+                self._actions_in.copy_(self._h_actions, non_blocking=True)
+            else:
+                self._actions_in.copy_(actions, non_blocking=True)
+            src = self._actions_in
+        else:
+            src = actions if actions.is_contiguous() else actions.contiguous()
+        self._actions_cache = None
+        self._actions_src = src
+        a = self._pre_args
+        rc = self._lib.bezk_pre_physics(_ptr(src), a[1], a[2], a[3], a[4], self._stream())
+        if rc:
+            _lib.check(rc, "bezk_pre_physics")
+        self.sim.set_dof_position_targets(self.targets)
+
+    def post_physics_step(self):
+        """vec_task.py:331-332 + kick_env.py:426-438 in one launch (two with ``fusion='split'``)."""
+        self._stage_in()
+        self._rng_step += 1
+        if self.fusion == "fused":
+            self._launch_post(_lib.PART_ALL)
+        else:
+            self._launch_post(_lib.PART_BOOKKEEP | _lib.PART_OBS)
+            self._launch_post(_lib.PART_REWARD)
+        if self._alias_prev:
+            self._prev_is_view = True       # kick_env.py:930: compute_imu hands back the velocity VIEW
+        if self.host_staged:
+            self.dof_state.copy_(self._d_dof, non_blocking=True)      # resets are written into the simulator tensor
+            if self._kcfg.flags & _lib.F_WRITE_CONTACT_FILTER:
+                self.net_contact.copy_(self._d_cf, non_blocking=True)
+            if self._kcfg.flags & _lib.F_RESET_ROOT_STATES:
+                self.root_states.copy_(self._d_root, non_blocking=True)
+
+    def compute_observations(self):
+        """kick_env.py:749-777 as a stand-alone call (observation kernel only, no bookkeeping)."""
+        self._stage_in()
+        prev = None if self._prev_is_view else self._prev_buf
+        ops.compute_observations(self._d_dof, self._d_rb, self._d_root, self._d_cf, self.goal, self.ball_init, self._kcfg,
+                                 self.obs_buf, prev_lin_vel=prev, obs_clipped=self.obs_clipped_buf)
+        if self._alias_prev:
+            self._prev_is_view = True
+
+    def compute_reward(self, actions=None):
+        """kick_env.py:724-747 as a stand-alone call (reward / termination kernel only)."""
+        ops.compute_reward(self._d_dof, self._d_rb, self._d_root, self.goal, self.ball_init, self.reset_buf,
+                           self.progress_buf, self._kcfg, self.rew_buf, self.reset_buf)
+
+    def reset_idx(self, env_ids):
+        """kick_env.py:779-850 for an explicit id list (the per-step path uses the masked reset inside the fused
+        kernel instead, which needs no ``nonzero()``)."""
+        env_ids = env_ids.to(device=self.compute_device, dtype=torch.long).contiguous()
+        self._stage_in()
+        ops.reset_idx(env_ids, self._d_dof, self._d_root, self.initial_root_states, self.progress_buf, self.reset_buf,
+                      self._kcfg, uniforms=None, seed=self._seed, step=self._rng_step)
+        if self.host_staged:
+            self.dof_state.copy_(self._d_dof)
+            if self._kcfg.flags & _lib.F_RESET_ROOT_STATES:
+                self.root_states.copy_(self._d_root)
+
+    def _observations_out(self):
+        return self.obs_buf if self.obs_clipped_buf is None else self.obs_clipped_buf
+
+    def step(self, actions):
+        if not self.host_staged:
+            return super().step(actions)
+        # host pipeline: same sequence, results leave through pinned buffers with ONE stream sync
+        self.pre_physics_step(actions)
+        for _ in range(self.control_freq_inv):
+            self.sim.simulate()
+        self.post_physics_step()
+        self._h_obs.copy_(self._observations_out(), non_blocking=True)
+        self._h_rew.copy_(self.rew_buf, non_blocking=True)
+        self._h_reset.copy_(self.reset_buf, non_blocking=True)
+        self._h_timeout.copy_(self.timeout_buf, non_blocking=True)
+        torch.cuda.current_stream(self.compute_device).synchronize()
+        rl = torch.device(self.rl_device)
+        if rl.type == "cpu":
+            self.extras["time_outs"] = self._h_timeout
+            self.obs_dict["obs"] = self._h_obs
+            return self.obs_dict, self._h_rew, self._h_reset, self.extras
+        self.extras["time_outs"] = self.timeout_buf.to(rl)
+        self.obs_dict["obs"] = self._observations_out().to(rl)
+        return self.obs_dict, self.rew_buf.to(rl), self.reset_buf.to(rl), self.extras

@@ -1,0 +1,190 @@
+/*
+ * bezk.h -- C ABI of libbezk.so, the B200 (sm_100a) BezKick hot path.
+ *
+ * Drop-in boundary for the per-step tensor path of utra-robosoccer/Bez_IsaacGym's BezKick task and
+ * the rl_games rollout math it feeds.  Every entry point takes caller-owned DEVICE pointers
+ * (Isaac-Gym-layout state tensors are borrowed, never reallocated), sizes and a CUDA stream
+ * (passed as void* so this header needs no CUDA include); nothing allocates, nothing synchronises,
+ * everything is stream-ordered.  Return value: 0 on success, otherwise a cudaError_t value or one
+ * of the BEZK_E_* codes below; bezk_last_error() gives the message.  There is no CPU fallback.
+ *
+ * "ref:" cites the reference interface each entry replaces, relative to
+ * /root/reference/bez_isaacgym/ (rl_games is third-party, un-vendored: cited by upstream file).
+ */
+#ifndef BEZK_H_
+#define BEZK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BEZK_VERSION 100          /* 0.1.0 */
+#define BEZK_NUM_DOF 18
+#define BEZK_NUM_OBS 54
+
+#define BEZK_E_BADARG   10001     /* null pointer / negative size / bad enum */
+#define BEZK_E_ALIGN    10002     /* pointer not aligned as documented */
+#define BEZK_E_CONFIG   10003     /* BezkTaskCfg inconsistent (body index >= num_bodies ...) */
+
+/* flags for BezkTaskCfg.flags */
+#define BEZK_F_CLEATS              1u  /* 8 cleat bodies instead of 2 foot bodies (tasks/kick_env.py:188-196) */
+#define BEZK_F_WRITE_CONTACT_FILTER 2u /* write the |f|<=0.01 -> 0 noise filter back into net_contact
+                                          (the reference does, tasks/kick_env.py:987-990) */
+#define BEZK_F_RESET_ROOT_STATES   4u  /* masked reset also copies initial_root_states rows into
+                                          root_states (what the simulator's indexed setters do,
+                                          tasks/kick_env.py:831-837); off when a real simulator owns that */
+
+/* Constants of one BezKick instance.  Passed BY VALUE into the kernels (constant bank).
+ * ref: tasks/kick_env.py:46-238 (constructor), cfg/task/bez_kick.yaml. */
+typedef struct BezkTaskCfg {
+    int32_t num_bodies;          /* rigid bodies per env incl. the ball: 22 (30 with cleats) */
+    int32_t imu_body;            /* 1   tasks/kick_env.py:175-177 */
+    int32_t left_foot_body;      /* 12  (:193)   with cleats: first of 4 cleat bodies, 13 (:188) */
+    int32_t right_foot_body;     /* 20  (:195)   with cleats: first of 4 cleat bodies, 25 (:190) */
+    int32_t max_episode_length;  /* 900 = int(15 / 0.01667 + 0.5)  (:126-127) */
+    uint32_t flags;              /* BEZK_F_* */
+    float dt;                    /* 0.01667 */
+    float imu_max_lin_acc;       /* 19.62   (:100) */
+    float imu_max_ang_vel;       /* 8.7266  (:99)  */
+    float clip_obs;              /* +inf by default (tasks/base/vec_task.py:97) */
+    float clip_actions;          /* 3.9 (cfg/task/bez_kick.yaml:11) */
+    float bez_init_xy[2];        /* (:160) */
+    /* torch_rand_float(lo, hi) = (hi - lo) * U + lo with (hi - lo) formed in double on the host:
+     * positions U(-0.15, 0.15) (:786) -> lo = -0.15f, span = (float)0.3; velocities U(-0.1, 0.1) (:787). */
+    float reset_pos_lo, reset_pos_span;
+    float reset_vel_lo, reset_vel_span;
+    float default_dof_pos[BEZK_NUM_DOF];   /* readyJointAngles in DOF order (:204-209) */
+    float dof_lower[BEZK_NUM_DOF];         /* (:393-406) */
+    float dof_upper[BEZK_NUM_DOF];
+} BezkTaskCfg;
+
+int  bezk_version(void);
+const char* bezk_last_error(void);
+
+/* ---------------------------------------------------------------- task side ------------------ */
+
+/* K0.  ref: tasks/base/vec_task.py:317 + tasks/kick_env.py:410-419 (KickEnv.pre_physics_step).
+ * actions (n,18) f32 -> targets (n,18) f32 = clamp(zero_head(clip(actions)) + default, lower, upper).
+ * actions_out (n,18) receives the stored `self.actions` (clipped, head zeroed); may be NULL. */
+int bezk_pre_physics(const float* actions, float* actions_out, float* targets,
+                     const BezkTaskCfg* cfg, int64_t n, void* stream);
+
+/* K1 (function level).  ref: KickEnv.compute_observations tasks/kick_env.py:749-777 and the jit
+ * functions :857-1069,1398-1417.  Reads dof_state (n*18,2), rigid_body (n*NB,13), root_states
+ * (n*2,13), net_contact (n*NB,3; filtered in place when BEZK_F_WRITE_CONTACT_FILTER), goal (n,2),
+ * ball_init (n,2).  prev_lin_vel (n,3) f32 is read then overwritten with the current IMU-link
+ * linear velocity; NULL selects the reference's steady-state aliasing (prev == current velocity,
+ * tasks/kick_env.py:930).  obs (n,54).  obs_clipped (n,54) or NULL (written only if non-NULL). */
+int bezk_compute_observations(const float* dof_state, const float* rigid_body, const float* root_states,
+                              float* net_contact, float* prev_lin_vel, const float* goal,
+                              const float* ball_init, const BezkTaskCfg* cfg, float* obs,
+                              float* obs_clipped, int64_t n, void* stream);
+
+/* K2 (function level).  ref: compute_bez_reward tasks/kick_env.py:1198-1395 (+ wrapper :724-747).
+ * reset_in / progress (n,) i64 are the function's reset_buf / progress_buf arguments;
+ * rew (n,) f32 and reset_out (n,) i64 its two results (reset_out may alias reset_in). */
+int bezk_compute_reward(const float* dof_state, const float* rigid_body, const float* root_states,
+                        const float* goal, const float* ball_init, const int64_t* reset_in,
+                        const int64_t* progress, const BezkTaskCfg* cfg, float* rew,
+                        int64_t* reset_out, int64_t n, void* stream);
+
+/* K3 (function level).  ref: KickEnv.reset_idx tasks/kick_env.py:779-850 for an explicit,
+ * ascending id list env_ids (k,) i64.  uniforms (k,36) f32 in [0,1): cols 0:18 feed the position
+ * draw, 18:36 the velocity draw (the two torch_rand_float calls, :786-787); NULL -> Philox4x32-10
+ * keyed (seed, step, env id).  Writes dof_state rows, root_states rows (flag), progress=0, reset=0. */
+int bezk_reset_idx(const int64_t* env_ids, int64_t k, const float* uniforms, uint64_t seed,
+                   uint64_t step, float* dof_state, float* root_states,
+                   const float* initial_root_states, int64_t* progress, int64_t* reset,
+                   const BezkTaskCfg* cfg, int64_t n, void* stream);
+
+/* Fused post-physics step = everything VecTask.step does after gym.simulate, in ONE launch.
+ * ref: tasks/base/vec_task.py:331-332 (timeout from pre-increment progress) +
+ * KickEnv.post_physics_step tasks/kick_env.py:426-438 (progress++, reset of envs whose reset_buf
+ * was set by the previous step, observations, reward/termination).
+ *   reset_buf    (n,) i64 in: previous step's mask; out: this step's mask
+ *   progress_buf (n,) i64 in/out;  timeout_buf (n,) i64 out;  randomize_buf (n,) i64 in/out or NULL
+ *   uniforms     (n,36) f32 per-ENV reset draws or NULL -> Philox keyed (seed, step, env id)
+ *   parts        bitmask: 1 = bookkeeping+masked reset, 2 = observations, 4 = reward/termination.
+ *                7 = whole step.  3 and 4 give the north-star's two kernels (obs kernel, reward kernel). */
+#define BEZK_PART_BOOKKEEP 1
+#define BEZK_PART_OBS      2
+#define BEZK_PART_REWARD   4
+int bezk_post_physics(float* dof_state, const float* rigid_body, float* root_states,
+                      float* net_contact, float* prev_lin_vel, const float* goal,
+                      const float* ball_init, const float* initial_root_states,
+                      const float* uniforms, uint64_t seed, uint64_t step,
+                      int64_t* reset_buf, int64_t* progress_buf, int64_t* timeout_buf,
+                      int64_t* randomize_buf, const BezkTaskCfg* cfg, float* obs, float* obs_clipped,
+                      float* rew, int parts, int64_t n, void* stream);
+
+/* The dense (n,36) uniforms the Philox path of bezk_post_physics / bezk_reset_idx consumes for
+ * (seed, step): lets a checker feed the identical draws to the reference's reset_idx. */
+int bezk_philox_uniforms(uint64_t seed, uint64_t step, float* out, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------- rollout / learner math ----- */
+
+/* K6.  ref: rl_games/common/a2c_common.py A2CBase.discount_values (+ mb_returns = advs + values).
+ * rewards, values (T,n) f32; dones (T,n): dones_kind 0 = uint8, 1 = float32; last_values (n,) f32;
+ * last_dones (n,) same kind.  Out: advs, returns (T,n) f32.  time-major, env fastest.
+ * gamma, tau are the Python doubles of the config; the kernel uses (float)gamma and (float)(gamma*tau)
+ * exactly as torch's scalar promotion does. */
+int bezk_gae(const float* rewards, const float* values, const void* dones, const float* last_values,
+             const void* last_dones, int dones_kind, double gamma, double tau, float* advs,
+             float* returns, int32_t horizon, int64_t n, void* stream);
+
+/* K4a.  Pivoted batch moments for RunningMeanStd (ref: rl_games/algos_torch/running_mean_std.py
+ * forward, training branch).  x (m,c) f32 row-major.  pivot = running_mean (c,) f64 (may be NULL -> 0).
+ * acc (1+2c,) f64 is OVERWRITTEN with [m, sum_j(x-p), sum_j(x-p)^2]: additive across ranks, so a
+ * single SUM all-reduce of acc merges shards exactly.  partials: scratch f64, >= bezk_rms_scratch_doubles(c). */
+int64_t bezk_rms_scratch_doubles(int32_t c);
+int bezk_rms_moments(const float* x, const double* pivot, double* acc, double* partials,
+                     int64_t m, int32_t c, void* stream);
+/* K4b.  Merge acc (from bezk_rms_moments, possibly all-reduced) into running_mean/var (c,) f64 and
+ * count () f64 with the reference's parallel-variance update (unbiased batch variance). */
+int bezk_rms_merge(const double* acc, const double* pivot, double* running_mean, double* running_var,
+                   double* count, int32_t c, void* stream);
+/* K5.  y = clamp((x - mean.float()) / sqrt(var.float() + eps), -5, 5)   (unnorm = 0)
+ *      y = sqrt(var.float() + eps) * clamp(x, -5, 5) + mean.float()      (unnorm = 1)
+ * x, y (m,c) f32 (y may alias x). */
+int bezk_rms_normalize(const float* x, const double* running_mean, const double* running_var,
+                       float eps, int unnorm, float* y, int64_t m, int32_t c, void* stream);
+
+/* K7.  ref: a2c_common.py prepare_dataset: adv = returns - values, then (adv - mean)/(std + 1e-8)
+ * with the unbiased std.  Step 1 accumulates acc (3,) f64 = [m, sum adv, sum adv^2] (additive across
+ * ranks); step 2 normalises.  returns, values (m,) f32; adv_out (m,) f32. */
+int bezk_adv_moments(const float* returns, const float* values, double* acc, double* partials,
+                     int64_t m, void* stream);
+int bezk_adv_normalize(const float* returns, const float* values, const double* acc, float* adv_out,
+                       int normalize, int64_t m, void* stream);
+
+/* K8.  ref: rl_games/algos_torch/a2c_continuous.py calc_gradients loss block +
+ * common_losses.actor_loss/critic_loss + bound_loss + torch_ext.policy_kl + models neglogp.
+ * Forward AND backward of
+ *   loss = mean(a) + 0.5*critic_coef*mean(c) - entropy_coef*mean(ent) + bounds_loss_coef*mean(b)
+ * in one pass.  Inputs (m = minibatch): actions, mu, old_mu, old_sigma (m,18); logstd (18,)
+ * (fixed_sigma); values, old_values, returns, old_neglogp, advantages (m,).
+ * Outputs: stats (8,) f64 = [loss, a_loss, c_loss, entropy, b_loss, kl, clip_frac, 0] (means);
+ * grad_mu (m,18), grad_values (m,), grad_logstd (18,) f32 = d loss / d(.)  (any may be NULL to
+ * skip); neglogp_out (m,) or NULL.  partials: scratch f64 >= bezk_ppo_scratch_doubles(). */
+typedef struct BezkPpoCfg {
+    float e_clip;            /* 0.2 */
+    float critic_coef;       /* 2   */
+    float entropy_coef;      /* 0   */
+    float bounds_loss_coef;  /* 0.001 */
+    float soft_bound;        /* 1.1 */
+    int32_t clip_value;      /* 1 */
+    int32_t bound_form;      /* 0 = rl_games 1.1.3 as recalled, 1 = later "outside" form */
+} BezkPpoCfg;
+int64_t bezk_ppo_scratch_doubles(void);
+int bezk_ppo_loss(const float* actions, const float* mu, const float* logstd, const float* old_mu,
+                  const float* old_sigma, const float* values, const float* old_values,
+                  const float* returns, const float* old_neglogp, const float* advantages,
+                  const BezkPpoCfg* cfg, double* stats, float* grad_mu, float* grad_values,
+                  float* grad_logstd, float* neglogp_out, double* partials, int64_t m, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEZK_H_ */

@@ -1,0 +1,102 @@
+"""Import the reference's OWN ``bez_isaacgym/tasks/kick_env.py`` on CPU (oracle; test infrastructure).
+
+Only usable where /root/reference exists (the authoring container).  It is used to (a) validate
+``oracle.task_oracle`` against the real reference functions and (b) generate the golden vectors
+under ``tests/golden`` (``oracle/make_golden.py``).  Nothing that runs on the GPU box imports this.
+
+The reference imports packages that are not installable offline (``isaacgym``, ``gym``,
+``matplotlib``); they are replaced by inert ``sys.modules`` stubs.  The only stub that carries
+arithmetic is ``isaacgym.torch_utils`` -> ``oracle.isaacgym_torch_utils`` (restated, see there).
+No reference source is copied: the module is executed from where it lies.
+"""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("BEZ_REFERENCE_ROOT", "/root/reference")
+_PKG_DIR = os.path.join(REFERENCE_ROOT, "bez_isaacgym")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(_PKG_DIR, "tasks", "kick_env.py"))
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+class _Anything:
+    """Attribute sink used for gymapi enums/classes that are only touched at sim-creation time."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __getattr__(self, item):
+        return _Anything()
+
+    def __call__(self, *a, **k):
+        return _Anything()
+
+
+def install_stubs():
+    if "isaacgym" in sys.modules and getattr(sys.modules["isaacgym"], "_bez_stub", False):
+        return
+    if not hasattr(np, "Inf"):          # removed in numpy 2; tasks/base/vec_task.py:92-97 uses it
+        np.Inf = np.inf
+    from oracle import isaacgym_torch_utils as tu
+
+    gymapi = _stub("isaacgym.gymapi", SimParams=_Anything, Vec3=_Anything, Quat=_Anything,
+                   Transform=_Anything, PlaneParams=_Anything, AssetOptions=_Anything,
+                   SIM_PHYSX=1, SIM_FLEX=0, UP_AXIS_Z=1, UP_AXIS_Y=0, DOMAIN_SIM=0,
+                   acquire_gym=lambda: _Anything())
+    gymtorch = _stub("isaacgym.gymtorch", wrap_tensor=lambda t: t, unwrap_tensor=lambda t: t)
+    noop = lambda *a, **k: None
+    gymutil = _stub("isaacgym.gymutil", get_property_setter_map=noop, get_property_getter_map=noop,
+                    get_default_setter_args=noop, apply_random_samples=noop, check_buckets=noop,
+                    generate_random_samples=noop)
+    torch_utils = _stub("isaacgym.torch_utils", **{k: getattr(tu, k) for k in tu.__all__})
+    torch_utils.__all__ = list(tu.__all__)
+    _stub("isaacgym", gymapi=gymapi, gymtorch=gymtorch, gymutil=gymutil, torch_utils=torch_utils,
+          _bez_stub=True)
+
+    pyplot = _stub("matplotlib.pyplot", subplots=noop)
+    _stub("matplotlib", use=noop, pyplot=pyplot)
+
+    class Box:                            # gym.spaces.Box as used by tasks/base/vec_task.py:92-95
+        def __init__(self, low, high, shape=None, dtype=np.float32):
+            self.low, self.high = np.asarray(low), np.asarray(high)
+            self.shape = self.low.shape if shape is None else shape
+
+    spaces = _stub("gym.spaces", Box=Box)
+    _stub("gym", spaces=spaces, Space=object)
+
+
+_cached = None
+
+
+def load_reference_kick_env():
+    """Return the reference module ``tasks.kick_env`` (executed from /root/reference)."""
+    global _cached
+    if _cached is not None:
+        return _cached
+    if not reference_available():
+        raise FileNotFoundError(f"reference not found under {REFERENCE_ROOT}")
+    install_stubs()
+    if _PKG_DIR not in sys.path:
+        sys.path.insert(0, _PKG_DIR)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        # tasks/__init__.py also imports walk_env/orient_env; import the module file directly
+        # under the package name so its relative import (.base.vec_task) resolves.
+        pkg = types.ModuleType("tasks")
+        pkg.__path__ = [os.path.join(_PKG_DIR, "tasks")]
+        sys.modules.setdefault("tasks", pkg)
+        _cached = importlib.import_module("tasks.kick_env")
+    return _cached
