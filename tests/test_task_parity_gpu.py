@@ -349,7 +349,9 @@ def test_fused_post_physics_follows_step_oracle(n, parts_mode, alias):
     obs = torch.zeros(n, 54, device="cuda"); rew = torch.zeros(n, device="cuda")
     reset = reset0.cuda(); progress = progress0.cuda(); timeout = torch.zeros(n, dtype=torch.long, device="cuda")
     randomize = torch.zeros(n, dtype=torch.long, device="cuda")
-    prev_d = None if alias else torch.zeros(n, 3, device="cuda")
+    # the reference starts from zeros (kick_env.py:183) and aliases the velocity view from the second
+    # observation on (:930): step 0 always reads a zero buffer, later steps pass NULL in aliasing mode
+    prev_d = torch.zeros(n, 3, device="cuda")
     g_d, b_d, ir_d = goal.cuda(), ball_init.cuda(), init_root.cuda()
 
     total_band = 0
@@ -362,9 +364,9 @@ def test_fused_post_physics_follows_step_oracle(n, parts_mode, alias):
             cpu.dof_state.add_(drift); d.dof_state.add_(drift.cuda())
         before = sg.SimState(cpu.root_states.clone(), cpu.dof_state.clone(), cpu.rigid_body.clone(),
                              cpu.net_contact.clone(), n, st.num_bodies)
-        prev_before = None if alias else orc.prev_lin_vel.clone()
+        prev_before = None if (alias and step > 0) else orc.prev_lin_vel.clone().float()
         want_obs, want_rew, want_reset, want_timeout = orc.post_physics_step()
-        kw = dict(prev_lin_vel=prev_d, seed=seed, step=step, randomize_buf=randomize)
+        kw = dict(prev_lin_vel=None if (alias and step > 0) else prev_d, seed=seed, step=step, randomize_buf=randomize)
         if parts_mode == "fused":
             ops.post_physics(d.dof_state, d.rigid_body, d.root_states, d.net_contact, g_d, b_d, ir_d, reset, progress,
                              timeout, cfg, obs, rew, **kw)
