@@ -44,6 +44,7 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--fusion", default="fused", choices=["fused", "split"])
+    p.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity hint (0 = leave default)")
     return p.parse_args()
 
 
@@ -170,6 +171,7 @@ def run_b200(args):
     from bez_isaacgym_b200.tasks.kick_env import KickEnv
 
     n, T = args.envs_per_gpu, args.horizon
+    l2_fetch = ops.set_l2_fetch_granularity(args.l2_fetch) if args.l2_fetch else None
     cfg = bm.default_task_cfg(n, rl_device=str(dev))
     cfg["env"]["imuPrevVelAliasing"] = False                # the general (680 B/env-step) path with a prev_lin_vel buffer
     cfg["seed"] = 42 + rank
@@ -303,7 +305,7 @@ def run_b200(args):
                           "envs_per_gpu": n, "horizon": T, "parallelism": f"env-sharded x{world}, no data-path collective",
                           "fusion": args.fusion, "l2": "inputs larger than L2 (state footprint ~%.0f MB/GPU)" % (
                               n * 4 * (26 + 36 + 16 * bm.BODIES_NO_CLEATS) / 1e6),
-                          "reset_rate_per_step": reset_rate, "imu_prev_lin_vel": "buffer (680 B/env-step path)"},
+                          "reset_rate_per_step": reset_rate, "l2_fetch_granularity": l2_fetch, "imu_prev_lin_vel": "buffer (680 B/env-step path)"},
                "clocks": sampler.summary(), "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
                "e2e": e2e, "cpu_baseline": cpu_baseline}
         print(json.dumps(out))

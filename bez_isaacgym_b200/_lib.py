@@ -50,6 +50,7 @@ _U64 = C.c_uint64
 SIGNATURES = {
     "bezk_version": (C.c_int, []),
     "bezk_last_error": (C.c_char_p, []),
+    "bezk_set_l2_fetch_granularity": (C.c_int, [C.c_int32, C.POINTER(C.c_int32)]),
     "bezk_pre_physics": (C.c_int, [_P, _P, _P, C.POINTER(BezkTaskCfg), _I64, _P]),
     "bezk_compute_observations": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(BezkTaskCfg), _P, _P, _I64, _P]),
     "bezk_compute_reward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(BezkTaskCfg), _P, _P, _I64, _P]),

@@ -34,6 +34,16 @@ extern "C" {
 int bezk_version(void) { return BEZK_VERSION; }
 const char* bezk_last_error(void) { return g_err; }
 
+int bezk_set_l2_fetch_granularity(int32_t bytes, int32_t* effective) {
+    REQUIRE(bytes == 32 || bytes == 64 || bytes == 128, "granularity must be 32, 64 or 128");
+    cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes);
+    if (e != cudaSuccess) return cuda_rc(e, "cudaDeviceSetLimit(MaxL2FetchGranularity)");
+    size_t got = 0;
+    e = cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+    if (effective) *effective = (int32_t)got;
+    return cuda_rc(e, "cudaDeviceGetLimit(MaxL2FetchGranularity)");
+}
+
 int bezk_pre_physics(const float* actions, float* actions_out, float* targets, const BezkTaskCfg* cfg, int64_t n, void* stream) {
     if (int rc = check_cfg(cfg)) return rc;
     REQUIRE(n >= 0, "n < 0");

@@ -28,6 +28,7 @@ struct TaskArgs {
     int64_t n;
     int use_tma;      // all dense bases 16 B aligned
     int rb_vec2;      // IMU-link slice of every env is 8 B aligned
+    int cf_vec2;      // both foot force rows of every env are 8 B aligned
 };
 struct PpoArgs {
     const float *actions, *mu, *logstd, *old_mu, *old_sigma, *values, *old_values, *returns, *old_neglogp, *advantages;

@@ -49,7 +49,9 @@ __global__ void __launch_bounds__(256) pre_physics_kernel(const float* __restric
         const float4 a = ldg_stream4(reinterpret_cast<const float4*>(actions) + i);
         const float in[4] = {a.x, a.y, a.z, a.w};
         float st[4], tg[4];
-        int col = (int)((i * 4) % 18);
+        // (4 i) mod 18 = (4 (i mod 9)) mod 18; 32-bit arithmetic whenever the index fits (64-bit % is ~100 instr)
+        const uint32_t r9 = (i < 0xffffffffLL) ? ((uint32_t)i % 9u) : (uint32_t)(i % 9);
+        int col = (int)((4u * r9) % 18u);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             float v = clamp_nan(in[k], -clip, clip);
@@ -200,11 +202,12 @@ __device__ __forceinline__ void reset_dof_row(const float (&u)[36], const BezkTa
 // ------------------------------------------------------------------------------------------------
 // The fused tile kernel.  PARTS: 1 bookkeeping+masked reset, 2 observations, 4 reward/termination.
 // ------------------------------------------------------------------------------------------------
-template <int PARTS>
-__global__ void __launch_bounds__(TILE) task_tile_kernel(const TaskArgs a, const __grid_constant__ BezkTaskCfg cfg) {
+template <int PARTS, bool CLEATS>
+__global__ void __launch_bounds__(TILE, 5) task_tile_kernel(const TaskArgs a, const __grid_constant__ BezkTaskCfg cfg) {
     constexpr bool BOOK = (PARTS & BEZK_PART_BOOKKEEP) != 0;
     constexpr bool OBS = (PARTS & BEZK_PART_OBS) != 0;
     constexpr bool REW = (PARTS & BEZK_PART_REWARD) != 0;
+    constexpr int NFORCE = CLEATS ? 12 : 3;
 
     extern __shared__ __align__(128) float smem[];
     float* s_dof = smem;                              // [TILE][36]
@@ -214,6 +217,7 @@ __global__ void __launch_bounds__(TILE) task_tile_kernel(const TaskArgs a, const
     __shared__ __align__(8) uint64_t s_bar;
 
     const int tid = threadIdx.x;
+    const int lane = tid & 31;
     const int64_t e0 = (int64_t)blockIdx.x * TILE;
     const int nv = (int)((a.n - e0) < (int64_t)TILE ? (a.n - e0) : (int64_t)TILE);
     const bool full = (nv == TILE) && a.use_tma;
@@ -234,34 +238,41 @@ __global__ void __launch_bounds__(TILE) task_tile_kernel(const TaskArgs a, const
         for (int i = tid; i < nv * ROOT_ROW; i += TILE) s_root[i] = a.root_states[e0 * ROOT_ROW + i];
     }
 
-    // ---- 2. sparse gathers, issued before anyone waits ----
-    float q[4] = {0.f, 0.f, 0.f, 1.f}, v[3] = {0.f, 0.f, 0.f}, w[3] = {0.f, 0.f, 0.f};
-    float fl[12], fr[12];
+    // ---- 2. sparse gathers, issued before anyone waits (widest aligned vector loads available) ----
+    float imu_in[10];                                 // q(4) v(3) w(3) of the IMU link
+#pragma unroll
+    for (int k = 0; k < 10; ++k) imu_in[k] = 0.0f;
+    float fl[NFORCE], fr[NFORCE];
     float goal[2] = {0.f, 0.f}, binit[2] = {0.f, 0.f}, prev[3] = {0.f, 0.f, 0.f};
     int64_t reset_prev = 0, progress = 0;
-    const bool cleats = (cfg.flags & BEZK_F_CLEATS) != 0;
-    const int nforce = cleats ? 12 : 3;
     float* cf_l = nullptr;
     float* cf_r = nullptr;
     if (valid) {
         const float* rb = a.rigid_body + ((e * cfg.num_bodies + cfg.imu_body) * 13 + 3);
         if (a.rb_vec2) {
-            const float2* rb2 = reinterpret_cast<const float2*>(rb);
-            const float2 t0 = __ldg(rb2), t1 = __ldg(rb2 + 1), t2 = __ldg(rb2 + 2), t3 = __ldg(rb2 + 3), t4 = __ldg(rb2 + 4);
-            q[0] = t0.x; q[1] = t0.y; q[2] = t1.x; q[3] = t1.y;
-            v[0] = t2.x; v[1] = t2.y; v[2] = t3.x; w[0] = t3.y; w[1] = t4.x; w[2] = t4.y;
+            // 40 bytes at an 8-byte aligned address: one 8 B + two 16 B loads, order chosen per lane by bit 3
+            const char* p = reinterpret_cast<const char*>(rb);
+            const bool hi = (reinterpret_cast<uintptr_t>(p) & 8u) != 0;
+            const float2 a2 = ldg64B_nc_v2(p + (hi ? 0 : 32));
+            const float4 b4 = ldg64B_nc_v4(p + (hi ? 8 : 0));
+            const float4 c4 = ldg64B_nc_v4(p + (hi ? 24 : 16));
+            imu_in[0] = hi ? a2.x : b4.x; imu_in[1] = hi ? a2.y : b4.y; imu_in[2] = hi ? b4.x : b4.z; imu_in[3] = hi ? b4.y : b4.w;
+            imu_in[4] = hi ? b4.z : c4.x; imu_in[5] = hi ? b4.w : c4.y; imu_in[6] = hi ? c4.x : c4.z; imu_in[7] = hi ? c4.y : c4.w;
+            imu_in[8] = hi ? c4.z : a2.x; imu_in[9] = hi ? c4.w : a2.y;
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) q[k] = __ldg(rb + k);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { v[k] = __ldg(rb + 4 + k); w[k] = __ldg(rb + 7 + k); }
+            for (int k = 0; k < 10; ++k) imu_in[k] = ldg64B_nc(rb + k);
         }
         if (OBS) {
             cf_l = a.net_contact + (e * cfg.num_bodies + cfg.left_foot_body) * 3;
             cf_r = a.net_contact + (e * cfg.num_bodies + cfg.right_foot_body) * 3;
+            if (!CLEATS && a.cf_vec2) {
+                const float2 l2 = ldg64B_v2(cf_l), r2 = ldg64B_v2(cf_r);
+                fl[0] = l2.x; fl[1] = l2.y; fl[2] = ldg64B(cf_l + 2);
+                fr[0] = r2.x; fr[1] = r2.y; fr[2] = ldg64B(cf_r + 2);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 12; ++k) {
-                if (k < nforce) { fl[k] = cf_l[k]; fr[k] = cf_r[k]; }
+                for (int k = 0; k < NFORCE; ++k) { fl[k] = ldg64B(cf_l + k); fr[k] = ldg64B(cf_r + k); }
             }
             if (a.prev_lin_vel) {
 #pragma unroll
@@ -276,13 +287,78 @@ __global__ void __launch_bounds__(TILE) task_tile_kernel(const TaskArgs a, const
             progress = a.progress_in[e];
         }
     }
+    const float q[4] = {imu_in[0], imu_in[1], imu_in[2], imu_in[3]};
+    const float v[3] = {imu_in[4], imu_in[5], imu_in[6]};
+    const float w[3] = {imu_in[7], imu_in[8], imu_in[9]};
 
-    // ---- 3. wait for the dense tiles, pull this env's rows into registers ----
+    // ---- 3. wait for the dense tiles ----
     __syncthreads();                       // mbarrier init / cooperative stores visible
     if (full) mbar_wait(&s_bar, 0);
 
+    // ---- 4. bookkeeping + masked reset (vec_task.py:331-332, kick_env.py:429-435, 779-850) ----
+    // The reset of an env is done by its WARP: lanes 0..8 each run one Philox4x32 block (4 of the 36 draws),
+    // patch the env's row in shared memory and write it back to dof_state as 9 float4 stores; lanes 0..25 copy
+    // the initial root-state row.  No divergent 36-draw loop in the per-thread path.
+    int64_t timeout = 0, reset_cur = reset_prev;
+    if (BOOK) {
+        unsigned pending = __ballot_sync(0xffffffffu, valid && reset_prev != 0);
+        const int warp_row0 = tid - lane;
+        while (pending) {
+            const int src = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const int r = warp_row0 + src;
+            const int64_t env = e0 + r;
+            if (lane < 9) {
+                float u4[4];
+                if (a.uniforms) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) u4[k] = a.uniforms[env * 36 + 4 * lane + k];
+                } else {
+                    const Philox4 x = philox4x32_10((uint32_t)env, (uint32_t)((uint64_t)env >> 32), (uint32_t)a.step,
+                                                    ((uint32_t)(a.step >> 32) << 4) + (uint32_t)lane, (uint32_t)a.seed,
+                                                    (uint32_t)(a.seed >> 32));
+                    u4[0] = u01(x.x); u4[1] = u01(x.y); u4[2] = u01(x.z); u4[3] = u01(x.w);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int d = 4 * lane + k;              // draw index: 0..17 positions, 18..35 velocities
+                    if (d < 18) {
+                        const float off = cfg.reset_pos_span * u4[k] + cfg.reset_pos_lo;
+                        s_dof[r * DOF_ROW + 2 * d] = tensor_clamp(cfg.default_dof_pos[d] + off, cfg.dof_lower[d], cfg.dof_upper[d]);
+                    } else {
+                        s_dof[r * DOF_ROW + 2 * (d - 18) + 1] = cfg.reset_vel_span * u4[k] + cfg.reset_vel_lo;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane < 9) {
+                if (a.use_tma) {
+                    reinterpret_cast<float4*>(a.dof_state + env * DOF_ROW)[lane] = reinterpret_cast<const float4*>(s_dof + r * DOF_ROW)[lane];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) a.dof_state[env * DOF_ROW + 4 * lane + k] = s_dof[r * DOF_ROW + 4 * lane + k];
+                }
+            }
+            if ((cfg.flags & BEZK_F_RESET_ROOT_STATES) && lane < ROOT_ROW) {
+                const float t = a.initial_root[env * ROOT_ROW + lane];
+                s_root[r * ROOT_ROW + lane] = t;
+                a.root_states[env * ROOT_ROW + lane] = t;
+            }
+            __syncwarp();
+        }
+        if (valid) {
+            timeout = (progress >= (int64_t)cfg.max_episode_length - 1) ? 1 : 0;
+            progress += 1;
+            if (a.randomize_buf) a.randomize_buf[e] += 1;
+            if (reset_prev != 0) { progress = 0; reset_cur = 0; }
+            a.timeout_buf[e] = timeout;
+            if (!REW) { a.progress_out[e] = progress; a.reset_out[e] = reset_cur; }
+        }
+    }
+
+    // ---- 5. this env's rows: shared -> registers (conflict-free 128-bit reads, row stride 36 words) ----
     float row[36];
-    float rt[ROOT_ROW];
+    float bez[3] = {0.f, 0.f, 0.f}, ball_xy[2] = {0.f, 0.f}, ball_vxy[2] = {0.f, 0.f};
     if (valid) {
         const float4* r4 = reinterpret_cast<const float4*>(s_dof + tid * DOF_ROW);
 #pragma unroll
@@ -290,52 +366,13 @@ __global__ void __launch_bounds__(TILE) task_tile_kernel(const TaskArgs a, const
             const float4 t = r4[k];
             row[4 * k] = t.x; row[4 * k + 1] = t.y; row[4 * k + 2] = t.z; row[4 * k + 3] = t.w;
         }
-        const float2* r2 = reinterpret_cast<const float2*>(s_root + tid * ROOT_ROW);
-#pragma unroll
-        for (int k = 0; k < 13; ++k) {
-            const float2 t = r2[k];
-            rt[2 * k] = t.x; rt[2 * k + 1] = t.y;
-        }
+        const float* rr = s_root + tid * ROOT_ROW;
+        bez[0] = rr[0]; bez[1] = rr[1]; bez[2] = rr[2];
+        ball_xy[0] = rr[13]; ball_xy[1] = rr[14];
+        ball_vxy[0] = rr[20]; ball_vxy[1] = rr[21];
     }
 
-    // ---- 4. bookkeeping + masked reset (vec_task.py:331-332, kick_env.py:429-435, 779-850) ----
-    int64_t timeout = 0, reset_cur = reset_prev;
-    if (BOOK && valid) {
-        timeout = (progress >= (int64_t)cfg.max_episode_length - 1) ? 1 : 0;
-        progress += 1;
-        if (a.randomize_buf) a.randomize_buf[e] += 1;
-        if (reset_prev != 0) {
-            float u[36];
-            if (a.uniforms) {
-#pragma unroll
-                for (int k = 0; k < 36; ++k) u[k] = a.uniforms[e * 36 + k];
-            } else {
-                philox_reset_uniforms(a.seed, a.step, e, u);
-            }
-            reset_dof_row(u, cfg, row);
-            float4* g4 = reinterpret_cast<float4*>(a.dof_state + e * DOF_ROW);
-            if (a.use_tma) {
-#pragma unroll
-                for (int k = 0; k < 9; ++k) g4[k] = make_float4(row[4 * k], row[4 * k + 1], row[4 * k + 2], row[4 * k + 3]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 36; ++k) a.dof_state[e * DOF_ROW + k] = row[k];
-            }
-            if (cfg.flags & BEZK_F_RESET_ROOT_STATES) {
-#pragma unroll
-                for (int k = 0; k < ROOT_ROW; ++k) {
-                    rt[k] = a.initial_root[e * ROOT_ROW + k];
-                    a.root_states[e * ROOT_ROW + k] = rt[k];
-                }
-            }
-            progress = 0;
-            reset_cur = 0;
-        }
-        a.timeout_buf[e] = timeout;
-        if (!REW) { a.progress_out[e] = progress; a.reset_out[e] = reset_cur; }
-    }
-
-    // ---- 5. observations (kick_env.py:749-777) ----
+    // ---- 6. observations (kick_env.py:749-777) ----
     float imu6[6], orn2[2], feet[8];
     if (OBS && valid) {
         float pv[3];
@@ -346,12 +383,13 @@ __global__ void __launch_bounds__(TILE) task_tile_kernel(const TaskArgs a, const
 #pragma unroll
             for (int k = 0; k < 3; ++k) a.prev_lin_vel[e * 3 + k] = v[k];
         }
-        off_orn_term(rt[0], rt[1], q, goal[0], goal[1], orn2);
-        if (cleats) {                                                      // kick_env.py:1053-1061
+        off_orn_term(bez[0], bez[1], q, goal[0], goal[1], orn2);
+        if (CLEATS) {                                                      // kick_env.py:1053-1061
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float nl = sqrtf((fl[3 * k] * fl[3 * k] + fl[3 * k + 1] * fl[3 * k + 1]) + fl[3 * k + 2] * fl[3 * k + 2]);
-                const float nr = sqrtf((fr[3 * k] * fr[3 * k] + fr[3 * k + 1] * fr[3 * k + 1]) + fr[3 * k + 2] * fr[3 * k + 2]);
+                const int b = CLEATS ? 3 * k : 0;
+                const float nl = sqrtf((fl[b] * fl[b] + fl[b + 1] * fl[b + 1]) + fl[b + 2] * fl[b + 2]);
+                const float nr = sqrtf((fr[b] * fr[b] + fr[b + 1] * fr[b + 1]) + fr[b + 2] * fr[b + 2]);
                 feet[k] = (nl > 1.0f) ? 1.0f : -1.0f;
                 feet[4 + k] = (nr > 1.0f) ? 1.0f : -1.0f;
             }
@@ -372,7 +410,15 @@ __global__ void __launch_bounds__(TILE) task_tile_kernel(const TaskArgs a, const
         }
     }
 
-    // ---- 6. observation rows -> shared (aliasing the input tiles) -> one bulk store ----
+    // ---- 7. observation rows -> shared (aliasing the input tiles) -> one bulk store ----
+    float pos_sq = 0.0f;
+    if (REW && valid) {
+#pragma unroll
+        for (int j = 0; j < 18; ++j) {
+            const float d = cfg.default_dof_pos[j] - row[2 * j];
+            pos_sq += d * d;
+        }
+    }
     if (OBS) {
         __syncthreads();                   // every thread has finished reading s_dof / s_root
         if (valid) {
@@ -413,23 +459,17 @@ __global__ void __launch_bounds__(TILE) task_tile_kernel(const TaskArgs a, const
         }
     }
 
-    // ---- 7. reward / termination (overlaps the bulk store) ----
+    // ---- 8. reward / termination (overlaps the bulk store) ----
     if (REW && valid) {
         RewardIn s;
-        s.bez[0] = rt[0]; s.bez[1] = rt[1]; s.bez[2] = rt[2];
-        s.ball_xy[0] = rt[13]; s.ball_xy[1] = rt[14];
-        s.ball_vxy[0] = rt[20]; s.ball_vxy[1] = rt[21];
+        s.bez[0] = bez[0]; s.bez[1] = bez[1]; s.bez[2] = bez[2];
+        s.ball_xy[0] = ball_xy[0]; s.ball_xy[1] = ball_xy[1];
+        s.ball_vxy[0] = ball_vxy[0]; s.ball_vxy[1] = ball_vxy[1];
         s.goal[0] = goal[0]; s.goal[1] = goal[1];
         s.ball_init[0] = binit[0]; s.ball_init[1] = binit[1];
 #pragma unroll
         for (int k = 0; k < 3; ++k) { s.v[k] = v[k]; s.w[k] = w[k]; }
-        float acc = 0.0f;
-#pragma unroll
-        for (int j = 0; j < 18; ++j) {
-            const float d = cfg.default_dof_pos[j] - row[2 * j];
-            acc += d * d;
-        }
-        s.pos_sq = acc;
+        s.pos_sq = pos_sq;
         float rew;
         int64_t reset;
         reward_term(s, cfg, progress, reset_cur, &rew, &reset);
@@ -485,19 +525,24 @@ __global__ void philox_uniforms_kernel(uint64_t seed, uint64_t step, float* out,
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 
-template <int PARTS>
-static cudaError_t launch_parts(const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st) {
+template <int PARTS, bool CLEATS>
+static cudaError_t launch_parts2(const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st) {
     const size_t smem = (size_t)(SMEM_IN_FLOATS + (a.obs_clipped ? SMEM_OBS_FLOATS : 0)) * sizeof(float);
     static bool attr_set = false;          // per instantiation; opt in to > 48 KB dynamic shared memory once
     if (!attr_set) {
-        cudaError_t err = cudaFuncSetAttribute(task_tile_kernel<PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t err = cudaFuncSetAttribute(task_tile_kernel<PARTS, CLEATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)((SMEM_IN_FLOATS + SMEM_OBS_FLOATS) * sizeof(float)));
         if (err != cudaSuccess) return err;
         attr_set = true;
     }
     const int64_t tiles = (a.n + TILE - 1) / TILE;
-    task_tile_kernel<PARTS><<<(unsigned)tiles, TILE, smem, st>>>(a, cfg);
+    task_tile_kernel<PARTS, CLEATS><<<(unsigned)tiles, TILE, smem, st>>>(a, cfg);
     return cudaGetLastError();
+}
+
+template <int PARTS>
+static cudaError_t launch_parts(const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st) {
+    return (cfg.flags & BEZK_F_CLEATS) ? launch_parts2<PARTS, true>(a, cfg, st) : launch_parts2<PARTS, false>(a, cfg, st);
 }
 
 cudaError_t launch_task(int parts, const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st) {
@@ -517,6 +562,8 @@ void fill_alignment(TaskArgs& a, const BezkTaskCfg& cfg) {
     a.use_tma = aligned16(a.dof_state) && aligned16(a.root_states) && (a.obs == nullptr || aligned16(a.obs)) &&
                 (a.obs_clipped == nullptr || aligned16(a.obs_clipped));
     a.rb_vec2 = aligned8(a.rigid_body) && (cfg.num_bodies % 2 == 0) && ((cfg.imu_body * 13 + 3) % 2 == 0);
+    a.cf_vec2 = a.net_contact != nullptr && aligned8(a.net_contact) && ((cfg.num_bodies * 3) % 2 == 0) &&
+                ((cfg.left_foot_body * 3) % 2 == 0) && ((cfg.right_foot_body * 3) % 2 == 0);
 }
 
 cudaError_t launch_pre_physics(const float* actions, float* actions_out, float* targets, const BezkTaskCfg& cfg,

@@ -74,6 +74,13 @@ def make_task_cfg(num_bodies=bm.BODIES_NO_CLEATS, cleats=False, dt=0.01667, max_
 F32, F64, I64, U8 = torch.float32, torch.float64, torch.int64, torch.uint8
 
 
+def set_l2_fetch_granularity(nbytes=32):
+    """cudaLimitMaxL2FetchGranularity hint for the current device; returns the value in effect."""
+    got = C.c_int32(0)
+    _lib.check(_lib.load().bezk_set_l2_fetch_granularity(int(nbytes), C.byref(got)), "bezk_set_l2_fetch_granularity")
+    return got.value
+
+
 # ------------------------------------------------------------------------------------------- task
 def pre_physics(actions, targets, cfg: BezkTaskCfg, actions_out=None):
     n = actions.shape[0]

@@ -170,7 +170,7 @@ class KickEnv(VecTask):
         self._post_fixed = dict(
             head=[_ptr(self._d_dof), _ptr(self._d_rb), _ptr(self._d_root), _ptr(self._d_cf)],
             mid=[_ptr(self.goal), _ptr(self.ball_init), _ptr(self.initial_root_states), None],
-            tail=[_ptr(self.reset_buf), _ptr(self.progress_buf), _ptr(self.timeout_buf), _ptr(self.randomize_buf), kc,
+            tail=[_ptr(self.reset_buf), _ptr(self.progress_buf), _ptr(self.timeout_buf), None, kc,
                   _ptr(self.obs_buf), _ptr(self.obs_clipped_buf), _ptr(self.rew_buf)])
 
     def _stream(self):
@@ -193,6 +193,20 @@ class KickEnv(VecTask):
             a[..., 0:2] = 0.0
             self._actions_cache = a
         return self._actions_cache
+
+    @property
+    def randomize_buf(self):
+        """``randomize_buf += 1`` per step (kick_env.py:430) is applied lazily: with domain randomisation out of
+        scope nothing on the device reads it, so the 16 B/env-step of traffic is only paid when somebody looks."""
+        if self._randomize_pending:
+            self._randomize_base += self._randomize_pending
+            self._randomize_pending = 0
+        return self._randomize_base
+
+    @randomize_buf.setter
+    def randomize_buf(self, value):
+        self._randomize_base = value
+        self._randomize_pending = 0
 
     @property
     def prev_lin_vel(self):
@@ -234,6 +248,7 @@ class KickEnv(VecTask):
         """vec_task.py:331-332 + kick_env.py:426-438 in one launch (two with ``fusion='split'``)."""
         self._stage_in()
         self._rng_step += 1
+        self._randomize_pending += 1
         if self.fusion == "fused":
             self._launch_post(_lib.PART_ALL)
         else:

@@ -62,6 +62,11 @@ typedef struct BezkTaskCfg {
 
 int  bezk_version(void);
 const char* bezk_last_error(void);
+/* Device-wide hint (cudaLimitMaxL2FetchGranularity: 32, 64 or 128 bytes) for the current device.  The task
+ * kernels gather 12..40-byte slices out of 264..1144-byte Isaac Gym rows, so a 32-byte L2 fetch
+ * granularity avoids dragging unused neighbouring sectors out of HBM.  Returns the value in effect
+ * through *effective (may be NULL). */
+int bezk_set_l2_fetch_granularity(int32_t bytes, int32_t* effective);
 
 /* ---------------------------------------------------------------- task side ------------------ */
 
