@@ -31,9 +31,12 @@ constexpr int SMEM_OBS_FLOATS = TILE * OBS_ROW;               // 6912 floats = 2
 // ------------------------------------------------------------------------------------------------
 // K0: pre-physics.  Pure streaming elementwise pass over (n,18): 72 B read + 72 B written per env.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pre_physics_kernel(const float* __restrict__ actions, float* __restrict__ actions_out,
-                                                          float* __restrict__ targets, const __grid_constant__ BezkTaskCfg cfg,
-                                                          int64_t total, int vec4) {
+constexpr int K0_THREADS = 256;
+constexpr int K0_UNROLL = 4;            // float4 loads in flight per thread
+
+__global__ void __launch_bounds__(K0_THREADS) pre_physics_kernel(const float* __restrict__ actions, float* __restrict__ actions_out,
+                                                                 float* __restrict__ targets, const __grid_constant__ BezkTaskCfg cfg,
+                                                                 int64_t total, int vec4) {
     __shared__ float s_def[18], s_lo[18], s_hi[18];
     if (threadIdx.x < 18) {
         s_def[threadIdx.x] = cfg.default_dof_pos[threadIdx.x];
@@ -42,28 +45,38 @@ __global__ void __launch_bounds__(256) pre_physics_kernel(const float* __restric
     }
     __syncthreads();
     const float clip = cfg.clip_actions;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nvec = vec4 ? (total >> 2) : 0;
-    for (int64_t i = tid; i < nvec; i += stride) {
-        const float4 a = ldg_stream4(reinterpret_cast<const float4*>(actions) + i);
-        const float in[4] = {a.x, a.y, a.z, a.w};
+    // main body: every thread issues K0_UNROLL independent 16-byte loads (block-contiguous), then computes + stores
+    const int64_t base = (int64_t)blockIdx.x * (K0_THREADS * K0_UNROLL) + threadIdx.x;
+    float4 in[K0_UNROLL];
+#pragma unroll
+    for (int u = 0; u < K0_UNROLL; ++u) {
+        const int64_t i = base + u * K0_THREADS;
+        if (i < nvec) in[u] = ldg_stream4(reinterpret_cast<const float4*>(actions) + i);
+    }
+#pragma unroll
+    for (int u = 0; u < K0_UNROLL; ++u) {
+        const int64_t i = base + u * K0_THREADS;
+        if (i >= nvec) continue;
+        const float a4[4] = {in[u].x, in[u].y, in[u].z, in[u].w};
         float st[4], tg[4];
         // (4 i) mod 18 = (4 (i mod 9)) mod 18; 32-bit arithmetic whenever the index fits (64-bit % is ~100 instr)
         const uint32_t r9 = (i < 0xffffffffLL) ? ((uint32_t)i % 9u) : (uint32_t)(i % 9);
         int col = (int)((4u * r9) % 18u);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            float v = clamp_nan(in[k], -clip, clip);
-            if (col < 2) v = 0.0f;
+            float v = clamp_nan(a4[k], -clip, clip);                       // vec_task.py:317
+            if (col < 2) v = 0.0f;                                         // kick_env.py:414 (head)
             st[k] = v;
-            tg[k] = tensor_clamp(v + s_def[col], s_lo[col], s_hi[col]);
+            tg[k] = tensor_clamp(v + s_def[col], s_lo[col], s_hi[col]);    // kick_env.py:417
             col = (col == 17) ? 0 : col + 1;
         }
         __stcs(reinterpret_cast<float4*>(targets) + i, make_float4(tg[0], tg[1], tg[2], tg[3]));
         if (actions_out) __stcs(reinterpret_cast<float4*>(actions_out) + i, make_float4(st[0], st[1], st[2], st[3]));
     }
-    for (int64_t i = nvec * 4 + tid; i < total; i += stride) {      // scalar tail / unaligned path
+    // scalar tail (total % 4 elements) or the whole array when the pointers are not 16-byte aligned
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = nvec * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const int col = (int)(i % 18);
         float v = clamp_nan(actions[i], -clip, clip);
         if (col < 2) v = 0.0f;
@@ -570,12 +583,11 @@ cudaError_t launch_pre_physics(const float* actions, float* actions_out, float* 
                                int64_t n, cudaStream_t st) {
     const int64_t total = n * 18;
     const int vec4 = aligned16(actions) && aligned16(targets) && (actions_out == nullptr || aligned16(actions_out));
-    const int threads = 256;
-    int64_t blocks = ((vec4 ? total / 4 : total) + threads - 1) / threads;
+    const int64_t per_block = (int64_t)K0_THREADS * K0_UNROLL;
+    int64_t blocks = vec4 ? ((total >> 2) + per_block - 1) / per_block : (total + K0_THREADS - 1) / K0_THREADS;
     if (blocks < 1) blocks = 1;
-    const int64_t cap = 148LL * 16;
-    if (blocks > cap) blocks = cap;
-    pre_physics_kernel<<<(unsigned)blocks, threads, 0, st>>>(actions, actions_out, targets, cfg, total, vec4);
+    if (!vec4 && blocks > 148LL * 64) blocks = 148LL * 64;      // scalar path is grid-strided
+    pre_physics_kernel<<<(unsigned)blocks, K0_THREADS, 0, st>>>(actions, actions_out, targets, cfg, total, vec4);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,61 @@
+"""``RunningMeanStd`` with rl_games' interface and state layout (rl_games/algos_torch/running_mean_std.py, v1.1.3;
+used by the reference at ``bez_isaacgym/utils/players.py:38,71-72`` and checkpointed as ``running_mean_std`` /
+``reward_mean_std``): fp64 buffers ``running_mean``, ``running_var``, ``count`` (so reference checkpoints load),
+``forward(input, unnorm=False)``, statistics updated in training mode only.
+
+Kernels: one pass of pivoted fp64 moments (block -> grid, fixed order), a one-block merge with the reference's
+parallel-variance update, one streaming normalise pass.  With a process group the pivoted sums of all ranks are
+SUM-all-reduced between moments and merge, which makes the update EXACT across shards."""
+import torch
+from torch import nn
+
+from .. import dist as bdist
+from .. import ops
+
+
+class RunningMeanStd(nn.Module):
+    def __init__(self, insize, epsilon=1e-05, per_channel=False, norm_only=False, process_group=None):
+        super().__init__()
+        if per_channel or norm_only:
+            raise NotImplementedError("per_channel / norm_only are not used by the BezKick configuration")
+        if isinstance(insize, (tuple, list)):
+            if len(insize) != 1:
+                raise NotImplementedError("only 1-D observation shapes")
+            insize = insize[0]
+        self.insize = int(insize)
+        self.epsilon = float(epsilon)
+        self.process_group = process_group
+        self.register_buffer("running_mean", torch.zeros(self.insize, dtype=torch.float64))
+        self.register_buffer("running_var", torch.ones(self.insize, dtype=torch.float64))
+        self.register_buffer("count", torch.ones((), dtype=torch.float64))
+        self._acc = None
+        self._scratch = None
+        self._pivot = None
+
+    def _workspace(self, device):
+        if self._acc is None or self._acc.device != device:
+            c = self.insize
+            self._acc = torch.empty(1 + 2 * c, dtype=torch.float64, device=device)
+            self._scratch = torch.empty(ops.rms_scratch_doubles(c), dtype=torch.float64, device=device)
+            self._pivot = torch.empty(c, dtype=torch.float64, device=device)
+
+    def update(self, x: torch.Tensor):
+        """Merge the batch moments of ``x`` (m, insize) into the running statistics."""
+        self._workspace(x.device)
+        self._pivot.copy_(self.running_mean)              # replicated on all ranks -> identical pivots
+        ops.rms_moments(x, self._pivot, self._acc, self._scratch)
+        bdist.allreduce_sum_(self._acc, self.process_group)
+        ops.rms_merge(self._acc, self._pivot, self.running_mean, self.running_var, self.count.view(1))
+
+    def forward(self, input: torch.Tensor, unnorm: bool = False, out: torch.Tensor = None) -> torch.Tensor:
+        x = input.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        if x.shape[-1] != self.insize and not (self.insize == 1 and x.dim() == 1):
+            raise ValueError(f"expected last dim {self.insize}, got {tuple(x.shape)}")
+        if self.training:
+            self.update(x.view(-1, self.insize))
+        y = out if out is not None else torch.empty_like(x)
+        ops.rms_normalize(x, self.running_mean, self.running_var, y, eps=self.epsilon, unnorm=unnorm)
+        return y

@@ -51,10 +51,12 @@ def install_stubs():
         np.Inf = np.inf
     from oracle import isaacgym_torch_utils as tu
 
-    gymapi = _stub("isaacgym.gymapi", SimParams=_Anything, Vec3=_Anything, Quat=_Anything,
-                   Transform=_Anything, PlaneParams=_Anything, AssetOptions=_Anything,
+    from oracle import fake_isaacgym as fg
+    gymapi = _stub("isaacgym.gymapi", SimParams=fg._Bag, Vec3=fg.Vec3, Quat=fg.Quat,
+                   Transform=fg.Transform, PlaneParams=fg._Bag, AssetOptions=fg._Bag,
+                   ContactCollection=lambda v: v, CameraProperties=fg._Bag,
                    SIM_PHYSX=1, SIM_FLEX=0, UP_AXIS_Z=1, UP_AXIS_Y=0, DOMAIN_SIM=0,
-                   acquire_gym=lambda: _Anything())
+                   acquire_gym=lambda: _current_gym[0] if _current_gym[0] is not None else _Anything())
     gymtorch = _stub("isaacgym.gymtorch", wrap_tensor=lambda t: t, unwrap_tensor=lambda t: t)
     noop = lambda *a, **k: None
     gymutil = _stub("isaacgym.gymutil", get_property_setter_map=noop, get_property_getter_map=noop,
@@ -78,6 +80,7 @@ def install_stubs():
 
 
 _cached = None
+_current_gym = [None]      # the FakeGym instance gymapi.acquire_gym() hands to the next reference KickEnv
 
 
 def load_reference_kick_env():
@@ -100,3 +103,48 @@ def load_reference_kick_env():
         sys.modules.setdefault("tasks", pkg)
         _cached = importlib.import_module("tasks.kick_env")
     return _cached
+
+
+def reference_task_cfg(num_envs, cleats=False):
+    """The reference's OWN task config (cfg/task/bez_kick_test.yaml is the interpolation-free twin of
+    bez_kick.yaml, SURVEY 5 'Config'), with numEnvs set and the CPU pipeline selected."""
+    import yaml
+    with open(os.path.join(_PKG_DIR, "cfg", "task", "bez_kick_test.yaml")) as f:
+        cfg = yaml.safe_load(f)
+    cfg["env"]["numEnvs"] = int(num_envs)
+    cfg["env"]["asset"]["cleats"] = bool(cleats)
+    cfg["sim"]["use_gpu_pipeline"] = False
+    cfg["sim"]["physx"]["use_gpu"] = False
+    cfg["rl_device"] = "cpu"
+    return cfg
+
+
+def make_reference_env(state, on_simulate=None, cleats=False, rand_source=None):
+    """Instantiate the UNMODIFIED reference ``KickEnv`` over the four tensors of ``state`` (a
+    ``bez_isaacgym_b200.synthetic_gym.SimState`` on CPU) through ``oracle.fake_isaacgym.FakeGym``.
+
+    ``rand_source(shape) -> Tensor in [0,1)`` replaces ``torch.rand`` inside the restated
+    ``torch_rand_float`` so a checker can feed the same reset draws to another implementation."""
+    from oracle import fake_isaacgym as fg
+    from oracle import isaacgym_torch_utils as tu
+    mod = load_reference_kick_env()
+    gym = fg.FakeGym(state.root_states, state.dof_state, state.rigid_body, state.net_contact, on_simulate)
+    _current_gym[0] = gym
+    if rand_source is not None:
+        def torch_rand_float(lower, upper, shape, device):
+            return (upper - lower) * rand_source(shape) + lower
+        mod.torch_rand_float = torch_rand_float
+    else:
+        mod.torch_rand_float = tu.torch_rand_float
+    cwd = os.getcwd()
+    try:
+        os.chdir(_PKG_DIR)        # assetRoot is relative to bez_isaacgym/ (README.md:43-46)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            env = mod.KickEnv(reference_task_cfg(state.num_envs, cleats), "cpu", 0, True)
+    finally:
+        os.chdir(cwd)
+        _current_gym[0] = None
+    env._fake_gym = gym
+    return env

@@ -1,0 +1,117 @@
+"""CPU: the C-ABI library loads and exports every symbol include/bezk.h declares; host-side logic that needs no GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "bezk.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(bezk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_build_entry_produces_library():
+    import __graft_entry__ as ge
+    ge.build()
+    assert os.path.isfile(ge.LIB)
+
+
+def test_library_exports_every_declared_symbol():
+    from bez_isaacgym_b200 import _lib
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/bezk.h but not exported by libbezk.so"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in bez_isaacgym_b200/_lib.py"
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes table and header disagree"
+    assert lib.bezk_version() == 100
+
+
+def test_struct_layout_matches_header():
+    """BezkTaskCfg / BezkPpoCfg are passed by pointer from Python and by value into kernels: sizes must agree."""
+    from bez_isaacgym_b200 import _lib
+    assert ctypes.sizeof(_lib.BezkTaskCfg) == 6 * 4 + 5 * 4 + 2 * 4 + 4 * 4 + 3 * 18 * 4
+    assert ctypes.sizeof(_lib.BezkPpoCfg) == 7 * 4
+
+
+def test_argument_validation_without_gpu():
+    """Entry points reject bad arguments before touching the device (error codes + bezk_last_error)."""
+    from bez_isaacgym_b200 import _lib, ops
+    lib = _lib.load()
+    cfg = ops.make_task_cfg()
+    assert lib.bezk_pre_physics(None, None, None, ctypes.byref(cfg), 4, None) == 10001
+    assert b"NULL" in lib.bezk_last_error()
+    assert lib.bezk_pre_physics(None, None, None, ctypes.byref(cfg), 0, None) == 0          # empty input is a no-op
+    bad = ops.make_task_cfg()
+    bad.imu_body = 99
+    assert lib.bezk_pre_physics(None, None, None, ctypes.byref(bad), 4, None) == 10003
+    assert lib.bezk_gae(None, None, None, None, None, 7, 0.99, 0.95, None, None, 32, 8, None) == 10001
+    assert lib.bezk_gae(None, None, None, None, None, 0, 0.99, 0.95, None, None, 0, 8, None) == 0
+    assert lib.bezk_post_physics(*([None] * 9), 0, 0, *([None] * 4), ctypes.byref(cfg), None, None, None, 0, 4, None) == 10001
+
+
+def test_ops_refuse_cpu_tensors_no_fallback():
+    from bez_isaacgym_b200 import ops
+    cfg = ops.make_task_cfg()
+    with pytest.raises(ops.BezkError, match="CUDA only"):
+        ops.pre_physics(torch.zeros(4, 18), torch.zeros(4, 18), cfg)
+    with pytest.raises(ops.BezkError, match="CUDA only"):
+        ops.gae(torch.zeros(2, 4), torch.zeros(2, 4), torch.zeros(2, 4, dtype=torch.uint8), torch.zeros(4),
+                torch.zeros(4, dtype=torch.uint8), 0.99, 0.95, torch.zeros(2, 4), torch.zeros(2, 4))
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from bez_isaacgym_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.BezkError, match="no CPU / torch fallback"):
+        _lib.load()
+
+
+def test_task_cfg_constants_follow_reference_semantics():
+    from bez_isaacgym_b200 import ops
+    c = ops.make_task_cfg()
+    assert c.max_episode_length == int(15 / 0.01667 + 0.5) == 900
+    assert c.reset_pos_span == pytest.approx(0.3) and c.reset_pos_lo == pytest.approx(-0.15)
+    # (hi - lo) is formed in double and THEN rounded to fp32, as torch does for python scalars
+    assert c.reset_pos_span == ctypes.c_float(0.15 - -0.15).value
+    assert c.left_foot_body == 12 and c.right_foot_body == 20 and c.imu_body == 1 and c.num_bodies == 22
+    cc = ops.make_task_cfg(num_bodies=30, cleats=True)
+    assert cc.left_foot_body == 13 and cc.right_foot_body == 25 and cc.flags & 1
+    swapped = ops.make_task_cfg(dof_lower=[1.0] * 18, dof_upper=[-1.0] * 18)     # kick_env.py:395-397
+    assert swapped.dof_lower[3] == -1.0 and swapped.dof_upper[3] == 1.0
+
+
+def test_model_constants_match_reference_urdf():
+    from oracle import reference_loader as rl
+    if not rl.reference_available():
+        pytest.skip("/root/reference not present")
+    import numpy as np
+    from bez_isaacgym_b200 import bez_model as bm
+    from oracle.urdf_layout import parse
+    base = os.path.join(rl.REFERENCE_ROOT, "resources", "assets", "bez", "model")
+    lay = parse(os.path.join(base, "soccerbot_stl.urdf"))
+    assert lay.dof_names == list(bm.DOF_NAMES)
+    assert np.array_equal(np.float32(lay.lower), np.float32(bm.DOF_LOWER))
+    assert np.array_equal(np.float32(lay.upper), np.float32(bm.DOF_UPPER))
+    assert len(lay.bodies) + 1 == bm.BODIES_NO_CLEATS
+    assert lay.bodies[bm.IMU_BODY] == "imu_link" and lay.bodies[bm.LEFT_FOOT_BODY] == "left_foot"
+    assert lay.bodies[bm.RIGHT_FOOT_BODY] == "right_foot"
+    sens = parse(os.path.join(base, "soccerbot_stl_sensor.urdf"))
+    assert len(sens.bodies) + 1 == bm.BODIES_CLEATS
+    assert all("left_foot_cleat" in b for b in sens.bodies[bm.LEFT_CLEATS[0]:bm.LEFT_CLEATS[1]])
+    assert all("right_foot_cleat" in b for b in sens.bodies[bm.RIGHT_CLEATS[0]:bm.RIGHT_CLEATS[1]])
+    import yaml
+    with open(os.path.join(rl.REFERENCE_ROOT, "bez_isaacgym", "cfg", "task", "bez_kick_test.yaml")) as f:
+        ref_cfg = yaml.safe_load(f)
+    mine = bm.default_task_cfg(1)
+    for key in ("bezInitState", "ballInitState", "goalState", "readyJointAngles"):
+        assert mine["env"][key] == ref_cfg["env"][key], key
+    assert mine["env"]["clipActions"] == ref_cfg["env"]["clipActions"] and mine["sim"]["dt"] == ref_cfg["sim"]["dt"]
+    assert mine["env"]["learn"]["episodeLength_s"] == ref_cfg["env"]["learn"]["episodeLength_s"]

@@ -1,0 +1,111 @@
+"""GPU: the rl_games-shaped host API (bez_isaacgym_b200.learner) against oracle.rl_games_oracle -- the calls an
+rl_games A2CAgent would make: RunningMeanStd module (train / eval / unnorm, checkpoint layout), discount_values,
+normalize_advantages and the fused PPO loss as an autograd Function feeding a policy MLP."""
+import json
+import os
+
+import pytest
+import torch
+
+from bez_isaacgym_b200 import synthetic_gym as sg
+from tests import _util as U
+
+pytestmark = pytest.mark.gpu
+FACTS = os.path.join(os.path.dirname(__file__), "golden", "checkpoint_facts.json")
+
+
+def test_running_mean_std_module_matches_oracle_and_loads_reference_checkpoint_layout():
+    from bez_isaacgym_b200.learner import RunningMeanStd
+    from oracle import rl_games_oracle as rg
+    mod = RunningMeanStd(54).cuda()
+    orc = rg.RunningMeanStd(54)
+    g = torch.Generator().manual_seed(0)
+    for it in range(4):                                        # 5 mini-epochs x minibatches in the real loop
+        x = torch.randn(32768, 54, generator=g) * 2 + it
+        want = orc(x)
+        got = mod(x.cuda())
+        assert torch.allclose(got.cpu(), want, rtol=1e-4, atol=1e-4)
+    assert mod.count.item() == orc.count.item() == 1 + 4 * 32768
+    assert torch.allclose(mod.running_mean.cpu(), orc.running_mean, rtol=2e-6, atol=1e-7)
+    assert torch.allclose(mod.running_var.cpu(), orc.running_var, rtol=2e-5, atol=1e-7)
+    mod.eval(); orc.training = False
+    x = torch.randn(4096, 54, generator=g)
+    before = mod.running_mean.clone()
+    U.assert_close(mod(x.cuda()), torch.clamp((x - mod.running_mean.cpu().float()) /
+                                              torch.sqrt(mod.running_var.cpu().float() + 1e-5), -5, 5), what="eval")
+    assert torch.equal(mod.running_mean, before)
+    # state-dict layout of the reference's shipped checkpoint loads as is
+    with open(FACTS) as f:
+        facts = json.load(f)
+    sd = {"running_mean": torch.tensor(facts["obs_running_mean"], dtype=torch.float64),
+          "running_var": torch.tensor(facts["obs_running_var"], dtype=torch.float64),
+          "count": torch.tensor(facts["obs_count"], dtype=torch.float64)}
+    mod.load_state_dict(sd)
+    assert mod.count.item() == 1 + 5 * facts["frame"]
+    y = mod(torch.zeros(2, 54, device="cuda"))
+    assert torch.isfinite(y).all() and y.abs().max() <= 5.0
+    val = RunningMeanStd((1,)).cuda()
+    v = torch.randn(1000, 1, generator=g)
+    out = val(v.cuda())
+    un = val(out, unnorm=True) if not val.eval() else None
+    val.eval()
+    assert torch.allclose(val(val(v.cuda()), unnorm=True).cpu(), v, rtol=1e-4, atol=1e-4)
+
+
+def test_discount_values_and_advantage_normalisation_api():
+    from bez_isaacgym_b200 import learner as L
+    from oracle import rl_games_oracle as rg
+    n, T = 4096, 32
+    rewards, values, dones, last_values, last_dones = sg.make_rollout(n, T, seed=5, p_done=0.02)
+    want_adv = rg.discount_values(last_dones.float(), last_values, dones.float(), values, rewards, 0.99, 0.95)
+    want_ret = want_adv + values
+    adv, ret = L.discount_values(last_dones.float().cuda(), last_values.cuda(), dones.float().cuda(), values.cuda(),
+                                 rewards.cuda(), 0.99, 0.95, return_returns=True)
+    scale = values.abs() + 1.0
+    U.assert_close(adv, want_adv, scale=scale, what="mb_advs")
+    U.assert_close(ret, want_ret, scale=scale, what="mb_returns")
+    flat_r, flat_v = rg.swap_and_flatten01(want_ret), rg.swap_and_flatten01(values)
+    assert torch.equal(L.swap_and_flatten01(ret).cpu(), rg.swap_and_flatten01(ret.cpu()))
+    want, _, _ = rg.prepare_dataset(flat_r, flat_v, rg.RunningMeanStd(1))
+    got = L.normalize_advantages(flat_r.cuda(), flat_v.cuda())
+    assert torch.allclose(got.cpu(), want, rtol=1e-5, atol=2e-6)
+    shaped = L.shape_rewards(torch.ones(3).cuda(), torch.full((3, 1), 2.0).cuda(), torch.tensor([0, 1, 0]).cuda(), 0.99)
+    assert torch.allclose(shaped.cpu(), rg.shape_rewards(torch.ones(3), torch.full((3, 1), 2.0), torch.tensor([0, 1, 0]), 0.99))
+
+
+@pytest.mark.parametrize("bound_form", ["v1.1.3", "outside"])
+def test_ppo_loss_autograd_through_policy_mlp(bound_form):
+    """Gradients w.r.t. the MLP parameters (124 237, the BezKick policy shape) equal the oracle's autograd ones."""
+    from bez_isaacgym_b200.learner import PPOLossConfig, ppo_loss
+    from oracle import rl_games_oracle as rg
+    m = 4096
+    torch.manual_seed(0)
+    def make():
+        torch.manual_seed(3)
+        trunk = torch.nn.Sequential(torch.nn.Linear(54, 400), torch.nn.ELU(), torch.nn.Linear(400, 200), torch.nn.ELU(),
+                                    torch.nn.Linear(200, 100), torch.nn.ELU())
+        return trunk, torch.nn.Linear(100, 18), torch.nn.Linear(100, 1), torch.nn.Parameter(torch.zeros(18) - 0.5)
+    mb = sg.make_minibatch(m, seed=9)
+    obs = torch.randn(m, 54, generator=torch.Generator().manual_seed(4))
+
+    trunk, mu_h, v_h, sigma = make()
+    h = trunk(obs)
+    o = rg.ppo_loss(dict(mb, mu=mu_h(h), values=v_h(h), logstd=sigma), bound_form=bound_form)
+    o["loss"].backward()
+    ref_grads = [p.grad.clone() for p in list(trunk.parameters()) + list(mu_h.parameters()) + list(v_h.parameters()) + [sigma]]
+    assert sum(g.numel() for g in ref_grads) == 124237
+
+    trunk, mu_h, v_h, sigma = make()
+    for mod in (trunk, mu_h, v_h):
+        mod.cuda()
+    sigma = torch.nn.Parameter(sigma.detach().cuda())
+    d = {k: v.cuda() for k, v in mb.items()}
+    h = trunk(obs.cuda())
+    loss, info = ppo_loss(mu_h(h), v_h(h), sigma, d["actions"], d["old_mu"], d["old_sigma"], d["old_values"], d["returns"],
+                          d["old_neglogp"], d["advantages"], PPOLossConfig(bound_form=bound_form))
+    loss.backward()
+    got = [p.grad for p in list(trunk.parameters()) + list(mu_h.parameters()) + list(v_h.parameters()) + [sigma]]
+    assert abs(loss.item() - o["loss"].item()) < 2e-5 * max(1.0, abs(o["loss"].item()))
+    assert abs(info["kl"].item() - o["kl"].item()) < 1e-5 and abs(info["a_loss"].item() - o["a_loss"].item()) < 1e-5
+    for a, b in zip(got, ref_grads):
+        assert torch.allclose(a.cpu(), b, rtol=2e-3, atol=2e-6), (a.cpu() - b).abs().max()

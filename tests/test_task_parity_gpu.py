@@ -5,6 +5,7 @@ tests/test_oracle_pinning.py).  Tolerances and the tie-band policy are documente
 """
 import math
 
+import numpy as np
 import pytest
 import torch
 
@@ -136,11 +137,10 @@ def test_observations_edge_cases():
     st = sg.make_state(n, seed=21)
     goal, ball_init, *_ = U.constants(n)
     cf = st.net_contact.view(n, -1, 3)
-    below, at, above = math.nextafter(0.01, 0.0), 0.01, math.nextafter(0.01, 1.0)
     f32 = lambda x: float(torch.tensor(x, dtype=torch.float32))
-    vals = [0.0, -0.0, f32(0.01), -f32(0.01), math.nextafter(f32(0.01), 1.0), 0.005, -0.005, 2.0, -2.0, float("nan"),
+    vals = [0.0, -0.0, f32(0.01), -f32(0.01), float(np.nextafter(np.float32(0.01), np.float32(1.0))), 0.005, -0.005, 2.0, -2.0, float("nan"),
             float("inf"), -float("inf")]
-    fz = [0.5, f32(0.999), 1.0, math.nextafter(1.0, 2.0), 2.0, 0.005, float("nan"), f32(0.99), f32(1.01)]
+    fz = [0.5, f32(0.999), 1.0, float(np.nextafter(np.float32(1.0), np.float32(2.0))), 2.0, 0.005, float("nan"), f32(0.99), f32(1.01)]
     k = 0
     for e in range(n):
         for body in (bm.LEFT_FOOT_BODY, bm.RIGHT_FOOT_BODY):
