@@ -33,14 +33,16 @@ GAE_BYTES_PER_SAMPLE = 17
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--steps", type=int, default=50)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--envs-per-gpu", type=int, default=262144)
     p.add_argument("--horizon", type=int, default=32)
     p.add_argument("--e2e-envs", type=int, default=65536, help="envs per GPU for the host-pipeline (e2e) leg")
-    p.add_argument("--e2e-steps", type=int, default=2)
+    p.add_argument("--e2e-mode", default="zero_copy", choices=["zero_copy", "staged"])
+    p.add_argument("--e2e-steps", type=int, default=5)
     p.add_argument("--cpu-sample-envs", type=int, default=65536)
+    p.add_argument("--cpu-rollouts", type=int, default=24, help="rollouts of the bounded CPU-baseline sample (~10-30 s)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--fusion", default="fused", choices=["fused", "split"])
@@ -80,7 +82,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:                   # noqa: BLE001
                 pass
-            time.sleep(0.02)
+            time.sleep(0.004)
 
     def summary(self):
         sm = sorted(self.sm)
@@ -252,6 +254,7 @@ def run_b200(args):
         ne = args.e2e_envs
         hcfg = bm.default_task_cfg(ne, use_gpu_pipeline=False, rl_device="cpu")
         hcfg["env"]["imuPrevVelAliasing"] = False
+        hcfg["env"]["hostPipeline"] = args.e2e_mode
         hsim = OwnedRootSim(ne, device=str(dev), seed=1234 + rank, host=True, filler=True)
         henv = KickEnv(hcfg, f"cuda:{local}", 0, True, sim=hsim, fusion=args.fusion)
         hact = sg.make_actions(ne, seed=1).pin_memory()
@@ -281,19 +284,26 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         nb = hsim.num_bodies
-        h2d_env = 4 * (26 + 36 + 13 * nb + 3 * nb + 18)
-        d2h_env = 4 * 54 + 4 + 8 + 8 + 4 * 36
+        if args.e2e_mode == "staged":
+            h2d_env = 4 * (26 + 36 + 13 * nb + 3 * nb + 18)       # all four simulator tensors + actions copied
+            d2h_env = 4 * 54 + 4 + 8 + 8 + 4 * 36 + 4 * 18        # obs, rew, reset, timeouts, dof_state back, targets
+        else:
+            # zero-copy: the kernels gather over PCIe -- dense dof_state + root_states + actions, and the sparse
+            # rows at the 64 B fetch granularity (IMU link ~96 B, two feet ~144 B, measured: profiles/r01_fetch_granularity.md)
+            h2d_env = 4 * (26 + 36 + 18) + 96 + 144
+            d2h_env = 4 * 54 + 4 + 8 + 8 + 4 * 18                 # obs, rew, reset, timeouts, targets (+ rare reset rows)
         e2e = {"value": ne * world * T * args.e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": (h2d_env * T + 9 * T + 5) * ne, "d2h_bytes_per_step": (d2h_env * T + 8 * T) * ne,
-               "envs_per_gpu": ne, "note": "KickEnv.step with use_gpu_pipeline=False: all four simulator tensors + actions "
-               "H2D and obs/rew/reset/timeouts/dof_state D2H every env step, rollout H2D + adv/returns D2H per GAE"}
+               "envs_per_gpu": ne, "host_pipeline": args.e2e_mode,
+               "note": "KickEnv.step with use_gpu_pipeline=False (simulator tensors, actions, targets in pinned HOST memory; "
+                       "obs/rew/reset/timeouts returned on the host every env step); rollout H2D + adv/returns D2H per GAE"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cn = args.cpu_sample_envs
-        rate, secs, threads = cpu_reference_rate(cn, T, 2)
+        rate, secs, threads = cpu_reference_rate(cn, T, args.cpu_rollouts)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"2 rollouts of {T} task steps + GAE at {cn} envs ({secs:.1f} s), reference torch ops "
+                        "sample": f"{args.cpu_rollouts} rollouts of {T} task steps + GAE at {cn} envs ({secs:.1f} s), reference torch ops "
                                   f"(oracle port) with torch.set_num_threads({threads})"}
 
     if rank == 0:

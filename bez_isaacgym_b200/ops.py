@@ -12,7 +12,8 @@ from ._lib import BezkPpoCfg, BezkTaskCfg, BezkError
 
 
 def _stream(t: torch.Tensor):
-    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    dev = t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
 def _p(t, dtype, name, numel=None, allow_none=False):
@@ -22,8 +23,10 @@ def _p(t, dtype, name, numel=None, allow_none=False):
         raise BezkError(f"{name} is None")
     if not isinstance(t, torch.Tensor):
         raise BezkError(f"{name} must be a torch.Tensor")
-    if not t.is_cuda:
-        raise BezkError(f"{name} is on {t.device}: bez_isaacgym_b200 ops run on CUDA only (no CPU fallback)")
+    if not t.is_cuda and not (t.device.type == "cpu" and t.is_pinned()):
+        # pinned host memory is device-accessible (UVA): the kernels may gather from / write to it over PCIe
+        raise BezkError(f"{name} is on {t.device}: bez_isaacgym_b200 ops run on CUDA only (no CPU fallback); "
+                        "host tensors must be pinned")
     if t.dtype != dtype:
         raise BezkError(f"{name} must be {dtype}, got {t.dtype}")
     if not t.is_contiguous():

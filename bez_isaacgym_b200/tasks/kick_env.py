@@ -84,7 +84,15 @@ class KickEnv(VecTask):
         # simulator tensors (borrowed) and their device images
         self.root_states, self.dof_state = self.sim.root_states, self.sim.dof_state
         self.rigid_body, self.net_contact = self.sim.rigid_body, self.sim.net_contact
-        if self.host_staged:
+        # host pipeline: "zero_copy" (default) hands the PINNED host tensors straight to the kernels -- they gather the
+        # few bytes they need over PCIe and write resets back in place; "staged" copies all four tensors to HBM first
+        self.host_mode = env_cfg.get("hostPipeline", "zero_copy") if self.host_staged else None
+        if self.host_mode not in (None, "zero_copy", "staged"):
+            raise ValueError(f"env.hostPipeline must be 'zero_copy' or 'staged', got {self.host_mode}")
+        if self.host_staged and self.host_mode == "zero_copy" and not all(
+                t.is_pinned() for t in (self.root_states, self.dof_state, self.rigid_body, self.net_contact)):
+            raise ValueError("hostPipeline='zero_copy' needs the simulator tensors in pinned (page-locked) host memory")
+        if self.host_mode == "staged":
             self._d_root, self._d_dof = (torch.empty_like(t, device=dev) for t in (self.root_states, self.dof_state))
             self._d_rb, self._d_cf = (torch.empty_like(t, device=dev) for t in (self.rigid_body, self.net_contact))
         else:
@@ -132,11 +140,21 @@ class KickEnv(VecTask):
         # persistent task state
         self._prev_buf = torch.zeros(n, 3, **f32)       # the reference's int64 zeros, promoted (kick_env.py:183)
         self._prev_is_view = False
-        self.targets = torch.zeros(n, 18, **f32)
+        # PD targets go to the simulator: pinned host memory (written by K0 over PCIe) when the simulator lives on the host
+        self.targets = torch.zeros(n, 18, dtype=torch.float32).pin_memory() if self.host_mode == "zero_copy" \
+            else torch.zeros(n, 18, **f32)
         self._actions_in = torch.zeros(n, 18, **f32)      # staging buffer for actions arriving from another device
         self._actions_src = self._actions_in
         self._actions_cache = None
         self.obs_clipped_buf = torch.zeros(n, 54, **f32) if math.isfinite(float(self.clip_obs)) else None
+        if self.host_mode == "zero_copy":
+            # write-only outputs live in pinned host memory: the kernel's stores (TMA bulk store for the obs tile) cross
+            # PCIe while its gathers come the other way (full duplex), and step() needs no D2H copies for them
+            self.obs_buf = torch.zeros(n, 54, dtype=torch.float32).pin_memory()
+            self.rew_buf = torch.zeros(n, dtype=torch.float32).pin_memory()
+            self.timeout_buf = torch.zeros(n, dtype=torch.long).pin_memory()
+            if self.obs_clipped_buf is not None:
+                self.obs_clipped_buf = torch.zeros(n, 54, dtype=torch.float32).pin_memory()
         self._rng_step = 0
         self._lib = _lib.load()
         if self.host_staged:
@@ -189,7 +207,7 @@ class KickEnv(VecTask):
     def actions(self):
         """``self.actions`` of the reference (clipped, head zeroed, kick_env.py:413-414), materialised on demand."""
         if self._actions_cache is None:
-            a = torch.clamp(self._actions_src, -self.clip_actions, self.clip_actions)
+            a = torch.clamp(self._actions_src.to(self.compute_device), -self.clip_actions, self.clip_actions)
             a[..., 0:2] = 0.0
             self._actions_cache = a
         return self._actions_cache
@@ -218,7 +236,7 @@ class KickEnv(VecTask):
 
     # ------------------------------------------------------------------ the step
     def _stage_in(self):
-        if self.host_staged:
+        if self.host_mode == "staged":
             for d, h in ((self._d_root, self.root_states), (self._d_dof, self.dof_state), (self._d_rb, self.rigid_body),
                          (self._d_cf, self.net_contact)):
                 d.copy_(h, non_blocking=True)
@@ -230,10 +248,12 @@ class KickEnv(VecTask):
         if actions.device != self.compute_device:
             if self.host_staged and actions.device.type == "cpu" and not actions.is_pinned():
                 self._h_actions.copy_(actions)
-                self._actions_in.copy_(self._h_actions, non_blocking=True)
+                actions = self._h_actions
+            if self.host_mode == "zero_copy" and actions.device.type == "cpu" and actions.is_contiguous():
+                src = actions                   # K0 reads the pinned host buffer directly
             else:
                 self._actions_in.copy_(actions, non_blocking=True)
-            src = self._actions_in
+                src = self._actions_in
         else:
             src = actions if actions.is_contiguous() else actions.contiguous()
         self._actions_cache = None
@@ -256,7 +276,7 @@ class KickEnv(VecTask):
             self._launch_post(_lib.PART_REWARD)
         if self._alias_prev:
             self._prev_is_view = True       # kick_env.py:930: compute_imu hands back the velocity VIEW
-        if self.host_staged:
+        if self.host_mode == "staged":
             self.dof_state.copy_(self._d_dof, non_blocking=True)      # resets are written into the simulator tensor
             if self._kcfg.flags & _lib.F_WRITE_CONTACT_FILTER:
                 self.net_contact.copy_(self._d_cf, non_blocking=True)
@@ -284,7 +304,7 @@ class KickEnv(VecTask):
         self._stage_in()
         ops.reset_idx(env_ids, self._d_dof, self._d_root, self.initial_root_states, self.progress_buf, self.reset_buf,
                       self._kcfg, uniforms=None, seed=self._seed, step=self._rng_step)
-        if self.host_staged:
+        if self.host_mode == "staged":
             self.dof_state.copy_(self._d_dof)
             if self._kcfg.flags & _lib.F_RESET_ROOT_STATES:
                 self.root_states.copy_(self._d_root)
@@ -300,16 +320,20 @@ class KickEnv(VecTask):
         for _ in range(self.control_freq_inv):
             self.sim.simulate()
         self.post_physics_step()
-        self._h_obs.copy_(self._observations_out(), non_blocking=True)
-        self._h_rew.copy_(self.rew_buf, non_blocking=True)
         self._h_reset.copy_(self.reset_buf, non_blocking=True)
-        self._h_timeout.copy_(self.timeout_buf, non_blocking=True)
+        if self.host_mode == "zero_copy":
+            h_obs, h_rew, h_timeout = self._observations_out(), self.rew_buf, self.timeout_buf   # already on the host
+        else:
+            h_obs, h_rew, h_timeout = self._h_obs, self._h_rew, self._h_timeout
+            h_obs.copy_(self._observations_out(), non_blocking=True)
+            h_rew.copy_(self.rew_buf, non_blocking=True)
+            h_timeout.copy_(self.timeout_buf, non_blocking=True)
         torch.cuda.current_stream(self.compute_device).synchronize()
         rl = torch.device(self.rl_device)
         if rl.type == "cpu":
-            self.extras["time_outs"] = self._h_timeout
-            self.obs_dict["obs"] = self._h_obs
-            return self.obs_dict, self._h_rew, self._h_reset, self.extras
+            self.extras["time_outs"] = h_timeout
+            self.obs_dict["obs"] = h_obs
+            return self.obs_dict, h_rew, self._h_reset, self.extras
         self.extras["time_outs"] = self.timeout_buf.to(rl)
         self.obs_dict["obs"] = self._observations_out().to(rl)
         return self.obs_dict, self.rew_buf.to(rl), self.reset_buf.to(rl), self.extras
