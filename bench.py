@@ -46,6 +46,7 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--fusion", default="fused", choices=["fused", "split"])
+    p.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay of the step")
     p.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity hint (0 = leave default)")
     return p.parse_args()
 
@@ -215,18 +216,43 @@ def run_b200(args):
     for _ in range(max(3, args.warmup)):
         bench_step(False)
     barrier()
+    graph = None
+    if not args.no_graph:
+        # the step is 65 dependent launches of 7..45 us kernels: replaying it as ONE CUDA graph removes the CPU-side
+        # launch cost and most of the inter-kernel gaps (the kernels, arguments and work are identical)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            bench_step(False)
+        stream = torch.cuda.current_stream(dev)
+        graph.replay()
+    barrier()
     sampler = ClockSampler(local)
     sampler.start()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record(stream)
     for _ in range(args.steps):
-        bench_step(True)
+        if graph is not None:
+            graph.replay()
+        else:
+            bench_step(True)
     end.record(stream)
     barrier()
+    ms = start.elapsed_time(end)
+    # per-launch CUDA events around the dominant kernel: inside the timed region when it is eager, otherwise in an
+    # eager pass of the same steps right after it (events cannot be read back from inside a replayed graph)
+    eager_ms = None
+    if graph is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(min(args.steps, 10)):
+            bench_step(True)
+        e1.record(stream)
+        barrier()
+        eager_ms = e0.elapsed_time(e1) / min(args.steps, 10)
     sampler.stop_flag = True
     sampler.join()
-    ms = start.elapsed_time(end)
     reset_rate = float(env.reset_buf.float().mean())
     post_ms = sum(a.elapsed_time(b) for a, b in post_events) / len(post_events)
     if world > 1:
@@ -242,6 +268,8 @@ def run_b200(args):
                 else "bezk::task_tile_kernel<3>+<4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_env": POST_BYTES, "envs_per_launch": n,
                 "avg_launch_ms": post_ms, "peak_source": peak_src,
+                "timing": "per-launch CUDA events, eager pass of the same steps right after the graph-replayed timed region"
+                if graph is not None else "per-launch CUDA events inside the (eager) timed region",
                 "whole_step_gbs": (TASK_BYTES_PER_ENV_STEP * n * T + GAE_BYTES_PER_SAMPLE * n * T) * args.steps / (ms * 1e-3) / 1e9}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
@@ -315,6 +343,7 @@ def run_b200(args):
                           "envs_per_gpu": n, "horizon": T, "parallelism": f"env-sharded x{world}, no data-path collective",
                           "fusion": args.fusion, "l2": "inputs larger than L2 (state footprint ~%.0f MB/GPU)" % (
                               n * 4 * (26 + 36 + 16 * bm.BODIES_NO_CLEATS) / 1e6),
+                          "launch": "cuda_graph_replay" if graph is not None else "eager", "ms_per_step_eager_with_events": eager_ms,
                           "reset_rate_per_step": reset_rate, "l2_fetch_granularity": l2_fetch, "imu_prev_lin_vel": "buffer (680 B/env-step path)"},
                "clocks": sampler.summary(), "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
                "e2e": e2e, "cpu_baseline": cpu_baseline}

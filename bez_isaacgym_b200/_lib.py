@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbezk.so")
+LIB_PATH = os.environ.get("BEZK_LIB", os.path.join(_HERE, "libbezk.so"))     # BEZK_LIB: A/B builds of the same library
 
 NUM_DOF = 18
 

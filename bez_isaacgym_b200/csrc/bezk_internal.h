@@ -29,6 +29,7 @@ struct TaskArgs {
     int use_tma;      // all dense bases 16 B aligned
     int rb_vec2;      // IMU-link slice of every env is 8 B aligned
     int cf_vec2;      // both foot force rows of every env are 8 B aligned
+    int smart_granule;  // per-lane 64 B / 128 B fill choice for the sparse gathers (env BEZK_SMART_GRANULE=0 disables)
 };
 struct PpoArgs {
     const float *actions, *mu, *logstd, *old_mu, *old_sigma, *values, *old_values, *returns, *old_neglogp, *advantages;

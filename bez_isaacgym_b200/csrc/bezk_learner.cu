@@ -81,7 +81,8 @@ cudaError_t launch_gae(const float* rewards, const float* values, const void* do
 // is a contiguous 128 B * VEC segment.
 // ------------------------------------------------------------------------------------------------
 constexpr int RMS_THREADS = 256;
-constexpr int RMS_MAX_BLOCKS = 148 * 4;
+constexpr int RMS_MAX_BLOCKS = 148 * 8;
+constexpr int RMS_UNROLL = 8;
 constexpr int RMS_MAX_C = 256;                  // columns supported by the multi-column kernel
 
 template <int VEC>
@@ -99,17 +100,17 @@ __global__ void __launch_bounds__(RMS_THREADS) rms_partials_kernel(const float* 
     if (active) {
         const int64_t row_stride = (int64_t)gridDim.x * rpi;
         int64_t r = (int64_t)blockIdx.x * rpi + rsub;
-        // 4 independent loads in flight per thread
-        for (; r + 3 * row_stride < m; r += 4 * row_stride) {
-            float xv[4][VEC];
+        // RMS_UNROLL independent loads in flight per thread
+        for (; r + (RMS_UNROLL - 1) * row_stride < m; r += RMS_UNROLL * row_stride) {
+            float xv[RMS_UNROLL][VEC];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < RMS_UNROLL; ++u) {
                 const float* p = x + (r + u * row_stride) * c + g * VEC;
                 if (VEC == 2) { const float2 t = *reinterpret_cast<const float2*>(p); xv[u][0] = t.x; xv[u][VEC - 1] = t.y; }
                 else xv[u][0] = *p;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < RMS_UNROLL; ++u)
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) { const double d = (double)xv[u][k] - pv[k]; s[k] += d; ss[k] += d * d; }
         }
@@ -167,14 +168,32 @@ __global__ void __launch_bounds__(RMS_THREADS) flat_partials_kernel(const float*
     }
 }
 
-// fold the per-block partials in block order -> acc = [m, sums(c), sumsqs(c)]
-__global__ void moments_finalize_kernel(const double* __restrict__ partials, int nblocks, int c, int64_t m, double* __restrict__ acc) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j == 0) acc[0] = (double)m;
-    if (j >= 2 * c) return;
+// Deterministic fold of per-block partials: ONE WARP per output column j.  Lane l sums blocks l, l+32, ... with up to 8
+// independent loads in flight, then the 32 lane sums are folded by a fixed xor-shuffle tree.  (A single thread walking
+// 592..8192 partials serially costs 40..600 us of pure L2 latency -- measured, profiles/r01_kernels.md.)
+__device__ __forceinline__ double fold_column(const double* __restrict__ partials, int nblocks, int ncols, int j, int lane) {
     double t = 0.0;
-    for (int b = 0; b < nblocks; ++b) t += partials[(int64_t)b * 2 * c + j];
-    acc[1 + j] = t;
+    int b = lane;
+    for (; b + 7 * 32 < nblocks; b += 8 * 32) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = partials[(int64_t)(b + u * 32) * ncols + j];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t += v[u];
+    }
+    for (; b < nblocks; b += 32) t += partials[(int64_t)b * ncols + j];
+    return warp_sum(t);
+}
+
+// acc = [m, sums(c), sumsqs(c)]
+__global__ void __launch_bounds__(256) moments_finalize_kernel(const double* __restrict__ partials, int nblocks, int c, int64_t m,
+                                                               double* __restrict__ acc) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j == 0 && lane == 0) acc[0] = (double)m;
+    if (j >= 2 * c) return;
+    const double t = fold_column(partials, nblocks, 2 * c, j, lane);
+    if (lane == 0) acc[1 + j] = t;
 }
 
 // K4b: merge (reference running_mean_std.py training branch, fp64):
@@ -261,7 +280,7 @@ cudaError_t launch_rms_moments(const float* x, const double* pivot, double* acc,
         const int cg = v2 ? c / 2 : c;
         const int rpi = RMS_THREADS / cg;
         int64_t b = (m + rpi - 1) / rpi;
-        b = (b + 3) / 4;                               // >= 4 row slots per thread where possible
+        b = (b + RMS_UNROLL - 1) / RMS_UNROLL;         // >= RMS_UNROLL row slots per thread where possible
         if (b < 1) b = 1;
         nblocks = (int)(b > RMS_MAX_BLOCKS ? RMS_MAX_BLOCKS : b);
         const size_t smem = (size_t)2 * rpi * c * sizeof(double);
@@ -270,7 +289,7 @@ cudaError_t launch_rms_moments(const float* x, const double* pivot, double* acc,
     }
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
-    moments_finalize_kernel<<<(2 * c + 127) / 128, 128, 0, st>>>(partials, nblocks, c, m, acc);
+    moments_finalize_kernel<<<(2 * c + 7) / 8, 256, 0, st>>>(partials, nblocks, c, m, acc);
     return cudaGetLastError();
 }
 
@@ -329,7 +348,7 @@ cudaError_t launch_adv_moments(const float* returns, const float* values, double
     flat_partials_kernel<<<nblocks, RMS_THREADS, 0, st>>>(returns, values, nullptr, partials, m, vec4);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
-    moments_finalize_kernel<<<1, 128, 0, st>>>(partials, nblocks, 1, m, acc);
+    moments_finalize_kernel<<<1, 256, 0, st>>>(partials, nblocks, 1, m, acc);
     return cudaGetLastError();
 }
 
@@ -351,8 +370,7 @@ cudaError_t launch_adv_normalize(const float* returns, const float* values, cons
 constexpr int PPO_TILE = 128;
 constexpr int PPO_NSTAT = 7;                    // a, c, b, kl, clipped, (spare), (spare)
 constexpr int PPO_PART = PPO_NSTAT + 18;        // doubles per block
-constexpr int PPO_MAX_BLOCKS = 1 << 16;
-
+constexpr int PPO_MAX_BLOCKS = 148 * 3;         // persistent grid: every CTA walks tiles blockIdx.x, +gridDim.x, ...
 
 __global__ void __launch_bounds__(PPO_TILE) ppo_loss_kernel(const PpoArgs a, const __grid_constant__ BezkPpoCfg cfg) {
     __shared__ __align__(128) float s_act[PPO_TILE * 18];
@@ -365,128 +383,140 @@ __global__ void __launch_bounds__(PPO_TILE) ppo_loss_kernel(const PpoArgs a, con
     __shared__ double s_red[PPO_TILE / 32][PPO_PART];
 
     const int tid = threadIdx.x;
-    const int64_t i0 = (int64_t)blockIdx.x * PPO_TILE;
-    const int nv = (int)((a.m - i0) < (int64_t)PPO_TILE ? (a.m - i0) : (int64_t)PPO_TILE);
-    const bool full = (nv == PPO_TILE) && a.use_tma;
-    const int64_t i = i0 + tid;
-    const bool valid = tid < nv;
     constexpr uint32_t TILE_BYTES = PPO_TILE * 18 * 4;
+    const int64_t ntiles = (a.m + PPO_TILE - 1) / PPO_TILE;
+    const float inv_m = 1.0f / (float)a.m;
 
-    if (full) {
-        if (tid == 0) {
-            mbar_init(&s_bar, 1);
-            fence_mbar_init();
-            mbar_arrive_expect_tx(&s_bar, 4 * TILE_BYTES);
-            bulk_g2s(s_act, a.actions + i0 * 18, TILE_BYTES, &s_bar);
-            bulk_g2s(s_mu, a.mu + i0 * 18, TILE_BYTES, &s_bar);
-            bulk_g2s(s_omu, a.old_mu + i0 * 18, TILE_BYTES, &s_bar);
-            bulk_g2s(s_osig, a.old_sigma + i0 * 18, TILE_BYTES, &s_bar);
-        }
-    } else {
-        for (int k = tid; k < nv * 18; k += PPO_TILE) {
-            s_act[k] = a.actions[i0 * 18 + k]; s_mu[k] = a.mu[i0 * 18 + k];
-            s_omu[k] = a.old_mu[i0 * 18 + k]; s_osig[k] = a.old_sigma[i0 * 18 + k];
-        }
-    }
+    if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
     if (tid < 18) { const float ls = a.logstd[tid]; s_logstd[tid] = ls; s_sigma[tid] = expf(ls); }
-    float val = 0.f, oval = 0.f, ret = 0.f, onlp = 0.f, adv = 0.f;
-    if (valid) { val = a.values[i]; oval = a.old_values[i]; ret = a.returns[i]; onlp = a.old_neglogp[i]; adv = a.advantages[i]; }
     __syncthreads();
-    if (full) mbar_wait(&s_bar, 0);
+    float sig[18], lsum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 18; ++j) { sig[j] = s_sigma[j]; lsum += s_logstd[j]; }
 
-    double part[PPO_PART];
+    double part[PPO_PART];                       // per-thread running sums over all of this CTA's tiles (fixed order)
 #pragma unroll
     for (int k = 0; k < PPO_PART; ++k) part[k] = 0.0;
+    uint32_t phase = 0;
+    bool store_pending = false;
 
-    if (valid) {
-        const float inv_m = 1.0f / (float)a.m;
-        // ---- neglogp (models.py), bound loss, KL: one sweep over the 18 action dims ----
-        float z[18];
-        float sq = 0.0f, lsum = 0.0f, bsum = 0.0f, kl = 0.0f;
-        float dbound[18];
-        const float2* act2 = reinterpret_cast<const float2*>(s_act + tid * 18);
-        const float2* mu2 = reinterpret_cast<const float2*>(s_mu + tid * 18);
-        const float2* omu2 = reinterpret_cast<const float2*>(s_omu + tid * 18);
-        const float2* osig2 = reinterpret_cast<const float2*>(s_osig + tid * 18);
-#pragma unroll
-        for (int h = 0; h < 9; ++h) {
-            const float2 A2 = act2[h], M2 = mu2[h], OM2 = omu2[h], OS2 = osig2[h];
-            const float av[2] = {A2.x, A2.y}, mv[2] = {M2.x, M2.y}, omv[2] = {OM2.x, OM2.y}, osv[2] = {OS2.x, OS2.y};
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int j = 2 * h + q;
-                const float sig = s_sigma[j];
-                const float zz = (av[q] - mv[q]) / sig;
-                z[j] = zz;
-                sq += zz * zz;
-                lsum += s_logstd[j];
-                float hi, lo, dh, dl;
-                if (cfg.bound_form == 0) {          // rl_games 1.1.3 as recalled
-                    hi = fminf(mv[q] - cfg.soft_bound, 0.0f); lo = fminf(-mv[q] + cfg.soft_bound, 0.0f);
-                    dh = 2.0f * hi; dl = -2.0f * lo;
-                } else {                            // later releases
-                    hi = fmaxf(mv[q] - cfg.soft_bound, 0.0f); lo = fminf(mv[q] + cfg.soft_bound, 0.0f);
-                    dh = 2.0f * hi; dl = 2.0f * lo;
-                }
-                bsum += lo * lo + hi * hi;
-                dbound[j] = dh + dl;
-                const float c1 = logf(osv[q] / sig + 1e-5f);
-                const float dm = omv[q] - mv[q];
-                const float c2 = (sig * sig + dm * dm) / (2.0f * (osv[q] * osv[q] + 1e-5f));
-                kl += (c1 + c2) + (-0.5f);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t i0 = tile * PPO_TILE;
+        const int nv = (int)((a.m - i0) < (int64_t)PPO_TILE ? (a.m - i0) : (int64_t)PPO_TILE);
+        const bool full = (nv == PPO_TILE) && a.use_tma;
+        const int64_t i = i0 + tid;
+        const bool valid = tid < nv;
+
+        if (tid == 0 && store_pending) bulk_wait_read0();          // s_gmu of the previous tile has been read out
+        __syncthreads();                                           // everybody is done with the previous tile's rows
+        if (full) {
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&s_bar, 4 * TILE_BYTES);
+                bulk_g2s(s_act, a.actions + i0 * 18, TILE_BYTES, &s_bar);
+                bulk_g2s(s_mu, a.mu + i0 * 18, TILE_BYTES, &s_bar);
+                bulk_g2s(s_omu, a.old_mu + i0 * 18, TILE_BYTES, &s_bar);
+                bulk_g2s(s_osig, a.old_sigma + i0 * 18, TILE_BYTES, &s_bar);
+            }
+        } else {
+            for (int k = tid; k < nv * 18; k += PPO_TILE) {
+                s_act[k] = a.actions[i0 * 18 + k]; s_mu[k] = a.mu[i0 * 18 + k];
+                s_omu[k] = a.old_mu[i0 * 18 + k]; s_osig[k] = a.old_sigma[i0 * 18 + k];
             }
         }
-        const float nlp = (0.5f * sq + (float)(0.5 * 1.8378770664093453 * 18.0)) + lsum;   // log(2*pi) = 1.83787706...
-        if (a.neglogp_out) a.neglogp_out[i] = nlp;
-        // ---- actor loss (common_losses.actor_loss) ----
-        const float ratio = expf(onlp - nlp);
-        const float lo_r = 1.0f - cfg.e_clip, hi_r = 1.0f + cfg.e_clip;
-        const float s1 = adv * ratio, s2 = adv * clamp_nan(ratio, lo_r, hi_r);
-        const float a_loss = max_nan(-s1, -s2);
-        const bool inside = (ratio >= lo_r) && (ratio <= hi_r);
-        const bool through = inside || (-s1 > -s2);
-        const float dnlp = through ? (adv * ratio) : 0.0f;            // d a_loss / d neglogp
-        // ---- critic loss (common_losses.critic_loss) ----
-        float c_loss, dval;
-        const float t1 = (val - ret) * (val - ret);
-        if (cfg.clip_value) {
-            const float dv = val - oval;
-            const float vpc = oval + clamp_nan(dv, -cfg.e_clip, cfg.e_clip);
-            const float t2 = (vpc - ret) * (vpc - ret);
-            c_loss = max_nan(t1, t2);
-            const float g1 = 2.0f * (val - ret);
-            const float g2 = (dv >= -cfg.e_clip && dv <= cfg.e_clip) ? 2.0f * (vpc - ret) : 0.0f;
-            dval = (t1 > t2) ? g1 : ((t2 > t1) ? g2 : 0.5f * (g1 + g2));
-        } else {
-            c_loss = t1;
-            dval = 2.0f * (val - ret);
-        }
-        if (a.grad_values) a.grad_values[i] = (0.5f * cfg.critic_coef) * dval * inv_m;
-        // ---- gradients wrt mu (row) and partials for logstd ----
-        float* g = s_gmu + tid * 18;
+        float val = 0.f, oval = 0.f, ret = 0.f, onlp = 0.f, adv = 0.f;
+        if (valid) { val = a.values[i]; oval = a.old_values[i]; ret = a.returns[i]; onlp = a.old_neglogp[i]; adv = a.advantages[i]; }
+        if (full) { mbar_wait(&s_bar, phase); phase ^= 1u; }
+        else __syncthreads();
+
+        if (valid) {
+            // ---- neglogp (models.py), bound loss, KL: one sweep over the 18 action dims ----
+            float z[18], dbound[18];
+            float sq = 0.0f, bsum = 0.0f, kl = 0.0f;
+            const float2* act2 = reinterpret_cast<const float2*>(s_act + tid * 18);
+            const float2* mu2 = reinterpret_cast<const float2*>(s_mu + tid * 18);
+            const float2* omu2 = reinterpret_cast<const float2*>(s_omu + tid * 18);
+            const float2* osig2 = reinterpret_cast<const float2*>(s_osig + tid * 18);
 #pragma unroll
-        for (int j = 0; j < 18; ++j) {
-            const float sig = s_sigma[j];
-            g[j] = (dnlp * (-z[j] / sig) + cfg.bounds_loss_coef * dbound[j]) * inv_m;
-            part[PPO_NSTAT + j] = (double)(dnlp * (1.0f - z[j] * z[j]));
+            for (int h = 0; h < 9; ++h) {
+                const float2 A2 = act2[h], M2 = mu2[h], OM2 = omu2[h], OS2 = osig2[h];
+                const float av[2] = {A2.x, A2.y}, mv[2] = {M2.x, M2.y}, omv[2] = {OM2.x, OM2.y}, osv[2] = {OS2.x, OS2.y};
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int j = 2 * h + q;
+                    const float zz = (av[q] - mv[q]) / sig[j];
+                    z[j] = zz;
+                    sq += zz * zz;
+                    float hi, lo, dh, dl;
+                    if (cfg.bound_form == 0) {          // rl_games 1.1.3 as recalled
+                        hi = fminf(mv[q] - cfg.soft_bound, 0.0f); lo = fminf(-mv[q] + cfg.soft_bound, 0.0f);
+                        dh = 2.0f * hi; dl = -2.0f * lo;
+                    } else {                            // later releases
+                        hi = fmaxf(mv[q] - cfg.soft_bound, 0.0f); lo = fminf(mv[q] + cfg.soft_bound, 0.0f);
+                        dh = 2.0f * hi; dl = 2.0f * lo;
+                    }
+                    bsum += lo * lo + hi * hi;
+                    dbound[j] = dh + dl;
+                    const float c1 = logf(osv[q] / sig[j] + 1e-5f);
+                    const float dm = omv[q] - mv[q];
+                    const float c2 = (sig[j] * sig[j] + dm * dm) / (2.0f * (osv[q] * osv[q] + 1e-5f));
+                    kl += (c1 + c2) + (-0.5f);
+                }
+            }
+            const float nlp = (0.5f * sq + (float)(0.5 * 1.8378770664093453 * 18.0)) + lsum;   // log(2*pi) = 1.83787706...
+            if (a.neglogp_out) a.neglogp_out[i] = nlp;
+            // ---- actor loss (common_losses.actor_loss) ----
+            const float ratio = expf(onlp - nlp);
+            const float lo_r = 1.0f - cfg.e_clip, hi_r = 1.0f + cfg.e_clip;
+            const float s1 = adv * ratio, s2 = adv * clamp_nan(ratio, lo_r, hi_r);
+            const float a_loss = max_nan(-s1, -s2);
+            const bool inside = (ratio >= lo_r) && (ratio <= hi_r);
+            const bool through = inside || (-s1 > -s2);
+            const float dnlp = through ? (adv * ratio) : 0.0f;            // d a_loss / d neglogp
+            // ---- critic loss (common_losses.critic_loss) ----
+            float c_loss, dval;
+            const float t1 = (val - ret) * (val - ret);
+            if (cfg.clip_value) {
+                const float dv = val - oval;
+                const float vpc = oval + clamp_nan(dv, -cfg.e_clip, cfg.e_clip);
+                const float t2 = (vpc - ret) * (vpc - ret);
+                c_loss = max_nan(t1, t2);
+                const float g1 = 2.0f * (val - ret);
+                const float g2 = (dv >= -cfg.e_clip && dv <= cfg.e_clip) ? 2.0f * (vpc - ret) : 0.0f;
+                dval = (t1 > t2) ? g1 : ((t2 > t1) ? g2 : 0.5f * (g1 + g2));
+            } else {
+                c_loss = t1;
+                dval = 2.0f * (val - ret);
+            }
+            if (a.grad_values) a.grad_values[i] = (0.5f * cfg.critic_coef) * dval * inv_m;
+            // ---- gradients wrt mu (row) and running sums for logstd ----
+            float2* g2p = reinterpret_cast<float2*>(s_gmu + tid * 18);
+#pragma unroll
+            for (int h = 0; h < 9; ++h) {
+                const int j = 2 * h;
+                const float ga = (dnlp * (-z[j] / sig[j]) + cfg.bounds_loss_coef * dbound[j]) * inv_m;
+                const float gb = (dnlp * (-z[j + 1] / sig[j + 1]) + cfg.bounds_loss_coef * dbound[j + 1]) * inv_m;
+                g2p[h] = make_float2(ga, gb);
+                part[PPO_NSTAT + j] += (double)(dnlp * (1.0f - z[j] * z[j]));
+                part[PPO_NSTAT + j + 1] += (double)(dnlp * (1.0f - z[j + 1] * z[j + 1]));
+            }
+            part[0] += (double)a_loss; part[1] += (double)c_loss; part[2] += (double)bsum; part[3] += (double)kl;
+            part[4] += inside ? 0.0 : 1.0;
         }
-        part[0] = (double)a_loss; part[1] = (double)c_loss; part[2] = (double)bsum; part[3] = (double)kl;
-        part[4] = inside ? 0.0 : 1.0;
+
+        // ---- grad_mu tile out ----
+        if (a.grad_mu) {
+            if (full) {
+                fence_proxy_async_smem();
+                __syncthreads();
+                if (tid == 0) { bulk_s2g(a.grad_mu + i0 * 18, s_gmu, TILE_BYTES); bulk_commit(); store_pending = true; }
+            } else {
+                __syncthreads();
+                for (int k = tid; k < nv * 18; k += PPO_TILE) a.grad_mu[i0 * 18 + k] = s_gmu[k];
+            }
+        }
     }
 
-    // ---- grad_mu tile out ----
-    if (a.grad_mu) {
-        if (full) {
-            fence_proxy_async_smem();
-            __syncthreads();
-            if (tid == 0) { bulk_s2g(a.grad_mu + i0 * 18, s_gmu, TILE_BYTES); bulk_commit(); }
-        } else {
-            __syncthreads();
-            for (int k = tid; k < nv * 18; k += PPO_TILE) a.grad_mu[i0 * 18 + k] = s_gmu[k];
-        }
-    }
-
-    // ---- block reduction of the partial sums (warp shuffle, then fixed-order fold over 4 warps) ----
+    // ---- block reduction of the running sums (warp shuffle, then fixed-order fold over 4 warps) ----
     const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
     for (int k = 0; k < PPO_PART; ++k) {
@@ -500,28 +530,30 @@ __global__ void __launch_bounds__(PPO_TILE) ppo_loss_kernel(const PpoArgs a, con
         for (int q = 0; q < PPO_TILE / 32; ++q) t += s_red[q][tid];
         a.partials[(int64_t)blockIdx.x * PPO_PART + tid] = t;
     }
-    if (a.grad_mu && full && tid == 0) bulk_wait_read0();
+    if (tid == 0 && store_pending) bulk_wait_read0();
 }
 
-__global__ void ppo_finalize_kernel(const double* __restrict__ partials, int nblocks, int64_t m, const float* __restrict__ logstd,
-                                    const __grid_constant__ BezkPpoCfg cfg, double* __restrict__ stats, float* __restrict__ grad_logstd) {
+// one warp per statistic folds the per-CTA partials (fixed order), thread 0 of warp 0 then forms the loss
+__global__ void __launch_bounds__(1024) ppo_finalize_kernel(const double* __restrict__ partials, int nblocks, int64_t m,
+                                                            const float* __restrict__ logstd, const __grid_constant__ BezkPpoCfg cfg,
+                                                            double* __restrict__ stats, float* __restrict__ grad_logstd) {
     __shared__ double s_tot[PPO_PART];
-    const int j = threadIdx.x;
+    const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
     if (j < PPO_PART) {
-        double t = 0.0;
-        for (int b = 0; b < nblocks; ++b) t += partials[(int64_t)b * PPO_PART + j];
-        s_tot[j] = t;
+        const double t = fold_column(partials, nblocks, PPO_PART, j, lane);
+        if (lane == 0) s_tot[j] = t;
     }
     __syncthreads();
     const double inv_m = 1.0 / (double)m;
-    if (j == 0) {
+    if (threadIdx.x == 0) {
         double ent = 0.0;
         for (int k = 0; k < 18; ++k) ent += (double)((0.5f + 0.9189385332046727f) + logstd[k]);   // 0.5*log(2*pi)
         const double a_m = s_tot[0] * inv_m, c_m = s_tot[1] * inv_m, b_m = s_tot[2] * inv_m, kl_m = s_tot[3] * inv_m;
         stats[1] = a_m; stats[2] = c_m; stats[3] = ent; stats[4] = b_m; stats[5] = kl_m; stats[6] = s_tot[4] * inv_m; stats[7] = 0.0;
         stats[0] = a_m + 0.5 * c_m * (double)cfg.critic_coef - ent * (double)cfg.entropy_coef + b_m * (double)cfg.bounds_loss_coef;
     }
-    if (grad_logstd && j < 18) grad_logstd[j] = (float)(s_tot[PPO_NSTAT + j] * inv_m - (double)cfg.entropy_coef);
+    if (grad_logstd && threadIdx.x < 18)
+        grad_logstd[threadIdx.x] = (float)(s_tot[PPO_NSTAT + threadIdx.x] * inv_m - (double)cfg.entropy_coef);
 }
 
 int64_t ppo_scratch_doubles() { return (int64_t)PPO_MAX_BLOCKS * PPO_PART; }
@@ -529,14 +561,14 @@ int64_t ppo_scratch_doubles() { return (int64_t)PPO_MAX_BLOCKS * PPO_PART; }
 cudaError_t launch_ppo_loss(const PpoArgs& args, const BezkPpoCfg& cfg, double* stats, float* grad_logstd, cudaStream_t st) {
     PpoArgs a = args;
     if (a.m <= 0) return cudaErrorInvalidValue;
-    const int64_t nblocks = (a.m + PPO_TILE - 1) / PPO_TILE;
-    if (nblocks > PPO_MAX_BLOCKS) return cudaErrorInvalidValue;
+    const int64_t ntiles = (a.m + PPO_TILE - 1) / PPO_TILE;
+    const int nblocks = (int)(ntiles < PPO_MAX_BLOCKS ? ntiles : PPO_MAX_BLOCKS);
     a.use_tma = aligned16(a.actions) && aligned16(a.mu) && aligned16(a.old_mu) && aligned16(a.old_sigma) &&
                 (a.grad_mu == nullptr || aligned16(a.grad_mu));
     ppo_loss_kernel<<<(unsigned)nblocks, PPO_TILE, 0, st>>>(a, cfg);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
-    ppo_finalize_kernel<<<1, 32, 0, st>>>(a.partials, (int)nblocks, a.m, a.logstd, cfg, stats, grad_logstd);
+    ppo_finalize_kernel<<<1, 32 * PPO_PART, 0, st>>>(a.partials, nblocks, a.m, a.logstd, cfg, stats, grad_logstd);
     return cudaGetLastError();
 }
 

@@ -17,71 +17,77 @@
 #include "bezk_common.cuh"
 #include "bezk_internal.h"
 #include <math.h>
+#include <stdlib.h>
 
 namespace bezk {
 
-constexpr int TILE = 128;            // envs per CTA = threads per CTA
+#ifndef BEZK_TILE_CTAS
+#define BEZK_TILE_CTAS 5            // resident one-tile CTAs per SM the register allocation is tuned for
+#endif
+// envs per CTA = threads per CTA is a template parameter (TILE).  128 is what ships: 64 was 3 % slower, 6 CTAs/SM (80
+// registers, spilling) 16 % slower, a persistent 2-stage pipelined variant (12 warps/SM) 28 % slower and cross-CTA L2
+// prefetch 15 % slower -- measured, profiles/r01_kernels.md.
 constexpr int DOF_ROW = 36;          // floats per env in dof_state
 constexpr int ROOT_ROW = 26;         // floats per env in root_states
 constexpr int OBS_ROW = 54;
-constexpr int SMEM_IN_FLOATS = TILE * (DOF_ROW + ROOT_ROW);   // 7936 floats = 31744 B >= TILE*54*4
-constexpr int SMEM_OBS_FLOATS = TILE * OBS_ROW;               // 6912 floats = 27648 B
+__host__ __device__ constexpr int smem_in_floats(int tile) { return tile * (DOF_ROW + ROOT_ROW); }   // TILE=128: 7936 floats = 31744 B >= TILE*54*4
+__host__ __device__ constexpr int smem_obs_floats(int tile) { return tile * OBS_ROW; }              // TILE=128: 6912 floats = 27648 B
 
 
 // ------------------------------------------------------------------------------------------------
 // K0: pre-physics.  Pure streaming elementwise pass over (n,18): 72 B read + 72 B written per env.
 // ------------------------------------------------------------------------------------------------
-constexpr int K0_THREADS = 256;
-constexpr int K0_UNROLL = 4;            // float4 loads in flight per thread
+constexpr int K0_THREADS = 288;         // 9 column pairs x 32 rows: a thread keeps ONE column pair -> its constants live in registers
+constexpr int K0_ROWS = K0_THREADS / 9;  // rows per block iteration
+constexpr int K0_UNROLL = 8;            // independent 8-byte loads in flight per thread
+
+__device__ __forceinline__ float k0_target(float a, bool head, float clip, float def, float lo, float hi, float* stored) {
+    a = clamp_nan(a, -clip, clip);                 // vec_task.py:317
+    if (head) a = 0.0f;                            // kick_env.py:414 (head DOFs 0, 1)
+    *stored = a;
+    return tensor_clamp(a + def, lo, hi);          // kick_env.py:417
+}
 
 __global__ void __launch_bounds__(K0_THREADS) pre_physics_kernel(const float* __restrict__ actions, float* __restrict__ actions_out,
                                                                  float* __restrict__ targets, const __grid_constant__ BezkTaskCfg cfg,
-                                                                 int64_t total, int vec4) {
-    __shared__ float s_def[18], s_lo[18], s_hi[18];
-    if (threadIdx.x < 18) {
-        s_def[threadIdx.x] = cfg.default_dof_pos[threadIdx.x];
-        s_lo[threadIdx.x] = cfg.dof_lower[threadIdx.x];
-        s_hi[threadIdx.x] = cfg.dof_upper[threadIdx.x];
-    }
-    __syncthreads();
+                                                                 int64_t n, int vec2) {
     const float clip = cfg.clip_actions;
-    const int64_t nvec = vec4 ? (total >> 2) : 0;
-    // main body: every thread issues K0_UNROLL independent 16-byte loads (block-contiguous), then computes + stores
-    const int64_t base = (int64_t)blockIdx.x * (K0_THREADS * K0_UNROLL) + threadIdx.x;
-    float4 in[K0_UNROLL];
+    if (vec2) {
+        const int pair = threadIdx.x % 9, rsub = threadIdx.x / 9;
+        const int c0 = 2 * pair;
+        const float d0 = cfg.default_dof_pos[c0], d1 = cfg.default_dof_pos[c0 + 1];
+        const float l0 = cfg.dof_lower[c0], l1 = cfg.dof_lower[c0 + 1];
+        const float h0 = cfg.dof_upper[c0], h1 = cfg.dof_upper[c0 + 1];
+        const bool head = (pair == 0);
+        const int64_t row0 = (int64_t)blockIdx.x * (K0_ROWS * K0_UNROLL) + rsub;
+        float2 in[K0_UNROLL];
 #pragma unroll
-    for (int u = 0; u < K0_UNROLL; ++u) {
-        const int64_t i = base + u * K0_THREADS;
-        if (i < nvec) in[u] = ldg_stream4(reinterpret_cast<const float4*>(actions) + i);
-    }
-#pragma unroll
-    for (int u = 0; u < K0_UNROLL; ++u) {
-        const int64_t i = base + u * K0_THREADS;
-        if (i >= nvec) continue;
-        const float a4[4] = {in[u].x, in[u].y, in[u].z, in[u].w};
-        float st[4], tg[4];
-        // (4 i) mod 18 = (4 (i mod 9)) mod 18; 32-bit arithmetic whenever the index fits (64-bit % is ~100 instr)
-        const uint32_t r9 = (i < 0xffffffffLL) ? ((uint32_t)i % 9u) : (uint32_t)(i % 9);
-        int col = (int)((4u * r9) % 18u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float v = clamp_nan(a4[k], -clip, clip);                       // vec_task.py:317
-            if (col < 2) v = 0.0f;                                         // kick_env.py:414 (head)
-            st[k] = v;
-            tg[k] = tensor_clamp(v + s_def[col], s_lo[col], s_hi[col]);    // kick_env.py:417
-            col = (col == 17) ? 0 : col + 1;
+        for (int u = 0; u < K0_UNROLL; ++u) {
+            const int64_t r = row0 + u * K0_ROWS;
+            if (r < n) {
+                const float2* p = reinterpret_cast<const float2*>(actions) + r * 9 + pair;
+                asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(in[u].x), "=f"(in[u].y) : "l"(p));
+            }
         }
-        __stcs(reinterpret_cast<float4*>(targets) + i, make_float4(tg[0], tg[1], tg[2], tg[3]));
-        if (actions_out) __stcs(reinterpret_cast<float4*>(actions_out) + i, make_float4(st[0], st[1], st[2], st[3]));
-    }
-    // scalar tail (total % 4 elements) or the whole array when the pointers are not 16-byte aligned
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = nvec * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int col = (int)(i % 18);
-        float v = clamp_nan(actions[i], -clip, clip);
-        if (col < 2) v = 0.0f;
-        targets[i] = tensor_clamp(v + s_def[col], s_lo[col], s_hi[col]);
-        if (actions_out) actions_out[i] = v;
+#pragma unroll
+        for (int u = 0; u < K0_UNROLL; ++u) {
+            const int64_t r = row0 + u * K0_ROWS;
+            if (r >= n) continue;
+            float s0, s1;
+            const float t0 = k0_target(in[u].x, head, clip, d0, l0, h0, &s0);
+            const float t1 = k0_target(in[u].y, head, clip, d1, l1, h1, &s1);
+            __stcs(reinterpret_cast<float2*>(targets) + r * 9 + pair, make_float2(t0, t1));
+            if (actions_out) __stcs(reinterpret_cast<float2*>(actions_out) + r * 9 + pair, make_float2(s0, s1));
+        }
+    } else {                                       // pointers not 8-byte aligned: scalar grid-stride path
+        const int64_t total = n * 18;
+        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+            const int col = (int)(i % 18);
+            float st;
+            targets[i] = k0_target(actions[i], col < 2, clip, cfg.default_dof_pos[col], cfg.dof_lower[col], cfg.dof_upper[col], &st);
+            if (actions_out) actions_out[i] = st;
+        }
     }
 }
 
@@ -213,10 +219,121 @@ __device__ __forceinline__ void reset_dof_row(const float (&u)[36], const BezkTa
 }
 
 // ------------------------------------------------------------------------------------------------
+// Per-env inputs that do not come through the dense TMA tiles: the IMU-link slice of rigid_body, the foot forces of
+// net_contact (sparse AoS gathers) and the small per-env scalars.  Kept in registers; all loads are independent, so a
+// caller can issue them long before the values are consumed.
+// ------------------------------------------------------------------------------------------------
+template <bool CLEATS>
+struct Gathered {
+    // raw load results: NOTHING depends on them until consume(), so issuing gather_env() never stalls the warp
+    float raw[10];                       // the 40-byte IMU-link slice in LOAD order (vector path: 8 B, 16 B, 16 B pieces)
+    float fl[CLEATS ? 12 : 3], fr[CLEATS ? 12 : 3];
+    float goal[2], binit[2], prev[3];
+    long long reset_prev, progress;
+};
+
+__device__ __forceinline__ long long ld_i64(const int64_t* p) {
+    long long v;
+    asm volatile("ld.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 ld_nc_v2(const void* p) {
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <bool OBS, bool BOOKREW, bool CLEATS>
+__device__ __forceinline__ void gather_env(const TaskArgs& a, const BezkTaskCfg& cfg, int64_t e, bool valid, Gathered<CLEATS>& g) {
+    constexpr int NFORCE = CLEATS ? 12 : 3;
+#pragma unroll
+    for (int k = 0; k < NFORCE; ++k) { g.fl[k] = 0.0f; g.fr[k] = 0.0f; }
+    g.goal[0] = g.goal[1] = g.binit[0] = g.binit[1] = 0.0f;
+    g.prev[0] = g.prev[1] = g.prev[2] = 0.0f;
+    g.reset_prev = 0; g.progress = 0;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) g.raw[k] = 0.0f;
+    if (valid) {
+        const float* rb = a.rigid_body + ((e * cfg.num_bodies + cfg.imu_body) * 13 + 3);
+        if (a.rb_vec2) {
+            // 40 bytes at an 8-byte aligned address: one 8 B + two 16 B loads, order chosen per lane by bit 3
+            const char* p = reinterpret_cast<const char*>(rb);
+            const bool hi = (reinterpret_cast<uintptr_t>(p) & 8u) != 0;
+            // request count matters as much as bytes (profiles/r01_fetch_granularity.md): when the 40-byte span straddles a
+            // 64-byte boundary but stays inside one 128-byte line, ONE full-line fill replaces two 64-byte ones
+            const uint32_t s128 = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 127u);
+            const bool one_line = a.smart_granule && ((s128 & 63u) + 40u > 64u) && (s128 + 40u <= 128u);
+            float2 a2; float4 b4, c4;
+            if (one_line) {
+                a2 = ldg128B_nc_v2(p + (hi ? 0 : 32)); b4 = ldg128B_nc_v4(p + (hi ? 8 : 0)); c4 = ldg128B_nc_v4(p + (hi ? 24 : 16));
+            } else {
+                a2 = ldg64B_nc_v2(p + (hi ? 0 : 32)); b4 = ldg64B_nc_v4(p + (hi ? 8 : 0)); c4 = ldg64B_nc_v4(p + (hi ? 24 : 16));
+            }
+            g.raw[0] = a2.x; g.raw[1] = a2.y; g.raw[2] = b4.x; g.raw[3] = b4.y; g.raw[4] = b4.z; g.raw[5] = b4.w;
+            g.raw[6] = c4.x; g.raw[7] = c4.y; g.raw[8] = c4.z; g.raw[9] = c4.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) g.raw[k] = ldg64B_nc(rb + k);
+        }
+        if (OBS) {
+            float* cf_l = a.net_contact + (e * cfg.num_bodies + cfg.left_foot_body) * 3;
+            float* cf_r = a.net_contact + (e * cfg.num_bodies + cfg.right_foot_body) * 3;
+            if (!CLEATS && a.cf_vec2) {
+                // same idea for the feet: a full-line fill when both feet (or a foot straddling a 64-byte boundary) sit
+                // inside one 128-byte line, 64-byte granules otherwise
+                const uint32_t sl = (uint32_t)(reinterpret_cast<uintptr_t>(cf_l) & 127u);
+                const uint32_t sr = (uint32_t)(reinterpret_cast<uintptr_t>(cf_r) & 127u);
+                const bool same_line = ((reinterpret_cast<uintptr_t>(cf_l) ^ (reinterpret_cast<uintptr_t>(cf_r) + 11u)) & ~(uintptr_t)127u) == 0;
+                const bool l_line = a.smart_granule && (same_line || (((sl & 63u) + 12u > 64u) && (sl + 12u <= 128u)));
+                const bool r_line = a.smart_granule && !same_line && (((sr & 63u) + 12u > 64u) && (sr + 12u <= 128u));
+                const float2 l2 = l_line ? ldg128B_v2(cf_l) : ldg64B_v2(cf_l);
+                const float2 r2 = r_line ? ldg128B_v2(cf_r) : ldg64B_v2(cf_r);
+                g.fl[0] = l2.x; g.fl[1] = l2.y; g.fl[2] = ldg64B(cf_l + 2);
+                g.fr[0] = r2.x; g.fr[1] = r2.y; g.fr[2] = ldg64B(cf_r + 2);
+            } else {
+#pragma unroll
+                for (int k = 0; k < NFORCE; ++k) { g.fl[k] = ldg64B(cf_l + k); g.fr[k] = ldg64B(cf_r + k); }
+            }
+            if (a.prev_lin_vel) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) g.prev[k] = ld_f32(a.prev_lin_vel + e * 3 + k);
+            }
+        }
+        const float2 g2 = ld_nc_v2(reinterpret_cast<const float2*>(a.goal) + e);
+        const float2 b2 = ld_nc_v2(reinterpret_cast<const float2*>(a.ball_init) + e);
+        g.goal[0] = g2.x; g.goal[1] = g2.y; g.binit[0] = b2.x; g.binit[1] = b2.y;
+        if (BOOKREW) {
+            g.reset_prev = ld_i64(a.reset_in + e);
+            g.progress = ld_i64(a.progress_in + e);
+        }
+    }
+}
+
+// First use of a gathered set: pin the raw registers behind an (empty) volatile asm so that the compiler cannot
+// hoist the unpacking selects up to the loads (which would stall the warp at issue time), then unpack.
+template <bool CLEATS>
+__device__ __forceinline__ void consume(const TaskArgs& a, const BezkTaskCfg& cfg, int64_t e, Gathered<CLEATS>& g, float (&imu)[10]) {
+    asm volatile("" : "+f"(g.raw[0]), "+f"(g.raw[1]), "+f"(g.raw[2]), "+f"(g.raw[3]), "+f"(g.raw[4]), "+f"(g.raw[5]),
+                      "+f"(g.raw[6]), "+f"(g.raw[7]), "+f"(g.raw[8]), "+f"(g.raw[9]));
+    asm volatile("" : "+l"(g.reset_prev), "+l"(g.progress));
+    const float* rb = a.rigid_body + ((e * cfg.num_bodies + cfg.imu_body) * 13 + 3);
+    // vector path, slice NOT 16-byte aligned (hi): pieces were loaded in memory order (8,16,16) -> raw is already in order;
+    // 16-byte aligned: pieces were loaded as (tail 8 B, first 16 B, second 16 B) -> rotate
+    const bool rot = a.rb_vec2 && ((reinterpret_cast<uintptr_t>(rb) & 8u) == 0);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) imu[k] = rot ? g.raw[(k + 2) % 10] : g.raw[k];
+}
+
+// ------------------------------------------------------------------------------------------------
 // The fused tile kernel.  PARTS: 1 bookkeeping+masked reset, 2 observations, 4 reward/termination.
 // ------------------------------------------------------------------------------------------------
-template <int PARTS, bool CLEATS>
-__global__ void __launch_bounds__(TILE, 5) task_tile_kernel(const TaskArgs a, const __grid_constant__ BezkTaskCfg cfg) {
+template <int PARTS, bool CLEATS, int TILE>
+__global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_kernel(const TaskArgs a, const __grid_constant__ BezkTaskCfg cfg) {
     constexpr bool BOOK = (PARTS & BEZK_PART_BOOKKEEP) != 0;
     constexpr bool OBS = (PARTS & BEZK_PART_OBS) != 0;
     constexpr bool REW = (PARTS & BEZK_PART_REWARD) != 0;
@@ -226,7 +343,7 @@ __global__ void __launch_bounds__(TILE, 5) task_tile_kernel(const TaskArgs a, co
     float* s_dof = smem;                              // [TILE][36]
     float* s_root = smem + TILE * DOF_ROW;            // [TILE][26]
     float* s_obs = smem;                              // [TILE][54], aliases the two input tiles
-    float* s_obs_clip = smem + SMEM_IN_FLOATS;        // [TILE][54], only when a.obs_clipped
+    float* s_obs_clip = smem + smem_in_floats(TILE);  // [TILE][54], only when a.obs_clipped
     __shared__ __align__(8) uint64_t s_bar;
 
     const int tid = threadIdx.x;
@@ -252,54 +369,20 @@ __global__ void __launch_bounds__(TILE, 5) task_tile_kernel(const TaskArgs a, co
     }
 
     // ---- 2. sparse gathers, issued before anyone waits (widest aligned vector loads available) ----
-    float imu_in[10];                                 // q(4) v(3) w(3) of the IMU link
-#pragma unroll
-    for (int k = 0; k < 10; ++k) imu_in[k] = 0.0f;
-    float fl[NFORCE], fr[NFORCE];
-    float goal[2] = {0.f, 0.f}, binit[2] = {0.f, 0.f}, prev[3] = {0.f, 0.f, 0.f};
-    int64_t reset_prev = 0, progress = 0;
-    float* cf_l = nullptr;
-    float* cf_r = nullptr;
-    if (valid) {
-        const float* rb = a.rigid_body + ((e * cfg.num_bodies + cfg.imu_body) * 13 + 3);
-        if (a.rb_vec2) {
-            // 40 bytes at an 8-byte aligned address: one 8 B + two 16 B loads, order chosen per lane by bit 3
-            const char* p = reinterpret_cast<const char*>(rb);
-            const bool hi = (reinterpret_cast<uintptr_t>(p) & 8u) != 0;
-            const float2 a2 = ldg64B_nc_v2(p + (hi ? 0 : 32));
-            const float4 b4 = ldg64B_nc_v4(p + (hi ? 8 : 0));
-            const float4 c4 = ldg64B_nc_v4(p + (hi ? 24 : 16));
-            imu_in[0] = hi ? a2.x : b4.x; imu_in[1] = hi ? a2.y : b4.y; imu_in[2] = hi ? b4.x : b4.z; imu_in[3] = hi ? b4.y : b4.w;
-            imu_in[4] = hi ? b4.z : c4.x; imu_in[5] = hi ? b4.w : c4.y; imu_in[6] = hi ? c4.x : c4.z; imu_in[7] = hi ? c4.y : c4.w;
-            imu_in[8] = hi ? c4.z : a2.x; imu_in[9] = hi ? c4.w : a2.y;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 10; ++k) imu_in[k] = ldg64B_nc(rb + k);
-        }
-        if (OBS) {
-            cf_l = a.net_contact + (e * cfg.num_bodies + cfg.left_foot_body) * 3;
-            cf_r = a.net_contact + (e * cfg.num_bodies + cfg.right_foot_body) * 3;
-            if (!CLEATS && a.cf_vec2) {
-                const float2 l2 = ldg64B_v2(cf_l), r2 = ldg64B_v2(cf_r);
-                fl[0] = l2.x; fl[1] = l2.y; fl[2] = ldg64B(cf_l + 2);
-                fr[0] = r2.x; fr[1] = r2.y; fr[2] = ldg64B(cf_r + 2);
-            } else {
-#pragma unroll
-                for (int k = 0; k < NFORCE; ++k) { fl[k] = ldg64B(cf_l + k); fr[k] = ldg64B(cf_r + k); }
-            }
-            if (a.prev_lin_vel) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) prev[k] = a.prev_lin_vel[e * 3 + k];
-            }
-        }
-        const float2 g2 = __ldg(reinterpret_cast<const float2*>(a.goal) + e);
-        const float2 b2 = __ldg(reinterpret_cast<const float2*>(a.ball_init) + e);
-        goal[0] = g2.x; goal[1] = g2.y; binit[0] = b2.x; binit[1] = b2.y;
-        if (BOOK || REW) {
-            reset_prev = a.reset_in[e];
-            progress = a.progress_in[e];
-        }
-    }
+    Gathered<CLEATS> g;
+    gather_env<OBS, (BOOK || REW), CLEATS>(a, cfg, e, valid, g);
+
+    float imu_in[10];
+    consume<CLEATS>(a, cfg, e, g, imu_in);
+    float (&fl)[NFORCE] = g.fl;
+    float (&fr)[NFORCE] = g.fr;
+    float (&goal)[2] = g.goal;
+    float (&binit)[2] = g.binit;
+    float (&prev)[3] = g.prev;
+    const int64_t reset_prev = (int64_t)g.reset_prev;
+    int64_t progress = (int64_t)g.progress;
+    float* cf_l = a.net_contact ? a.net_contact + (e * cfg.num_bodies + cfg.left_foot_body) * 3 : nullptr;
+    float* cf_r = a.net_contact ? a.net_contact + (e * cfg.num_bodies + cfg.right_foot_body) * 3 : nullptr;
     const float q[4] = {imu_in[0], imu_in[1], imu_in[2], imu_in[3]};
     const float v[3] = {imu_in[4], imu_in[5], imu_in[6]};
     const float w[3] = {imu_in[7], imu_in[8], imu_in[9]};
@@ -538,24 +621,24 @@ __global__ void philox_uniforms_kernel(uint64_t seed, uint64_t step, float* out,
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 
-template <int PARTS, bool CLEATS>
-static cudaError_t launch_parts2(const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st) {
-    const size_t smem = (size_t)(SMEM_IN_FLOATS + (a.obs_clipped ? SMEM_OBS_FLOATS : 0)) * sizeof(float);
+template <int PARTS, bool CLEATS, int TILE>
+static cudaError_t launch_parts3(const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st) {
+    const size_t smem = (size_t)(smem_in_floats(TILE) + (a.obs_clipped ? smem_obs_floats(TILE) : 0)) * sizeof(float);
     static bool attr_set = false;          // per instantiation; opt in to > 48 KB dynamic shared memory once
     if (!attr_set) {
-        cudaError_t err = cudaFuncSetAttribute(task_tile_kernel<PARTS, CLEATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)((SMEM_IN_FLOATS + SMEM_OBS_FLOATS) * sizeof(float)));
+        cudaError_t err = cudaFuncSetAttribute(task_tile_kernel<PARTS, CLEATS, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)((smem_in_floats(TILE) + smem_obs_floats(TILE)) * sizeof(float)));
         if (err != cudaSuccess) return err;
         attr_set = true;
     }
     const int64_t tiles = (a.n + TILE - 1) / TILE;
-    task_tile_kernel<PARTS, CLEATS><<<(unsigned)tiles, TILE, smem, st>>>(a, cfg);
+    task_tile_kernel<PARTS, CLEATS, TILE><<<(unsigned)tiles, TILE, smem, st>>>(a, cfg);
     return cudaGetLastError();
 }
 
 template <int PARTS>
 static cudaError_t launch_parts(const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st) {
-    return (cfg.flags & BEZK_F_CLEATS) ? launch_parts2<PARTS, true>(a, cfg, st) : launch_parts2<PARTS, false>(a, cfg, st);
+    return (cfg.flags & BEZK_F_CLEATS) ? launch_parts3<PARTS, true, 128>(a, cfg, st) : launch_parts3<PARTS, false, 128>(a, cfg, st);
 }
 
 cudaError_t launch_task(int parts, const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st) {
@@ -575,19 +658,20 @@ void fill_alignment(TaskArgs& a, const BezkTaskCfg& cfg) {
     a.use_tma = aligned16(a.dof_state) && aligned16(a.root_states) && (a.obs == nullptr || aligned16(a.obs)) &&
                 (a.obs_clipped == nullptr || aligned16(a.obs_clipped));
     a.rb_vec2 = aligned8(a.rigid_body) && (cfg.num_bodies % 2 == 0) && ((cfg.imu_body * 13 + 3) % 2 == 0);
+    const char* sg = getenv("BEZK_SMART_GRANULE");
+    a.smart_granule = (sg == nullptr) ? 1 : (sg[0] != '0');
     a.cf_vec2 = a.net_contact != nullptr && aligned8(a.net_contact) && ((cfg.num_bodies * 3) % 2 == 0) &&
                 ((cfg.left_foot_body * 3) % 2 == 0) && ((cfg.right_foot_body * 3) % 2 == 0);
 }
 
 cudaError_t launch_pre_physics(const float* actions, float* actions_out, float* targets, const BezkTaskCfg& cfg,
                                int64_t n, cudaStream_t st) {
-    const int64_t total = n * 18;
-    const int vec4 = aligned16(actions) && aligned16(targets) && (actions_out == nullptr || aligned16(actions_out));
-    const int64_t per_block = (int64_t)K0_THREADS * K0_UNROLL;
-    int64_t blocks = vec4 ? ((total >> 2) + per_block - 1) / per_block : (total + K0_THREADS - 1) / K0_THREADS;
+    const int vec2 = aligned8(actions) && aligned8(targets) && (actions_out == nullptr || aligned8(actions_out));
+    const int64_t per_block = (int64_t)K0_ROWS * K0_UNROLL;
+    int64_t blocks = vec2 ? (n + per_block - 1) / per_block : (n * 18 + K0_THREADS - 1) / K0_THREADS;
     if (blocks < 1) blocks = 1;
-    if (!vec4 && blocks > 148LL * 64) blocks = 148LL * 64;      // scalar path is grid-strided
-    pre_physics_kernel<<<(unsigned)blocks, K0_THREADS, 0, st>>>(actions, actions_out, targets, cfg, total, vec4);
+    if (!vec2 && blocks > 148LL * 64) blocks = 148LL * 64;      // scalar path is grid-strided
+    pre_physics_kernel<<<(unsigned)blocks, K0_THREADS, 0, st>>>(actions, actions_out, targets, cfg, n, vec2);
     return cudaGetLastError();
 }
 
