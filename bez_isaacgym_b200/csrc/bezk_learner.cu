@@ -106,9 +106,19 @@ __global__ void __launch_bounds__(RMS_THREADS) rms_partials_kernel(const float* 
 #pragma unroll
             for (int u = 0; u < RMS_UNROLL; ++u) {
                 const float* p = x + (r + u * row_stride) * c + g * VEC;
-                if (VEC == 2) { const float2 t = *reinterpret_cast<const float2*>(p); xv[u][0] = t.x; xv[u][VEC - 1] = t.y; }
-                else xv[u][0] = *p;
+                // volatile asm loads: issued as one batch (the compiler otherwise interleaves load/use and keeps 1-2 in flight)
+                if (VEC == 2) asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(xv[u][0]), "=f"(xv[u][VEC - 1]) : "l"(p));
+                else xv[u][0] = ldg_stream(p);
             }
+            // one opaque statement that "uses" every loaded register: nothing below can be scheduled between the loads
+            static_assert(RMS_UNROLL == 8, "fence lists 8 rows");
+            if (VEC == 2)
+                asm volatile("" : "+f"(xv[0][0]), "+f"(xv[1][0]), "+f"(xv[2][0]), "+f"(xv[3][0]), "+f"(xv[4][0]), "+f"(xv[5][0]),
+                                  "+f"(xv[6][0]), "+f"(xv[7][0]), "+f"(xv[0][VEC - 1]), "+f"(xv[1][VEC - 1]), "+f"(xv[2][VEC - 1]),
+                                  "+f"(xv[3][VEC - 1]), "+f"(xv[4][VEC - 1]), "+f"(xv[5][VEC - 1]), "+f"(xv[6][VEC - 1]), "+f"(xv[7][VEC - 1]));
+            else
+                asm volatile("" : "+f"(xv[0][0]), "+f"(xv[1][0]), "+f"(xv[2][0]), "+f"(xv[3][0]), "+f"(xv[4][0]), "+f"(xv[5][0]),
+                                  "+f"(xv[6][0]), "+f"(xv[7][0]));
 #pragma unroll
             for (int u = 0; u < RMS_UNROLL; ++u)
 #pragma unroll
@@ -130,6 +140,78 @@ __global__ void __launch_bounds__(RMS_THREADS) rms_partials_kernel(const float* 
         const int stat = j / c, col = j - stat * c;
         double acc = 0.0;
         for (int q = 0; q < rpi; ++q) acc += s_red[(stat * rpi + q) * c + col];
+        partials[(int64_t)blockIdx.x * 2 * c + j] = acc;
+    }
+}
+
+// TMA variant of the multi-column moments kernel (used when x is 16-byte aligned and c*4*2 is a multiple of 16, i.e.
+// always for the 54-wide observations).  The per-thread-load version above keeps only 1-2 loads per thread in flight
+// (ptxas interleaves load/use whatever the source order; measured 2.6 TB/s); here persistent CTAs stream contiguous tiles
+// of RMS_TR rows through a 4-stage ring of cp.async.bulk copies, so ~3 tiles (41 KB for c = 54) per CTA are always in
+// flight, and the fp64 accumulation reads shared memory (consecutive threads = consecutive columns, conflict-free).
+constexpr int RMS_TR = 64;                      // rows per tile
+constexpr int RMS_STAGES = 4;
+
+__global__ void __launch_bounds__(RMS_THREADS) rms_partials_tma_kernel(const float* __restrict__ x, const double* __restrict__ pivot,
+                                                                       double* __restrict__ partials, int64_t m, int c) {
+    extern __shared__ __align__(128) unsigned char rms_smem[];
+    __shared__ __align__(8) uint64_t s_full[RMS_STAGES];
+    float* s_tile = reinterpret_cast<float*>(rms_smem);                       // [RMS_STAGES][RMS_TR * c]
+    double* s_red = reinterpret_cast<double*>(rms_smem);                      // reused after the loop: [2][rpb][c]
+    const int tid = threadIdx.x;
+    const int rpb = RMS_THREADS / c;                                          // row groups per block (>= 1)
+    const int rg = tid / c, col = tid - rg * c;
+    const bool active = rg < rpb;
+    const double pv = (pivot && active) ? pivot[col] : 0.0;
+    const int64_t ntiles = (m + RMS_TR - 1) / RMS_TR;
+    const int tile_floats = RMS_TR * c;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < RMS_STAGES; ++s) mbar_init(&s_full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int64_t tile, int stage) {          // thread 0 only
+        const int64_t r0 = tile * RMS_TR;
+        const int64_t rows = (m - r0) < (int64_t)RMS_TR ? (m - r0) : (int64_t)RMS_TR;
+        const uint32_t bytes = (uint32_t)(rows * c * 4);
+        mbar_arrive_expect_tx(&s_full[stage], bytes);
+        bulk_g2s(s_tile + (size_t)stage * tile_floats, x + r0 * c, bytes, &s_full[stage]);
+    };
+    // this CTA's tiles: blockIdx.x, +gridDim.x, ...
+    int64_t my_tiles = 0;
+    if ((int64_t)blockIdx.x < ntiles) my_tiles = (ntiles - 1 - blockIdx.x) / gridDim.x + 1;
+    if (tid == 0) {
+        for (int k = 0; k < RMS_STAGES - 1 && k < my_tiles; ++k) issue((int64_t)blockIdx.x + (int64_t)k * gridDim.x, k);
+    }
+    double s = 0.0, ss = 0.0;
+    for (int64_t k = 0; k < my_tiles; ++k) {
+        const int stage = (int)(k % RMS_STAGES);
+        const uint32_t parity = (uint32_t)((k / RMS_STAGES) & 1);
+        // refill the stage that was consumed in the previous iteration (all threads passed the barrier below)
+        if (tid == 0 && k + RMS_STAGES - 1 < my_tiles)
+            issue((int64_t)blockIdx.x + (k + RMS_STAGES - 1) * gridDim.x, (int)((k + RMS_STAGES - 1) % RMS_STAGES));
+        mbar_wait(&s_full[stage], parity);
+        const int64_t r0 = ((int64_t)blockIdx.x + k * gridDim.x) * RMS_TR;
+        const int rows = (int)((m - r0) < (int64_t)RMS_TR ? (m - r0) : (int64_t)RMS_TR);
+        if (active) {
+            const float* t = s_tile + (size_t)stage * tile_floats + col;
+            for (int r = rg; r < rows; r += rpb) {
+                const double d = (double)t[r * c] - pv;
+                s += d;
+                ss += d * d;
+            }
+        }
+        __syncthreads();                                   // stage fully consumed before thread 0 may refill it
+    }
+    // fixed-order fold over the row groups (shared memory is free now)
+    if (active) { s_red[(0 * rpb + rg) * c + col] = s; s_red[(1 * rpb + rg) * c + col] = ss; }
+    __syncthreads();
+    for (int j = tid; j < 2 * c; j += RMS_THREADS) {
+        const int stat = j / c, cc = j - stat * c;
+        double acc = 0.0;
+        for (int q = 0; q < rpb; ++q) acc += s_red[(stat * rpb + q) * c + cc];
         partials[(int64_t)blockIdx.x * 2 * c + j] = acc;
     }
 }
@@ -276,6 +358,31 @@ cudaError_t launch_rms_moments(const float* x, const double* pivot, double* acc,
         flat_partials_kernel<<<nblocks, RMS_THREADS, 0, st>>>(x, nullptr, pivot, partials, m, vec4);
     } else {
         if (c > RMS_MAX_C) return cudaErrorInvalidValue;
+        // TMA path: every tile start (64 rows) and every tile size must be a multiple of 16 bytes
+        const bool tma_ok = aligned16(x) && ((RMS_TR * c * 4) % 16 == 0) && (((m % RMS_TR) * c * 4) % 16 == 0) && m >= 4 * RMS_TR;
+        if (tma_ok) {
+            const int64_t ntiles = (m + RMS_TR - 1) / RMS_TR;
+            size_t smem = (size_t)RMS_STAGES * RMS_TR * c * sizeof(float);
+            const size_t red = (size_t)2 * (RMS_THREADS / c) * c * sizeof(double);     // fold buffer aliases the ring
+            if (red > smem) smem = red;
+            static size_t attr_set = 0;
+            if (smem > attr_set) {
+                cudaError_t e2 = cudaFuncSetAttribute(rms_partials_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e2 != cudaSuccess) return e2;
+                attr_set = smem;
+            }
+            int per_sm = (int)((220 * 1024) / (smem + 1024));
+            if (per_sm > 8) per_sm = 8;
+            if (per_sm < 1) per_sm = 1;
+            int64_t cap = 148LL * per_sm;
+            if (cap > RMS_MAX_BLOCKS) cap = RMS_MAX_BLOCKS;
+            nblocks = (int)(ntiles < cap ? ntiles : cap);
+            rms_partials_tma_kernel<<<nblocks, RMS_THREADS, smem, st>>>(x, pivot, partials, m, c);
+            cudaError_t err = cudaGetLastError();
+            if (err != cudaSuccess) return err;
+            moments_finalize_kernel<<<(2 * c + 7) / 8, 256, 0, st>>>(partials, nblocks, c, m, acc);
+            return cudaGetLastError();
+        }
         const bool v2 = (c % 2 == 0) && aligned8(x);
         const int cg = v2 ? c / 2 : c;
         const int rpi = RMS_THREADS / cg;
@@ -370,16 +477,17 @@ cudaError_t launch_adv_normalize(const float* returns, const float* values, cons
 constexpr int PPO_TILE = 128;
 constexpr int PPO_NSTAT = 7;                    // a, c, b, kl, clipped, (spare), (spare)
 constexpr int PPO_PART = PPO_NSTAT + 18;        // doubles per block
-constexpr int PPO_MAX_BLOCKS = 148 * 3;         // persistent grid: every CTA walks tiles blockIdx.x, +gridDim.x, ...
+constexpr int PPO_FLUSH = 8;                    // tiles between fp32 -> fp64 flushes
+constexpr int PPO_MAX_BLOCKS = 148 * 4;         // persistent grid: every CTA walks tiles blockIdx.x, +gridDim.x, ...
 
-__global__ void __launch_bounds__(PPO_TILE) ppo_loss_kernel(const PpoArgs a, const __grid_constant__ BezkPpoCfg cfg) {
+__global__ void __launch_bounds__(PPO_TILE, 4) ppo_loss_kernel(const PpoArgs a, const __grid_constant__ BezkPpoCfg cfg) {
     __shared__ __align__(128) float s_act[PPO_TILE * 18];
     __shared__ __align__(128) float s_mu[PPO_TILE * 18];
     __shared__ __align__(128) float s_omu[PPO_TILE * 18];
     __shared__ __align__(128) float s_osig[PPO_TILE * 18];
     __shared__ __align__(128) float s_gmu[PPO_TILE * 18];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ float s_sigma[18], s_logstd[18];
+    __shared__ float s_sigma[18], s_logstd[18], s_isig[18];
     __shared__ double s_red[PPO_TILE / 32][PPO_PART];
 
     const int tid = threadIdx.x;
@@ -390,13 +498,35 @@ __global__ void __launch_bounds__(PPO_TILE) ppo_loss_kernel(const PpoArgs a, con
     if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
     if (tid < 18) { const float ls = a.logstd[tid]; s_logstd[tid] = ls; s_sigma[tid] = expf(ls); }
     __syncthreads();
-    float sig[18], lsum = 0.0f;
+    // per-column constants.  Divisions by sigma are multiplications by 1/sigma (sigma is one (18,) row for the whole
+    // minibatch): 3 IEEE divides per sample-dimension become 2 multiplies + 1 divide, ~25 % fewer instructions; the
+    // extra rounding (<= 1 ulp) is far inside the fp32 tolerance of the loss.
+    // (the 2 x 18 constants are read from shared memory -- broadcast loads -- instead of living in 36 registers)
+    if (tid < 18) s_isig[tid] = 1.0f / s_sigma[tid];
+    __syncthreads();
+    const float* sig = s_sigma;
+    const float* isig = s_isig;
+    float lsum = 0.0f;
 #pragma unroll
-    for (int j = 0; j < 18; ++j) { sig[j] = s_sigma[j]; lsum += s_logstd[j]; }
+    for (int j = 0; j < 18; ++j) lsum += s_logstd[j];
 
-    double part[PPO_PART];                       // per-thread running sums over all of this CTA's tiles (fixed order)
+    // per-thread fp32 running sums, flushed every PPO_FLUSH tiles (a thread adds one sample per tile) through a
+    // fixed-order fp64 warp reduction into per-warp fp64 accumulators in shared memory: 25 registers instead of 50,
+    // deterministic, and the fp32 partial sums never hold more than PPO_FLUSH terms
+    float part[PPO_PART];
 #pragma unroll
-    for (int k = 0; k < PPO_PART; ++k) part[k] = 0.0;
+    for (int k = 0; k < PPO_PART; ++k) part[k] = 0.0f;
+    for (int k = tid; k < (PPO_TILE / 32) * PPO_PART; k += PPO_TILE) (&s_red[0][0])[k] = 0.0;
+    int since_flush = 0;
+    const int lane = tid & 31, wid = tid >> 5;
+    auto flush = [&]() {
+#pragma unroll
+        for (int k = 0; k < PPO_PART; ++k) {
+            const double t = warp_sum((double)part[k]);
+            if (lane == 0) s_red[wid][k] += t;
+            part[k] = 0.0f;
+        }
+    };
     uint32_t phase = 0;
     bool store_pending = false;
 
@@ -430,7 +560,6 @@ __global__ void __launch_bounds__(PPO_TILE) ppo_loss_kernel(const PpoArgs a, con
 
         if (valid) {
             // ---- neglogp (models.py), bound loss, KL: one sweep over the 18 action dims ----
-            float z[18], dbound[18];
             float sq = 0.0f, bsum = 0.0f, kl = 0.0f;
             const float2* act2 = reinterpret_cast<const float2*>(s_act + tid * 18);
             const float2* mu2 = reinterpret_cast<const float2*>(s_mu + tid * 18);
@@ -443,20 +572,16 @@ __global__ void __launch_bounds__(PPO_TILE) ppo_loss_kernel(const PpoArgs a, con
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const int j = 2 * h + q;
-                    const float zz = (av[q] - mv[q]) / sig[j];
-                    z[j] = zz;
+                    const float zz = (av[q] - mv[q]) * isig[j];
                     sq += zz * zz;
-                    float hi, lo, dh, dl;
+                    float hi, lo;
                     if (cfg.bound_form == 0) {          // rl_games 1.1.3 as recalled
                         hi = fminf(mv[q] - cfg.soft_bound, 0.0f); lo = fminf(-mv[q] + cfg.soft_bound, 0.0f);
-                        dh = 2.0f * hi; dl = -2.0f * lo;
                     } else {                            // later releases
                         hi = fmaxf(mv[q] - cfg.soft_bound, 0.0f); lo = fminf(mv[q] + cfg.soft_bound, 0.0f);
-                        dh = 2.0f * hi; dl = 2.0f * lo;
                     }
                     bsum += lo * lo + hi * hi;
-                    dbound[j] = dh + dl;
-                    const float c1 = logf(osv[q] / sig[j] + 1e-5f);
+                    const float c1 = logf(osv[q] * isig[j] + 1e-5f);
                     const float dm = omv[q] - mv[q];
                     const float c2 = (sig[j] * sig[j] + dm * dm) / (2.0f * (osv[q] * osv[q] + 1e-5f));
                     kl += (c1 + c2) + (-0.5f);
@@ -489,19 +614,30 @@ __global__ void __launch_bounds__(PPO_TILE) ppo_loss_kernel(const PpoArgs a, con
             }
             if (a.grad_values) a.grad_values[i] = (0.5f * cfg.critic_coef) * dval * inv_m;
             // ---- gradients wrt mu (row) and running sums for logstd ----
+            // second sweep: z and the bound-loss derivative are recomputed from the shared-memory rows (cheaper than
+            // keeping 36 values alive across the actor / critic block)
             float2* g2p = reinterpret_cast<float2*>(s_gmu + tid * 18);
 #pragma unroll
             for (int h = 0; h < 9; ++h) {
                 const int j = 2 * h;
-                const float ga = (dnlp * (-z[j] / sig[j]) + cfg.bounds_loss_coef * dbound[j]) * inv_m;
-                const float gb = (dnlp * (-z[j + 1] / sig[j + 1]) + cfg.bounds_loss_coef * dbound[j + 1]) * inv_m;
-                g2p[h] = make_float2(ga, gb);
-                part[PPO_NSTAT + j] += (double)(dnlp * (1.0f - z[j] * z[j]));
-                part[PPO_NSTAT + j + 1] += (double)(dnlp * (1.0f - z[j + 1] * z[j + 1]));
+                const float2 A2 = act2[h], M2 = mu2[h];
+                const float av[2] = {A2.x, A2.y}, mv[2] = {M2.x, M2.y};
+                float gout[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const float zz = (av[q] - mv[q]) * isig[j + q];
+                    float dbound;
+                    if (cfg.bound_form == 0) dbound = 2.0f * fminf(mv[q] - cfg.soft_bound, 0.0f) + (-2.0f) * fminf(-mv[q] + cfg.soft_bound, 0.0f);
+                    else dbound = 2.0f * fmaxf(mv[q] - cfg.soft_bound, 0.0f) + 2.0f * fminf(mv[q] + cfg.soft_bound, 0.0f);
+                    gout[q] = (dnlp * (-zz * isig[j + q]) + cfg.bounds_loss_coef * dbound) * inv_m;
+                    part[PPO_NSTAT + j + q] += dnlp * (1.0f - zz * zz);
+                }
+                g2p[h] = make_float2(gout[0], gout[1]);
             }
-            part[0] += (double)a_loss; part[1] += (double)c_loss; part[2] += (double)bsum; part[3] += (double)kl;
-            part[4] += inside ? 0.0 : 1.0;
+            part[0] += a_loss; part[1] += c_loss; part[2] += bsum; part[3] += kl;
+            part[4] += inside ? 0.0f : 1.0f;
         }
+        if (++since_flush == PPO_FLUSH) { flush(); since_flush = 0; }
 
         // ---- grad_mu tile out ----
         if (a.grad_mu) {
@@ -516,13 +652,8 @@ __global__ void __launch_bounds__(PPO_TILE) ppo_loss_kernel(const PpoArgs a, con
         }
     }
 
-    // ---- block reduction of the running sums (warp shuffle, then fixed-order fold over 4 warps) ----
-    const int lane = tid & 31, wid = tid >> 5;
-#pragma unroll
-    for (int k = 0; k < PPO_PART; ++k) {
-        const double t = warp_sum(part[k]);
-        if (lane == 0) s_red[wid][k] = t;
-    }
+    // ---- final flush, then a fixed-order fold over the 4 warps ----
+    flush();
     __syncthreads();
     if (tid < PPO_PART) {
         double t = 0.0;

@@ -29,8 +29,9 @@ def shard_range(num_envs: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def allreduce_sum_(acc: torch.Tensor, group=None) -> torch.Tensor:
-    """In-place SUM all-reduce of an additive statistics vector (no-op when not distributed)."""
-    if is_distributed(group):
+    """In-place SUM all-reduce of an additive statistics vector over ``group``.  ``group=None`` means LOCAL statistics
+    (no collective) -- pass ``torch.distributed.group.WORLD`` explicitly to merge over all ranks."""
+    if group is not None and is_distributed(group):
         dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
     return acc
 

@@ -83,8 +83,8 @@ def feet_no_cleats(force: Tensor) -> Tensor:
     """tasks/kick_env.py:987-1038 for ONE foot.  ``force`` (N,3) is filtered IN PLACE (the reference
     writes the noise filter back into the simulator's contact buffer, :987-990)."""
     force[..., 0:3] = torch.where(torch.abs(force[..., 0:3]) > 0.01, force[..., 0:3],
-                                  torch.zeros(3))
-    one, zero = torch.ones(1), torch.zeros(1)
+                                  force.new_zeros(3))
+    one, zero = force.new_ones(1), force.new_zeros(1)
     x = torch.where(torch.abs(force[..., 0]) > 0.0, one, zero)
     x = torch.where(force[..., 0] == 0, 2.0 * one, x)
     y = torch.where(torch.abs(force[..., 1]) > 0.0, one, 3.0 * one)
@@ -92,10 +92,11 @@ def feet_no_cleats(force: Tensor) -> Tensor:
     sensor = torch.where(x == 1.0, zero, 4.0 * one)
     sensor = torch.where(x == 2.0, 8.0 * one, sensor)
     case = torch.add(y, sensor).reshape(-1, 1)
-    out = torch.tensor([[-1.0] * 4]).repeat(force.shape[0], 1)
+    dev = force.device
+    out = torch.tensor([[-1.0] * 4], device=dev).repeat(force.shape[0], 1)
     for code, row in _FOOT_ROWS.items():
-        out = torch.where(case == code, torch.tensor(row), out)
-    return torch.where(force[..., 2].reshape(-1, 1) < 1, torch.tensor([-1.0] * 4), out)
+        out = torch.where(case == code, torch.tensor(row, device=dev), out)
+    return torch.where(force[..., 2].reshape(-1, 1) < 1, torch.tensor([-1.0] * 4, device=dev), out)
 
 
 def feet_cleats(left: Tensor, right: Tensor) -> Tensor:
@@ -212,25 +213,27 @@ class KickStepOracle:
             self.right_c = cf[..., right_cleats[0]:right_cleats[1], 0:3]
         else:
             self.left_f, self.right_f = cf[..., left_foot, 0:3], cf[..., right_foot, 0:3]
-        self.gravity_vec = torch.tensor([[0.0, 0.0, -1.0]]).repeat(n, 1)       # :217
-        self.prev_lin_vel = torch.tensor([[0, 0, 0]]).repeat(n, 1)             # int64 zeros, :183
+        dev = root_states.device              # CPU for the oracle proper; a CUDA device = "the reference's torch ops on the GPU"
+        self.gravity_vec = torch.tensor([[0.0, 0.0, -1.0]], device=dev).repeat(n, 1)       # :217
+        self.prev_lin_vel = torch.tensor([[0, 0, 0]], device=dev).repeat(n, 1)             # int64 zeros, :183
         # vec_task.py:226-249 (reset_buf starts at ones, KickEnv.__init__ then resets everything, :238)
-        self.obs_buf = torch.zeros(n, 54)
-        self.rew_buf = torch.zeros(n)
-        self.reset_buf = torch.ones(n, dtype=torch.long)
-        self.timeout_buf = torch.zeros(n, dtype=torch.long)
-        self.progress_buf = torch.zeros(n, dtype=torch.long)
-        self.randomize_buf = torch.zeros(n, dtype=torch.long)
+        self.obs_buf = torch.zeros(n, 54, device=dev)
+        self.rew_buf = torch.zeros(n, device=dev)
+        self.reset_buf = torch.ones(n, dtype=torch.long, device=dev)
+        self.timeout_buf = torch.zeros(n, dtype=torch.long, device=dev)
+        self.progress_buf = torch.zeros(n, dtype=torch.long, device=dev)
+        self.randomize_buf = torch.zeros(n, dtype=torch.long, device=dev)
         self.step_count = 0
         self.targets = None
-        self.actions = torch.zeros(n, 18)
+        self.actions = torch.zeros(n, 18, device=dev)
 
     def reset_idx(self, env_ids: Tensor, uniforms: Optional[Tensor] = None):
         """tasks/kick_env.py:779-850; the four indexed setters are modelled as row copies of
         ``initial_root_states`` (what a simulator does with them)."""
         if uniforms is None and self.reset_uniforms is None:
             # the reference's own draw order: positions then velocities, (k,18) each (:786-787)
-            u = torch.cat((torch.rand(len(env_ids), 18), torch.rand(len(env_ids), 18)), 1)
+            dev = self.dof.device
+            u = torch.cat((torch.rand(len(env_ids), 18, device=dev), torch.rand(len(env_ids), 18, device=dev)), 1)
         else:
             if uniforms is None:
                 uniforms = self.reset_uniforms(self.step_count)

@@ -51,7 +51,9 @@ def _worker(rank, world, port, tmp):
         adv_acc = torch.tensor([hi - lo, float(x_all[lo:hi, 0].double().sum()), float((x_all[lo:hi, 0].double() ** 2).sum())],
                                dtype=torch.float64)
         flat, (acc_v, adv_v) = bdist.pack([acc, adv_acc])            # ONE collective for both statistics
-        bdist.allreduce_sum_(flat)
+        bdist.allreduce_sum_(flat, dist.group.WORLD)
+        local_only = acc.clone()
+        assert torch.equal(bdist.allreduce_sum_(local_only), acc)       # group=None -> local statistics, no collective
         whole = _pivoted_moments(x_all, pivot)
         assert torch.allclose(acc_v, whole, rtol=1e-13, atol=1e-9)
         assert adv_v[0].item() == n_envs

@@ -87,7 +87,8 @@ def _rms_forward_gpu(x, mean, var, count, train=True, unnorm=False):
     return y
 
 
-@pytest.mark.parametrize("m,c", [(2, 54), (37, 54), (4096, 54), (32768, 54), (1000, 1), (131072, 1), (333, 7), (64, 200)])
+@pytest.mark.parametrize("m,c", [(2, 54), (37, 54), (1000, 54), (4096, 54), (4099, 54), (32768, 54), (100040, 54), (1000, 1),
+                                 (131072, 1), (333, 7), (4096, 2), (512, 200), (64, 200)])
 def test_running_mean_std_train_forward(m, c):
     from oracle import rl_games_oracle as rg
     g = torch.Generator().manual_seed(m + c)
