@@ -167,6 +167,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the ONE JSON line: this image exports NCCL_DEBUG=VERSION, which prints a banner on rank 0
+        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     ge.build()
     from bez_isaacgym_b200 import bez_model as bm, ops, synthetic_gym as sg
