@@ -4,15 +4,18 @@
 //
 // Layout facts (Isaac Gym AoS): per env, dof_state is 36 contiguous floats, root_states
 // 26 contiguous floats (2 actors x 13); rigid_body / net_contact are sparse (10 of 286 resp. 6 of 66
-// floats used).  One CTA owns a tile of TILE consecutive envs, one thread per env:
-//   * the two dense inputs of the tile are contiguous byte ranges -> two cp.async.bulk (TMA 1-D)
-//     copies into shared memory, completion on one mbarrier;
+// floats used).  One thread per env; every WARP owns a sub-tile of 32 consecutive envs (its own shared-memory
+// slice, mbarrier and bulk copies -- the kernel has no CTA-wide barrier):
+//   * the two dense inputs of the sub-tile are contiguous byte ranges -> two cp.async.bulk (TMA 1-D)
+//     copies into shared memory, completion on the warp's mbarrier;
 //   * the sparse rows are gathered with per-thread sector-aligned vector loads issued BEFORE the
 //     barrier wait, so they fly together with the bulk copies;
 //   * each thread reads its rows out of shared memory with bank-conflict-free 128-bit loads (row stride
 //     36 words), computes everything in registers, then the 54-float observation rows are written
-//     back into the SAME shared region (after a CTA barrier) and leave as one cp.async.bulk store of
-//     TILE*216 contiguous bytes.
+//     back into the SAME shared region (after a warp barrier) and leave as one cp.async.bulk store of
+//     32*216 contiguous bytes per warp.
+// Kernels are launched with the programmatic-dependent-launch attribute (prologue overlaps the previous kernel's
+// drain; griddepcontrol.wait precedes the first global access).
 // HBM-bound: 656-680 algorithmic B/env-step, no tensor cores.
 #include "bezk_common.cuh"
 #include "bezk_internal.h"
@@ -52,6 +55,8 @@ __global__ void __launch_bounds__(K0_THREADS) pre_physics_kernel(const float* __
                                                                  float* __restrict__ targets, const __grid_constant__ BezkTaskCfg cfg,
                                                                  int64_t n, int vec2) {
     const float clip = cfg.clip_actions;
+    pdl_launch_dependents();
+    pdl_wait();
     if (vec2) {
         const int pair = threadIdx.x % 9, rsub = threadIdx.x / 9;
         const int c0 = 2 * pair;
@@ -339,33 +344,46 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
     constexpr bool REW = (PARTS & BEZK_PART_REWARD) != 0;
     constexpr int NFORCE = CLEATS ? 12 : 3;
 
+    // Every WARP owns a sub-tile of 32 consecutive envs: its own slice of shared memory, its own mbarrier, its own bulk
+    // copies and bulk store.  Nothing in the kernel is CTA-wide (no __syncthreads): a warp whose data has arrived never
+    // waits for a sibling whose gathers are still in flight.
+    constexpr int WT = 32;
+    constexpr int WARPS = TILE / WT;
     extern __shared__ __align__(128) float smem[];
-    float* s_dof = smem;                              // [TILE][36]
-    float* s_root = smem + TILE * DOF_ROW;            // [TILE][26]
-    float* s_obs = smem;                              // [TILE][54], aliases the two input tiles
-    float* s_obs_clip = smem + smem_in_floats(TILE);  // [TILE][54], only when a.obs_clipped
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_bars[WARPS];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int64_t e0 = (int64_t)blockIdx.x * TILE;
-    const int nv = (int)((a.n - e0) < (int64_t)TILE ? (a.n - e0) : (int64_t)TILE);
-    const bool full = (nv == TILE) && a.use_tma;
-    const int64_t e = e0 + tid;
-    const bool valid = tid < nv;
+    const int warp = tid >> 5;
+    float* s_dof = smem + warp * smem_in_floats(WT);                              // [32][36]
+    float* s_root = s_dof + WT * DOF_ROW;                                          // [32][26]
+    float* s_obs = s_dof;                                                          // [32][54], aliases this warp's input tiles
+    float* s_obs_clip = smem + smem_in_floats(TILE) + warp * smem_obs_floats(WT);  // [32][54], only when a.obs_clipped
+    uint64_t* s_bar = &s_bars[warp];
 
-    // ---- 1. dense tiles: TMA bulk copies (full tiles) or cooperative coalesced loads (tail tile) ----
+    const int64_t e0 = (int64_t)blockIdx.x * TILE + warp * WT;                     // first env of this warp's sub-tile
+    const int64_t left = a.n - e0;
+    const int nv = (int)(left < 0 ? 0 : (left < (int64_t)WT ? left : (int64_t)WT));
+    const bool full = (nv == WT) && a.use_tma;
+    const int64_t e = e0 + lane;
+    const bool valid = lane < nv;
+
+    // ---- 1. dense tiles: TMA bulk copies (full sub-tiles) or cooperative coalesced loads (tail) ----
+    pdl_launch_dependents();               // the next kernel on the stream may be scheduled as our CTAs retire
+    if (full && lane == 0) {
+        mbar_init(s_bar, 1);
+        fence_mbar_init();
+    }
+    pdl_wait();                            // nothing above touches global memory
     if (full) {
-        if (tid == 0) {
-            mbar_init(&s_bar, 1);
-            fence_mbar_init();
-            mbar_arrive_expect_tx(&s_bar, TILE * (DOF_ROW + ROOT_ROW) * 4);
-            bulk_g2s(s_dof, a.dof_state + e0 * DOF_ROW, TILE * DOF_ROW * 4, &s_bar);
-            bulk_g2s(s_root, a.root_states + e0 * ROOT_ROW, TILE * ROOT_ROW * 4, &s_bar);
+        if (lane == 0) {
+            mbar_arrive_expect_tx(s_bar, WT * (DOF_ROW + ROOT_ROW) * 4);
+            bulk_g2s(s_dof, a.dof_state + e0 * DOF_ROW, WT * DOF_ROW * 4, s_bar);
+            bulk_g2s(s_root, a.root_states + e0 * ROOT_ROW, WT * ROOT_ROW * 4, s_bar);
         }
     } else {
-        for (int i = tid; i < nv * DOF_ROW; i += TILE) s_dof[i] = a.dof_state[e0 * DOF_ROW + i];
-        for (int i = tid; i < nv * ROOT_ROW; i += TILE) s_root[i] = a.root_states[e0 * ROOT_ROW + i];
+        for (int i = lane; i < nv * DOF_ROW; i += WT) s_dof[i] = a.dof_state[e0 * DOF_ROW + i];
+        for (int i = lane; i < nv * ROOT_ROW; i += WT) s_root[i] = a.root_states[e0 * ROOT_ROW + i];
     }
 
     // ---- 2. sparse gathers, issued before anyone waits (widest aligned vector loads available) ----
@@ -388,8 +406,8 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
     const float w[3] = {imu_in[7], imu_in[8], imu_in[9]};
 
     // ---- 3. wait for the dense tiles ----
-    __syncthreads();                       // mbarrier init / cooperative stores visible
-    if (full) mbar_wait(&s_bar, 0);
+    __syncwarp();                          // mbarrier init / cooperative stores visible to the whole warp
+    if (full) mbar_wait(s_bar, 0);
 
     // ---- 4. bookkeeping + masked reset (vec_task.py:331-332, kick_env.py:429-435, 779-850) ----
     // The reset of an env is done by its WARP: lanes 0..8 each run one Philox4x32 block (4 of the 36 draws),
@@ -398,11 +416,9 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
     int64_t timeout = 0, reset_cur = reset_prev;
     if (BOOK) {
         unsigned pending = __ballot_sync(0xffffffffu, valid && reset_prev != 0);
-        const int warp_row0 = tid - lane;
         while (pending) {
-            const int src = __ffs(pending) - 1;
+            const int r = __ffs(pending) - 1;
             pending &= pending - 1;
-            const int r = warp_row0 + src;
             const int64_t env = e0 + r;
             if (lane < 9) {
                 float u4[4];
@@ -456,13 +472,13 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
     float row[36];
     float bez[3] = {0.f, 0.f, 0.f}, ball_xy[2] = {0.f, 0.f}, ball_vxy[2] = {0.f, 0.f};
     if (valid) {
-        const float4* r4 = reinterpret_cast<const float4*>(s_dof + tid * DOF_ROW);
+        const float4* r4 = reinterpret_cast<const float4*>(s_dof + lane * DOF_ROW);
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
             const float4 t = r4[k];
             row[4 * k] = t.x; row[4 * k + 1] = t.y; row[4 * k + 2] = t.z; row[4 * k + 3] = t.w;
         }
-        const float* rr = s_root + tid * ROOT_ROW;
+        const float* rr = s_root + lane * ROOT_ROW;
         bez[0] = rr[0]; bez[1] = rr[1]; bez[2] = rr[2];
         ball_xy[0] = rr[13]; ball_xy[1] = rr[14];
         ball_vxy[0] = rr[20]; ball_vxy[1] = rr[21];
@@ -516,9 +532,9 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
         }
     }
     if (OBS) {
-        __syncthreads();                   // every thread has finished reading s_dof / s_root
+        __syncwarp();                      // every lane has finished reading its s_dof / s_root rows
         if (valid) {
-            float2* o2 = reinterpret_cast<float2*>(s_obs + tid * OBS_ROW);
+            float2* o2 = reinterpret_cast<float2*>(s_obs + lane * OBS_ROW);
 #pragma unroll
             for (int k = 0; k < 9; ++k) {  // dof_pos 0:18, dof_vel 18:36 (de-interleave of [pos, vel] pairs)
                 o2[k] = make_float2(row[4 * k], row[4 * k + 2]);
@@ -530,7 +546,7 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
             o2[24] = make_float2(feet[4], feet[5]); o2[25] = make_float2(feet[6], feet[7]);
             o2[26] = make_float2(binit[0], binit[1]);
             if (a.obs_clipped) {           // vec_task.py:343 clamp(obs_buf, -clip_obs, clip_obs)
-                float2* c2 = reinterpret_cast<float2*>(s_obs_clip + tid * OBS_ROW);
+                float2* c2 = reinterpret_cast<float2*>(s_obs_clip + lane * OBS_ROW);
                 const float lim = cfg.clip_obs;
 #pragma unroll
                 for (int k = 0; k < 27; ++k) {
@@ -541,17 +557,17 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
         }
         if (full) {
             fence_proxy_async_smem();
-            __syncthreads();
-            if (tid == 0) {
-                bulk_s2g(a.obs + e0 * OBS_ROW, s_obs, TILE * OBS_ROW * 4);
-                if (a.obs_clipped) bulk_s2g(a.obs_clipped + e0 * OBS_ROW, s_obs_clip, TILE * OBS_ROW * 4);
+            __syncwarp();
+            if (lane == 0) {
+                bulk_s2g(a.obs + e0 * OBS_ROW, s_obs, WT * OBS_ROW * 4);
+                if (a.obs_clipped) bulk_s2g(a.obs_clipped + e0 * OBS_ROW, s_obs_clip, WT * OBS_ROW * 4);
                 bulk_commit();
             }
         } else {
-            __syncthreads();
-            for (int i = tid; i < nv * OBS_ROW; i += TILE) a.obs[e0 * OBS_ROW + i] = s_obs[i];
+            __syncwarp();
+            for (int i = lane; i < nv * OBS_ROW; i += WT) a.obs[e0 * OBS_ROW + i] = s_obs[i];
             if (a.obs_clipped)
-                for (int i = tid; i < nv * OBS_ROW; i += TILE) a.obs_clipped[e0 * OBS_ROW + i] = s_obs_clip[i];
+                for (int i = lane; i < nv * OBS_ROW; i += WT) a.obs_clipped[e0 * OBS_ROW + i] = s_obs_clip[i];
         }
     }
 
@@ -574,7 +590,7 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
         if (BOOK) a.progress_out[e] = progress;
     }
 
-    if (OBS && full && tid == 0) bulk_wait_read0();   // shared memory must outlive the bulk store's reads
+    if (OBS && full && lane == 0) bulk_wait_read0();   // shared memory must outlive the bulk store's reads
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -632,8 +648,7 @@ static cudaError_t launch_parts3(const TaskArgs& a, const BezkTaskCfg& cfg, cuda
         attr_set = true;
     }
     const int64_t tiles = (a.n + TILE - 1) / TILE;
-    task_tile_kernel<PARTS, CLEATS, TILE><<<(unsigned)tiles, TILE, smem, st>>>(a, cfg);
-    return cudaGetLastError();
+    return launch_ex(task_tile_kernel<PARTS, CLEATS, TILE>, dim3((unsigned)tiles), dim3(TILE), smem, st, a, cfg);
 }
 
 template <int PARTS>
@@ -671,8 +686,7 @@ cudaError_t launch_pre_physics(const float* actions, float* actions_out, float* 
     int64_t blocks = vec2 ? (n + per_block - 1) / per_block : (n * 18 + K0_THREADS - 1) / K0_THREADS;
     if (blocks < 1) blocks = 1;
     if (!vec2 && blocks > 148LL * 64) blocks = 148LL * 64;      // scalar path is grid-strided
-    pre_physics_kernel<<<(unsigned)blocks, K0_THREADS, 0, st>>>(actions, actions_out, targets, cfg, n, vec2);
-    return cudaGetLastError();
+    return launch_ex(pre_physics_kernel, dim3((unsigned)blocks), dim3(K0_THREADS), 0, st, actions, actions_out, targets, cfg, n, vec2);
 }
 
 cudaError_t launch_reset_idx(const int64_t* env_ids, int64_t k, const float* uniforms, uint64_t seed, uint64_t step,
