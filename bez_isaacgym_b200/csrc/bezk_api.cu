@@ -141,7 +141,23 @@ int64_t bezk_rms_scratch_doubles(int32_t c) { return bezk::rms_scratch_doubles(c
 int bezk_rms_moments(const float* x, const double* pivot, double* acc, double* partials, int64_t m, int32_t c, void* stream) {
     REQUIRE(m > 0 && c > 0, "m/c must be positive");
     REQUIRE(x && acc && partials, "rms buffers NULL");
-    return cuda_rc(bezk::launch_rms_moments(x, pivot, acc, partials, m, c, (cudaStream_t)stream), "bezk_rms_moments");
+    return cuda_rc(bezk::launch_rms_moments(x, pivot, acc, partials, m, c, m, m, (cudaStream_t)stream), "bezk_rms_moments");
+}
+
+static int check_slabs(int64_t& slab_rows, int64_t& slab_stride, int64_t m) {
+    if (slab_rows <= 0 || slab_rows >= m) { slab_rows = m; slab_stride = m; return 0; }
+    REQUIRE(m % slab_rows == 0, "m must be a multiple of slab_rows");
+    REQUIRE(slab_stride >= slab_rows, "slab_stride < slab_rows (slabs would overlap)");
+    return 0;
+}
+
+int bezk_rms_moments_slabs(const float* x, int64_t slab_rows, int64_t slab_stride, const double* pivot, double* acc,
+                           double* partials, int64_t m, int32_t c, void* stream) {
+    REQUIRE(m > 0 && c > 0, "m/c must be positive");
+    REQUIRE(x && acc && partials, "rms buffers NULL");
+    if (int rc = check_slabs(slab_rows, slab_stride, m)) return rc;
+    return cuda_rc(bezk::launch_rms_moments(x, pivot, acc, partials, m, c, slab_rows, slab_stride, (cudaStream_t)stream),
+                   "bezk_rms_moments_slabs");
 }
 
 int bezk_rms_merge(const double* acc, const double* pivot, double* running_mean, double* running_var, double* count, int32_t c,
@@ -156,8 +172,19 @@ int bezk_rms_normalize(const float* x, const double* running_mean, const double*
     REQUIRE(m >= 0 && c > 0 && c <= 4096, "bad m/c");
     if (m == 0) return 0;
     REQUIRE(x && y && running_mean && running_var, "rms buffers NULL");
-    return cuda_rc(bezk::launch_rms_normalize(x, running_mean, running_var, eps, unnorm, y, m, c, (cudaStream_t)stream),
+    return cuda_rc(bezk::launch_rms_normalize(x, running_mean, running_var, eps, unnorm, y, m, c, m, m, (cudaStream_t)stream),
                    "bezk_rms_normalize");
+}
+
+int bezk_rms_normalize_slabs(const float* x, int64_t slab_rows, int64_t slab_stride, const double* running_mean,
+                             const double* running_var, float eps, int unnorm, float* y, int64_t m, int32_t c, void* stream) {
+    REQUIRE(m >= 0 && c > 0 && c <= 4096, "bad m/c");
+    if (m == 0) return 0;
+    REQUIRE(x && y && running_mean && running_var, "rms buffers NULL");
+    if (int rc = check_slabs(slab_rows, slab_stride, m)) return rc;
+    REQUIRE(m / slab_rows <= 65535, "more than 65535 slabs");
+    return cuda_rc(bezk::launch_rms_normalize(x, running_mean, running_var, eps, unnorm, y, m, c, slab_rows, slab_stride,
+                                              (cudaStream_t)stream), "bezk_rms_normalize_slabs");
 }
 
 int bezk_adv_moments(const float* returns, const float* values, double* acc, double* partials, int64_t m, void* stream) {
@@ -176,10 +203,11 @@ int bezk_adv_normalize(const float* returns, const float* values, const double* 
 
 int64_t bezk_ppo_scratch_doubles(void) { return bezk::ppo_scratch_doubles(); }
 
-int bezk_ppo_loss(const float* actions, const float* mu, const float* logstd, const float* old_mu, const float* old_sigma,
-                  const float* values, const float* old_values, const float* returns, const float* old_neglogp,
-                  const float* advantages, const BezkPpoCfg* cfg, double* stats, float* grad_mu, float* grad_values,
-                  float* grad_logstd, float* neglogp_out, double* partials, int64_t m, void* stream) {
+static int ppo_impl(const float* actions, const float* mu, const float* logstd, const float* old_mu, const float* old_sigma,
+                    const float* values, const float* old_values, const float* returns, const float* old_neglogp,
+                    const float* advantages, int64_t slab_rows, int64_t slab_stride, const BezkPpoCfg* cfg, double* stats,
+                    float* grad_mu, float* grad_values, float* grad_logstd, float* neglogp_out, double* partials, int64_t m,
+                    void* stream) {
     REQUIRE(cfg, "cfg NULL");
     REQUIRE(m > 0, "m must be positive");
     REQUIRE(actions && mu && logstd && old_mu && old_sigma && values && old_values && returns && old_neglogp && advantages &&
@@ -190,7 +218,60 @@ int bezk_ppo_loss(const float* actions, const float* mu, const float* logstd, co
     a.actions = actions; a.mu = mu; a.logstd = logstd; a.old_mu = old_mu; a.old_sigma = old_sigma; a.values = values;
     a.old_values = old_values; a.returns = returns; a.old_neglogp = old_neglogp; a.advantages = advantages;
     a.grad_mu = grad_mu; a.grad_values = grad_values; a.neglogp_out = neglogp_out; a.partials = partials; a.m = m; a.use_tma = 0;
+    if (int rc = check_slabs(slab_rows, slab_stride, m)) return rc;
+    a.slab_rows = slab_rows; a.slab_stride = slab_stride; a.slabs = 0;
     return cuda_rc(bezk::launch_ppo_loss(a, *cfg, stats, grad_logstd, (cudaStream_t)stream), "bezk_ppo_loss");
+}
+
+int bezk_ppo_loss(const float* actions, const float* mu, const float* logstd, const float* old_mu, const float* old_sigma,
+                  const float* values, const float* old_values, const float* returns, const float* old_neglogp,
+                  const float* advantages, const BezkPpoCfg* cfg, double* stats, float* grad_mu, float* grad_values,
+                  float* grad_logstd, float* neglogp_out, double* partials, int64_t m, void* stream) {
+    return ppo_impl(actions, mu, logstd, old_mu, old_sigma, values, old_values, returns, old_neglogp, advantages, m, m, cfg, stats,
+                    grad_mu, grad_values, grad_logstd, neglogp_out, partials, m, stream);
+}
+
+int bezk_ppo_loss_slabs(const float* actions, const float* mu, const float* logstd, const float* old_mu, const float* old_sigma,
+                        const float* values, const float* old_values, const float* returns, const float* old_neglogp,
+                        const float* advantages, int64_t slab_rows, int64_t slab_stride, const BezkPpoCfg* cfg, double* stats,
+                        float* grad_mu, float* grad_values, float* grad_logstd, float* neglogp_out, double* partials, int64_t m,
+                        void* stream) {
+    return ppo_impl(actions, mu, logstd, old_mu, old_sigma, values, old_values, returns, old_neglogp, advantages, slab_rows,
+                    slab_stride, cfg, stats, grad_mu, grad_values, grad_logstd, neglogp_out, partials, m, stream);
+}
+
+int bezk_swap_and_flatten01(const void* src, void* dst, int32_t horizon, int64_t num_envs, int64_t env0, int64_t envs,
+                            int32_t row_bytes, void* stream) {
+    REQUIRE(horizon >= 0 && num_envs >= 0 && env0 >= 0 && envs >= 0 && row_bytes >= 0, "negative size");
+    REQUIRE(env0 + envs <= num_envs, "env range outside num_envs");
+    if (horizon == 0 || envs == 0 || row_bytes == 0) return 0;
+    REQUIRE(src && dst, "src/dst NULL");
+    return cuda_rc(bezk::launch_swap_flatten(src, dst, horizon, num_envs, env0, envs, row_bytes, (cudaStream_t)stream),
+                   "bezk_swap_and_flatten01");
+}
+
+int bezk_policy_head(const float* mu, const float* logstd, const float* value_norm, const double* value_mean,
+                     const double* value_var, float value_eps, const float* noise, uint64_t seed, uint64_t step, float* actions,
+                     float* neglogp, float* values, float* mus, float* sigmas, const BezkTaskCfg* task_cfg, float* env_actions,
+                     float* targets, int64_t n, void* stream) {
+    REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return 0;
+    REQUIRE(mu && logstd, "mu/logstd NULL");
+    REQUIRE(!values || value_norm, "values requested without value_norm");
+    REQUIRE((value_mean == nullptr) == (value_var == nullptr), "value_mean and value_var go together");
+    REQUIRE(!targets || task_cfg, "targets requested without task_cfg");
+    if (task_cfg) { if (int rc = check_cfg(task_cfg)) return rc; }
+    REQUIRE(ALIGNED(mu, 8) && (!noise || ALIGNED(noise, 8)), "mu / noise must be 8-byte aligned");
+    return cuda_rc(bezk::launch_policy_head(mu, logstd, value_norm, value_mean, value_var, value_eps, noise, seed, step, actions,
+                                            neglogp, values, mus, sigmas, task_cfg, env_actions, targets, n, (cudaStream_t)stream),
+                   "bezk_policy_head");
+}
+
+int bezk_normal_noise(uint64_t seed, uint64_t step, float* out, int64_t n, void* stream) {
+    REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return 0;
+    REQUIRE(out, "out NULL");
+    return cuda_rc(bezk::launch_normal_noise(seed, step, out, n, (cudaStream_t)stream), "bezk_normal_noise");
 }
 
 }  // extern "C"

@@ -36,6 +36,8 @@ struct PpoArgs {
     float *grad_mu, *grad_values, *neglogp_out;
     double* partials;
     int64_t m;
+    int64_t slab_rows, slab_stride;   // rollout-side tensors as slabs of time-major storage (slab_rows == m: contiguous)
+    int slabs;
     int use_tma;
 };
 cudaError_t launch_task(int parts, const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st);
@@ -47,11 +49,17 @@ cudaError_t launch_philox_uniforms(uint64_t, uint64_t, float*, int64_t, cudaStre
 cudaError_t launch_gae(const float*, const float*, const void*, const float*, const void*, int, double, double, float*, float*,
                        int, int64_t, cudaStream_t);
 int64_t rms_scratch_doubles(int c);
-cudaError_t launch_rms_moments(const float*, const double*, double*, double*, int64_t, int, cudaStream_t);
+cudaError_t launch_rms_moments(const float*, const double*, double*, double*, int64_t, int, int64_t, int64_t, cudaStream_t);
 cudaError_t launch_rms_merge(const double*, const double*, double*, double*, double*, int, cudaStream_t);
-cudaError_t launch_rms_normalize(const float*, const double*, const double*, float, int, float*, int64_t, int, cudaStream_t);
+cudaError_t launch_rms_normalize(const float*, const double*, const double*, float, int, float*, int64_t, int, int64_t, int64_t,
+                                 cudaStream_t);
 cudaError_t launch_adv_moments(const float*, const float*, double*, double*, int64_t, cudaStream_t);
 cudaError_t launch_adv_normalize(const float*, const float*, const double*, float*, int, int64_t, cudaStream_t);
+cudaError_t launch_swap_flatten(const void*, void*, int, int64_t, int64_t, int64_t, int, cudaStream_t);
+cudaError_t launch_policy_head(const float*, const float*, const float*, const double*, const double*, float, const float*, uint64_t,
+                               uint64_t, float*, float*, float*, float*, float*, const BezkTaskCfg*, float*, float*, int64_t,
+                               cudaStream_t);
+cudaError_t launch_normal_noise(uint64_t, uint64_t, float*, int64_t, cudaStream_t);
 int64_t ppo_scratch_doubles();
 cudaError_t launch_ppo_loss(const PpoArgs&, const BezkPpoCfg&, double*, float*, cudaStream_t);
 }  // namespace bezk

@@ -9,6 +9,13 @@
 
 namespace bezk {
 
+// Slab addressing: a batch of m rows read straight out of time-major rollout storage.  Batch row r lives at source row
+// (r / slab_rows) * slab_stride + r % slab_rows of the (already offset) base pointer; slab_rows == m means contiguous.
+__device__ __forceinline__ int64_t slab_src_row(int64_t r, int64_t slab_rows, int64_t slab_stride) {
+    const int64_t s = r / slab_rows;
+    return s * slab_stride + (r - s * slab_rows);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K6: GAE.  One thread per env keeps (lastgaelam, next value, next non-terminal) in registers and
 // walks the horizon backwards; for a fixed t a warp touches 32 consecutive floats of every array.
@@ -87,7 +94,8 @@ constexpr int RMS_MAX_C = 256;                  // columns supported by the mult
 
 template <int VEC>
 __global__ void __launch_bounds__(RMS_THREADS) rms_partials_kernel(const float* __restrict__ x, const double* __restrict__ pivot,
-                                                                   double* __restrict__ partials, int64_t m, int c) {
+                                                                   double* __restrict__ partials, int64_t m, int c,
+                                                                   int64_t slab_rows, int64_t slab_stride) {
     extern __shared__ double s_red[];           // [2][rpi][c]
     const int cg = c / VEC;
     const int rpi = RMS_THREADS / cg;           // rows per iteration (>= 1 because c <= RMS_MAX_C)
@@ -105,7 +113,7 @@ __global__ void __launch_bounds__(RMS_THREADS) rms_partials_kernel(const float* 
             float xv[RMS_UNROLL][VEC];
 #pragma unroll
             for (int u = 0; u < RMS_UNROLL; ++u) {
-                const float* p = x + (r + u * row_stride) * c + g * VEC;
+                const float* p = x + slab_src_row(r + u * row_stride, slab_rows, slab_stride) * c + g * VEC;
                 // volatile asm loads: issued as one batch (the compiler otherwise interleaves load/use and keeps 1-2 in flight)
                 if (VEC == 2) asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(xv[u][0]), "=f"(xv[u][VEC - 1]) : "l"(p));
                 else xv[u][0] = ldg_stream(p);
@@ -125,7 +133,7 @@ __global__ void __launch_bounds__(RMS_THREADS) rms_partials_kernel(const float* 
                 for (int k = 0; k < VEC; ++k) { const double d = (double)xv[u][k] - pv[k]; s[k] += d; ss[k] += d * d; }
         }
         for (; r < m; r += row_stride) {
-            const float* p = x + r * c + g * VEC;
+            const float* p = x + slab_src_row(r, slab_rows, slab_stride) * c + g * VEC;
 #pragma unroll
             for (int k = 0; k < VEC; ++k) { const double d = (double)p[k] - pv[k]; s[k] += d; ss[k] += d * d; }
         }
@@ -153,7 +161,8 @@ constexpr int RMS_TR = 64;                      // rows per tile
 constexpr int RMS_STAGES = 4;
 
 __global__ void __launch_bounds__(RMS_THREADS) rms_partials_tma_kernel(const float* __restrict__ x, const double* __restrict__ pivot,
-                                                                       double* __restrict__ partials, int64_t m, int c) {
+                                                                       double* __restrict__ partials, int64_t m, int c,
+                                                                       int64_t slab_rows, int64_t slab_stride) {
     extern __shared__ __align__(128) unsigned char rms_smem[];
     __shared__ __align__(8) uint64_t s_full[RMS_STAGES];
     float* s_tile = reinterpret_cast<float*>(rms_smem);                       // [RMS_STAGES][RMS_TR * c]
@@ -177,7 +186,8 @@ __global__ void __launch_bounds__(RMS_THREADS) rms_partials_tma_kernel(const flo
         const int64_t rows = (m - r0) < (int64_t)RMS_TR ? (m - r0) : (int64_t)RMS_TR;
         const uint32_t bytes = (uint32_t)(rows * c * 4);
         mbar_arrive_expect_tx(&s_full[stage], bytes);
-        bulk_g2s(s_tile + (size_t)stage * tile_floats, x + r0 * c, bytes, &s_full[stage]);
+        // slab mode: slab_rows is a multiple of RMS_TR (checked by the launcher), so a tile never straddles two slabs
+        bulk_g2s(s_tile + (size_t)stage * tile_floats, x + slab_src_row(r0, slab_rows, slab_stride) * c, bytes, &s_full[stage]);
     };
     // this CTA's tiles: blockIdx.x, +gridDim.x, ...
     int64_t my_tiles = 0;
@@ -219,23 +229,26 @@ __global__ void __launch_bounds__(RMS_THREADS) rms_partials_tma_kernel(const flo
 // flat (c == 1) moments of x, or of (a - b) when b != nullptr (advantage = returns - values in fp32)
 __global__ void __launch_bounds__(RMS_THREADS) flat_partials_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                                     const double* __restrict__ pivot, double* __restrict__ partials,
-                                                                    int64_t m, int vec4) {
+                                                                    int64_t m, int vec4, int64_t slab_rows, int64_t slab_stride) {
     __shared__ double s_w[2][RMS_THREADS / 32];
     const double pv = pivot ? pivot[0] : 0.0;
     double s = 0.0, ss = 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nvec = vec4 ? (m >> 2) : 0;
+    const bool slabs = slab_rows < m;                     // vec4 then implies slab_rows % 4 == 0 and slab_stride % 4 == 0
     for (int64_t i = tid; i < nvec; i += stride) {
-        float4 t = ldg_stream4(reinterpret_cast<const float4*>(a) + i);
-        if (b) { const float4 u = ldg_stream4(reinterpret_cast<const float4*>(b) + i); t.x -= u.x; t.y -= u.y; t.z -= u.z; t.w -= u.w; }
+        const int64_t si = slabs ? (slab_src_row(i * 4, slab_rows, slab_stride) >> 2) : i;
+        float4 t = ldg_stream4(reinterpret_cast<const float4*>(a) + si);
+        if (b) { const float4 u = ldg_stream4(reinterpret_cast<const float4*>(b) + si); t.x -= u.x; t.y -= u.y; t.z -= u.z; t.w -= u.w; }
         const double d0 = (double)t.x - pv, d1 = (double)t.y - pv, d2 = (double)t.z - pv, d3 = (double)t.w - pv;
         s += (d0 + d1) + (d2 + d3);
         ss += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
     }
     for (int64_t i = nvec * 4 + tid; i < m; i += stride) {
-        float t = a[i];
-        if (b) t -= b[i];
+        const int64_t si = slabs ? slab_src_row(i, slab_rows, slab_stride) : i;
+        float t = a[si];
+        if (b) t -= b[si];
         const double d = (double)t - pv;
         s += d; ss += d * d;
     }
@@ -307,7 +320,12 @@ __global__ void rms_merge_kernel(const double* __restrict__ acc, const double* _
 // K5: normalise / un-normalise
 __global__ void __launch_bounds__(256) rms_normalize_kernel(const float* __restrict__ x, const double* __restrict__ running_mean,
                                                             const double* __restrict__ running_var, float eps, int unnorm,
-                                                            float* __restrict__ y, int64_t total, int c, int vec4) {
+                                                            float* __restrict__ y, int64_t total, int c, int vec4,
+                                                            int64_t slab_src_elems) {
+    // blockIdx.y = slab: `total` elements of THIS slab, read from x + blockIdx.y * slab_src_elems, written to
+    // y + blockIdx.y * total (one slab = the whole array in the contiguous case)
+    x += (int64_t)blockIdx.y * slab_src_elems;
+    y += (int64_t)blockIdx.y * total;
     extern __shared__ float s_stat[];       // [2][c]: mean.float(), sqrt(var.float() + eps)
     for (int j = threadIdx.x; j < c; j += blockDim.x) {
         s_stat[j] = (float)running_mean[j];
@@ -350,16 +368,20 @@ static inline int stream_blocks(int64_t work_items, int threads, int per_sm) {
 int64_t rms_scratch_doubles(int c) { return (int64_t)RMS_MAX_BLOCKS * 2 * (c > 0 ? c : 1); }
 
 cudaError_t launch_rms_moments(const float* x, const double* pivot, double* acc, double* partials, int64_t m, int c,
-                               cudaStream_t st) {
+                               int64_t slab_rows, int64_t slab_stride, cudaStream_t st) {
     int nblocks;
+    if (slab_rows <= 0 || slab_rows >= m) { slab_rows = m; slab_stride = m; }
+    if (m % slab_rows != 0) return cudaErrorInvalidValue;
+    const bool slabs = slab_rows < m;
     if (c == 1) {
-        const int vec4 = aligned16(x);
+        const int vec4 = aligned16(x) && (!slabs || (slab_rows % 4 == 0 && slab_stride % 4 == 0));
         nblocks = stream_blocks(vec4 ? m / 4 : m, RMS_THREADS, 4);
-        flat_partials_kernel<<<nblocks, RMS_THREADS, 0, st>>>(x, nullptr, pivot, partials, m, vec4);
+        flat_partials_kernel<<<nblocks, RMS_THREADS, 0, st>>>(x, nullptr, pivot, partials, m, vec4, slab_rows, slab_stride);
     } else {
         if (c > RMS_MAX_C) return cudaErrorInvalidValue;
         // TMA path: every tile start (64 rows) and every tile size must be a multiple of 16 bytes
-        const bool tma_ok = aligned16(x) && ((RMS_TR * c * 4) % 16 == 0) && (((m % RMS_TR) * c * 4) % 16 == 0) && m >= 4 * RMS_TR;
+        const bool tma_ok = aligned16(x) && ((RMS_TR * c * 4) % 16 == 0) && (((m % RMS_TR) * c * 4) % 16 == 0) && m >= 4 * RMS_TR &&
+                            (!slabs || (slab_rows % RMS_TR == 0 && (slab_stride * c * 4) % 16 == 0));
         if (tma_ok) {
             const int64_t ntiles = (m + RMS_TR - 1) / RMS_TR;
             size_t smem = (size_t)RMS_STAGES * RMS_TR * c * sizeof(float);
@@ -377,13 +399,13 @@ cudaError_t launch_rms_moments(const float* x, const double* pivot, double* acc,
             int64_t cap = 148LL * per_sm;
             if (cap > RMS_MAX_BLOCKS) cap = RMS_MAX_BLOCKS;
             nblocks = (int)(ntiles < cap ? ntiles : cap);
-            rms_partials_tma_kernel<<<nblocks, RMS_THREADS, smem, st>>>(x, pivot, partials, m, c);
+            rms_partials_tma_kernel<<<nblocks, RMS_THREADS, smem, st>>>(x, pivot, partials, m, c, slab_rows, slab_stride);
             cudaError_t err = cudaGetLastError();
             if (err != cudaSuccess) return err;
             moments_finalize_kernel<<<(2 * c + 7) / 8, 256, 0, st>>>(partials, nblocks, c, m, acc);
             return cudaGetLastError();
         }
-        const bool v2 = (c % 2 == 0) && aligned8(x);
+        const bool v2 = (c % 2 == 0) && aligned8(x);      // rows start at multiples of c floats: even c keeps 8-byte alignment in slab mode too
         const int cg = v2 ? c / 2 : c;
         const int rpi = RMS_THREADS / cg;
         int64_t b = (m + rpi - 1) / rpi;
@@ -391,8 +413,8 @@ cudaError_t launch_rms_moments(const float* x, const double* pivot, double* acc,
         if (b < 1) b = 1;
         nblocks = (int)(b > RMS_MAX_BLOCKS ? RMS_MAX_BLOCKS : b);
         const size_t smem = (size_t)2 * rpi * c * sizeof(double);
-        if (v2) rms_partials_kernel<2><<<nblocks, RMS_THREADS, smem, st>>>(x, pivot, partials, m, c);
-        else rms_partials_kernel<1><<<nblocks, RMS_THREADS, smem, st>>>(x, pivot, partials, m, c);
+        if (v2) rms_partials_kernel<2><<<nblocks, RMS_THREADS, smem, st>>>(x, pivot, partials, m, c, slab_rows, slab_stride);
+        else rms_partials_kernel<1><<<nblocks, RMS_THREADS, smem, st>>>(x, pivot, partials, m, c, slab_rows, slab_stride);
     }
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
@@ -408,12 +430,19 @@ cudaError_t launch_rms_merge(const double* acc, const double* pivot, double* run
 }
 
 cudaError_t launch_rms_normalize(const float* x, const double* running_mean, const double* running_var, float eps,
-                                 int unnorm, float* y, int64_t m, int c, cudaStream_t st) {
-    const int64_t total = m * c;
-    if (total == 0) return cudaSuccess;
-    const int vec4 = aligned16(x) && aligned16(y);
-    const int blocks = stream_blocks(vec4 ? total / 4 : total, 256, 8);
-    rms_normalize_kernel<<<blocks, 256, 2 * c * sizeof(float), st>>>(x, running_mean, running_var, eps, unnorm, y, total, c, vec4);
+                                 int unnorm, float* y, int64_t m, int c, int64_t slab_rows, int64_t slab_stride, cudaStream_t st) {
+    if (m * c == 0) return cudaSuccess;
+    if (slab_rows <= 0 || slab_rows >= m) { slab_rows = m; slab_stride = m; }
+    if (m % slab_rows != 0) return cudaErrorInvalidValue;
+    const int64_t nslabs = m / slab_rows;
+    if (nslabs > 65535) return cudaErrorInvalidValue;
+    const int64_t total = slab_rows * c;                 // elements per slab
+    const int vec4 = aligned16(x) && aligned16(y) && (nslabs == 1 || (total % 4 == 0 && (slab_stride * c) % 4 == 0));
+    int blocks = stream_blocks(vec4 ? total / 4 : total, 256, 8);
+    const int per_slab_cap = (int)((148 * 8 + nslabs - 1) / nslabs);
+    if (blocks > per_slab_cap) blocks = per_slab_cap;
+    rms_normalize_kernel<<<dim3((unsigned)blocks, (unsigned)nslabs), 256, 2 * c * sizeof(float), st>>>(
+        x, running_mean, running_var, eps, unnorm, y, total, c, vec4, slab_stride * c);
     return cudaGetLastError();
 }
 
@@ -452,7 +481,7 @@ cudaError_t launch_adv_moments(const float* returns, const float* values, double
                                cudaStream_t st) {
     const int vec4 = aligned16(returns) && aligned16(values);
     const int nblocks = stream_blocks(vec4 ? m / 4 : m, RMS_THREADS, 4);
-    flat_partials_kernel<<<nblocks, RMS_THREADS, 0, st>>>(returns, values, nullptr, partials, m, vec4);
+    flat_partials_kernel<<<nblocks, RMS_THREADS, 0, st>>>(returns, values, nullptr, partials, m, vec4, m, m);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     moments_finalize_kernel<<<1, 256, 0, st>>>(partials, nblocks, 1, m, acc);
@@ -536,25 +565,31 @@ __global__ void __launch_bounds__(PPO_TILE, 4) ppo_loss_kernel(const PpoArgs a, 
         const bool full = (nv == PPO_TILE) && a.use_tma;
         const int64_t i = i0 + tid;
         const bool valid = tid < nv;
+        // rollout-side tensors (actions, old_*, returns, advantages) may be slabs of time-major storage; the network-side
+        // ones (mu, values) and every output are contiguous batch rows.  TMA tiles never straddle a slab (launcher check).
+        const int64_t j0 = a.slabs ? slab_src_row(i0, a.slab_rows, a.slab_stride) : i0;
+        const int64_t ji = a.slabs ? ((full || !valid) ? j0 + tid : slab_src_row(i, a.slab_rows, a.slab_stride)) : i;
 
         if (tid == 0 && store_pending) bulk_wait_read0();          // s_gmu of the previous tile has been read out
         __syncthreads();                                           // everybody is done with the previous tile's rows
         if (full) {
             if (tid == 0) {
                 mbar_arrive_expect_tx(&s_bar, 4 * TILE_BYTES);
-                bulk_g2s(s_act, a.actions + i0 * 18, TILE_BYTES, &s_bar);
+                bulk_g2s(s_act, a.actions + j0 * 18, TILE_BYTES, &s_bar);
                 bulk_g2s(s_mu, a.mu + i0 * 18, TILE_BYTES, &s_bar);
-                bulk_g2s(s_omu, a.old_mu + i0 * 18, TILE_BYTES, &s_bar);
-                bulk_g2s(s_osig, a.old_sigma + i0 * 18, TILE_BYTES, &s_bar);
+                bulk_g2s(s_omu, a.old_mu + j0 * 18, TILE_BYTES, &s_bar);
+                bulk_g2s(s_osig, a.old_sigma + j0 * 18, TILE_BYTES, &s_bar);
             }
         } else {
             for (int k = tid; k < nv * 18; k += PPO_TILE) {
-                s_act[k] = a.actions[i0 * 18 + k]; s_mu[k] = a.mu[i0 * 18 + k];
-                s_omu[k] = a.old_mu[i0 * 18 + k]; s_osig[k] = a.old_sigma[i0 * 18 + k];
+                const int row = k / 18;
+                const int64_t jk = (a.slabs ? slab_src_row(i0 + row, a.slab_rows, a.slab_stride) : (i0 + row)) * 18 + (k - row * 18);
+                s_act[k] = a.actions[jk]; s_mu[k] = a.mu[i0 * 18 + k];
+                s_omu[k] = a.old_mu[jk]; s_osig[k] = a.old_sigma[jk];
             }
         }
         float val = 0.f, oval = 0.f, ret = 0.f, onlp = 0.f, adv = 0.f;
-        if (valid) { val = a.values[i]; oval = a.old_values[i]; ret = a.returns[i]; onlp = a.old_neglogp[i]; adv = a.advantages[i]; }
+        if (valid) { val = a.values[i]; oval = a.old_values[ji]; ret = a.returns[ji]; onlp = a.old_neglogp[ji]; adv = a.advantages[ji]; }
         if (full) { mbar_wait(&s_bar, phase); phase ^= 1u; }
         else __syncthreads();
 
@@ -694,8 +729,12 @@ cudaError_t launch_ppo_loss(const PpoArgs& args, const BezkPpoCfg& cfg, double* 
     if (a.m <= 0) return cudaErrorInvalidValue;
     const int64_t ntiles = (a.m + PPO_TILE - 1) / PPO_TILE;
     const int nblocks = (int)(ntiles < PPO_MAX_BLOCKS ? ntiles : PPO_MAX_BLOCKS);
+    if (a.slab_rows <= 0 || a.slab_rows >= a.m) { a.slab_rows = a.m; a.slab_stride = a.m; }
+    if (a.m % a.slab_rows != 0) return cudaErrorInvalidValue;
+    a.slabs = a.slab_rows < a.m;
     a.use_tma = aligned16(a.actions) && aligned16(a.mu) && aligned16(a.old_mu) && aligned16(a.old_sigma) &&
-                (a.grad_mu == nullptr || aligned16(a.grad_mu));
+                (a.grad_mu == nullptr || aligned16(a.grad_mu)) &&
+                (!a.slabs || (a.slab_rows % PPO_TILE == 0 && (a.slab_stride * 18 * 4) % 16 == 0));
     ppo_loss_kernel<<<(unsigned)nblocks, PPO_TILE, 0, st>>>(a, cfg);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;

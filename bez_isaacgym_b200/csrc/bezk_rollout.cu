@@ -1,0 +1,275 @@
+// Rollout plumbing either side of the task step for B200 (sm_100a):
+//   * swap_and_flatten01 -- rl_games' (T, N, ...) -> (N*T, ...) env-major flattening as ONE tiled shared-memory
+//     transposition per tensor (the slab-addressed learner kernels in bezk_learner.cu need no flattening pass at all;
+//     this entry exists for callers that want rl_games' exact dataset layout);
+//   * policy_head -- everything rl_games does between the policy MLP and the simulator in play_steps: Normal sampling,
+//     neglogp, value un-normalisation, the experience-buffer writes (actions / neglogpacs / values / mus / sigmas slot t),
+//     preprocess_actions' clamp and K0's PD targets, in one pass over the (N,18) network output.
+// Both are HBM-bound streaming kernels.
+#include "bezk_common.cuh"
+#include "bezk_internal.h"
+#include <math.h>
+#include <string.h>
+
+namespace bezk {
+
+// ------------------------------------------------------------------------------------------------
+// swap_and_flatten01: dst[(e - env0) * T + t][:] = src[t * N + e][:],  rows of `w` elements of type E.
+// CTA tile = tb timesteps x eb envs: coalesced reads of eb*w-element runs (one per t), transposed placement in shared
+// memory, then the tile leaves as eb runs of tb*w elements (ONE contiguous run when tb == T).
+// ------------------------------------------------------------------------------------------------
+template <typename E>
+__global__ void __launch_bounds__(256) swap_flatten_kernel(const E* __restrict__ src, E* __restrict__ dst, int horizon, int64_t n,
+                                                           int64_t env0, int64_t envs, int w, int eb, int tb) {
+    extern __shared__ __align__(16) unsigned char sf_smem[];
+    E* tile = reinterpret_cast<E*>(sf_smem);                    // [eb][tb][w]
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t eblk0 = (int64_t)blockIdx.x * eb;
+    const int t0 = blockIdx.y * tb;
+    const int ebc = (int)((envs - eblk0) < (int64_t)eb ? (envs - eblk0) : (int64_t)eb);
+    const int tbc = (horizon - t0) < tb ? (horizon - t0) : tb;
+    const int run = ebc * w;                                     // contiguous source elements per timestep
+    const int total = tbc * run;
+    const int orun = tbc * w;                                    // contiguous destination elements per env
+    const int pitch = orun | 1;                                  // odd row pitch: the transposed placement below walks a column
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int t = idx / run, rem = idx - t * run;
+        const int e = rem / w, c = rem - e * w;
+        tile[e * pitch + t * w + c] = src[((int64_t)(t0 + t) * n + env0 + eblk0) * w + rem];
+    }
+    __syncthreads();
+    // with the whole horizon in the tile (tbc == horizon) the eb destination runs are adjacent: one linear run
+    E* d = dst + (eblk0 * (int64_t)horizon + t0) * w;
+    const int64_t dpitch = (int64_t)horizon * w;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int e = idx / orun, rem = idx - e * orun;
+        d[e * dpitch + rem] = tile[e * pitch + rem];
+    }
+}
+
+template <typename E>
+static cudaError_t launch_sf(const void* src, void* dst, int horizon, int64_t n, int64_t env0, int64_t envs, int w, cudaStream_t st) {
+    const int tb = horizon < 32 ? horizon : 32;
+    int64_t eb = 32768 / ((int64_t)tb * w * (int64_t)sizeof(E));
+    if (eb < 1) eb = 1;
+    if (eb > 256) eb = 256;
+    if (eb > envs) eb = envs;
+    const size_t smem = (size_t)(((int64_t)tb * w) | 1) * eb * sizeof(E);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;         // rows wider than 6 KB are not rollout tensors
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(swap_flatten_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = smem;
+    }
+    const dim3 grid((unsigned)((envs + eb - 1) / eb), (unsigned)((horizon + tb - 1) / tb));
+    return launch_ex(swap_flatten_kernel<E>, grid, dim3(256), smem, st, (const E*)src, (E*)dst, horizon, n, env0, envs, w, (int)eb, tb);
+}
+
+cudaError_t launch_swap_flatten(const void* src, void* dst, int horizon, int64_t n, int64_t env0, int64_t envs, int row_bytes,
+                                cudaStream_t st) {
+    if (envs == 0 || horizon == 0 || row_bytes == 0) return cudaSuccess;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst);
+    if (row_bytes % 8 == 0 && (al & 7u) == 0) return launch_sf<uint64_t>(src, dst, horizon, n, env0, envs, row_bytes / 8, st);
+    if (row_bytes % 4 == 0 && (al & 3u) == 0) return launch_sf<uint32_t>(src, dst, horizon, n, env0, envs, row_bytes / 4, st);
+    return launch_sf<uint8_t>(src, dst, horizon, n, env0, envs, row_bytes, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// policy_head.  rl_games ModelA2CContinuousLogStd.forward (is_train=False) + A2CBase.get_action_values (value
+// un-normalisation) + play_steps' experience-buffer writes + preprocess_actions + (optionally) K0.
+//   sigma = exp(logstd);  action = mu + sigma * eps;  neglogp = 0.5*sum(((a-mu)/sigma)^2) + 0.5*log(2pi)*18 + sum(logstd)
+//   value = sqrt(var.float() + eps_v) * clamp(v, -5, 5) + mean.float()
+//   env action = clamp(action, -1, 1) * 1 + 0  -> K0 (clip, zero head, + default pose, joint limits) -> targets
+// eps: caller's N(0,1) draws, or Philox4x32-10 keyed (seed, step, env) + Box-Muller (5 blocks -> 9 pairs per env).
+// One thread per env; the (128,18) tiles move by cp.async.bulk like the PPO-loss kernel's.
+// ------------------------------------------------------------------------------------------------
+constexpr int PH_TILE = 128;
+
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float* z0, float* z1) {
+    const float u1 = (float)((a >> 8) + 1u) * (1.0f / 16777216.0f);       // (0, 1]
+    const float u2 = (float)(b >> 8) * (1.0f / 16777216.0f);              // [0, 1)
+    const float r = sqrtf(-2.0f * logf(u1));
+    const float th = 6.283185307179586f * u2;
+    float sn, cs;
+    sincosf(th, &sn, &cs);                                                // one shared range reduction
+    *z0 = r * cs;
+    *z1 = r * sn;
+}
+
+// the 18 standard normals of env `e` at (seed, step): blocks j = 0..4 -> uniforms (x,y), (z,w) -> pairs 2j, 2j+1
+__device__ __forceinline__ void philox_normals18(uint64_t seed, uint64_t step, int64_t e, float (&z)[18]) {
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const uint32_t c0 = (uint32_t)e, c1 = (uint32_t)((uint64_t)e >> 32);
+    const uint32_t c2 = (uint32_t)step, c3h = ((uint32_t)(step >> 32) << 4);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const Philox4 r = philox4x32_10(c0, c1, c2, c3h + (uint32_t)j, k0 ^ 0x5851F42Du, k1);     // key tweak: stream distinct from the reset draws
+        float a, b;
+        box_muller(r.x, r.y, &a, &b);
+        if (4 * j < 18) { z[4 * j] = a; z[4 * j + 1] = b; }
+        box_muller(r.z, r.w, &a, &b);
+        if (4 * j + 2 < 18) { z[4 * j + 2] = a; z[4 * j + 3] = b; }
+    }
+}
+
+struct HeadArgs {
+    const float *mu, *logstd, *value_norm, *noise;
+    const double *value_mean, *value_var;
+    float value_eps;
+    uint64_t seed, step;
+    float *actions, *neglogp, *values, *mus, *sigmas, *env_actions, *targets;
+    int64_t n;
+    int use_tma, has_task;
+};
+
+__global__ void __launch_bounds__(PH_TILE) policy_head_kernel(const HeadArgs a, const __grid_constant__ BezkTaskCfg cfg) {
+    __shared__ __align__(128) float s_mu[PH_TILE * 18];
+    __shared__ __align__(128) float s_eps[PH_TILE * 18];       // noise in, then env actions out
+    __shared__ __align__(128) float s_act[PH_TILE * 18];
+    __shared__ __align__(128) float s_tgt[PH_TILE * 18];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ float s_sigma[18], s_logstd[18], s_isig[18];
+    const int tid = threadIdx.x;
+    constexpr uint32_t TILE_BYTES = PH_TILE * 18 * 4;
+    const int64_t i0 = (int64_t)blockIdx.x * PH_TILE;
+    const int nv = (int)((a.n - i0) < (int64_t)PH_TILE ? (a.n - i0) : (int64_t)PH_TILE);
+    const bool full = (nv == PH_TILE) && a.use_tma;
+    const int64_t i = i0 + tid;
+    const bool valid = tid < nv;
+
+    pdl_launch_dependents();
+    if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+    pdl_wait();
+    // 1/sigma once per CTA: (a - mu) / sigma becomes a multiply (<= 1 ulp from the reference's divide, as in the PPO-loss kernel)
+    if (tid < 18) { const float ls = a.logstd[tid]; s_logstd[tid] = ls; const float sg = expf(ls); s_sigma[tid] = sg; s_isig[tid] = 1.0f / sg; }
+    __syncthreads();
+    if (full) {
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&s_bar, a.noise ? 2 * TILE_BYTES : TILE_BYTES);
+            bulk_g2s(s_mu, a.mu + i0 * 18, TILE_BYTES, &s_bar);
+            if (a.noise) bulk_g2s(s_eps, a.noise + i0 * 18, TILE_BYTES, &s_bar);
+        }
+    } else {
+        for (int k = tid; k < nv * 18; k += PH_TILE) {
+            s_mu[k] = a.mu[i0 * 18 + k];
+            if (a.noise) s_eps[k] = a.noise[i0 * 18 + k];
+        }
+    }
+    float vnorm = 0.0f;
+    if (valid && a.value_norm) vnorm = a.value_norm[i];
+    float z[18];
+    if (!a.noise && valid) philox_normals18(a.seed, a.step, i, z);       // overlaps the tile load
+    if (full) mbar_wait(&s_bar, 0);
+    else __syncthreads();
+
+    if (valid) {
+        float lsum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 18; ++j) lsum += s_logstd[j];
+        float sq = 0.0f;
+        float2* mu2 = reinterpret_cast<float2*>(s_mu + tid * 18);
+        float2* eps2 = reinterpret_cast<float2*>(s_eps + tid * 18);
+        float2* act2 = reinterpret_cast<float2*>(s_act + tid * 18);
+        float2* tgt2 = reinterpret_cast<float2*>(s_tgt + tid * 18);
+#pragma unroll
+        for (int h = 0; h < 9; ++h) {
+            const float2 M = mu2[h];
+            float2 E;
+            if (a.noise) E = eps2[h]; else E = make_float2(z[2 * h], z[2 * h + 1]);
+            const float mv[2] = {M.x, M.y}, ev[2] = {E.x, E.y};
+            float av[2], cv[2], tv[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int j = 2 * h + q;
+                const float sg = s_sigma[j];
+                av[q] = mv[q] + sg * ev[q];                              // Normal(mu, sigma).sample()
+                const float zz = (av[q] - mv[q]) * s_isig[j];            // models.py neglogp
+                sq += zz * zz;
+                cv[q] = clamp_nan(av[q], -1.0f, 1.0f) * 1.0f + 0.0f;     // preprocess_actions: clamp, rescale_actions(-1, 1)
+                float stored;
+                tv[q] = a.has_task ? k0_target(cv[q], j < 2, cfg.clip_actions, cfg.default_dof_pos[j], cfg.dof_lower[j],
+                                                   cfg.dof_upper[j], &stored) : 0.0f;
+            }
+            act2[h] = make_float2(av[0], av[1]);
+            eps2[h] = make_float2(cv[0], cv[1]);                         // s_eps now holds the env actions
+            tgt2[h] = make_float2(tv[0], tv[1]);
+        }
+        if (a.neglogp) a.neglogp[i] = (0.5f * sq + (float)(0.5 * 1.8378770664093453 * 18.0)) + lsum;
+        if (a.values) {
+            float v = vnorm;
+            if (a.value_mean) {
+                const float mean = (float)a.value_mean[0];
+                const float den = sqrtf((float)a.value_var[0] + a.value_eps);
+                v = den * clamp_nan(vnorm, -5.0f, 5.0f) + mean;          // RunningMeanStd(unnorm=True)
+            }
+            a.values[i] = v;
+        }
+    }
+    // ---- tiles out ----
+    if (full) {
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            if (a.actions) bulk_s2g(a.actions + i0 * 18, s_act, TILE_BYTES);
+            if (a.mus) bulk_s2g(a.mus + i0 * 18, s_mu, TILE_BYTES);
+            if (a.env_actions) bulk_s2g(a.env_actions + i0 * 18, s_eps, TILE_BYTES);
+            if (a.targets) bulk_s2g(a.targets + i0 * 18, s_tgt, TILE_BYTES);
+            bulk_commit();
+        }
+        // sigmas rows are all the same 18 values: the tile is an 18-periodic pattern, written as coalesced float4 stores
+        if (a.sigmas) {
+            float4* d4 = reinterpret_cast<float4*>(a.sigmas + i0 * 18);
+            for (int k = tid; k < PH_TILE * 18 / 4; k += PH_TILE) {
+                const int c = (4 * k) % 18;
+                __stcs(d4 + k, make_float4(s_sigma[c], s_sigma[(c + 1) % 18], s_sigma[(c + 2) % 18], s_sigma[(c + 3) % 18]));
+            }
+        }
+        if (tid == 0) bulk_wait_read0();
+    } else {
+        __syncthreads();
+        for (int k = tid; k < nv * 18; k += PH_TILE) {
+            if (a.actions) a.actions[i0 * 18 + k] = s_act[k];
+            if (a.mus) a.mus[i0 * 18 + k] = s_mu[k];
+            if (a.sigmas) a.sigmas[i0 * 18 + k] = s_sigma[k % 18];
+            if (a.env_actions) a.env_actions[i0 * 18 + k] = s_eps[k];
+            if (a.targets) a.targets[i0 * 18 + k] = s_tgt[k];
+        }
+    }
+}
+
+__global__ void normal_noise_kernel(uint64_t seed, uint64_t step, float* out, int64_t n) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float z[18];
+    philox_normals18(seed, step, e, z);
+#pragma unroll
+    for (int c = 0; c < 18; ++c) out[e * 18 + c] = z[c];
+}
+
+static inline bool al16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+cudaError_t launch_policy_head(const float* mu, const float* logstd, const float* value_norm, const double* value_mean,
+                               const double* value_var, float value_eps, const float* noise, uint64_t seed, uint64_t step,
+                               float* actions, float* neglogp, float* values, float* mus, float* sigmas, const BezkTaskCfg* cfg,
+                               float* env_actions, float* targets, int64_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    HeadArgs a;
+    a.mu = mu; a.logstd = logstd; a.value_norm = value_norm; a.noise = noise; a.value_mean = value_mean; a.value_var = value_var;
+    a.value_eps = value_eps; a.seed = seed; a.step = step; a.actions = actions; a.neglogp = neglogp; a.values = values;
+    a.mus = mus; a.sigmas = sigmas; a.env_actions = env_actions; a.targets = cfg ? targets : nullptr; a.n = n;
+    a.has_task = cfg != nullptr;
+    a.use_tma = al16(mu) && al16(noise) && al16(actions) && al16(mus) && al16(sigmas) && al16(env_actions) && al16(targets);
+    BezkTaskCfg c;
+    if (cfg) c = *cfg; else memset(&c, 0, sizeof(c));
+    return launch_ex(policy_head_kernel, dim3((unsigned)((n + PH_TILE - 1) / PH_TILE)), dim3(PH_TILE), 0, st, a, c);
+}
+
+cudaError_t launch_normal_noise(uint64_t seed, uint64_t step, float* out, int64_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    normal_noise_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seed, step, out, n);
+    return cudaGetLastError();
+}
+
+}  // namespace bezk

@@ -44,13 +44,6 @@ constexpr int K0_THREADS = 288;         // 9 column pairs x 32 rows: a thread ke
 constexpr int K0_ROWS = K0_THREADS / 9;  // rows per block iteration
 constexpr int K0_UNROLL = 8;            // independent 8-byte loads in flight per thread
 
-__device__ __forceinline__ float k0_target(float a, bool head, float clip, float def, float lo, float hi, float* stored) {
-    a = clamp_nan(a, -clip, clip);                 // vec_task.py:317
-    if (head) a = 0.0f;                            // kick_env.py:414 (head DOFs 0, 1)
-    *stored = a;
-    return tensor_clamp(a + def, lo, hi);          // kick_env.py:417
-}
-
 __global__ void __launch_bounds__(K0_THREADS) pre_physics_kernel(const float* __restrict__ actions, float* __restrict__ actions_out,
                                                                  float* __restrict__ targets, const __grid_constant__ BezkTaskCfg cfg,
                                                                  int64_t n, int vec2) {

@@ -4,6 +4,8 @@ an ``A2CAgent`` can call them in place of its own."""
 from .running_mean_std import RunningMeanStd
 from .a2c_common import discount_values, normalize_advantages, shape_rewards, swap_and_flatten01
 from .losses import ppo_loss, PPOLossConfig
+from .experience import ExperienceBuffer, PPODataset, SlabDataset
+from .policy_head import policy_head
 
 __all__ = ["RunningMeanStd", "discount_values", "normalize_advantages", "shape_rewards", "swap_and_flatten01",
-           "ppo_loss", "PPOLossConfig"]
+           "ppo_loss", "PPOLossConfig", "ExperienceBuffer", "PPODataset", "SlabDataset", "policy_head"]

@@ -23,9 +23,9 @@ def discount_values(fdones, last_extrinsic_values, mb_fdones, mb_extrinsic_value
 
 
 def swap_and_flatten01(arr: torch.Tensor) -> torch.Tensor:
-    """(T, N, ...) -> (N*T, ...) env-major, as rl_games' helper of the same name."""
-    s = arr.size()
-    return arr.transpose(0, 1).reshape(s[0] * s[1], *s[2:])
+    """(T, N, ...) -> (N*T, ...) env-major, as rl_games' helper of the same name: one tiled transposition kernel
+    (``bezk_swap_and_flatten01``).  The ``SlabDataset`` path of ``learner.experience`` avoids the pass altogether."""
+    return ops.swap_and_flatten01(arr.contiguous())
 
 
 class _AdvWorkspace:

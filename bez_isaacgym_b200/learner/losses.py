@@ -26,6 +26,7 @@ class _PPOLoss(torch.autograd.Function):
         m = mu.shape[0]
         dev = mu.device
         f = lambda t, shape: t.detach().float().reshape(shape).contiguous()
+        slabs = not actions.is_contiguous()          # rollout-side tensors given as slab views of time-major storage
         kcfg = ops.make_ppo_cfg(cfg.e_clip, cfg.critic_coef, cfg.entropy_coef, cfg.bounds_loss_coef, cfg.soft_bound,
                                 cfg.clip_value, cfg.bound_form)
         stats = torch.empty(8, dtype=torch.float64, device=dev)
@@ -34,9 +35,15 @@ class _PPOLoss(torch.autograd.Function):
         g_v = torch.empty(m, dtype=torch.float32, device=dev)
         g_ls = torch.empty(18, dtype=torch.float32, device=dev)
         nlp = torch.empty(m, dtype=torch.float32, device=dev)
-        ops.ppo_loss(f(actions, (m, 18)), f(mu, (m, 18)), f(logstd, (18,)), f(old_mu, (m, 18)), f(old_sigma, (m, 18)),
-                     f(values, (m,)), f(old_values, (m,)), f(returns, (m,)), f(old_neglogp, (m,)), f(advantages, (m,)),
-                     kcfg, stats, partials, grad_mu=g_mu, grad_values=g_v, grad_logstd=g_ls, neglogp_out=nlp)
+        if slabs:
+            ops.ppo_loss_slabs(actions.detach(), f(mu, (m, 18)), f(logstd, (18,)), old_mu.detach(), old_sigma.detach(),
+                               f(values, (m,)), old_values.detach(), returns.detach(), old_neglogp.detach(),
+                               advantages.detach(), kcfg, stats, partials, grad_mu=g_mu, grad_values=g_v, grad_logstd=g_ls,
+                               neglogp_out=nlp)
+        else:
+            ops.ppo_loss(f(actions, (m, 18)), f(mu, (m, 18)), f(logstd, (18,)), f(old_mu, (m, 18)), f(old_sigma, (m, 18)),
+                         f(values, (m,)), f(old_values, (m,)), f(returns, (m,)), f(old_neglogp, (m,)), f(advantages, (m,)),
+                         kcfg, stats, partials, grad_mu=g_mu, grad_values=g_v, grad_logstd=g_ls, neglogp_out=nlp)
         ctx.save_for_backward(g_mu, g_v, g_ls)
         ctx.shapes = (mu.shape, values.shape, logstd.shape, mu.dtype, values.dtype, logstd.dtype)
         ctx.mark_non_differentiable(stats, nlp)
@@ -62,7 +69,11 @@ def _scratch(device):
 
 def ppo_loss(mu, values, logstd, actions, old_mu, old_sigma, old_values, returns, old_neglogp, advantages,
              cfg: PPOLossConfig = PPOLossConfig()):
-    """Returns ``(loss, info)``; ``loss`` is differentiable w.r.t. ``mu`` (M,18), ``values`` (M,1)/(M,) and ``logstd``
+    """``actions, old_mu, old_sigma, old_values, returns, old_neglogp, advantages`` may be contiguous minibatch tensors or
+    slab views ``storage[:, e0:e0+E]`` of time-major rollout tensors (``SlabDataset``); ``mu`` / ``values`` are the network
+    outputs for the same batch rows.
+
+    Returns ``(loss, info)``; ``loss`` is differentiable w.r.t. ``mu`` (M,18), ``values`` (M,1)/(M,) and ``logstd``
     (18,).  ``info``: a_loss, c_loss, entropy, b_loss, kl, clip_frac (fp64 scalars on device, no host sync) and
     ``neglogp`` (M,)."""
     loss, stats, nlp = _PPOLoss.apply(mu, values, logstd, actions, old_mu, old_sigma, old_values, returns, old_neglogp,

@@ -40,10 +40,14 @@ class RunningMeanStd(nn.Module):
             self._pivot = torch.empty(c, dtype=torch.float64, device=device)
 
     def update(self, x: torch.Tensor):
-        """Merge the batch moments of ``x`` (m, insize) into the running statistics."""
+        """Merge the batch moments of ``x`` into the running statistics.  ``x``: (m, insize) contiguous, or a slab view
+        ``obses[:, e0:e0+E]`` of time-major rollout storage (read in place, see ``learner.experience.SlabDataset``)."""
         self._workspace(x.device)
         self._pivot.copy_(self.running_mean)              # replicated on all ranks -> identical pivots
-        ops.rms_moments(x, self._pivot, self._acc, self._scratch)
+        if x.is_contiguous():
+            ops.rms_moments(x.view(-1, self.insize), self._pivot, self._acc, self._scratch)
+        else:
+            ops.rms_moments_slabs(x, self._pivot, self._acc, self._scratch)
         bdist.allreduce_sum_(self._acc, self.process_group)
         ops.rms_merge(self._acc, self._pivot, self.running_mean, self.running_var, self.count.view(1))
 
@@ -51,11 +55,19 @@ class RunningMeanStd(nn.Module):
         x = input.detach()
         if x.dtype != torch.float32:
             x = x.float()
-        x = x.contiguous()
+        slab = (not x.is_contiguous()) and x.dim() == 3 and x.stride(2) == 1 and x.stride(1) == x.shape[2] \
+            and x.shape[2] == self.insize
+        if not slab:
+            x = x.contiguous()
         if x.shape[-1] != self.insize and not (self.insize == 1 and x.dim() == 1):
             raise ValueError(f"expected last dim {self.insize}, got {tuple(x.shape)}")
         if self.training:
-            self.update(x.view(-1, self.insize))
+            self.update(x)
+        if slab:
+            # minibatch read in place from time-major storage: the output is the contiguous (T*E, insize) network input
+            y = out if out is not None else torch.empty(x.shape[0] * x.shape[1], self.insize, dtype=torch.float32, device=x.device)
+            ops.rms_normalize_slabs(x, self.running_mean, self.running_var, y, eps=self.epsilon, unnorm=unnorm)
+            return y
         y = out if out is not None else torch.empty_like(x)
         ops.rms_normalize(x, self.running_mean, self.running_var, y, eps=self.epsilon, unnorm=unnorm)
         return y

@@ -254,3 +254,123 @@ def ppo_loss(actions, mu, logstd, old_mu, old_sigma, values, old_values, returns
         _p(grad_logstd, F32, "grad_logstd", 18, True), _p(neglogp_out, F32, "neglogp_out", m, True),
         _p(partials, F64, "partials"), m, _stream(mu)), "bezk_ppo_loss")
     return stats
+
+
+# ------------------------------------------------------------------------------------------- rollout storage
+def _slab_view(t, dtype, name, width):
+    """Pointer + slab geometry of a rollout-side tensor.  Accepts a contiguous (m, width) / (m,) tensor, or a VIEW
+    ``storage[:, e0:e0+E]`` of time-major rollout storage: shape (T, E, width) (or (T, E) / (T, E, 1) for width 1)
+    whose inner dims are contiguous and whose time stride is a whole number of rows.
+    Returns (ptr, slab_rows, slab_stride, m)."""
+    if not isinstance(t, torch.Tensor) or t.dtype != dtype:
+        raise BezkError(f"{name} must be a {dtype} tensor")
+    if not t.is_cuda:
+        raise BezkError(f"{name} is on {t.device}: bez_isaacgym_b200 ops run on CUDA only (no CPU fallback)")
+    if t.is_contiguous():
+        if t.numel() % width:
+            raise BezkError(f"{name}: {t.numel()} elements is not a multiple of the row width {width}")
+        m = t.numel() // width
+        return C.c_void_p(t.data_ptr()), m, m, m
+    v = t
+    if width == 1 and v.dim() == 3 and v.shape[-1] == 1:
+        v = v.squeeze(-1)
+    want_dim = 2 if width == 1 else 3
+    if v.dim() != want_dim or (width > 1 and (v.shape[-1] != width or v.stride(-1) != 1)):
+        raise BezkError(f"{name}: expected a contiguous tensor or a (T, E{', ' + str(width) if width > 1 else ''}) slab view")
+    T, E = v.shape[0], v.shape[1]
+    if v.stride(1) != width or v.stride(0) % width or v.stride(0) < E * width:
+        raise BezkError(f"{name}: not a slab view of time-major storage (strides {tuple(v.stride())})")
+    return C.c_void_p(v.data_ptr()), E, v.stride(0) // width, T * E
+
+
+def _same_slabs(geoms, names):
+    g0 = geoms[0][1:]
+    for g, nme in zip(geoms[1:], names[1:]):
+        if g[1:] != g0:
+            raise BezkError(f"{nme} has slab geometry {g[1:]}, {names[0]} has {g0}: rollout tensors must share one (T, N, E)")
+    return g0
+
+
+def rms_moments_slabs(x, pivot, acc, partials):
+    """``rms_moments`` over ``x = obses[:, e0:e0+E]`` (a slab view of time-major storage) without flattening it."""
+    c = x.shape[-1]
+    ptr, rows, stride, m = _slab_view(x, F32, "x", c)
+    if partials.numel() < rms_scratch_doubles(c):
+        raise BezkError("partials scratch too small")
+    lib = _lib.load()
+    _lib.check(lib.bezk_rms_moments_slabs(ptr, rows, stride, _p(pivot, F64, "pivot", c, True), _p(acc, F64, "acc", 1 + 2 * c),
+                                          _p(partials, F64, "partials"), m, c, _stream(x)), "bezk_rms_moments_slabs")
+    return acc
+
+
+def rms_normalize_slabs(x, running_mean, running_var, y, eps=1e-5, unnorm=False):
+    """``y`` (m, c) contiguous = normalise(rows of the slab view ``x``), batch row = t * E + (env - e0)."""
+    c = running_mean.numel()
+    ptr, rows, stride, m = _slab_view(x, F32, "x", c)
+    lib = _lib.load()
+    _lib.check(lib.bezk_rms_normalize_slabs(ptr, rows, stride, _p(running_mean, F64, "running_mean", c),
+                                            _p(running_var, F64, "running_var", c), eps, int(bool(unnorm)),
+                                            _p(y, F32, "y", m * c), m, c, _stream(x)), "bezk_rms_normalize_slabs")
+    return y
+
+
+def ppo_loss_slabs(actions, mu, logstd, old_mu, old_sigma, values, old_values, returns, old_neglogp, advantages, cfg,
+                   stats, partials, grad_mu=None, grad_values=None, grad_logstd=None, neglogp_out=None):
+    """``ppo_loss`` with the rollout-side tensors given as slab views (``storage[:, e0:e0+E]``); ``mu`` / ``values`` and
+    the gradients are contiguous batch rows in the same time-major-within-batch order."""
+    m = mu.shape[0]
+    wide = [_slab_view(t, F32, nme, 18) for t, nme in ((actions, "actions"), (old_mu, "old_mu"), (old_sigma, "old_sigma"))]
+    flat = [_slab_view(t, F32, nme, 1) for t, nme in ((old_values, "old_values"), (returns, "returns"),
+                                                      (old_neglogp, "old_neglogp"), (advantages, "advantages"))]
+    rows, stride, mm = _same_slabs(wide + flat, ["actions", "old_mu", "old_sigma", "old_values", "returns", "old_neglogp",
+                                                 "advantages"])
+    if mm != m:
+        raise BezkError(f"rollout tensors hold {mm} rows, mu has {m}")
+    lib = _lib.load()
+    _lib.check(lib.bezk_ppo_loss_slabs(
+        wide[0][0], _p(mu, F32, "mu", m * 18), _p(logstd, F32, "logstd", 18), wide[1][0], wide[2][0],
+        _p(values, F32, "values", m), flat[0][0], flat[1][0], flat[2][0], flat[3][0], rows, stride, C.byref(cfg),
+        _p(stats, F64, "stats", 8), _p(grad_mu, F32, "grad_mu", m * 18, True), _p(grad_values, F32, "grad_values", m, True),
+        _p(grad_logstd, F32, "grad_logstd", 18, True), _p(neglogp_out, F32, "neglogp_out", m, True),
+        _p(partials, F64, "partials"), m, _stream(mu)), "bezk_ppo_loss_slabs")
+    return stats
+
+
+def swap_and_flatten01(src, out=None, env0=0, envs=None):
+    """rl_games' ``swap_and_flatten01`` on a contiguous time-major tensor (T, N, ...) of any dtype:
+    returns (envs*T, ...) with row (e - env0)*T + t = src[t, e]."""
+    if not src.is_cuda or not src.is_contiguous() or src.dim() < 2:
+        raise BezkError("src must be a contiguous CUDA tensor of shape (T, N, ...)")
+    T, N = src.shape[0], src.shape[1]
+    envs = N - env0 if envs is None else envs
+    row_bytes = (src.numel() // max(T * N, 1)) * src.element_size()
+    if out is None:
+        out = torch.empty((envs * T,) + tuple(src.shape[2:]), dtype=src.dtype, device=src.device)
+    if not out.is_contiguous() or out.dtype != src.dtype or out.numel() * out.element_size() != envs * T * row_bytes:
+        raise BezkError("out must be contiguous, of src's dtype, with envs*T rows")
+    lib = _lib.load()
+    _lib.check(lib.bezk_swap_and_flatten01(C.c_void_p(src.data_ptr()), C.c_void_p(out.data_ptr()), T, N, env0, envs, row_bytes,
+                                           _stream(src)), "bezk_swap_and_flatten01")
+    return out
+
+
+def policy_head(mu, logstd, value_norm=None, value_mean=None, value_var=None, value_eps=1e-5, noise=None, seed=0, step=0,
+                actions=None, neglogp=None, values=None, mus=None, sigmas=None, task_cfg=None, env_actions=None, targets=None):
+    """Sampling / neglogp / value un-normalisation / experience-slot writes / clamp / K0 in one launch (see bezk.h)."""
+    n = mu.shape[0]
+    lib = _lib.load()
+    _lib.check(lib.bezk_policy_head(
+        _p(mu, F32, "mu", n * 18), _p(logstd, F32, "logstd", 18), _p(value_norm, F32, "value_norm", n, True),
+        _p(value_mean, F64, "value_mean", 1, True), _p(value_var, F64, "value_var", 1, True), float(value_eps),
+        _p(noise, F32, "noise", n * 18, True), int(seed), int(step), _p(actions, F32, "actions", n * 18, True),
+        _p(neglogp, F32, "neglogp", n, True), _p(values, F32, "values", n, True), _p(mus, F32, "mus", n * 18, True),
+        _p(sigmas, F32, "sigmas", n * 18, True), C.byref(task_cfg) if task_cfg is not None else None,
+        _p(env_actions, F32, "env_actions", n * 18, True), _p(targets, F32, "targets", n * 18, True), n, _stream(mu)),
+        "bezk_policy_head")
+
+
+def normal_noise(seed, step, out):
+    n = out.shape[0]
+    lib = _lib.load()
+    _lib.check(lib.bezk_normal_noise(int(seed), int(step), _p(out, F32, "out", n * 18), n, _stream(out)), "bezk_normal_noise")
+    return out

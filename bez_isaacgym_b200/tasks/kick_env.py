@@ -312,6 +312,36 @@ class KickEnv(VecTask):
     def _observations_out(self):
         return self.obs_buf if self.obs_clipped_buf is None else self.obs_clipped_buf
 
+    # ------------------------------------------------------------------ rollout-storage hooks
+    def set_obs_target(self, tensor):
+        """Make the step kernel write its (N,54) observation rows straight into ``tensor`` -- e.g.
+        ``experience.slot('obses', t)`` -- instead of a private buffer (rl_games copies ``obs`` into its experience
+        buffer after every step; here the copy never happens).  ``obs_buf`` becomes that tensor."""
+        if self.host_staged:
+            raise NotImplementedError("set_obs_target needs the GPU pipeline")
+        if tensor.shape != (self.num_envs, 54) or tensor.dtype != torch.float32 or not tensor.is_contiguous() \
+                or tensor.device != self.compute_device:
+            raise ValueError(f"obs target must be a contiguous float32 ({self.num_envs}, 54) tensor on {self.compute_device}")
+        self.obs_buf = tensor
+        self._post_fixed["tail"][5] = _ptr(tensor)
+
+    def step_precomputed_targets(self, env_actions=None):
+        """``step`` for callers whose PD ``targets`` were already written by ``learner.policy_head(..., env=self)`` (the
+        policy-head kernel runs K0 in its epilogue): simulate + post-physics only.  ``env_actions``: what ``self.actions``
+        should report (the clamped actions the head produced)."""
+        if self.host_staged:
+            raise NotImplementedError("step_precomputed_targets needs the GPU pipeline")
+        if env_actions is not None:
+            self._actions_cache = None
+            self._actions_src = env_actions
+        self.sim.set_dof_position_targets(self.targets)
+        for _ in range(self.control_freq_inv):
+            self.sim.simulate()
+        self.post_physics_step()
+        self.extras["time_outs"] = self.timeout_buf.to(self.rl_device)
+        self.obs_dict["obs"] = self._observations_out().to(self.rl_device)
+        return self.obs_dict, self.rew_buf.to(self.rl_device), self.reset_buf.to(self.rl_device), self.extras
+
     def step(self, actions):
         if not self.host_staged:
             return super().step(actions)

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BEZK_VERSION 100          /* 0.1.0 */
+#define BEZK_VERSION 110          /* 0.1.1 */
 #define BEZK_NUM_DOF 18
 #define BEZK_NUM_OBS 54
 
@@ -188,6 +188,55 @@ int bezk_ppo_loss(const float* actions, const float* mu, const float* logstd, co
                   const float* returns, const float* old_neglogp, const float* advantages,
                   const BezkPpoCfg* cfg, double* stats, float* grad_mu, float* grad_values,
                   float* grad_logstd, float* neglogp_out, double* partials, int64_t m, void* stream);
+
+/* ---------------------------------------------------------------- rollout storage ----- */
+
+/* Slab addressing.  rl_games keeps the rollout time-major -- ExperienceBuffer tensors are (T, N, ...) -- and builds its
+ * dataset with swap_and_flatten01 (a full read + write of every tensor) before slicing minibatches of consecutive
+ * env-major rows (rl_games/common/a2c_common.py play_steps / prepare_dataset, rl_games/common/datasets.py PPODataset).
+ * Minibatch i of E = minibatch_size / T envs is the sample set {(t, e): e0 <= e < e0 + E}.  The *_slabs entries read that
+ * set IN PLACE: the m = T * E batch rows are T slabs of `slab_rows` (= E) consecutive source rows, slab s starting at row
+ * s * slab_stride (= N) of the base pointer (= tensor + e0 * row width).  Batch row r = t * E + (e - e0): the same samples
+ * as rl_games' minibatch, ordered time-major inside the batch (a permutation that no mean / moment / gradient depends on).
+ * slab_rows == m (or <= 0) means "contiguous", which makes every *_slabs entry equal to its plain counterpart. */
+int bezk_rms_moments_slabs(const float* x, int64_t slab_rows, int64_t slab_stride, const double* pivot, double* acc,
+                           double* partials, int64_t m, int32_t c, void* stream);
+/* y (m,c) is written contiguously in batch-row order (the network input). */
+int bezk_rms_normalize_slabs(const float* x, int64_t slab_rows, int64_t slab_stride, const double* running_mean,
+                             const double* running_var, float eps, int unnorm, float* y, int64_t m, int32_t c,
+                             void* stream);
+/* bezk_ppo_loss with the ROLLOUT-side tensors (actions, old_mu, old_sigma (.,18); old_values, returns, old_neglogp,
+ * advantages (.,)) read as slabs; mu, values (network outputs) and all outputs are contiguous batch rows. */
+int bezk_ppo_loss_slabs(const float* actions, const float* mu, const float* logstd, const float* old_mu,
+                        const float* old_sigma, const float* values, const float* old_values,
+                        const float* returns, const float* old_neglogp, const float* advantages,
+                        int64_t slab_rows, int64_t slab_stride,
+                        const BezkPpoCfg* cfg, double* stats, float* grad_mu, float* grad_values,
+                        float* grad_logstd, float* neglogp_out, double* partials, int64_t m, void* stream);
+
+/* ref: rl_games/common/a2c_common.py swap_and_flatten01 (+ the minibatch slice of PPODataset):
+ *   dst[(e - env0) * horizon + t][:] = src[t * num_envs + e][:]   for env0 <= e < env0 + envs, 0 <= t < horizon
+ * rows of row_bytes bytes (any dtype; 216 for observations, 72 for actions, 4 for scalars, 1 for uint8 dones).
+ * One tiled shared-memory transposition; src and dst must not overlap. */
+int bezk_swap_and_flatten01(const void* src, void* dst, int32_t horizon, int64_t num_envs, int64_t env0, int64_t envs,
+                            int32_t row_bytes, void* stream);
+
+/* Policy-head epilogue: what rl_games does between the MLP and env.step in play_steps, in one kernel.
+ * ref: rl_games/algos_torch/models.py ModelA2CContinuousLogStd.forward (is_train=False: sigma = exp(logstd),
+ * Normal(mu, sigma).sample(), neglogp), a2c_common.py get_action_values (values = value_mean_std(values, unnorm=True)),
+ * play_steps (experience_buffer.update_data of actions / neglogpacs / values / mus / sigmas), preprocess_actions
+ * (clamp(-1,1) + rescale_actions; cf. the in-tree fork utils/players.py:11-15,63-64) and KickEnv.pre_physics_step.
+ *   mu (n,18), logstd (18,), value_norm (n,) [NULL: no values]; value_mean/value_var: () f64 running stats [NULL: copy]
+ *   noise (n,18) N(0,1) draws, or NULL -> Philox4x32-10 keyed (seed, step, env id) + Box-Muller
+ *   outputs (each may be NULL): actions (n,18), neglogp (n,), values (n,), mus (n,18), sigmas (n,18),
+ *   env_actions (n,18) = clamp(actions,-1,1); targets (n,18) = K0(env_actions) when task_cfg != NULL. */
+int bezk_policy_head(const float* mu, const float* logstd, const float* value_norm, const double* value_mean,
+                     const double* value_var, float value_eps, const float* noise, uint64_t seed, uint64_t step,
+                     float* actions, float* neglogp, float* values, float* mus, float* sigmas,
+                     const BezkTaskCfg* task_cfg, float* env_actions, float* targets, int64_t n, void* stream);
+/* The (n,18) normals the Philox path of bezk_policy_head uses for (seed, step): lets a checker feed identical noise
+ * to the reference's Normal.sample() replacement. */
+int bezk_normal_noise(uint64_t seed, uint64_t step, float* out, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

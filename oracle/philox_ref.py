@@ -47,3 +47,30 @@ def reset_uniforms(seed: int, step: int, n: int, first_env: int = 0) -> np.ndarr
     key[..., 1] = np.uint32((seed >> 32) & 0xFFFFFFFF)
     x = philox4x32_10(ctr, key).reshape(n, 36)
     return ((x >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)).astype(np.float32)
+
+
+def normals18(seed: int, step: int, envs) -> np.ndarray:
+    """(len(envs), 18) float32 standard normals identical (to libm rounding) to ``bezk_normal_noise`` /
+    the Philox path of ``bezk_policy_head`` (``bez_isaacgym_b200/csrc/bezk_rollout.cu: philox_normals18``):
+    key = (seed_lo ^ 0x5851F42D, seed_hi), ctr = (e_lo, e_hi, s_lo, (s_hi << 4) + j), j = 0..4; each block's
+    (x, y) and (z, w) feed one Box-Muller pair: u1 = ((a >> 8) + 1) * 2^-24 in (0, 1], u2 = (b >> 8) * 2^-24,
+    r = sqrt(-2 ln u1), (r cos 2 pi u2, r sin 2 pi u2).  Replaces torch's Normal.sample() draw (documented
+    deviation: keyed by env id, so sharding and batch size do not change the noise)."""
+    env = np.asarray(list(envs), dtype=np.uint64)
+    n = env.shape[0]
+    ctr = np.zeros((n, 5, 4), dtype=np.uint32)
+    ctr[:, :, 0] = (env & MASK).astype(np.uint32)[:, None]
+    ctr[:, :, 1] = (env >> np.uint64(32)).astype(np.uint32)[:, None]
+    ctr[:, :, 2] = np.uint32(step & 0xFFFFFFFF)
+    ctr[:, :, 3] = np.uint32(((step >> 32) << 4) & 0xFFFFFFFF) + np.arange(5, dtype=np.uint32)[None, :]
+    key = np.zeros((n, 5, 2), dtype=np.uint32)
+    key[..., 0] = np.uint32((seed & 0xFFFFFFFF) ^ 0x5851F42D)
+    key[..., 1] = np.uint32((seed >> 32) & 0xFFFFFFFF)
+    x = philox4x32_10(ctr, key).reshape(n, 10, 2)           # 10 (a, b) pairs per env
+    scale = np.float32(1.0 / 16777216.0)
+    u1 = ((x[..., 0] >> np.uint32(8)) + np.uint32(1)).astype(np.float32) * scale
+    u2 = (x[..., 1] >> np.uint32(8)).astype(np.float32) * scale
+    r = np.sqrt(np.float32(-2.0) * np.log(u1)).astype(np.float32)
+    th = (np.float32(6.283185307179586) * u2).astype(np.float32)
+    z = np.stack((r * np.cos(th), r * np.sin(th)), axis=-1).astype(np.float32).reshape(n, 20)
+    return z[:, :18]

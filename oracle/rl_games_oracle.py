@@ -184,3 +184,85 @@ def adaptive_lr(lr: float, kl: float, kl_threshold: float = 0.008, min_lr=1e-6, 
     if kl < 0.5 * kl_threshold:
         lr = min(lr * 1.5, max_lr)
     return lr
+
+
+# ------------------------------------------------------------------------------------------------
+# Rollout storage either side of the task step.  Restated from rl_games v1.1.3
+# rl_games/common/experience.py (ExperienceBuffer), rl_games/common/datasets.py (PPODataset),
+# rl_games/algos_torch/models.py (ModelA2CContinuousLogStd.forward), rl_games/common/a2c_common.py
+# (get_action_values, play_steps, preprocess_actions) and rl_games/algos_torch/torch_ext.py (rescale_actions;
+# the reference's in-tree fork has the same function at utils/players.py:11-15).  PARITY UNPINNED.
+# ------------------------------------------------------------------------------------------------
+class ExperienceBuffer:
+    """rl_games/common/experience.py for the continuous-action, non-RNN case BezKick uses: time-major
+    ``tensor_dict[name]`` of shape (horizon, num_actors, ...); ``update_data(name, index, val)`` writes slot
+    ``index``; ``get_transformed_list(fn, names)`` applies ``fn`` (swap_and_flatten01) to the named tensors."""
+
+    def __init__(self, num_actors: int, horizon: int, obs_dim: int = 54, act_dim: int = 18, device="cpu"):
+        self.num_actors, self.horizon_length = num_actors, horizon
+        base = (horizon, num_actors)
+        f32 = dict(dtype=torch.float32, device=device)
+        self.tensor_dict = {
+            "obses": torch.zeros(base + (obs_dim,), **f32),
+            "rewards": torch.zeros(base + (1,), **f32),
+            "values": torch.zeros(base + (1,), **f32),
+            "neglogpacs": torch.zeros(base, **f32),
+            "dones": torch.zeros(base, dtype=torch.uint8, device=device),
+            "actions": torch.zeros(base + (act_dim,), **f32),
+            "mus": torch.zeros(base + (act_dim,), **f32),
+            "sigmas": torch.zeros(base + (act_dim,), **f32),
+        }
+
+    def update_data(self, name: str, index: int, val: Tensor):
+        self.tensor_dict[name][index, :] = val
+
+    def get_transformed_list(self, transform_op, tensor_list):
+        return {k: transform_op(self.tensor_dict[k]) for k in tensor_list if self.tensor_dict.get(k) is not None}
+
+
+class PPODataset:
+    """rl_games/common/datasets.py: minibatch ``idx`` = rows [idx*mb, (idx+1)*mb) of every flattened tensor
+    (no shuffling for the non-RNN path)."""
+
+    def __init__(self, batch_size: int, minibatch_size: int):
+        assert batch_size % minibatch_size == 0
+        self.batch_size, self.minibatch_size = batch_size, minibatch_size
+        self.length = batch_size // minibatch_size
+        self.values_dict = None
+
+    def update_values_dict(self, values_dict):
+        self.values_dict = values_dict
+
+    def __len__(self):
+        return self.length
+
+    def __getitem__(self, idx):
+        start, end = idx * self.minibatch_size, (idx + 1) * self.minibatch_size
+        return {k: (v[start:end] if v is not None else None) for k, v in self.values_dict.items()}
+
+
+def rescale_actions(low, high, action):
+    """torch_ext.rescale_actions (= utils/players.py:11-15 of the reference's fork)."""
+    d = (high - low) / 2.0
+    m = (high + low) / 2.0
+    return action * d + m
+
+
+def preprocess_actions(actions: Tensor, low: float = -1.0, high: float = 1.0) -> Tensor:
+    """A2CBase.preprocess_actions with clip_actions=True: clamp to [-1, 1] then rescale to the action space."""
+    return rescale_actions(low, high, torch.clamp(actions, -1.0, 1.0))
+
+
+def policy_head(mu: Tensor, logstd: Tensor, value_norm: Tensor, value_rms: RunningMeanStd, noise: Tensor):
+    """ModelA2CContinuousLogStd.forward (is_train=False) + get_action_values' value un-normalisation, with the
+    Normal sample written as ``mu + sigma * noise`` (``noise`` ~ N(0,1) supplied by the caller so that both sides
+    of a parity test see the same draws).  mu (N,18), logstd (18,), value_norm (N,1)."""
+    logstd_rows = mu * 0.0 + logstd
+    sigma = torch.exp(logstd_rows)
+    actions = mu + sigma * noise
+    nlp = neglogp(actions, mu, sigma, logstd_rows)
+    was_training = value_rms.training
+    value_rms.training = False
+    values = value_rms(value_norm, unnorm=True)
+    value_rms.training = was_training
+    return dict(actions=actions, neglogpacs=nlp, values=values, mus=mu, sigmas=sigma)

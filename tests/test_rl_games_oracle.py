@@ -145,3 +145,61 @@ def test_prepare_dataset_updates_value_rms_twice():
     assert abs(adv.mean().item()) < 1e-5 and abs(adv.std().item() - 1.0) < 1e-4
     shaped = rg.shape_rewards(torch.ones(3), torch.full((3, 1), 2.0), torch.tensor([0, 1, 0]), 0.99)
     assert torch.allclose(shaped.view(-1), torch.tensor([0.01, 0.01 + 0.99 * 2.0, 0.01]))
+
+
+# ----------------------------------------------------------------------------------------------- rollout storage (8f rows 1-2)
+def test_slab_dataset_is_the_ppo_dataset_sample_set_cpu():
+    """Host logic only (no kernels): SlabDataset minibatch i == PPODataset minibatch i as a sample set, and
+    permutation_to_env_major() maps one row order onto the other."""
+    from bez_isaacgym_b200.learner import experience as ex
+
+    class Box:
+        def __init__(self, n):
+            self.shape = (n,)
+    T, N, mb = 4, 24, 16
+    buf = ex.ExperienceBuffer(dict(observation_space=Box(54), action_space=Box(18)), dict(num_actors=N, horizon_length=T), "cpu")
+    orc = rg.ExperienceBuffer(N, T)
+    g = torch.Generator().manual_seed(1)
+    for t in range(T):
+        for name, shape in (("obses", (N, 54)), ("values", (N, 1)), ("neglogpacs", (N,)), ("actions", (N, 18))):
+            val = torch.randn(shape, generator=g)
+            buf.update_data(name, t, val); orc.update_data(name, t, val)
+    names = ["obses", "values", "neglogpacs", "actions"]
+    flat = orc.get_transformed_list(rg.swap_and_flatten01, names)
+    ods = rg.PPODataset(N * T, mb); ods.update_values_dict(flat)
+    sds = ex.SlabDataset(buf, mb)
+    perm = sds.permutation_to_env_major()
+    assert len(sds) == len(ods) == 6
+    for i in range(len(sds)):
+        for k in names:
+            rows = sds[i][k].reshape(mb, *sds[i][k].shape[2:])
+            assert torch.equal(rows[perm], ods[i][k]), (i, k)
+    with pytest.raises(ValueError):
+        ex.SlabDataset(buf, 6)              # not a multiple of the horizon
+    with pytest.raises(ValueError):
+        ex.PPODataset(96, 36)
+
+
+def test_philox_normals_reference_is_gaussian():
+    from oracle import philox_ref
+    z = philox_ref.normals18(seed=3, step=9, envs=range(20000)).astype("float64")
+    assert z.shape == (20000, 18)
+    assert abs(z.mean()) < 5e-3 and abs(z.var() - 1.0) < 1e-2 and abs((z ** 4).mean() - 3.0) < 0.1
+    again = philox_ref.normals18(seed=3, step=9, envs=range(100, 110))
+    assert (again == philox_ref.normals18(seed=3, step=9, envs=range(20000))[100:110]).all()     # keyed by env id
+
+
+def test_policy_head_oracle_identities():
+    """neglogp of the sampled action reduces to 0.5*|noise|^2 + const + sum(logstd); un-normalisation inverts normalisation
+    inside the clamp."""
+    g = torch.Generator().manual_seed(0)
+    mu, logstd, noise = torch.randn(64, 18, generator=g), torch.randn(18, generator=g) * 0.2, torch.randn(64, 18, generator=g)
+    vr = rg.RunningMeanStd(1)
+    vr.running_mean = torch.tensor([1.5], dtype=torch.float64); vr.running_var = torch.tensor([4.0], dtype=torch.float64)
+    vr.training = False
+    raw = torch.randn(64, 1, generator=g) * 2 + 1.5
+    out = rg.policy_head(mu, logstd, vr(raw), vr, noise)
+    want = 0.5 * (noise ** 2).sum(-1) + 0.5 * math.log(2 * math.pi) * 18 + logstd.sum()
+    torch.testing.assert_close(out["neglogpacs"], want, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(out["values"], raw, rtol=1e-5, atol=1e-5)
+    assert torch.equal(rg.preprocess_actions(torch.tensor([-3.0, -0.5, 0.25, 7.0])), torch.tensor([-1.0, -0.5, 0.25, 1.0]))

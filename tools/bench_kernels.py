@@ -53,6 +53,7 @@ def timeit(fn, iters=20, warm=3, flush=None, reps=10):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
+    ap.add_argument("--only", default="all", choices=["all", "task", "learner", "rollout"])
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     pk = peak()
@@ -66,7 +67,7 @@ def main():
         print(json.dumps(rows[-1]))
 
     # ---- task kernels across env counts
-    for n in (4096, 65536, 262144, 1048576):
+    for n in (4096, 65536, 262144, 1048576) if args.only in ("all", "task") else ():
         st = sg.make_state(n, seed=1, device=dev, filler=(n <= 262144))
         goal, ball_init, default, lo, hi = sg.make_constants(n, dev)
         cfg = ops.make_task_cfg(reset_root_states=False)
@@ -89,13 +90,13 @@ def main():
                                                reset, progress, None, cfg, None, rew, parts=4), flush=fl), f"n={n}")
         del st
     # ---- GAE
-    for n in (4096, 262144):
+    for n in (4096, 262144) if args.only in ("all", "learner") else ():
         r, v, d, lv, ld = sg.make_rollout(n, 32, device=dev)
         adv, ret = torch.empty_like(r), torch.empty_like(r)
         report("gae(T=32)", n * 32, 17, timeit(lambda: ops.gae(r, v, d, lv, ld, 0.99, 0.95, adv, ret),
                                                flush=flush if n < 262144 else None), f"n={n}")
     # ---- RunningMeanStd train forward, advantage normalisation, PPO loss
-    for m in (32768, 131072, 1048576, 8388608):
+    for m in (32768, 131072, 1048576, 8388608) if args.only in ("all", "learner") else ():
         x = torch.randn(m, 54, device=dev)
         mean = torch.zeros(54, dtype=torch.float64, device=dev); var = torch.ones(54, dtype=torch.float64, device=dev)
         count = torch.ones(1, dtype=torch.float64, device=dev)
@@ -131,6 +132,46 @@ def main():
             ops.adv_moments(ret, val, a3, sc1)
             ops.adv_normalize(ret, val, a3, out)
         report("adv_normalize(2 pass)", m, 20, timeit(advn, flush=fl), f"m={m}")
+    # ---- rollout storage: flattening pass vs slab-addressed minibatches, policy head
+    if args.only in ("all", "rollout"):
+        T = 32
+        for n in (4096, 262144):
+            obses = torch.randn(T, n, 54, device=dev)
+            flat = torch.empty(n * T, 54, device=dev)
+            fl = flush if n * T * 216 < (200 << 20) else None
+            report("swap_and_flatten01(obses)", n * T, 432, timeit(lambda: ops.swap_and_flatten01(obses, out=flat), flush=fl),
+                   f"(32,{n},54) f32: 216 B read + 216 B written per sample")
+            acts = torch.randn(T, n, 18, device=dev); flat_a = torch.empty(n * T, 18, device=dev)
+            report("swap_and_flatten01(actions)", n * T, 144, timeit(lambda: ops.swap_and_flatten01(acts, out=flat_a), flush=fl),
+                   f"(32,{n},18) f32")
+            vals = torch.randn(T, n, 1, device=dev); flat_v = torch.empty(n * T, 1, device=dev)
+            report("swap_and_flatten01(values)", n * T, 8, timeit(lambda: ops.swap_and_flatten01(vals, out=flat_v), flush=fl),
+                   f"(32,{n},1) f32")
+            t0 = timeit(lambda: flat.copy_(obses.transpose(0, 1).reshape(n * T, 54)), flush=fl)
+            report("torch transpose+reshape copy (obses)", n * T, 432, t0, "what rl_games' swap_and_flatten01 costs in torch")
+            # one minibatch (32768 samples = 1024 envs x 32): flattened-contiguous vs slab view, normalise and moments
+            mb, E = 32768, 1024
+            mean = torch.zeros(54, dtype=torch.float64, device=dev); var = torch.ones(54, dtype=torch.float64, device=dev)
+            acc = torch.empty(109, dtype=torch.float64, device=dev)
+            scratch = torch.empty(ops.rms_scratch_doubles(54), dtype=torch.float64, device=dev)
+            y = torch.empty(mb, 54, device=dev)
+            cont = flat[:mb]
+            view = obses[:, :E]
+            report("rms_normalize(minibatch, contiguous)", mb, 432, timeit(lambda: ops.rms_normalize(cont, mean, var, y), flush=flush), f"n={n}")
+            report("rms_normalize_slabs(minibatch view)", mb, 432, timeit(lambda: ops.rms_normalize_slabs(view, mean, var, y), flush=flush), f"n={n}")
+            report("rms_moments(minibatch, contiguous)", mb, 216, timeit(lambda: ops.rms_moments(cont, mean, acc, scratch), flush=flush), f"n={n}")
+            report("rms_moments_slabs(minibatch view)", mb, 216, timeit(lambda: ops.rms_moments_slabs(view, mean, acc, scratch), flush=flush), f"n={n}")
+            del obses, flat, acts, flat_a
+            # policy head: mu 72 + value 4 read; actions, mus, sigmas, targets 4 x 72 + neglogp 4 + values 4 written
+            mu = torch.randn(n, 18, device=dev); logstd = torch.zeros(18, device=dev); vn = torch.randn(n, device=dev)
+            vm = torch.zeros(1, dtype=torch.float64, device=dev); vv = torch.ones(1, dtype=torch.float64, device=dev)
+            o = [torch.empty(n, 18, device=dev) for _ in range(4)]
+            nl = torch.empty(n, device=dev); vo = torch.empty(n, device=dev)
+            cfg = ops.make_task_cfg()
+            fl2 = flush if n < 262144 else None
+            report("policy_head(philox)", n, 372,
+                   timeit(lambda: ops.policy_head(mu, logstd, vn, vm, vv, 1e-5, noise=None, seed=1, step=2, actions=o[0], neglogp=nl,
+                                                  values=vo, mus=o[1], sigmas=o[2], task_cfg=cfg, targets=o[3]), flush=fl2), f"n={n}")
     if args.out:
         with open(args.out, "w") as f:
             for r in rows:
