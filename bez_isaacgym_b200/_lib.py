@@ -20,6 +20,8 @@ PART_OBS = 2
 PART_REWARD = 4
 PART_ALL = 7
 
+TASK_KICK, TASK_WALK, TASK_ORIENT = 0, 1, 2
+
 
 class BezkTaskCfg(C.Structure):
     _fields_ = [
@@ -67,6 +69,10 @@ SIGNATURES = {
     "bezk_adv_normalize": (C.c_int, [_P, _P, _P, _P, C.c_int, _I64, _P]),
     "bezk_ppo_scratch_doubles": (_I64, []),
     "bezk_ppo_loss": (C.c_int, [_P] * 10 + [C.POINTER(BezkPpoCfg)] + [_P] * 6 + [_I64, _P]),
+    "bezk_post_physics_task": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U64, _U64, _P, _P, _P, _P,
+                                         C.POINTER(BezkTaskCfg), _P, _P, _P, C.c_int, _I64, _P]),
+    "bezk_reset_idx_task": (C.c_int, [C.c_int, _P, _I64, _P, _P, _U64, _U64, _P, _P, _P, _P, _P, _P, C.POINTER(BezkTaskCfg), _I64, _P]),
+    "bezk_goal_uniforms": (C.c_int, [_U64, _U64, _P, _P]),
     "bezk_rms_moments_slabs": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _I64, C.c_int32, _P]),
     "bezk_rms_normalize_slabs": (C.c_int, [_P, _I64, _I64, _P, _P, C.c_float, C.c_int, _P, _I64, C.c_int32, _P]),
     "bezk_ppo_loss_slabs": (C.c_int, [_P] * 10 + [_I64, _I64, C.POINTER(BezkPpoCfg)] + [_P] * 6 + [_I64, _P]),

@@ -50,13 +50,44 @@ OBS_OFF_ORN = slice(42, 44)
 OBS_FEET = slice(44, 52)
 OBS_BALL_INIT = slice(52, 54)
 
+#: sibling tasks (tasks/walk_env.py, tasks/orient_env.py): the robot only, 52-wide observation (walk_env.py:104)
+TASKS = ("kick", "walk", "orient")
+NUM_OBS_WALK = 52
+BODIES_NO_CLEATS_WALK = 21
+BODIES_CLEATS_WALK = 29
+
+
+def task_dims(task="kick", cleats=False):
+    """(actors per env, bodies per env, observation width) of a task."""
+    if task == "kick":
+        return 2, (BODIES_CLEATS if cleats else BODIES_NO_CLEATS), NUM_OBS
+    if task in ("walk", "orient"):
+        return 1, (BODIES_CLEATS_WALK if cleats else BODIES_NO_CLEATS_WALK), NUM_OBS_WALK
+    raise ValueError(f"unknown task {task!r}")
+
+
 IMU_MAX_ANG_VEL = 8.7266       # kick_env.py:99
 IMU_MAX_LIN_ACC = 2.0 * 9.81   # kick_env.py:100
 
 
-def default_task_cfg(num_envs=4096, cleats=False, use_gpu_pipeline=True, rl_device="cuda:0"):
+def default_task_cfg(num_envs=4096, cleats=False, use_gpu_pipeline=True, rl_device="cuda:0", task="kick"):
     """The subset of ``cfg/task/bez_kick.yaml`` (+ the three top-level keys ``VecTask`` reads) that the
-    per-step path consumes, with the Hydra interpolations resolved by hand."""
+    per-step path consumes, with the Hydra interpolations resolved by hand.  ``task="walk"`` / ``"orient"``:
+    the same for ``cfg/task/bez_walk.yaml`` / ``bez_orient.yaml`` (goal (2, 0), 10 s episodes, no ball; orient adds
+    ``goal_angle`` 1.5708)."""
+    if task != "kick":
+        cfg = default_task_cfg(num_envs, cleats, use_gpu_pipeline, rl_device)
+        cfg["name"] = f"bez_{task}"
+        env = cfg["env"]
+        del env["ballInitState"]
+        env["envSpacing"] = 5
+        env["goalState"] = {"goal": [2.0, 0.0]}
+        if task == "orient":
+            env["goalState"]["goal_angle"] = 1.5708
+        elif task != "walk":
+            raise ValueError(f"unknown task {task!r}")
+        env["learn"]["episodeLength_s"] = 10
+        return cfg
     ready = {n: 0.0 for n in DOF_NAMES}
     for side in ("left", "right"):
         ready[f"{side}_leg_motor_2"] = 0.564

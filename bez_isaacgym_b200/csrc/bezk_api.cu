@@ -52,12 +52,20 @@ int bezk_pre_physics(const float* actions, float* actions_out, float* targets, c
     return cuda_rc(bezk::launch_pre_physics(actions, actions_out, targets, *cfg, n, (cudaStream_t)stream), "bezk_pre_physics");
 }
 
-static int run_task(int parts, bezk::TaskArgs& a, const BezkTaskCfg* cfg, void* stream, const char* where) {
+static int run_task(int parts, bezk::TaskArgs& a, const BezkTaskCfg* cfg, void* stream, const char* where, int task = BEZK_TASK_KICK) {
     if (int rc = check_cfg(cfg)) return rc;
     REQUIRE(a.n >= 0, "n < 0");
     if (a.n == 0) return 0;
-    REQUIRE(a.dof_state && a.rigid_body && a.root_states && a.goal && a.ball_init, "state tensor NULL");
-    if (!ALIGNED(a.goal, 8) || !ALIGNED(a.ball_init, 8)) return fail(BEZK_E_ALIGN, "goal / ball_init must be 8-byte aligned");
+    REQUIRE(a.dof_state && a.rigid_body && a.root_states, "state tensor NULL");
+    if (task == BEZK_TASK_KICK) {
+        REQUIRE(a.goal && a.ball_init, "goal / ball_init NULL");
+        if (!ALIGNED(a.goal, 8) || !ALIGNED(a.ball_init, 8)) return fail(BEZK_E_ALIGN, "goal / ball_init must be 8-byte aligned");
+    } else {
+        REQUIRE(parts == 2 || parts == 3 || parts == 4 || parts == 7, "walk / orient: parts must be 2, 3, 4 or 7");
+        REQUIRE(a.goal, "goal NULL");
+        if (!ALIGNED(a.goal, 8)) return fail(BEZK_E_ALIGN, "goal must be 8-byte aligned");
+        if (task == BEZK_TASK_ORIENT) REQUIRE(a.goal_angle, "goal_angle NULL");
+    }
     if (parts & BEZK_PART_OBS) REQUIRE(a.net_contact && a.obs, "net_contact/obs NULL");
     if (parts & BEZK_PART_REWARD) REQUIRE(a.rew && a.reset_in && a.reset_out && a.progress_in, "reward buffers NULL");
     if (parts & BEZK_PART_BOOKKEEP) {
@@ -65,7 +73,7 @@ static int run_task(int parts, bezk::TaskArgs& a, const BezkTaskCfg* cfg, void* 
         if (cfg->flags & BEZK_F_RESET_ROOT_STATES) REQUIRE(a.initial_root, "initial_root_states NULL");
     }
     bezk::fill_alignment(a, *cfg);
-    return cuda_rc(bezk::launch_task(parts, a, *cfg, (cudaStream_t)stream), where);
+    return cuda_rc(bezk::launch_task(task, parts, a, *cfg, (cudaStream_t)stream), where);
 }
 
 int bezk_compute_observations(const float* dof_state, const float* rigid_body, const float* root_states, float* net_contact,
@@ -74,7 +82,7 @@ int bezk_compute_observations(const float* dof_state, const float* rigid_body, c
     bezk::TaskArgs a;
     memset(&a, 0, sizeof(a));
     a.dof_state = const_cast<float*>(dof_state); a.rigid_body = rigid_body; a.root_states = const_cast<float*>(root_states);
-    a.net_contact = net_contact; a.prev_lin_vel = prev_lin_vel; a.goal = goal; a.ball_init = ball_init;
+    a.net_contact = net_contact; a.prev_lin_vel = prev_lin_vel; a.goal = const_cast<float*>(goal); a.ball_init = ball_init;
     a.obs = obs; a.obs_clipped = obs_clipped; a.n = n;
     return run_task(BEZK_PART_OBS, a, cfg, stream, "bezk_compute_observations");
 }
@@ -85,7 +93,7 @@ int bezk_compute_reward(const float* dof_state, const float* rigid_body, const f
     bezk::TaskArgs a;
     memset(&a, 0, sizeof(a));
     a.dof_state = const_cast<float*>(dof_state); a.rigid_body = rigid_body; a.root_states = const_cast<float*>(root_states);
-    a.goal = goal; a.ball_init = ball_init; a.reset_in = reset_in; a.reset_out = reset_out; a.progress_in = progress;
+    a.goal = const_cast<float*>(goal); a.ball_init = ball_init; a.reset_in = reset_in; a.reset_out = reset_out; a.progress_in = progress;
     a.rew = rew; a.n = n;
     return run_task(BEZK_PART_REWARD, a, cfg, stream, "bezk_compute_reward");
 }
@@ -99,7 +107,21 @@ int bezk_reset_idx(const int64_t* env_ids, int64_t k, const float* uniforms, uin
     REQUIRE(env_ids && dof_state && progress && reset, "reset_idx buffers NULL");
     if (cfg->flags & BEZK_F_RESET_ROOT_STATES) REQUIRE(root_states && initial_root_states, "root state buffers NULL");
     return cuda_rc(bezk::launch_reset_idx(env_ids, k, uniforms, seed, step, dof_state, root_states, initial_root_states, progress,
-                                          reset, *cfg, n, (cudaStream_t)stream), "bezk_reset_idx");
+                                          reset, *cfg, n, BEZK_TASK_KICK, nullptr, nullptr, (cudaStream_t)stream), "bezk_reset_idx");
+}
+
+int bezk_reset_idx_task(int task, const int64_t* env_ids, int64_t k, const float* uniforms, const float* goal_uniforms, uint64_t seed,
+                        uint64_t step, float* dof_state, float* root_states, const float* initial_root_states, float* goal,
+                        int64_t* progress, int64_t* reset, const BezkTaskCfg* cfg, int64_t n, void* stream) {
+    REQUIRE(task == BEZK_TASK_KICK || task == BEZK_TASK_WALK || task == BEZK_TASK_ORIENT, "unknown task");
+    if (int rc = check_cfg(cfg)) return rc;
+    REQUIRE(k >= 0 && n >= 0, "k/n < 0");
+    if (k == 0) return 0;
+    REQUIRE(env_ids && dof_state && progress && reset, "reset_idx buffers NULL");
+    if (task != BEZK_TASK_KICK) REQUIRE(goal, "goal NULL");
+    if (cfg->flags & BEZK_F_RESET_ROOT_STATES) REQUIRE(root_states && initial_root_states, "root state buffers NULL");
+    return cuda_rc(bezk::launch_reset_idx(env_ids, k, uniforms, seed, step, dof_state, root_states, initial_root_states, progress,
+                                          reset, *cfg, n, task, goal, goal_uniforms, (cudaStream_t)stream), "bezk_reset_idx_task");
 }
 
 int bezk_post_physics(float* dof_state, const float* rigid_body, float* root_states, float* net_contact, float* prev_lin_vel,
@@ -111,12 +133,35 @@ int bezk_post_physics(float* dof_state, const float* rigid_body, float* root_sta
     bezk::TaskArgs a;
     memset(&a, 0, sizeof(a));
     a.dof_state = dof_state; a.rigid_body = rigid_body; a.root_states = root_states; a.net_contact = net_contact;
-    a.prev_lin_vel = prev_lin_vel; a.goal = goal; a.ball_init = ball_init; a.initial_root = initial_root_states;
+    a.prev_lin_vel = prev_lin_vel; a.goal = const_cast<float*>(goal); a.ball_init = ball_init; a.initial_root = initial_root_states;
     a.uniforms = uniforms; a.seed = seed; a.step = step;
     a.reset_in = reset_buf; a.reset_out = reset_buf; a.progress_in = progress_buf; a.progress_out = progress_buf;
     a.timeout_buf = timeout_buf; a.randomize_buf = randomize_buf;
     a.obs = obs; a.obs_clipped = obs_clipped; a.rew = rew; a.n = n;
     return run_task(parts, a, cfg, stream, "bezk_post_physics");
+}
+
+int bezk_post_physics_task(int task, float* dof_state, const float* rigid_body, float* root_states, float* net_contact,
+                           float* prev_lin_vel, float* goal, const float* goal_angle, const float* ball_init,
+                           const float* initial_root_states, const float* uniforms, const float* goal_uniforms, uint64_t seed,
+                           uint64_t step, int64_t* reset_buf, int64_t* progress_buf, int64_t* timeout_buf, int64_t* randomize_buf,
+                           const BezkTaskCfg* cfg, float* obs, float* obs_clipped, float* rew, int parts, int64_t n, void* stream) {
+    REQUIRE(task == BEZK_TASK_KICK || task == BEZK_TASK_WALK || task == BEZK_TASK_ORIENT, "unknown task");
+    REQUIRE(parts >= 1 && parts <= 7, "parts must be a non-empty subset of {1,2,4}");
+    bezk::TaskArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dof_state = dof_state; a.rigid_body = rigid_body; a.root_states = root_states; a.net_contact = net_contact;
+    a.prev_lin_vel = prev_lin_vel; a.goal = goal; a.goal_angle = goal_angle; a.goal_uniforms = goal_uniforms; a.ball_init = ball_init;
+    a.initial_root = initial_root_states; a.uniforms = uniforms; a.seed = seed; a.step = step;
+    a.reset_in = reset_buf; a.reset_out = reset_buf; a.progress_in = progress_buf; a.progress_out = progress_buf;
+    a.timeout_buf = timeout_buf; a.randomize_buf = randomize_buf;
+    a.obs = obs; a.obs_clipped = obs_clipped; a.rew = rew; a.n = n;
+    return run_task(parts, a, cfg, stream, "bezk_post_physics_task", task);
+}
+
+int bezk_goal_uniforms(uint64_t seed, uint64_t step, float* out2, void* stream) {
+    REQUIRE(out2, "out2 NULL");
+    return cuda_rc(bezk::launch_goal_uniforms(seed, step, out2, (cudaStream_t)stream), "bezk_goal_uniforms");
 }
 
 int bezk_philox_uniforms(uint64_t seed, uint64_t step, float* out, int64_t n, void* stream) {

@@ -11,8 +11,10 @@ struct TaskArgs {
     float* root_states;          // (n*2, 13)
     float* net_contact;          // (n*NB, 3)
     float* prev_lin_vel;         // (n, 3) or nullptr (aliasing mode)
-    const float* goal;           // (n, 2)
-    const float* ball_init;      // (n, 2)
+    float* goal;                 // (n, 2); rewritten on reset by the walk / orient tasks
+    const float* goal_angle;     // (n,)  orient task only
+    const float* goal_uniforms;  // (2,)  per-step goal draw or nullptr (Philox)
+    const float* ball_init;      // (n, 2)  BezKick only
     const float* initial_root;   // (n*2, 13)
     const float* uniforms;       // (n, 36) or nullptr (Philox)
     uint64_t seed, step;
@@ -40,11 +42,12 @@ struct PpoArgs {
     int slabs;
     int use_tma;
 };
-cudaError_t launch_task(int parts, const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st);
+cudaError_t launch_task(int task, int parts, const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st);
+cudaError_t launch_goal_uniforms(uint64_t seed, uint64_t step, float* out2, cudaStream_t st);
 void fill_alignment(TaskArgs& a, const BezkTaskCfg& cfg);
 cudaError_t launch_pre_physics(const float*, float*, float*, const BezkTaskCfg&, int64_t, cudaStream_t);
 cudaError_t launch_reset_idx(const int64_t*, int64_t, const float*, uint64_t, uint64_t, float*, float*, const float*, int64_t*,
-                             int64_t*, const BezkTaskCfg&, int64_t, cudaStream_t);
+                             int64_t*, const BezkTaskCfg&, int64_t, int, float*, const float*, cudaStream_t);
 cudaError_t launch_philox_uniforms(uint64_t, uint64_t, float*, int64_t, cudaStream_t);
 cudaError_t launch_gae(const float*, const float*, const void*, const float*, const void*, int, double, double, float*, float*,
                        int, int64_t, cudaStream_t);

@@ -31,10 +31,15 @@ namespace bezk {
 // registers, spilling) 16 % slower, a persistent 2-stage pipelined variant (12 warps/SM) 28 % slower and cross-CTA L2
 // prefetch 15 % slower -- measured, profiles/r01_kernels.md.
 constexpr int DOF_ROW = 36;          // floats per env in dof_state
-constexpr int ROOT_ROW = 26;         // floats per env in root_states
-constexpr int OBS_ROW = 54;
-__host__ __device__ constexpr int smem_in_floats(int tile) { return tile * (DOF_ROW + ROOT_ROW); }   // TILE=128: 7936 floats = 31744 B >= TILE*54*4
-__host__ __device__ constexpr int smem_obs_floats(int tile) { return tile * OBS_ROW; }              // TILE=128: 6912 floats = 27648 B
+// Task variants (tasks/kick_env.py, tasks/walk_env.py, tasks/orient_env.py share one skeleton): BezKick has two actors per env
+// (robot + ball -> 26 root floats) and a 54-wide observation; walk / orient have the robot only (13) and 52 columns.
+__host__ __device__ constexpr int root_row(int task) { return task == BEZK_TASK_KICK ? 26 : 13; }
+__host__ __device__ constexpr int obs_row(int task) { return task == BEZK_TASK_KICK ? 54 : 52; }
+// per-tile shared memory: the observation rows alias the input tiles, so the region is the larger of the two
+__host__ __device__ constexpr int smem_in_floats(int tile, int task = BEZK_TASK_KICK) {
+    return tile * (DOF_ROW + root_row(task)) > tile * obs_row(task) ? tile * (DOF_ROW + root_row(task)) : tile * obs_row(task);
+}
+__host__ __device__ constexpr int smem_obs_floats(int tile, int task = BEZK_TASK_KICK) { return tile * obs_row(task); }
 
 
 // ------------------------------------------------------------------------------------------------
@@ -151,6 +156,100 @@ __device__ __forceinline__ void foot_bits(float (&f)[3], float (&bits)[4]) {
     bits[0] = b0; bits[1] = b1; bits[2] = b2; bits[3] = b3;
 }
 
+// yaw of isaacgym.torch_utils.get_euler_xyz (mod 2 pi)
+__device__ __forceinline__ float yaw_mod_2pi(const float (&q)[4]) {
+    const float x = q[0], y = q[1], z = q[2], w = q[3];
+    const float siny = 2.0f * (w * z + x * y);
+    const float cosy = ((w * w + x * x) - y * y) - z * z;
+    return py_mod(atan2f(siny, cosy), 6.283185307179586f);
+}
+
+// compute_off_angle, orient_env.py:720-733: (cos, sin) of goal_angle - normalize_angle(yaw)
+__device__ __forceinline__ float angle_to_goal(const float (&q)[4], float goal_angle) {
+    const float yaw = yaw_mod_2pi(q);
+    const float na = atan2f(sinf(yaw), cosf(yaw));       // normalize_angle
+    return goal_angle - na;
+}
+
+// quantities walk_env.py:849-876 / orient_env.py:875-897 share
+struct WalkTerms { float up_proj, vel6, vel_lin, vel_ang, pos; };
+__device__ __forceinline__ WalkTerms walk_terms(const float (&q)[4], const float (&v)[3], const float (&w)[3], float pos_sq) {
+    WalkTerms t;
+    // get_basis_vector(q, (0,0,1))[2] = quat_rotate z component: a + b + c
+    const float qx = q[0], qy = q[1], qz = q[2], qw = q[3];
+    const float a_z = 1.0f * (2.0f * (qw * qw) - 1.0f);
+    const float b_z = ((qx * 0.0f - qy * 0.0f) * qw) * 2.0f;            // cross(q_vec, v).z * q_w * 2
+    const float dot = (qx * 0.0f + qy * 0.0f) + qz * 1.0f;              // bmm(q_vec, v)
+    const float c_z = (qz * dot) * 2.0f;
+    t.up_proj = (a_z + b_z) + c_z;
+    float s3 = v[0] * v[0]; s3 += v[1] * v[1]; s3 += v[2] * v[2];
+    float a3 = w[0] * w[0]; a3 += w[1] * w[1]; a3 += w[2] * w[2];
+    float s6 = s3; s6 += w[0] * w[0]; s6 += w[1] * w[1]; s6 += w[2] * w[2];
+    t.vel6 = sqrtf(s6); t.vel_lin = sqrtf(s3); t.vel_ang = sqrtf(a3);
+    t.pos = sqrtf(pos_sq);
+    return t;
+}
+
+// shared tail of the two reward functions: fall, win state, (task rule), horizon
+__device__ __forceinline__ void walk_tail(const WalkTerms& t, bool close, float rew, bool out_rule, float out_value, const BezkTaskCfg& c,
+                                          int64_t progress, int64_t reset_cur, float* rew_out, int64_t* reset_out) {
+    int64_t reset = reset_cur;
+    if (t.up_proj < 0.7f) { reset = 1; rew = -100.0f; }                                          // fall
+    float state = close ? 1.0f : 0.0f;
+    if (t.pos < 0.15f) state += 1.0f;
+    if (t.vel_ang < 0.1f) state += 1.0f;
+    if (t.vel_lin < 0.1f) state += 1.0f;
+    if (state == 4.0f) {                                                                          // win state
+        reset = 1;
+        rew = 1.0f * (1000.0f - 1000.0f * ((float)progress / (float)c.max_episode_length));
+    }
+    if (out_rule) { reset = 1; rew = out_value; }                                                 // out of bound
+    if (progress >= (int64_t)c.max_episode_length) { reset = 1; rew = 0.0f; }                     // horizon
+    *rew_out = rew;
+    *reset_out = reset;
+}
+
+// compute_bez_reward of tasks/walk_env.py:827-997 (debug prints and dead terms dropped)
+__device__ __forceinline__ void reward_walk(const float (&bez)[3], const float (&q)[4], const float (&v)[3], const float (&w)[3],
+                                            float pos_sq, const float (&goal)[2], const BezkTaskCfg& c, int64_t progress,
+                                            int64_t reset_cur, float* rew_out, int64_t* reset_out) {
+    const float dx = goal[0] - bez[0], dy = goal[1] - bez[1];
+    const float n_goal = sqrtf(dx * dx + dy * dy);
+    const float ux = dx / n_goal, uy = dy / n_goal;
+    const float vel_fwd = ux * v[0] + uy * v[1];
+    const WalkTerms t = walk_terms(q, v, w, pos_sq);
+    const float dist_h = fabsf(1.0f - t.up_proj);
+    const float vel_s = t.vel6 * 0.05f, pos_s = t.pos * 0.05f;
+    const float height_vel_pos = -((vel_s + pos_s) + dist_h);
+    const float vel_height = (vel_fwd * 10.0f - (dist_h + 5.0f * pos_s)) * 1.0f;
+    const bool close = n_goal < 0.05f;
+    const float rew = close ? height_vel_pos : vel_height;
+    // out of bound: angle between (goal - (0,0)) and (goal - bez_xy)   (walk_env.py:966-989; bez_init_state is zeroed in place)
+    const float ix = goal[0] - 0.0f, iy = goal[1] - 0.0f;
+    const float n_i = sqrtf(ix * ix + iy * iy);
+    const float ang_now = atan2f(uy, ux);
+    const float ang_init = atan2f(iy / n_i, ix / n_i);
+    const bool out = fabsf(ang_init - ang_now) > 1.5708f;
+    walk_tail(t, close, rew, out, -100.0f, c, progress, reset_cur, rew_out, reset_out);
+}
+
+// compute_bez_reward of tasks/orient_env.py:845-1014
+__device__ __forceinline__ void reward_orient(const float (&bez)[3], const float (&q)[4], const float (&v)[3], const float (&w)[3],
+                                              float pos_sq, float goal_angle, const BezkTaskCfg& c, int64_t progress,
+                                              int64_t reset_cur, float* rew_out, int64_t* reset_out) {
+    const float ang = angle_to_goal(q, goal_angle);
+    const WalkTerms t = walk_terms(q, v, w, pos_sq);
+    const float dist_h = fabsf(1.0f - t.up_proj);
+    const float vel_s = t.vel6 * 0.05f, pos_s = t.pos * 0.05f;
+    const float height_vel_pos = -((vel_s + pos_s) + dist_h);
+    const float vel_height = (fabsf(ang) * -0.5f - (dist_h + 0.05f * pos_s)) * 1.0f;
+    const bool close = ang < 0.05f;                       // the SIGNED angle, as the reference compares it
+    const float rew = close ? height_vel_pos : vel_height;
+    const float tx = bez[0] - c.bez_init_xy[0], ty = bez[1] - c.bez_init_xy[1];
+    const bool out = sqrtf(tx * tx + ty * ty) > 0.3f;
+    walk_tail(t, close, rew, out, -5.0f, c, progress, reset_cur, rew_out, reset_out);
+}
+
 struct RewardIn {
     float bez[3];          // torso root position
     float ball_xy[2];
@@ -221,12 +320,20 @@ __device__ __forceinline__ void reset_dof_row(const float (&u)[36], const BezkTa
 // net_contact (sparse AoS gathers) and the small per-env scalars.  Kept in registers; all loads are independent, so a
 // caller can issue them long before the values are consumed.
 // ------------------------------------------------------------------------------------------------
+// the per-step goal draw of the walk / orient reset: counter (2^32-1, 2^32-1, step_lo, step_hi*16 + 15) never collides with
+// an env's reset counters (env ids are < 2^63, sub-counter 0..8)
+__device__ __forceinline__ Philox4 philox_goal(uint64_t seed, uint64_t step) {
+    return philox4x32_10(0xFFFFFFFFu, 0xFFFFFFFFu, (uint32_t)step, ((uint32_t)(step >> 32) << 4) + 15u, (uint32_t)seed,
+                         (uint32_t)(seed >> 32));
+}
+
 template <bool CLEATS>
 struct Gathered {
     // raw load results: NOTHING depends on them until consume(), so issuing gather_env() never stalls the warp
     float raw[10];                       // the 40-byte IMU-link slice in LOAD order (vector path: 8 B, 16 B, 16 B pieces)
     float fl[CLEATS ? 12 : 3], fr[CLEATS ? 12 : 3];
     float goal[2], binit[2], prev[3];
+    float gang;                          // orient task: goal angle
     long long reset_prev, progress;
 };
 
@@ -246,13 +353,14 @@ __device__ __forceinline__ float ld_f32(const float* p) {
     return v;
 }
 
-template <bool OBS, bool BOOKREW, bool CLEATS>
+template <bool OBS, bool BOOKREW, bool CLEATS, int TASK>
 __device__ __forceinline__ void gather_env(const TaskArgs& a, const BezkTaskCfg& cfg, int64_t e, bool valid, Gathered<CLEATS>& g) {
     constexpr int NFORCE = CLEATS ? 12 : 3;
 #pragma unroll
     for (int k = 0; k < NFORCE; ++k) { g.fl[k] = 0.0f; g.fr[k] = 0.0f; }
     g.goal[0] = g.goal[1] = g.binit[0] = g.binit[1] = 0.0f;
     g.prev[0] = g.prev[1] = g.prev[2] = 0.0f;
+    g.gang = 0.0f;
     g.reset_prev = 0; g.progress = 0;
 #pragma unroll
     for (int k = 0; k < 10; ++k) g.raw[k] = 0.0f;
@@ -302,9 +410,16 @@ __device__ __forceinline__ void gather_env(const TaskArgs& a, const BezkTaskCfg&
                 for (int k = 0; k < 3; ++k) g.prev[k] = ld_f32(a.prev_lin_vel + e * 3 + k);
             }
         }
-        const float2 g2 = ld_nc_v2(reinterpret_cast<const float2*>(a.goal) + e);
-        const float2 b2 = ld_nc_v2(reinterpret_cast<const float2*>(a.ball_init) + e);
-        g.goal[0] = g2.x; g.goal[1] = g2.y; g.binit[0] = b2.x; g.binit[1] = b2.y;
+        if (TASK == BEZK_TASK_KICK) {
+            const float2 g2 = ld_nc_v2(reinterpret_cast<const float2*>(a.goal) + e);
+            const float2 b2 = ld_nc_v2(reinterpret_cast<const float2*>(a.ball_init) + e);
+            g.goal[0] = g2.x; g.goal[1] = g2.y; g.binit[0] = b2.x; g.binit[1] = b2.y;
+        } else if (TASK == BEZK_TASK_WALK) {      // goal is rewritten by this kernel on reset: coherent load
+            const float2 g2 = ldg128B_v2(reinterpret_cast<const float2*>(a.goal) + e);
+            g.goal[0] = g2.x; g.goal[1] = g2.y;
+        } else {
+            g.gang = ld_f32(a.goal_angle + e);
+        }
         if (BOOKREW) {
             g.reset_prev = ld_i64(a.reset_in + e);
             g.progress = ld_i64(a.progress_in + e);
@@ -330,8 +445,10 @@ __device__ __forceinline__ void consume(const TaskArgs& a, const BezkTaskCfg& cf
 // ------------------------------------------------------------------------------------------------
 // The fused tile kernel.  PARTS: 1 bookkeeping+masked reset, 2 observations, 4 reward/termination.
 // ------------------------------------------------------------------------------------------------
-template <int PARTS, bool CLEATS, int TILE>
+template <int PARTS, bool CLEATS, int TILE, int TASK>
 __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_kernel(const TaskArgs a, const __grid_constant__ BezkTaskCfg cfg) {
+    constexpr int ROOT_ROW = root_row(TASK);
+    constexpr int OBS_ROW = obs_row(TASK);
     constexpr bool BOOK = (PARTS & BEZK_PART_BOOKKEEP) != 0;
     constexpr bool OBS = (PARTS & BEZK_PART_OBS) != 0;
     constexpr bool REW = (PARTS & BEZK_PART_REWARD) != 0;
@@ -348,10 +465,10 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    float* s_dof = smem + warp * smem_in_floats(WT);                              // [32][36]
-    float* s_root = s_dof + WT * DOF_ROW;                                          // [32][26]
-    float* s_obs = s_dof;                                                          // [32][54], aliases this warp's input tiles
-    float* s_obs_clip = smem + smem_in_floats(TILE) + warp * smem_obs_floats(WT);  // [32][54], only when a.obs_clipped
+    float* s_dof = smem + warp * smem_in_floats(WT, TASK);                         // [32][36]
+    float* s_root = s_dof + WT * DOF_ROW;                                          // [32][26 | 13]
+    float* s_obs = s_dof;                                                          // [32][54 | 52], aliases this warp's input tiles
+    float* s_obs_clip = smem + smem_in_floats(TILE, TASK) + warp * smem_obs_floats(WT, TASK);   // only when a.obs_clipped
     uint64_t* s_bar = &s_bars[warp];
 
     const int64_t e0 = (int64_t)blockIdx.x * TILE + warp * WT;                     // first env of this warp's sub-tile
@@ -381,7 +498,7 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
 
     // ---- 2. sparse gathers, issued before anyone waits (widest aligned vector loads available) ----
     Gathered<CLEATS> g;
-    gather_env<OBS, (BOOK || REW), CLEATS>(a, cfg, e, valid, g);
+    gather_env<OBS, (BOOK || REW), CLEATS, TASK>(a, cfg, e, valid, g);
 
     float imu_in[10];
     consume<CLEATS>(a, cfg, e, g, imu_in);
@@ -455,7 +572,18 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
             timeout = (progress >= (int64_t)cfg.max_episode_length - 1) ? 1 : 0;
             progress += 1;
             if (a.randomize_buf) a.randomize_buf[e] += 1;
-            if (reset_prev != 0) { progress = 0; reset_cur = 0; }
+            if (reset_prev != 0) {
+                progress = 0; reset_cur = 0;
+                if (TASK != BEZK_TASK_KICK) {
+                    // goal randomisation (walk_env.py:566-574): ONE draw per reset batch, i.e. per step
+                    float ux, uy;
+                    if (a.goal_uniforms) { ux = a.goal_uniforms[0]; uy = a.goal_uniforms[1]; }
+                    else { const Philox4 x = philox_goal(a.seed, a.step); ux = u01(x.x); uy = u01(x.y); }
+                    goal[0] = 4.0f * ux + -2.0f;                 // torch_rand_float(-2, 2): (hi - lo) * u + lo
+                    goal[1] = 4.0f * uy + -2.0f;
+                    reinterpret_cast<float2*>(a.goal)[e] = make_float2(goal[0], goal[1]);
+                }
+            }
             a.timeout_buf[e] = timeout;
             if (!REW) { a.progress_out[e] = progress; a.reset_out[e] = reset_cur; }
         }
@@ -473,8 +601,10 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
         }
         const float* rr = s_root + lane * ROOT_ROW;
         bez[0] = rr[0]; bez[1] = rr[1]; bez[2] = rr[2];
-        ball_xy[0] = rr[13]; ball_xy[1] = rr[14];
-        ball_vxy[0] = rr[20]; ball_vxy[1] = rr[21];
+        if (TASK == BEZK_TASK_KICK) {
+            ball_xy[0] = rr[13]; ball_xy[1] = rr[14];
+            ball_vxy[0] = rr[20]; ball_vxy[1] = rr[21];
+        }
     }
 
     // ---- 6. observations (kick_env.py:749-777) ----
@@ -488,7 +618,12 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
 #pragma unroll
             for (int k = 0; k < 3; ++k) a.prev_lin_vel[e * 3 + k] = v[k];
         }
-        off_orn_term(bez[0], bez[1], q, goal[0], goal[1], orn2);
+        if (TASK == BEZK_TASK_ORIENT) {                                    // compute_off_angle, orient_env.py:720-733
+            const float d = angle_to_goal(q, g.gang);
+            orn2[0] = cosf(d); orn2[1] = sinf(d);
+        } else {
+            off_orn_term(bez[0], bez[1], q, goal[0], goal[1], orn2);
+        }
         if (CLEATS) {                                                      // kick_env.py:1053-1061
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -537,12 +672,12 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
             o2[21] = make_float2(orn2[0], orn2[1]);
             o2[22] = make_float2(feet[0], feet[1]); o2[23] = make_float2(feet[2], feet[3]);
             o2[24] = make_float2(feet[4], feet[5]); o2[25] = make_float2(feet[6], feet[7]);
-            o2[26] = make_float2(binit[0], binit[1]);
+            if (TASK == BEZK_TASK_KICK) o2[26] = make_float2(binit[0], binit[1]);
             if (a.obs_clipped) {           // vec_task.py:343 clamp(obs_buf, -clip_obs, clip_obs)
                 float2* c2 = reinterpret_cast<float2*>(s_obs_clip + lane * OBS_ROW);
                 const float lim = cfg.clip_obs;
 #pragma unroll
-                for (int k = 0; k < 27; ++k) {
+                for (int k = 0; k < OBS_ROW / 2; ++k) {
                     const float2 t = o2[k];
                     c2[k] = make_float2(clamp_nan(t.x, -lim, lim), clamp_nan(t.y, -lim, lim));
                 }
@@ -565,7 +700,16 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
     }
 
     // ---- 8. reward / termination (overlaps the bulk store) ----
-    if (REW && valid) {
+    if (REW && valid && TASK != BEZK_TASK_KICK) {
+        float rew;
+        int64_t reset;
+        if (TASK == BEZK_TASK_WALK) reward_walk(bez, q, v, w, pos_sq, goal, cfg, progress, reset_cur, &rew, &reset);
+        else reward_orient(bez, q, v, w, pos_sq, g.gang, cfg, progress, reset_cur, &rew, &reset);
+        a.rew[e] = rew;
+        a.reset_out[e] = reset;
+        if (BOOK) a.progress_out[e] = progress;
+    }
+    if (REW && valid && TASK == BEZK_TASK_KICK) {
         RewardIn s;
         s.bez[0] = bez[0]; s.bez[1] = bez[1]; s.bez[2] = bez[2];
         s.ball_xy[0] = ball_xy[0]; s.ball_xy[1] = ball_xy[1];
@@ -592,7 +736,8 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
 __global__ void __launch_bounds__(128) reset_idx_kernel(const int64_t* __restrict__ env_ids, int64_t k, const float* __restrict__ uniforms,
                                                         uint64_t seed, uint64_t step, float* dof_state, float* root_states,
                                                         const float* __restrict__ initial_root, int64_t* progress, int64_t* reset,
-                                                        const __grid_constant__ BezkTaskCfg cfg, int64_t n) {
+                                                        const __grid_constant__ BezkTaskCfg cfg, int64_t n, int root_floats,
+                                                        float* goal, const float* __restrict__ goal_uniforms) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= k) return;
     const int64_t e = env_ids[i];
@@ -608,8 +753,14 @@ __global__ void __launch_bounds__(128) reset_idx_kernel(const int64_t* __restric
 #pragma unroll
     for (int c = 0; c < 36; ++c) dof_state[e * DOF_ROW + c] = row[c];
     if (cfg.flags & BEZK_F_RESET_ROOT_STATES) {
-#pragma unroll
-        for (int c = 0; c < ROOT_ROW; ++c) root_states[e * ROOT_ROW + c] = initial_root[e * ROOT_ROW + c];
+        for (int c = 0; c < root_floats; ++c) root_states[e * root_floats + c] = initial_root[e * root_floats + c];
+    }
+    if (goal) {                                    // walk / orient: one goal draw per reset batch (walk_env.py:566-574)
+        float ux, uy;
+        if (goal_uniforms) { ux = goal_uniforms[0]; uy = goal_uniforms[1]; }
+        else { const Philox4 x = philox_goal(seed, step); ux = u01(x.x); uy = u01(x.y); }
+        goal[e * 2] = 4.0f * ux + -2.0f;
+        goal[e * 2 + 1] = 4.0f * uy + -2.0f;
     }
     progress[e] = 0;
     reset[e] = 0;
@@ -630,36 +781,60 @@ __global__ void philox_uniforms_kernel(uint64_t seed, uint64_t step, float* out,
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 
-template <int PARTS, bool CLEATS, int TILE>
+template <int PARTS, bool CLEATS, int TILE, int TASK>
 static cudaError_t launch_parts3(const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st) {
-    const size_t smem = (size_t)(smem_in_floats(TILE) + (a.obs_clipped ? smem_obs_floats(TILE) : 0)) * sizeof(float);
+    const size_t smem = (size_t)(smem_in_floats(TILE, TASK) + (a.obs_clipped ? smem_obs_floats(TILE, TASK) : 0)) * sizeof(float);
     static bool attr_set = false;          // per instantiation; opt in to > 48 KB dynamic shared memory once
     if (!attr_set) {
-        cudaError_t err = cudaFuncSetAttribute(task_tile_kernel<PARTS, CLEATS, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)((smem_in_floats(TILE) + smem_obs_floats(TILE)) * sizeof(float)));
+        cudaError_t err = cudaFuncSetAttribute(task_tile_kernel<PARTS, CLEATS, TILE, TASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)((smem_in_floats(TILE, TASK) + smem_obs_floats(TILE, TASK)) * sizeof(float)));
         if (err != cudaSuccess) return err;
         attr_set = true;
     }
     const int64_t tiles = (a.n + TILE - 1) / TILE;
-    return launch_ex(task_tile_kernel<PARTS, CLEATS, TILE>, dim3((unsigned)tiles), dim3(TILE), smem, st, a, cfg);
+    return launch_ex(task_tile_kernel<PARTS, CLEATS, TILE, TASK>, dim3((unsigned)tiles), dim3(TILE), smem, st, a, cfg);
 }
 
-template <int PARTS>
+template <int PARTS, int TASK>
 static cudaError_t launch_parts(const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st) {
-    return (cfg.flags & BEZK_F_CLEATS) ? launch_parts3<PARTS, true, 128>(a, cfg, st) : launch_parts3<PARTS, false, 128>(a, cfg, st);
+    return (cfg.flags & BEZK_F_CLEATS) ? launch_parts3<PARTS, true, 128, TASK>(a, cfg, st) : launch_parts3<PARTS, false, 128, TASK>(a, cfg, st);
 }
 
-cudaError_t launch_task(int parts, const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st) {
+// walk / orient: the fused step (7), the observation kernel (2 or 3) and the reward kernel (4)
+template <int TASK>
+static cudaError_t launch_sibling(int parts, const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st) {
     switch (parts) {
-        case 1: return launch_parts<1>(a, cfg, st);
-        case 2: return launch_parts<2>(a, cfg, st);
-        case 3: return launch_parts<3>(a, cfg, st);
-        case 4: return launch_parts<4>(a, cfg, st);
-        case 5: return launch_parts<5>(a, cfg, st);
-        case 6: return launch_parts<6>(a, cfg, st);
-        case 7: return launch_parts<7>(a, cfg, st);
+        case 2: return launch_parts<2, TASK>(a, cfg, st);
+        case 3: return launch_parts<3, TASK>(a, cfg, st);
+        case 4: return launch_parts<4, TASK>(a, cfg, st);
+        case 7: return launch_parts<7, TASK>(a, cfg, st);
         default: return cudaErrorInvalidValue;
     }
+}
+
+cudaError_t launch_task(int task, int parts, const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st) {
+    if (task == BEZK_TASK_WALK) return launch_sibling<BEZK_TASK_WALK>(parts, a, cfg, st);
+    if (task == BEZK_TASK_ORIENT) return launch_sibling<BEZK_TASK_ORIENT>(parts, a, cfg, st);
+    if (task != BEZK_TASK_KICK) return cudaErrorInvalidValue;
+    switch (parts) {
+        case 1: return launch_parts<1, BEZK_TASK_KICK>(a, cfg, st);
+        case 2: return launch_parts<2, BEZK_TASK_KICK>(a, cfg, st);
+        case 3: return launch_parts<3, BEZK_TASK_KICK>(a, cfg, st);
+        case 4: return launch_parts<4, BEZK_TASK_KICK>(a, cfg, st);
+        case 5: return launch_parts<5, BEZK_TASK_KICK>(a, cfg, st);
+        case 6: return launch_parts<6, BEZK_TASK_KICK>(a, cfg, st);
+        case 7: return launch_parts<7, BEZK_TASK_KICK>(a, cfg, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+__global__ void goal_uniforms_kernel(uint64_t seed, uint64_t step, float* out2) {
+    const Philox4 x = philox_goal(seed, step);
+    out2[0] = u01(x.x); out2[1] = u01(x.y);
+}
+cudaError_t launch_goal_uniforms(uint64_t seed, uint64_t step, float* out2, cudaStream_t st) {
+    goal_uniforms_kernel<<<1, 1, 0, st>>>(seed, step, out2);
+    return cudaGetLastError();
 }
 
 void fill_alignment(TaskArgs& a, const BezkTaskCfg& cfg) {
@@ -684,10 +859,12 @@ cudaError_t launch_pre_physics(const float* actions, float* actions_out, float* 
 
 cudaError_t launch_reset_idx(const int64_t* env_ids, int64_t k, const float* uniforms, uint64_t seed, uint64_t step,
                              float* dof_state, float* root_states, const float* initial_root, int64_t* progress,
-                             int64_t* reset, const BezkTaskCfg& cfg, int64_t n, cudaStream_t st) {
+                             int64_t* reset, const BezkTaskCfg& cfg, int64_t n, int task, float* goal, const float* goal_uniforms,
+                             cudaStream_t st) {
     if (k == 0) return cudaSuccess;
     reset_idx_kernel<<<(unsigned)((k + 127) / 128), 128, 0, st>>>(env_ids, k, uniforms, seed, step, dof_state, root_states,
-                                                                  initial_root, progress, reset, cfg, n);
+                                                                  initial_root, progress, reset, cfg, n, root_row(task),
+                                                                  task == BEZK_TASK_KICK ? nullptr : goal, goal_uniforms);
     return cudaGetLastError();
 }
 

@@ -151,6 +151,51 @@ def post_physics(dof_state, rigid_body, root_states, net_contact, goal, ball_ini
         _stream(progress_buf)), "bezk_post_physics")
 
 
+_TASK_ID = {"kick": _lib.TASK_KICK, "walk": _lib.TASK_WALK, "orient": _lib.TASK_ORIENT}
+
+
+def post_physics_task(task, dof_state, rigid_body, root_states, net_contact, goal, initial_root_states, reset_buf,
+                      progress_buf, timeout_buf, cfg, obs, rew, goal_angle=None, ball_init=None, prev_lin_vel=None,
+                      uniforms=None, goal_uniforms=None, seed=0, step=0, randomize_buf=None, obs_clipped=None,
+                      parts=_lib.PART_ALL):
+    """``post_physics`` for any of the three tasks (``"kick"``, ``"walk"``, ``"orient"``): see ``bezk_post_physics_task``."""
+    n = progress_buf.shape[0] if progress_buf is not None else (obs.shape[0] if obs is not None else rew.shape[0])
+    nb = cfg.num_bodies
+    actors, _, width = bm.task_dims(task)
+    lib = _lib.load()
+    _lib.check(lib.bezk_post_physics_task(
+        _TASK_ID[task], _p(dof_state, F32, "dof_state", n * 36), _p(rigid_body, F32, "rigid_body", n * nb * 13),
+        _p(root_states, F32, "root_states", n * actors * 13), _p(net_contact, F32, "net_contact", n * nb * 3, True),
+        _p(prev_lin_vel, F32, "prev_lin_vel", n * 3, True), _p(goal, F32, "goal", n * 2),
+        _p(goal_angle, F32, "goal_angle", n, True), _p(ball_init, F32, "ball_init", n * 2, True),
+        _p(initial_root_states, F32, "initial_root_states", n * actors * 13, True),
+        _p(uniforms, F32, "uniforms", n * 36, True), _p(goal_uniforms, F32, "goal_uniforms", 2, True), seed, step,
+        _p(reset_buf, I64, "reset_buf", n, True), _p(progress_buf, I64, "progress_buf", n, True),
+        _p(timeout_buf, I64, "timeout_buf", n, True), _p(randomize_buf, I64, "randomize_buf", n, True), C.byref(cfg),
+        _p(obs, F32, "obs", n * width, True), _p(obs_clipped, F32, "obs_clipped", n * width, True), _p(rew, F32, "rew", n, True),
+        int(parts), n, _stream(dof_state)), "bezk_post_physics_task")
+
+
+def reset_idx_task(task, env_ids, dof_state, root_states, initial_root_states, goal, progress, reset, cfg, uniforms=None,
+                   goal_uniforms=None, seed=0, step=0):
+    k = int(env_ids.numel())
+    n = progress.shape[0]
+    actors = bm.task_dims(task)[0]
+    lib = _lib.load()
+    _lib.check(lib.bezk_reset_idx_task(
+        _TASK_ID[task], _p(env_ids, I64, "env_ids"), k, _p(uniforms, F32, "uniforms", k * 36, True),
+        _p(goal_uniforms, F32, "goal_uniforms", 2, True), seed, step, _p(dof_state, F32, "dof_state", n * 36),
+        _p(root_states, F32, "root_states", n * actors * 13, True),
+        _p(initial_root_states, F32, "initial_root_states", n * actors * 13, True), _p(goal, F32, "goal", n * 2, True),
+        _p(progress, I64, "progress", n), _p(reset, I64, "reset", n), C.byref(cfg), n, _stream(progress)), "bezk_reset_idx_task")
+
+
+def goal_uniforms(seed, step, out=None, device="cuda"):
+    out = torch.empty(2, dtype=F32, device=device) if out is None else out
+    _lib.check(_lib.load().bezk_goal_uniforms(seed, step, _p(out, F32, "out", 2), _stream(out)), "bezk_goal_uniforms")
+    return out
+
+
 def philox_uniforms(seed, step, out):
     n = out.shape[0]
     lib = _lib.load()

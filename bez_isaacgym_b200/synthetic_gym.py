@@ -41,11 +41,13 @@ class SimState:
 READY_POSE = tuple(bm.default_task_cfg(1)["env"]["readyJointAngles"][n] for n in bm.DOF_NAMES)
 
 
-def make_state(num_envs, seed=1234, device="cpu", cleats=False, filler=True) -> SimState:
+def make_state(num_envs, seed=1234, device="cpu", cleats=False, filler=True, task="kick") -> SimState:
     """Seeded synthetic simulator state.  ``filler=False`` leaves the rigid-body / contact rows the
-    task never reads at zero (cheaper to build at 1M envs; the kernels never touch them)."""
+    task never reads at zero (cheaper to build at 1M envs; the kernels never touch them).
+    ``task="walk"`` / ``"orient"``: one actor per env (root_states (N,13)) and no ball body; quaternions are drawn near
+    upright so that the up-vector rules (up_proj < 0.7) and the win state both occur."""
     n = int(num_envs)
-    nb = bm.BODIES_CLEATS if cleats else bm.BODIES_NO_CLEATS
+    actors, nb, _ = bm.task_dims(task, cleats)
     g = torch.Generator(device=device)
     g.manual_seed(int(seed))
     f32 = dict(dtype=torch.float32, device=device)
@@ -78,6 +80,27 @@ def make_state(num_envs, seed=1234, device="cpu", cleats=False, filler=True) -> 
     dof = torch.empty(n, 18, 2, **f32)
     dof[..., 0] = torch.tensor(READY_POSE, **f32) + 0.2 * randn(n, 18)
     dof[..., 1] = 3.3 * randn(n, 18)
+    if actors == 1:
+        # walk / orient: mostly upright robots (small tilt about x/y, any yaw); a few percent at rest in the ready pose near
+        # the goal / goal heading so that the win state (4 conditions at once) fires; positions spread over +-0.4 m
+        tilt = 0.15 * randn(n, 2)                               # up_proj = 1 - 2(qx^2+qy^2) ~ 0.91; ~4 % below the 0.7 fall rule
+        yaw = 6.283185307179586 * rand(n)
+        q = torch.stack((tilt[:, 0], tilt[:, 1], torch.sin(yaw / 2), torch.cos(yaw / 2)), 1)
+        rb[:, bm.IMU_BODY, 3:7] = q / q.norm(dim=1, keepdim=True)
+        root = root[:, 0:1].clone()
+        root[:, 0, 0:2] = 0.2 * randn(n, 2)
+        calm = rand(n) < 0.03
+        rb[:, bm.IMU_BODY, 7:13] = torch.where(calm.unsqueeze(1), 0.02 * randn(n, 6), rb[:, bm.IMU_BODY, 7:13])
+        dof[..., 0] = torch.where(calm.view(n, 1), torch.tensor(READY_POSE, **f32) + 0.01 * randn(n, 18), dof[..., 0])
+        at_goal = calm & (rand(n) < 0.5)
+        if task == "walk":      # just short of the goal ON the start->goal line (elsewhere within 5 cm the angle rule fires first)
+            near = torch.tensor([2.0, 0.0], **f32) * (1.0 - 0.02 * rand(n, 1)) + 0.0005 * randn(n, 2)
+        else:                   # orient: within 0.3 m of the start
+            near = 0.05 * randn(n, 2)
+        root[:, 0, 0:2] = torch.where(at_goal.unsqueeze(1), near, root[:, 0, 0:2])
+        facing = 1.5708 + 0.02 * randn(n)                       # orient: yaw at the goal angle (signed angle_to_goal < 0.05)
+        qf = torch.stack((torch.zeros(n, **f32), torch.zeros(n, **f32), torch.sin(facing / 2), torch.cos(facing / 2)), 1)
+        rb[:, bm.IMU_BODY, 3:7] = torch.where(at_goal.unsqueeze(1), qf, rb[:, bm.IMU_BODY, 3:7])
 
     cf = randn(n, nb, 3) if filler else torch.zeros(n, nb, 3, **f32)
 
@@ -98,7 +121,7 @@ def make_state(num_envs, seed=1234, device="cpu", cleats=False, filler=True) -> 
         cf[:, bm.LEFT_FOOT_BODY] = foot(1)[:, 0]
         cf[:, bm.RIGHT_FOOT_BODY] = foot(1)[:, 0]
 
-    return SimState(root.reshape(n * 2, 13), dof.reshape(n * 18, 2), rb.reshape(n * nb, 13),
+    return SimState(root.reshape(n * actors, 13), dof.reshape(n * 18, 2), rb.reshape(n * nb, 13),
                     cf.reshape(n * nb, 3), n, nb)
 
 
@@ -161,8 +184,13 @@ def make_constants(num_envs, device="cpu"):
     return goal, ball_init, default, lower, upper
 
 
-def make_initial_root_states(num_envs, device="cpu"):
-    """(N*2,13) rows the reference restores on reset (kick_env.py:163-166)."""
+def make_initial_root_states(num_envs, device="cpu", task="kick"):
+    """(N*2,13) rows the reference restores on reset (kick_env.py:163-166); (N,13) for walk / orient (walk_env.py:146-149)."""
+    if task != "kick":
+        r = torch.zeros(num_envs, 13, device=device)
+        r[:, 0:3] = torch.tensor([0.0, 0.0, 0.34], device=device)
+        r[:, 6] = 1.0
+        return r
     r = torch.zeros(num_envs, 2, 13, device=device)
     r[:, 0, 0:3] = torch.tensor([0.0, 0.0, 0.34], device=device)
     r[:, 0, 6] = 1.0

@@ -36,9 +36,9 @@ class SyntheticGym(SimBackend):
     (the reference's ``sim_device=cpu pipeline=cpu`` configuration)."""
 
     def __init__(self, num_envs, device="cuda:0", cleats=False, seed=1234, host=False, on_simulate=None,
-                 filler=True, state=None):
+                 filler=True, state=None, task="kick"):
         st = state if state is not None else sg.make_state(num_envs, seed=seed, device="cpu" if host else device,
-                                                           cleats=cleats, filler=filler)
+                                                           cleats=cleats, filler=filler, task=task)
         if host:
             st = sg.SimState(*(t.pin_memory() if torch.cuda.is_available() else t for t in
                                (st.root_states, st.dof_state, st.rigid_body, st.net_contact)), st.num_envs, st.num_bodies)

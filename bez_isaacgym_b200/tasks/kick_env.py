@@ -40,6 +40,9 @@ def _ptr(t):
 
 
 class KickEnv(VecTask):
+    #: "kick" here; the sibling tasks (tasks/walk_env.py, tasks/orient_env.py) subclass this with "walk" / "orient": same
+    #: skeleton, one actor per env, 52-wide observation, their own heading term / reward / goal randomisation (bezk.h)
+    TASK = "kick"
 
     def __init__(self, cfg, sim_device, graphics_device_id, headless, sim: SimBackend = None, fusion="fused"):
         self.cfg = cfg
@@ -57,8 +60,10 @@ class KickEnv(VecTask):
             return list(s["pos"]) + list(s["rot"]) + list(s["vLinear"]) + list(s["vAngular"])
 
         self.bez_init_state = state13("bezInitState")
-        self.ball_init_state = state13("ballInitState")
+        if self.TASK == "kick":
+            self.ball_init_state = state13("ballInitState")
         goal = env_cfg["goalState"]["goal"]
+        self._actors, _, self._obs_width = bm.task_dims(self.TASK)
         self.cleats = env_cfg["asset"]["cleats"]
         self.debug_rewards = env_cfg.get("debug", {}).get("rewards", False)
         self.named_default_joint_angles = env_cfg["readyJointAngles"]
@@ -68,7 +73,7 @@ class KickEnv(VecTask):
         self.orn_dim, self.imu_dim, self.feet_dim, self.dof_dim, self.rnn_dim, self.ball_dim = 2, 6, 8, 18, 1, 2
         self.imu_max_ang_vel = bm.IMU_MAX_ANG_VEL
         self.imu_max_lin_acc = bm.IMU_MAX_LIN_ACC
-        env_cfg["numObservations"] = bm.NUM_OBS
+        env_cfg["numObservations"] = self._obs_width
         env_cfg["numActions"] = bm.NUM_ACTIONS
         self._sim_arg = sim
         self._seed = int(cfg.get("seed", 42))
@@ -87,6 +92,8 @@ class KickEnv(VecTask):
         # host pipeline: "zero_copy" (default) hands the PINNED host tensors straight to the kernels -- they gather the
         # few bytes they need over PCIe and write resets back in place; "staged" copies all four tensors to HBM first
         self.host_mode = env_cfg.get("hostPipeline", "zero_copy") if self.host_staged else None
+        if self.host_staged and self.TASK != "kick":
+            raise NotImplementedError("the host pipeline is implemented for BezKick only; walk / orient need the GPU pipeline")
         if self.host_mode not in (None, "zero_copy", "staged"):
             raise ValueError(f"env.hostPipeline must be 'zero_copy' or 'staged', got {self.host_mode}")
         if self.host_staged and self.host_mode == "zero_copy" and not all(
@@ -97,7 +104,7 @@ class KickEnv(VecTask):
             self._d_rb, self._d_cf = (torch.empty_like(t, device=dev) for t in (self.rigid_body, self.net_contact))
         else:
             self._d_root, self._d_dof, self._d_rb, self._d_cf = self.root_states, self.dof_state, self.rigid_body, self.net_contact
-        for name, t, width in (("root_states", self.root_states, 26), ("dof_state", self.dof_state, 36),
+        for name, t, width in (("root_states", self.root_states, 13 * self._actors), ("dof_state", self.dof_state, 36),
                                ("rigid_body", self.rigid_body, 13 * self.sim.num_bodies),
                                ("net_contact", self.net_contact, 3 * self.sim.num_bodies)):
             if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n * width:
@@ -105,8 +112,16 @@ class KickEnv(VecTask):
 
         self.goal = torch.tensor([goal], **f32).repeat((n, 1))
         self.bez_init_xy = torch.tensor(self.bez_init_state[0:2], **f32)
-        self.ball_init = torch.tensor([self.ball_init_state[0:2]], **f32).repeat((n, 1))
-        self.initial_root_states = torch.tensor([self.bez_init_state, self.ball_init_state], **f32).repeat((n, 1))
+        if self.TASK == "kick":
+            self.ball_init = torch.tensor([self.ball_init_state[0:2]], **f32).repeat((n, 1))
+            self.initial_root_states = torch.tensor([self.bez_init_state, self.ball_init_state], **f32).repeat((n, 1))
+        else:
+            self.ball_init = None
+            self.initial_root_states = torch.tensor([self.bez_init_state], **f32).repeat((n, 1))      # walk_env.py:146-149
+            if self.TASK == "walk":
+                self.bez_init_xy.zero_()                # compute_bez_reward zeroes it in place, walk_env.py:966-967
+        self.goal_angle = torch.tensor([[float(env_cfg["goalState"]["goal_angle"])]], **f32).repeat((n, 1)) \
+            if self.TASK == "orient" else None          # orient_env.py:145
         self.initial_root_states[:, 7:13] = 0
         self.num_dof = bm.NUM_DOF
         self.num_dofs = bm.NUM_DOF
@@ -119,9 +134,10 @@ class KickEnv(VecTask):
         self.root_orient_bez = self.rigid_body.view(n, -1, 13)[..., bm.IMU_BODY, 3:7]
         self.root_vel_bez = self.rigid_body.view(n, -1, 13)[..., bm.IMU_BODY, 7:10]
         self.root_ang_bez = self.rigid_body.view(n, -1, 13)[..., bm.IMU_BODY, 10:13]
-        self.root_pos_ball = self.root_states.view(n, -1, 13)[..., 1, 0:3]
-        self.root_orient_ball = self.root_states.view(n, -1, 13)[..., 1, 3:7]
-        self.root_vel_ball = self.root_states.view(n, -1, 13)[..., 1, 7:10]
+        if self.TASK == "kick":
+            self.root_pos_ball = self.root_states.view(n, -1, 13)[..., 1, 0:3]
+            self.root_orient_ball = self.root_states.view(n, -1, 13)[..., 1, 3:7]
+            self.root_vel_ball = self.root_states.view(n, -1, 13)[..., 1, 7:10]
 
         ready = [float(self.named_default_joint_angles[name]) for name in bm.DOF_NAMES]
         self.default_dof_pos = torch.tensor(ready, **f32).repeat((n, 1))
@@ -146,7 +162,7 @@ class KickEnv(VecTask):
         self._actions_in = torch.zeros(n, 18, **f32)      # staging buffer for actions arriving from another device
         self._actions_src = self._actions_in
         self._actions_cache = None
-        self.obs_clipped_buf = torch.zeros(n, 54, **f32) if math.isfinite(float(self.clip_obs)) else None
+        self.obs_clipped_buf = torch.zeros(n, self._obs_width, **f32) if math.isfinite(float(self.clip_obs)) else None
         if self.host_mode == "zero_copy":
             # write-only outputs live in pinned host memory: the kernel's stores (TMA bulk store for the obs tile) cross
             # PCIe while its gathers come the other way (full duplex), and step() needs no D2H copies for them
@@ -175,7 +191,7 @@ class KickEnv(VecTask):
         else:
             host = self.device == "cpu"
             self.sim = SyntheticGym(self.num_environments, device=f"cuda:{self.device_id}", cleats=self.cfg["env"]["asset"]["cleats"],
-                                    seed=int(self.cfg.get("seed", 42)), host=host)
+                                    seed=int(self.cfg.get("seed", 42)), host=host, task=self.TASK)
         if self.sim.root_states.is_cuda != (self.device != "cpu"):
             raise ValueError("simulator tensors must live on the pipeline device "
                              f"({'cuda' if self.device != 'cpu' else 'pinned host'})")
@@ -188,6 +204,8 @@ class KickEnv(VecTask):
         self._post_fixed = dict(
             head=[_ptr(self._d_dof), _ptr(self._d_rb), _ptr(self._d_root), _ptr(self._d_cf)],
             mid=[_ptr(self.goal), _ptr(self.ball_init), _ptr(self.initial_root_states), None],
+            # bezk_post_physics_task: goal, goal_angle, ball_init, initial_root_states, uniforms, goal_uniforms
+            mid_task=[_ptr(self.goal), _ptr(self.goal_angle), _ptr(self.ball_init), _ptr(self.initial_root_states), None, None],
             tail=[_ptr(self.reset_buf), _ptr(self.progress_buf), _ptr(self.timeout_buf), None, kc,
                   _ptr(self.obs_buf), _ptr(self.obs_clipped_buf), _ptr(self.rew_buf)])
 
@@ -197,8 +215,12 @@ class KickEnv(VecTask):
     def _launch_post(self, parts):
         f = self._post_fixed
         prev = None if self._prev_is_view else _ptr(self._prev_buf)
-        rc = self._lib.bezk_post_physics(*f["head"], prev, *f["mid"], self._seed, self._rng_step, *f["tail"], parts,
-                                         self.num_envs, self._stream())
+        if self.TASK == "kick":
+            rc = self._lib.bezk_post_physics(*f["head"], prev, *f["mid"], self._seed, self._rng_step, *f["tail"], parts,
+                                             self.num_envs, self._stream())
+        else:
+            rc = self._lib.bezk_post_physics_task(ops._TASK_ID[self.TASK], *f["head"], prev, *f["mid_task"], self._seed,
+                                                  self._rng_step, *f["tail"], parts, self.num_envs, self._stream())
         if rc:
             _lib.check(rc, "bezk_post_physics")
 
@@ -287,23 +309,37 @@ class KickEnv(VecTask):
         """kick_env.py:749-777 as a stand-alone call (observation kernel only, no bookkeeping)."""
         self._stage_in()
         prev = None if self._prev_is_view else self._prev_buf
-        ops.compute_observations(self._d_dof, self._d_rb, self._d_root, self._d_cf, self.goal, self.ball_init, self._kcfg,
-                                 self.obs_buf, prev_lin_vel=prev, obs_clipped=self.obs_clipped_buf)
+        if self.TASK == "kick":
+            ops.compute_observations(self._d_dof, self._d_rb, self._d_root, self._d_cf, self.goal, self.ball_init, self._kcfg,
+                                     self.obs_buf, prev_lin_vel=prev, obs_clipped=self.obs_clipped_buf)
+        else:
+            ops.post_physics_task(self.TASK, self._d_dof, self._d_rb, self._d_root, self._d_cf, self.goal, None, None, None, None,
+                                  self._kcfg, self.obs_buf, None, goal_angle=self.goal_angle, prev_lin_vel=prev,
+                                  obs_clipped=self.obs_clipped_buf, parts=_lib.PART_OBS)
         if self._alias_prev:
             self._prev_is_view = True
 
     def compute_reward(self, actions=None):
         """kick_env.py:724-747 as a stand-alone call (reward / termination kernel only)."""
-        ops.compute_reward(self._d_dof, self._d_rb, self._d_root, self.goal, self.ball_init, self.reset_buf,
-                           self.progress_buf, self._kcfg, self.rew_buf, self.reset_buf)
+        if self.TASK == "kick":
+            ops.compute_reward(self._d_dof, self._d_rb, self._d_root, self.goal, self.ball_init, self.reset_buf,
+                               self.progress_buf, self._kcfg, self.rew_buf, self.reset_buf)
+        else:
+            ops.post_physics_task(self.TASK, self._d_dof, self._d_rb, self._d_root, None, self.goal, None, self.reset_buf,
+                                  self.progress_buf, None, self._kcfg, None, self.rew_buf, goal_angle=self.goal_angle,
+                                  parts=_lib.PART_REWARD)
 
     def reset_idx(self, env_ids):
         """kick_env.py:779-850 for an explicit id list (the per-step path uses the masked reset inside the fused
         kernel instead, which needs no ``nonzero()``)."""
         env_ids = env_ids.to(device=self.compute_device, dtype=torch.long).contiguous()
         self._stage_in()
-        ops.reset_idx(env_ids, self._d_dof, self._d_root, self.initial_root_states, self.progress_buf, self.reset_buf,
-                      self._kcfg, uniforms=None, seed=self._seed, step=self._rng_step)
+        if self.TASK == "kick":
+            ops.reset_idx(env_ids, self._d_dof, self._d_root, self.initial_root_states, self.progress_buf, self.reset_buf,
+                          self._kcfg, uniforms=None, seed=self._seed, step=self._rng_step)
+        else:
+            ops.reset_idx_task(self.TASK, env_ids, self._d_dof, self._d_root, self.initial_root_states, self.goal,
+                               self.progress_buf, self.reset_buf, self._kcfg, seed=self._seed, step=self._rng_step)
         if self.host_mode == "staged":
             self.dof_state.copy_(self._d_dof)
             if self._kcfg.flags & _lib.F_RESET_ROOT_STATES:
@@ -319,9 +355,10 @@ class KickEnv(VecTask):
         buffer after every step; here the copy never happens).  ``obs_buf`` becomes that tensor."""
         if self.host_staged:
             raise NotImplementedError("set_obs_target needs the GPU pipeline")
-        if tensor.shape != (self.num_envs, 54) or tensor.dtype != torch.float32 or not tensor.is_contiguous() \
+        if tensor.shape != (self.num_envs, self._obs_width) or tensor.dtype != torch.float32 or not tensor.is_contiguous() \
                 or tensor.device != self.compute_device:
-            raise ValueError(f"obs target must be a contiguous float32 ({self.num_envs}, 54) tensor on {self.compute_device}")
+            raise ValueError(f"obs target must be a contiguous float32 ({self.num_envs}, {self._obs_width}) tensor on "
+                             f"{self.compute_device}")
         self.obs_buf = tensor
         self._post_fixed["tail"][5] = _ptr(tensor)
 

@@ -189,6 +189,38 @@ int bezk_ppo_loss(const float* actions, const float* mu, const float* logstd, co
                   const BezkPpoCfg* cfg, double* stats, float* grad_mu, float* grad_values,
                   float* grad_logstd, float* neglogp_out, double* partials, int64_t m, void* stream);
 
+/* ---------------------------------------------------------------- sibling tasks ----- */
+
+/* WalkEnv / OrientEnv (ref: tasks/walk_env.py, tasks/orient_env.py) share BezKick's skeleton: same K0, same IMU / feet /
+ * bookkeeping / masked reset; they differ in
+ *   - layout: ONE actor per env (root_states (n,13)), 21 bodies (29 with cleats), observation (n,52) =
+ *     [dof_pos 18, dof_vel 18, imu 6, heading 2, feet 8]   (walk_env.py:1032-1050)
+ *   - heading: walk = compute_off_orn vs goal (n,2) (walk_env.py:379-386); orient = compute_off_angle =
+ *     (cos, sin)(goal_angle - normalize_angle(yaw)) with goal_angle (n,) (orient_env.py:719-733)
+ *   - reward / termination: walk_env.py:827-997, orient_env.py:845-1014 (up-vector projection, win state, out of bound)
+ *   - reset: additionally goal[env] = (U(-2,2), U(-2,2)); the reference assigns the FIRST draw of the reset batch to every
+ *     env resetting in that step (walk_env.py:570-574 `self.goal[env_ids, 0] = goal_x[0]`), so the draw is per STEP:
+ *     goal_uniforms (2,) f32 in [0,1) or NULL -> Philox keyed (seed, step) alone.
+ * goal (n,2) is read AND written.  goal_angle is read by BEZK_TASK_ORIENT only.  Everything else as bezk_post_physics
+ * (task = BEZK_TASK_KICK forwards to it; ball_init is then required and goal is not written). */
+#define BEZK_TASK_KICK   0
+#define BEZK_TASK_WALK   1
+#define BEZK_TASK_ORIENT 2
+int bezk_post_physics_task(int task, float* dof_state, const float* rigid_body, float* root_states,
+                           float* net_contact, float* prev_lin_vel, float* goal, const float* goal_angle,
+                           const float* ball_init, const float* initial_root_states,
+                           const float* uniforms, const float* goal_uniforms, uint64_t seed, uint64_t step,
+                           int64_t* reset_buf, int64_t* progress_buf, int64_t* timeout_buf,
+                           int64_t* randomize_buf, const BezkTaskCfg* cfg, float* obs, float* obs_clipped,
+                           float* rew, int parts, int64_t n, void* stream);
+/* bezk_reset_idx for any task: root rows are 13 floats for walk / orient, and their goal (n,2) rows are redrawn. */
+int bezk_reset_idx_task(int task, const int64_t* env_ids, int64_t k, const float* uniforms, const float* goal_uniforms,
+                        uint64_t seed, uint64_t step, float* dof_state, float* root_states,
+                        const float* initial_root_states, float* goal, int64_t* progress, int64_t* reset,
+                        const BezkTaskCfg* cfg, int64_t n, void* stream);
+/* The (2,) uniforms the Philox path uses for the goal draw of (seed, step). */
+int bezk_goal_uniforms(uint64_t seed, uint64_t step, float* out2, void* stream);
+
 /* ---------------------------------------------------------------- rollout storage ----- */
 
 /* Slab addressing.  rl_games keeps the rollout time-major -- ExperienceBuffer tensors are (T, N, ...) -- and builds its

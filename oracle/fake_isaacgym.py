@@ -51,7 +51,8 @@ DOF_PROP_DTYPE = np.dtype([("hasLimits", "?"), ("lower", "f4"), ("upper", "f4"),
 
 
 class FakeGym:
-    def __init__(self, root_states, dof_state, rigid_body, net_contact, on_simulate=None):
+    def __init__(self, root_states, dof_state, rigid_body, net_contact, on_simulate=None, actors_per_env=2):
+        self.actors_per_env = actors_per_env        # 2 for BezKick (robot + ball), 1 for walk / orient
         self.root_states, self.dof_state = root_states, dof_state
         self.rigid_body, self.net_contact = rigid_body, net_contact
         self.on_simulate = on_simulate
@@ -129,7 +130,7 @@ class FakeGym:
         pass
 
     def get_actor_index(self, env, handle, domain):
-        return env * 2 + handle
+        return env * self.actors_per_env + handle
 
     def get_actor_dof_properties(self, env, handle):
         return self._dof_props(self._last_bez_asset)

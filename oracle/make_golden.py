@@ -168,6 +168,171 @@ def step_trace(n=64, steps=8, cleats=False):
     return out
 
 
+# ----------------------------------------------------------------------------------------------- sibling tasks
+_FEET_ROWS = [[1., -1., -1., -1.], [-1., -1., 1., -1.], [1., -1., 1., -1.], [-1., 1., -1., -1.], [-1., -1., -1., 1.],
+              [-1., 1., -1., 1.], [1., 1., -1., -1.], [-1., -1., 1., 1.], [1., 1., 1., 1.], [-1.] * 4]
+
+
+def sibling_constants(task, n):
+    """goal (N,2), goal_angle (N,1), default (N,18) as WalkEnv / OrientEnv build them (walk_env.py:143, orient_env.py:145)."""
+    goal = torch.tensor([[2.0, 0.0]]).repeat(n, 1)
+    goal_angle = torch.tensor([[1.5708]]).repeat(n, 1)
+    default = torch.tensor(sg.READY_POSE).repeat(n, 1)
+    return goal, goal_angle, default
+
+
+def function_level_sibling(task, ref, st, prev, progress, reset_in, goal):
+    """The reference walk_env / orient_env jit functions on the state (no cleats)."""
+    n = st.num_envs
+    st = st.clone()
+    root, rb = st.root_states.view(n, 1, 13), st.rigid_body.view(n, -1, 13)
+    cf, dof = st.net_contact.view(n, -1, 3), st.dof_state.view(n, 18, 2)
+    quat, lin, ang = rb[:, 1, 3:7], rb[:, 1, 7:10], rb[:, 1, 10:13]
+    bez_pos = root[:, 0, 0:3]
+    _, goal_angle, default = sibling_constants(task, n)
+    gravity = torch.tensor([[0.0, 0.0, -1.0]]).repeat(n, 1)
+    imu6, _ = ref.compute_imu(quat, lin, ang, prev, gravity, 2.0 * 9.81, 8.7266, 0.01667, n)
+    heading = ref.compute_off_orn(bez_pos, quat, goal) if task == "walk" else ref.compute_off_angle(quat, goal_angle)
+    args = [torch.tensor([[-1.0] * 4]).repeat(n, 1), torch.ones(1), torch.zeros(1), torch.zeros(3)] + \
+           [torch.tensor(r) for r in _FEET_ROWS]
+    feet = torch.cat((ref.compute_feet_sensors_no_cleats(cf[:, 12, :], *args),
+                      ref.compute_feet_sensors_no_cleats(cf[:, 20, :], *args)), 1)
+    obs = ref.compute_bez_observations(dof[..., 0], dof[..., 1], imu6, heading, feet)
+    up = torch.tensor([[0.0, 0.0, 1.0]]).repeat(n, 1)
+    rew, reset = ref.compute_bez_reward(dof[..., 0], default, lin, ang, bez_pos, quat, up, goal if task == "walk" else goal_angle,
+                                        reset_in, progress, feet, torch.tensor([0.0, 0.0]), 600, n, 0.01667, False)
+    return dict(ref_obs=_np(obs), ref_rew=_np(rew), ref_reset=_np(reset), ref_net_contact_after=_np(st.net_contact),
+                in_goal=_np(goal))
+
+
+def sibling_edge_state(task, n=64, seed=31):
+    """Fall threshold (up_proj around 0.7), win state on / just off each of its four conditions, out-of-bound rules,
+    progress in {598..601}, zero distance to the goal."""
+    st = sg.make_state(n, seed=seed, task=task)
+    root, rb, dof = st.root_states.view(n, 1, 13), st.rigid_body.view(n, -1, 13), st.dof_state.view(n, 18, 2)
+    goal = torch.tensor([[2.0, 0.0]]).repeat(n, 1)
+    goal[20:30] = torch.tensor([0.3, -1.1])
+    if task == "orient":
+        root[:, 0, 0:2] *= 0.25           # keep the edge envs inside orient's 0.3 m out-of-bound circle unless a rule moves them
+    ready = torch.tensor(sg.READY_POSE)
+    import math
+
+    def yaw_quat(yaw, tilt=0.0):
+        return torch.tensor([math.sin(tilt / 2), 0.0, math.sin(yaw / 2) * math.cos(tilt / 2), math.cos(yaw / 2) * math.cos(tilt / 2)])
+    # win state: at the goal (walk) / facing the goal angle (orient), ready pose, at rest
+    for e in range(0, 6):
+        # walk: 3 cm short of the goal on the start->goal line; orient: next to the start (its out-of-bound rule is 0.3 m)
+        root[e, 0, 0:2] = goal[e] * (1.0 - 0.015) if task == "walk" else torch.tensor([0.05, 0.02])
+        rb[e, bm.IMU_BODY, 3:7] = yaw_quat(1.5708 + 0.01)
+        rb[e, bm.IMU_BODY, 7:13] = 0.01
+        dof[e, :, 0] = ready + 0.005
+    dof[1, :, 0] = ready + 0.05            # pos_reward = 0.05*sqrt(18) = 0.212 > 0.15: one condition short
+    rb[2, bm.IMU_BODY, 10:13] = torch.tensor([0.2, 0.0, 0.0])          # angular velocity too high
+    rb[3, bm.IMU_BODY, 7:10] = torch.tensor([0.0, 0.2, 0.0])           # linear velocity too high
+    root[4, 0, 0:2] = goal[4] * 0.9 if task == "walk" else torch.tensor([0.05, 0.02])    # walk: 20 cm short -> not close
+    rb[5, bm.IMU_BODY, 3:7] = yaw_quat(1.5708 - 0.2)                   # orient: signed angle 0.2 > 0.05
+    # fall rule: tilt so that up_proj = cos(tilt) straddles 0.7
+    for e, c in zip(range(6, 10), (0.69, 0.7, 0.71, -0.5)):
+        rb[e, bm.IMU_BODY, 3:7] = yaw_quat(0.3, math.acos(c))
+    root[10, 0, 0:2] = goal[10]                                        # zero distance: NaN heading
+    root[11, 0, 0:2] = torch.tensor([3.0, 0.5])                        # walk: beyond the goal -> angle rule
+    root[12, 0, 0:2] = torch.tensor([0.29, 0.0]); root[13, 0, 0:2] = torch.tensor([0.31, 0.0])     # orient: 0.3 m rule
+    rb[14, bm.IMU_BODY, 3:7] = torch.tensor([0.0, 0.0, 0.0, 1.0])
+    rb[15, bm.IMU_BODY, 3:7] = torch.tensor([0.3, -0.2, 0.1, 2.5])     # non-unit
+    progress = torch.full((n,), 10, dtype=torch.long)
+    progress[16:20] = torch.tensor([598, 599, 600, 601])
+    progress[0] = 300                                                  # win reward 500
+    reset_in = torch.zeros(n, dtype=torch.long)
+    reset_in[30] = 1
+    return st, torch.zeros(n, 3), progress, reset_in, goal
+
+
+def step_trace_sibling(task, n=64, steps=8):
+    """The unmodified reference WalkEnv / OrientEnv stepped over the fake gym; DOF reset draws from the Philox table, goal
+    draws (the reference uses element [0] of each (k,1) draw, walk_env.py:570-574) from a per-step table."""
+    st0 = sg.make_state(n, seed=5000, task=task)
+    init = state_arrays(st0, "init_")
+    fresh = [sg.make_state(n, seed=5100 + k, task=task) for k in range(steps)]
+    drift = [0.01 * torch.randn(n * 18, 2, generator=torch.Generator().manual_seed(60 + k)) for k in range(steps)]
+    goal_u = torch.rand(steps + 1, 2, generator=torch.Generator().manual_seed(77))
+    pending = []
+    counter = {"sim": 0}
+
+    def rand_source(shape):
+        return pending.pop(0)
+
+    def on_simulate(gym):
+        k = counter["sim"]
+        # .detach(): the legacy jit executor the reference selects (vec_task.py:170-172) conservatively marks tensors it
+        # wrote in place as requiring grad; the simulator refresh is not part of any graph
+        gym.root_states.detach().copy_(fresh[k].root_states); gym.rigid_body.detach().copy_(fresh[k].rigid_body)
+        gym.net_contact.detach().copy_(fresh[k].net_contact); gym.dof_state.detach().add_(drift[k])
+        counter["sim"] += 1
+
+    def queue(env_ids, rng_step):
+        u = torch.from_numpy(reset_uniforms(TRACE_SEED, rng_step, n))[env_ids]
+        k = len(env_ids)
+        pending.extend([u[:, 0:18].clone(), u[:, 18:36].clone(), goal_u[rng_step, 0].repeat(k, 1), goal_u[rng_step, 1].repeat(k, 1)])
+
+    queue(torch.arange(n), 0)
+    env = rl.make_reference_env(st0, on_simulate=on_simulate, rand_source=rand_source, task=task)
+    assert not pending
+    out = dict(init)
+    out["init_dof_state_after_ctor"] = _np(st0.dof_state)
+    out["init_goal_after_ctor"] = _np(env.goal)
+    progress0 = torch.randint(0, 590, (n,), generator=torch.Generator().manual_seed(9))
+    progress0[0:4] = torch.tensor([596, 597, 598, 599])
+    env.progress_buf[:] = progress0
+    out["init_progress"] = _np(progress0)
+    actions = [sg.make_actions(n, seed=80 + k) * (4.5 if k == 2 else 1.0) for k in range(steps)]
+    rows = {k: [] for k in ("obs", "rew", "reset", "timeout", "progress", "dof_state", "root_states", "net_contact",
+                            "targets", "goal")}
+    for k in range(steps):
+        env_ids = env.reset_buf.nonzero(as_tuple=False).squeeze(-1)
+        if len(env_ids) > 0:
+            queue(env_ids, k + 1)
+        obs_dict, rew, reset, extras = env.step(actions[k].clone())
+        assert not pending
+        rows["obs"].append(_np(obs_dict["obs"])); rows["rew"].append(_np(rew)); rows["reset"].append(_np(reset))
+        rows["timeout"].append(_np(extras["time_outs"])); rows["progress"].append(_np(env.progress_buf))
+        rows["dof_state"].append(_np(env.dof_state)); rows["root_states"].append(_np(env.root_states))
+        rows["net_contact"].append(_np(st0.net_contact)); rows["targets"].append(_np(env._fake_gym.targets))
+        rows["goal"].append(_np(env.goal))
+    for key, v in rows.items():
+        out["ref_" + key] = np.stack(v)
+    out["in_actions"] = np.stack([_np(a) for a in actions])
+    out["in_goal_uniforms"] = _np(goal_u)
+    for name in ("root_states", "rigid_body", "net_contact"):
+        out["sim_" + name] = np.stack([_np(getattr(f, name)) for f in fresh])
+    out["sim_dof_drift"] = np.stack([_np(d) for d in drift])
+    out["meta_seed"] = np.int64(TRACE_SEED)
+    out["meta_resets_per_step"] = np.array([int(r.sum()) for r in rows["reset"]])
+    return out
+
+
+def siblings():
+    for task in ("walk", "orient"):
+        ref = rl.load_reference_task(task)
+        for n in (31, 257):
+            st = sg.make_state(n, seed=3000 + n, task=task)
+            prev = 0.3 * torch.randn(n, 3, generator=torch.Generator().manual_seed(n))
+            progress, reset_in = sg.make_bookkeeping(n, seed=n, p_reset=0.1, max_episode_length=600)
+            progress[:4] = torch.tensor([598, 599, 600, 601])
+            goal = torch.tensor([[2.0, 0.0]]).repeat(n, 1)
+            goal[n // 2:] = 4.0 * torch.rand(n - n // 2, 2, generator=torch.Generator().manual_seed(5)) - 2.0
+            d = dict(state_arrays(st), in_prev_lin_vel=_np(prev), in_progress=_np(progress), in_reset=_np(reset_in))
+            d.update(function_level_sibling(task, ref, st, prev, progress, reset_in, goal))
+            np.savez_compressed(os.path.join(OUT, f"fn_{task}_n{n}.npz"), **d)
+        st, prev, progress, reset_in, goal = sibling_edge_state(task)
+        d = dict(state_arrays(st), in_prev_lin_vel=_np(prev), in_progress=_np(progress), in_reset=_np(reset_in))
+        d.update(function_level_sibling(task, ref, st, prev, progress, reset_in, goal))
+        np.savez_compressed(os.path.join(OUT, f"fn_{task}_edges.npz"), **d)
+        print(task, "edge resets:", d["ref_reset"][:20], "rew:", np.round(d["ref_rew"][:8], 3))
+        tr = step_trace_sibling(task)
+        np.savez_compressed(os.path.join(OUT, f"step_trace_{task}_n64.npz"), **tr)
+        print(task, "resets per step in the trace:", tr["meta_resets_per_step"])
+
+
 def checkpoint_facts():
     """Facts of the shipped checkpoint that pin the rl_games state layout and update cadence."""
     import json
@@ -200,6 +365,9 @@ def main():
     if not rl.reference_available():
         raise SystemExit("needs /root/reference")
     os.makedirs(OUT, exist_ok=True)
+    if "--siblings-only" in sys.argv:
+        siblings()
+        return
     ref = rl.load_reference_kick_env()
     for n in (1, 31, 64, 257):
         st = sg.make_state(n, seed=1000 + n)
@@ -223,6 +391,7 @@ def main():
     tr = step_trace()
     np.savez_compressed(os.path.join(OUT, "step_trace_n64.npz"), **tr)
     print("resets per step in the trace:", tr["meta_resets_per_step"])
+    siblings()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 

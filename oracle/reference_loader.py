@@ -79,15 +79,19 @@ def install_stubs():
     _stub("gym", spaces=spaces, Space=object)
 
 
-_cached = None
+_cached = {}
 _current_gym = [None]      # the FakeGym instance gymapi.acquire_gym() hands to the next reference KickEnv
 
 
 def load_reference_kick_env():
     """Return the reference module ``tasks.kick_env`` (executed from /root/reference)."""
-    global _cached
-    if _cached is not None:
-        return _cached
+    return load_reference_task("kick")
+
+
+def load_reference_task(task="kick"):
+    """Return the reference module ``tasks.{kick,walk,orient}_env`` (executed from /root/reference)."""
+    if task in _cached:
+        return _cached[task]
     if not reference_available():
         raise FileNotFoundError(f"reference not found under {REFERENCE_ROOT}")
     install_stubs()
@@ -101,16 +105,24 @@ def load_reference_kick_env():
         pkg = types.ModuleType("tasks")
         pkg.__path__ = [os.path.join(_PKG_DIR, "tasks")]
         sys.modules.setdefault("tasks", pkg)
-        _cached = importlib.import_module("tasks.kick_env")
-    return _cached
+        _cached[task] = importlib.import_module(f"tasks.{task}_env")
+    return _cached[task]
 
 
-def reference_task_cfg(num_envs, cleats=False):
+def reference_task_cfg(num_envs, cleats=False, task="kick"):
     """The reference's OWN task config (cfg/task/bez_kick_test.yaml is the interpolation-free twin of
-    bez_kick.yaml, SURVEY 5 'Config'), with numEnvs set and the CPU pipeline selected."""
+    bez_kick.yaml, SURVEY 5 'Config'; bez_walk_test.yaml likewise for bez_walk.yaml; bez_orient.yaml = bez_walk.yaml +
+    ``goalState.goal_angle: 1.5708`` and has no interpolation-free twin, so the walk twin is used with that key added),
+    with numEnvs set, the CPU pipeline selected and the debug printing switched off."""
     import yaml
-    with open(os.path.join(_PKG_DIR, "cfg", "task", "bez_kick_test.yaml")) as f:
+    with open(os.path.join(_PKG_DIR, "cfg", "task", "bez_kick_test.yaml" if task == "kick" else "bez_walk_test.yaml")) as f:
         cfg = yaml.safe_load(f)
+    if task != "kick":
+        cfg["env"]["debug"]["rewards"] = False
+        cfg["env"]["envSpacing"] = 5
+        if task == "orient":
+            with open(os.path.join(_PKG_DIR, "cfg", "task", "bez_orient.yaml")) as f:
+                cfg["env"]["goalState"]["goal_angle"] = yaml.safe_load(f)["env"]["goalState"]["goal_angle"]
     cfg["env"]["numEnvs"] = int(num_envs)
     cfg["env"]["asset"]["cleats"] = bool(cleats)
     cfg["sim"]["use_gpu_pipeline"] = False
@@ -119,7 +131,7 @@ def reference_task_cfg(num_envs, cleats=False):
     return cfg
 
 
-def make_reference_env(state, on_simulate=None, cleats=False, rand_source=None):
+def make_reference_env(state, on_simulate=None, cleats=False, rand_source=None, task="kick"):
     """Instantiate the UNMODIFIED reference ``KickEnv`` over the four tensors of ``state`` (a
     ``bez_isaacgym_b200.synthetic_gym.SimState`` on CPU) through ``oracle.fake_isaacgym.FakeGym``.
 
@@ -127,8 +139,9 @@ def make_reference_env(state, on_simulate=None, cleats=False, rand_source=None):
     ``torch_rand_float`` so a checker can feed the same reset draws to another implementation."""
     from oracle import fake_isaacgym as fg
     from oracle import isaacgym_torch_utils as tu
-    mod = load_reference_kick_env()
-    gym = fg.FakeGym(state.root_states, state.dof_state, state.rigid_body, state.net_contact, on_simulate)
+    mod = load_reference_task(task)
+    gym = fg.FakeGym(state.root_states, state.dof_state, state.rigid_body, state.net_contact, on_simulate,
+                     actors_per_env=2 if task == "kick" else 1)
     _current_gym[0] = gym
     if rand_source is not None:
         def torch_rand_float(lower, upper, shape, device):
@@ -142,7 +155,8 @@ def make_reference_env(state, on_simulate=None, cleats=False, rand_source=None):
         import warnings
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            env = mod.KickEnv(reference_task_cfg(state.num_envs, cleats), "cpu", 0, True)
+            cls = {"kick": "KickEnv", "walk": "WalkEnv", "orient": "OrientEnv"}[task]
+            env = getattr(mod, cls)(reference_task_cfg(state.num_envs, cleats, task), "cpu", 0, True)
     finally:
         os.chdir(cwd)
         _current_gym[0] = None

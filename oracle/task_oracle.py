@@ -16,7 +16,7 @@ from typing import Optional, Tuple
 import torch
 from torch import Tensor
 
-from oracle.isaacgym_torch_utils import get_euler_xyz, tensor_clamp
+from oracle.isaacgym_torch_utils import get_basis_vector, get_euler_xyz, normalize_angle, tensor_clamp
 
 IMU_MAX_LIN_ACC = 2.0 * 9.81     # tasks/kick_env.py:100
 IMU_MAX_ANG_VEL = 8.7266         # tasks/kick_env.py:99
@@ -158,6 +158,88 @@ def reward(dof_pos, default_dof_pos, imu_lin, imu_ang, bez_pos, ball_pos, ball_v
     reset = torch.where(over, ones, reset)
     rew = torch.where(over, torch.zeros_like(rew), rew)
     return rew, reset
+
+
+# --------------------------------------------------------------------------- sibling tasks
+def off_angle(quat_xyzw: Tensor, goal_angle: Tensor) -> Tensor:
+    """tasks/orient_env.py:720-733 (compute_off_angle): (cos, sin) of goal_angle - normalize_angle(yaw); goal_angle (N,1)."""
+    _, _, yaw = get_euler_xyz(quat_xyzw[..., 0:4])
+    d = goal_angle - normalize_angle(yaw).unsqueeze(-1)
+    return torch.cat((torch.cos(d).reshape(-1, 1), torch.sin(d).reshape(-1, 1)), dim=-1)
+
+
+def observations_walk(dof_pos, dof_vel, imu6, heading2, feet8) -> Tensor:
+    """tasks/walk_env.py:1032-1050 / orient_env.py: the 52-wide row."""
+    return torch.cat((dof_pos, dof_vel, imu6, heading2, feet8), dim=-1)
+
+
+def _walk_terms(dof_pos, default_dof_pos, imu_lin, imu_ang, quat, num_envs):
+    up = get_basis_vector(quat[..., 0:4], torch.tensor([[0.0, 0.0, 1.0]], device=quat.device).repeat(num_envs, 1)).view(num_envs, 3)
+    up_proj = up[:, 2]
+    vel6 = torch.linalg.norm(torch.cat((imu_lin, imu_ang), dim=1), dim=1)
+    vel_lin = torch.linalg.norm(imu_lin, dim=1)
+    vel_ang = torch.linalg.norm(imu_ang, dim=1)
+    pos = torch.linalg.norm(default_dof_pos - dof_pos, dim=1)
+    return up_proj, vel6, vel_lin, vel_ang, pos
+
+
+def _walk_tail(rew, reset_buf, close, up_proj, pos, vel_ang, vel_lin, out, out_value, progress_buf, max_episode_length):
+    ones = torch.ones_like(reset_buf)
+    reset = torch.where(up_proj < 0.7, ones, reset_buf)
+    rew = torch.where(up_proj < 0.7, torch.ones_like(rew) * -100.0, rew)
+    state = torch.where(close, ones, torch.zeros_like(rew))
+    state = torch.where(pos < 0.15, state + torch.ones_like(rew), state)
+    state = torch.where(vel_ang < 0.1, state + torch.ones_like(rew), state)
+    state = torch.where(vel_lin < 0.1, state + torch.ones_like(rew), state)
+    reset = torch.where(state == 4.0, ones, reset)
+    rew = torch.where(state == 4.0, torch.ones_like(rew) * (1000.0 - 1000.0 * (progress_buf / max_episode_length)), rew)
+    reset = torch.where(out, ones, reset)
+    rew = torch.where(out, torch.ones_like(rew) * out_value, rew)
+    reset = torch.where(progress_buf >= max_episode_length, ones, reset)
+    rew = torch.where(progress_buf >= max_episode_length, torch.zeros_like(rew), rew)
+    return rew, reset
+
+
+def reward_walk(dof_pos, default_dof_pos, imu_lin, imu_ang, bez_pos, quat, goal, reset_buf, progress_buf,
+                max_episode_length: int) -> Tuple[Tensor, Tensor]:
+    """tasks/walk_env.py:848-997 with the dead computations (feet term, legacy branch, debug prints) removed;
+    ``bez_init_state`` is (0, 0) (zeroed in place at :966-967)."""
+    n = dof_pos.shape[0]
+    d = torch.sub(goal, bez_pos[..., 0:2])
+    n_goal = torch.linalg.norm(d, dim=1).reshape(-1, 1)
+    u = torch.div(d, n_goal)
+    vel_fwd = torch.sum(torch.mul(u, imu_lin[..., 0:2]), dim=-1)
+    up_proj, vel6, vel_lin, vel_ang, pos = _walk_terms(dof_pos, default_dof_pos, imu_lin, imu_ang, quat, n)
+    dist_h = torch.abs(1 - up_proj)
+    vel_s, pos_s = torch.mul(vel6, 0.05), torch.mul(pos, 0.05)
+    height_vel_pos = -torch.add(torch.add(vel_s, pos_s), dist_h)
+    vel_height = torch.mul(torch.sub(torch.mul(vel_fwd, 10), torch.add(dist_h, 5 * pos_s)), 1)
+    n_goal = n_goal.reshape(-1)
+    close = n_goal < 0.05
+    rew = torch.where(close, height_vel_pos, vel_height)
+    init = torch.sub(goal, torch.zeros(2, device=goal.device))
+    ui = torch.div(init, torch.linalg.norm(init, dim=1).reshape(-1, 1))
+    ang_now = torch.atan2(u[..., 1], u[..., 0])
+    ang_init = torch.atan2(ui[..., 1], ui[..., 0])
+    out = torch.abs(ang_init - ang_now).reshape(-1) > 1.5708
+    return _walk_tail(rew, reset_buf, close, up_proj, pos, vel_ang, vel_lin, out, -100.0, progress_buf, max_episode_length)
+
+
+def reward_orient(dof_pos, default_dof_pos, imu_lin, imu_ang, bez_pos, quat, goal_angle, reset_buf, progress_buf,
+                  bez_init_xy, max_episode_length: int) -> Tuple[Tensor, Tensor]:
+    """tasks/orient_env.py:866-1014 with the dead computations removed; goal_angle (N,1)."""
+    n = dof_pos.shape[0]
+    _, _, yaw = get_euler_xyz(quat[..., 0:4])
+    ang = torch.sub(goal_angle, normalize_angle(yaw).unsqueeze(-1)).reshape(-1)
+    up_proj, vel6, vel_lin, vel_ang, pos = _walk_terms(dof_pos, default_dof_pos, imu_lin, imu_ang, quat, n)
+    dist_h = torch.abs(1 - up_proj)
+    vel_s, pos_s = torch.mul(vel6, 0.05), torch.mul(pos, 0.05)
+    height_vel_pos = -torch.add(torch.add(vel_s, pos_s), dist_h)
+    vel_height = torch.mul(torch.sub(torch.mul(torch.abs(ang), -0.5), torch.add(dist_h, 0.05 * pos_s)), 1)
+    close = ang < 0.05
+    rew = torch.where(close, height_vel_pos, vel_height)
+    out = torch.linalg.norm(torch.sub(bez_pos[..., 0:2], bez_init_xy), dim=1).reshape(-1) > 0.3
+    return _walk_tail(rew, reset_buf, close, up_proj, pos, vel_ang, vel_lin, out, -5.0, progress_buf, max_episode_length)
 
 
 # --------------------------------------------------------------------------- reset
