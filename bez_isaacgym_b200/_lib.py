@@ -36,6 +36,11 @@ class BezkTaskCfg(C.Structure):
     ]
 
 
+class BezkNoiseCfg(C.Structure):
+    _fields_ = [("distribution", C.c_int32), ("operation", C.c_int32), ("a", C.c_float), ("b", C.c_float),
+                ("a_corr", C.c_float), ("b_corr", C.c_float)]
+
+
 class BezkPpoCfg(C.Structure):
     _fields_ = [
         ("e_clip", C.c_float), ("critic_coef", C.c_float), ("entropy_coef", C.c_float),
@@ -80,6 +85,8 @@ SIGNATURES = {
     "bezk_policy_head": (C.c_int, [_P, _P, _P, _P, _P, C.c_float, _P, _U64, _U64, _P, _P, _P, _P, _P,
                                    C.POINTER(BezkTaskCfg), _P, _P, _I64, _P]),
     "bezk_normal_noise": (C.c_int, [_U64, _U64, _P, _I64, _P]),
+    "bezk_dr_noise": (C.c_int, [_P, _P, _P, _U64, _U64, C.POINTER(BezkNoiseCfg), _P, _I64, _P]),
+    "bezk_dr_fill": (C.c_int, [_U64, _U64, C.c_int32, _P, _I64, _P]),
 }
 
 _lib = None

@@ -312,6 +312,23 @@ int bezk_policy_head(const float* mu, const float* logstd, const float* value_no
                    "bezk_policy_head");
 }
 
+int bezk_dr_noise(const float* x, const float* corr, const float* white, uint64_t seed, uint64_t step, const BezkNoiseCfg* cfg,
+                  float* y, int64_t total, void* stream) {
+    REQUIRE(cfg, "cfg NULL");
+    REQUIRE(total >= 0, "total < 0");
+    REQUIRE((cfg->distribution == 0 || cfg->distribution == 1) && (cfg->operation == 0 || cfg->operation == 1), "bad distribution / operation");
+    if (total == 0) return 0;
+    REQUIRE(x && y, "x / y NULL");
+    return cuda_rc(bezk::launch_dr_noise(x, corr, white, seed, step, *cfg, y, total, (cudaStream_t)stream), "bezk_dr_noise");
+}
+
+int bezk_dr_fill(uint64_t seed, uint64_t step, int32_t distribution, float* out, int64_t total, void* stream) {
+    REQUIRE(total >= 0 && (distribution == 0 || distribution == 1), "bad total / distribution");
+    if (total == 0) return 0;
+    REQUIRE(out, "out NULL");
+    return cuda_rc(bezk::launch_dr_fill(seed, step, distribution, out, total, (cudaStream_t)stream), "bezk_dr_fill");
+}
+
 int bezk_normal_noise(uint64_t seed, uint64_t step, float* out, int64_t n, void* stream) {
     REQUIRE(n >= 0, "n < 0");
     if (n == 0) return 0;

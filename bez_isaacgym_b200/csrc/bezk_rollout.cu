@@ -273,3 +273,91 @@ cudaError_t launch_normal_noise(uint64_t seed, uint64_t step, float* out, int64_
 }
 
 }  // namespace bezk
+
+// ------------------------------------------------------------------------------------------------
+// Domain-randomisation noise lambdas (tasks/base/vec_task.py:562-618, applied at :314-315 to the actions
+// and at :338-339 to obs_buf):   y = op(x, (corr * a_corr + b_corr) + w * a + b)
+// with corr a persistent N(0,1) tensor (drawn once per randomisation period), w fresh N(0,1) ("gaussian") or U[0,1)
+// ("uniform") noise per call, op = + ("additive") or * ("scaling").  Evaluation order as the reference's Python expression:
+// ((corr' + w * a) + b).  w: caller's tensor, or Philox4x32-10 keyed (seed, step, element/4) -- 4 draws per block, one
+// float4 of elements per thread -- so the pass moves 12 B/element (x, corr in; y out) and generates its noise in registers.
+// ------------------------------------------------------------------------------------------------
+namespace bezk {
+
+__device__ __forceinline__ float dr_one(float x, float corr, float w, const BezkNoiseCfg& c) {
+    const float cc = corr * c.a_corr + c.b_corr;
+    const float nz = (cc + w * c.a) + c.b;
+    return c.operation == 0 ? x + nz : x * nz;
+}
+
+__global__ void __launch_bounds__(256) dr_noise_kernel(const float* __restrict__ x, const float* __restrict__ corr,
+                                                       const float* __restrict__ white, uint64_t seed, uint64_t step,
+                                                       const __grid_constant__ BezkNoiseCfg cfg, float* __restrict__ y, int64_t total,
+                                                       int vec4) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t nq = (total + 3) >> 2;                         // quads of elements; quad q owns Philox counter q
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+        const int64_t i0 = q * 4;
+        const int cnt = (int)((total - i0) < 4 ? (total - i0) : 4);
+        float xv[4] = {0.f, 0.f, 0.f, 0.f}, cv[4] = {0.f, 0.f, 0.f, 0.f}, wv[4];
+        if (vec4 && cnt == 4) {
+            const float4 t = ldg_stream4(reinterpret_cast<const float4*>(x) + q);
+            xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+            if (corr) { const float4 u = ldg_stream4(reinterpret_cast<const float4*>(corr) + q); cv[0] = u.x; cv[1] = u.y; cv[2] = u.z; cv[3] = u.w; }
+        } else {
+            for (int k = 0; k < cnt; ++k) { xv[k] = x[i0 + k]; if (corr) cv[k] = corr[i0 + k]; }
+        }
+        if (white) {
+            for (int k = 0; k < cnt; ++k) wv[k] = white[i0 + k];
+            for (int k = cnt; k < 4; ++k) wv[k] = 0.0f;
+        } else {
+            const Philox4 r = philox4x32_10((uint32_t)q, (uint32_t)((uint64_t)q >> 32), (uint32_t)step, (uint32_t)(step >> 32),
+                                            (uint32_t)seed ^ 0x2545F491u, (uint32_t)(seed >> 32));
+            if (cfg.distribution == 0) { box_muller(r.x, r.y, &wv[0], &wv[1]); box_muller(r.z, r.w, &wv[2], &wv[3]); }
+            else { wv[0] = u01(r.x); wv[1] = u01(r.y); wv[2] = u01(r.z); wv[3] = u01(r.w); }
+        }
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = dr_one(xv[k], cv[k], wv[k], cfg);
+        if (vec4 && cnt == 4) __stcs(reinterpret_cast<float4*>(y) + q, make_float4(o[0], o[1], o[2], o[3]));
+        else for (int k = 0; k < cnt; ++k) y[i0 + k] = o[k];
+    }
+}
+
+// white noise exactly as the Philox path above draws it (checker / corr initialisation): gaussian (0) or uniform (1)
+__global__ void __launch_bounds__(256) dr_fill_kernel(uint64_t seed, uint64_t step, int distribution, float* __restrict__ out, int64_t total) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t nq = (total + 3) >> 2;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+        const Philox4 r = philox4x32_10((uint32_t)q, (uint32_t)((uint64_t)q >> 32), (uint32_t)step, (uint32_t)(step >> 32),
+                                        (uint32_t)seed ^ 0x2545F491u, (uint32_t)(seed >> 32));
+        float wv[4];
+        if (distribution == 0) { box_muller(r.x, r.y, &wv[0], &wv[1]); box_muller(r.z, r.w, &wv[2], &wv[3]); }
+        else { wv[0] = u01(r.x); wv[1] = u01(r.y); wv[2] = u01(r.z); wv[3] = u01(r.w); }
+        for (int k = 0; k < 4 && q * 4 + k < total; ++k) out[q * 4 + k] = wv[k];
+    }
+}
+
+static inline int dr_blocks(int64_t total) {
+    int64_t b = ((total + 3) / 4 + 255) / 256;
+    if (b < 1) b = 1;
+    const int64_t cap = 148LL * 8;
+    return (int)(b > cap ? cap : b);
+}
+
+cudaError_t launch_dr_noise(const float* x, const float* corr, const float* white, uint64_t seed, uint64_t step,
+                            const BezkNoiseCfg& cfg, float* y, int64_t total, cudaStream_t st) {
+    if (total == 0) return cudaSuccess;
+    const int vec4 = al16(x) && al16(corr) && al16(y);
+    return launch_ex(dr_noise_kernel, dim3((unsigned)dr_blocks(total)), dim3(256), 0, st, x, corr, white, seed, step, cfg, y, total, vec4);
+}
+
+cudaError_t launch_dr_fill(uint64_t seed, uint64_t step, int distribution, float* out, int64_t total, cudaStream_t st) {
+    if (total == 0) return cudaSuccess;
+    dr_fill_kernel<<<dr_blocks(total), 256, 0, st>>>(seed, step, distribution, out, total);
+    return cudaGetLastError();
+}
+
+}  // namespace bezk

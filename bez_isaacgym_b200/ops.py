@@ -8,7 +8,7 @@ import torch
 
 from . import _lib
 from . import bez_model as bm
-from ._lib import BezkPpoCfg, BezkTaskCfg, BezkError
+from ._lib import BezkNoiseCfg, BezkPpoCfg, BezkTaskCfg, BezkError
 
 
 def _stream(t: torch.Tensor):
@@ -418,4 +418,30 @@ def normal_noise(seed, step, out):
     n = out.shape[0]
     lib = _lib.load()
     _lib.check(lib.bezk_normal_noise(int(seed), int(step), _p(out, F32, "out", n * 18), n, _stream(out)), "bezk_normal_noise")
+    return out
+
+
+# ------------------------------------------------------------------------------------------- domain-randomisation noise
+def make_noise_cfg(distribution="gaussian", operation="additive", a=0.0, b=0.0, a_corr=0.0, b_corr=0.0) -> BezkNoiseCfg:
+    """``y = op(x, (corr * a_corr + b_corr) + w * a + b)``; gaussian: (a, b) = (var, mu); uniform: (a, b) = (hi - lo, lo)."""
+    c = BezkNoiseCfg()
+    c.distribution = {"gaussian": 0, "uniform": 1}[distribution]
+    c.operation = {"additive": 0, "scaling": 1}[operation]
+    c.a, c.b, c.a_corr, c.b_corr = float(a), float(b), float(a_corr), float(b_corr)
+    return c
+
+
+def dr_noise(x, cfg: BezkNoiseCfg, corr=None, white=None, seed=0, step=0, out=None):
+    total = x.numel()
+    y = x if out is None else out
+    lib = _lib.load()
+    _lib.check(lib.bezk_dr_noise(_p(x, F32, "x"), _p(corr, F32, "corr", total, True), _p(white, F32, "white", total, True),
+                                 int(seed), int(step), C.byref(cfg), _p(y, F32, "y", total), total, _stream(x)), "bezk_dr_noise")
+    return y
+
+
+def dr_fill(seed, step, out, distribution="gaussian"):
+    lib = _lib.load()
+    _lib.check(lib.bezk_dr_fill(int(seed), int(step), {"gaussian": 0, "uniform": 1}[distribution], _p(out, F32, "out"),
+                                out.numel(), _stream(out)), "bezk_dr_fill")
     return out

@@ -88,7 +88,7 @@ def make_state(num_envs, seed=1234, device="cpu", cleats=False, filler=True, tas
         q = torch.stack((tilt[:, 0], tilt[:, 1], torch.sin(yaw / 2), torch.cos(yaw / 2)), 1)
         rb[:, bm.IMU_BODY, 3:7] = q / q.norm(dim=1, keepdim=True)
         root = root[:, 0:1].clone()
-        root[:, 0, 0:2] = 0.2 * randn(n, 2)
+        root[:, 0, 0:2] = 0.1 * randn(n, 2)                     # ~1 % beyond orient's 0.3 m out-of-bound circle
         calm = rand(n) < 0.03
         rb[:, bm.IMU_BODY, 7:13] = torch.where(calm.unsqueeze(1), 0.02 * randn(n, 6), rb[:, bm.IMU_BODY, 7:13])
         dof[..., 0] = torch.where(calm.view(n, 1), torch.tensor(READY_POSE, **f32) + 0.01 * randn(n, 18), dof[..., 0])

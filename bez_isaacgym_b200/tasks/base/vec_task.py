@@ -116,6 +116,8 @@ class VecTask(Env):
         self.host_staged = self.device == "cpu"
         self.dr_randomizations = {}
         self.first_randomization = True
+        self.last_step = self.last_rand_step = -1
+        self._dr_seed = int(config.get("seed", 42)) ^ 0x5DEECE66D
         self.sim_initialized = False
         self.create_sim()
         self.sim_initialized = True
@@ -172,11 +174,91 @@ class VecTask(Env):
         self.post_physics_step()
         if self.dr_randomizations.get("observations", None):
             self.obs_buf = self.dr_randomizations["observations"]["noise_lambda"](self.obs_buf)
+            clipped = getattr(self, "obs_clipped_buf", None)
+            if clipped is not None:       # the kernel clipped the noise-free rows; the reference clamps AFTER the noise (:343)
+                torch.clamp(self.obs_buf, -self.clip_obs, self.clip_obs, out=clipped)
         self.extras["time_outs"] = self.timeout_buf.to(self.rl_device)
         self.obs_dict["obs"] = self._observations_out().to(self.rl_device)
         if self.num_states > 0:
             self.obs_dict["states"] = self.get_state()
         return self.obs_dict, self.rew_buf.to(self.rl_device), self.reset_buf.to(self.rl_device), self.extras
+
+    # ------------------------------------------------------------------ domain randomisation: the tensor-path part
+    def apply_randomizations(self, dr_params):
+        """The "observations" / "actions" half of the reference's ``apply_randomizations`` (tasks/base/vec_task.py:505-618):
+        builds ``dr_randomizations[name]`` = parameters + ``noise_lambda`` with the reference's frequency gate, schedule
+        scaling ('linear' / 'constant') and additive / scaling operation for the gaussian and uniform distributions.  The
+        lambdas are ONE kernel each (``bezk_dr_noise``: Philox white noise generated in registers, the persistent correlated
+        draw read from memory).  The "sim_params" / "actor_params" half drives PhysX property setters and is out of scope:
+        such keys raise."""
+        from ... import ops
+        for key in ("sim_params", "actor_params"):
+            if dr_params.get(key):
+                raise NotImplementedError(f"randomization_params.{key} drives PhysX property setters: out of scope (SURVEY 8)")
+        rand_freq = dr_params.get("frequency", 1)
+        self.last_step = int(getattr(self.sim, "frame", 0))           # gym.get_frame_count(sim)
+        if self.first_randomization:
+            do_nonenv_randomize = True
+        else:
+            do_nonenv_randomize = (self.last_step - self.last_rand_step) >= rand_freq
+            rand_envs = (self.randomize_buf >= rand_freq) & (self.reset_buf != 0)
+            self.randomize_buf[rand_envs] = 0
+        if do_nonenv_randomize:
+            self.last_rand_step = self.last_step
+        for name in ("observations", "actions"):
+            if name not in dr_params or not do_nonenv_randomize:
+                continue
+            p = dr_params[name]
+            dist, op_type = p["distribution"], p["operation"]
+            sched_type = p.get("schedule")
+            sched_step = p.get("schedule_steps") if "schedule" in p else None
+            if sched_type == "linear":
+                s = 1.0 / sched_step * min(self.last_step, sched_step)
+            elif sched_type == "constant":
+                s = 0 if self.last_step < sched_step else 1
+            else:
+                s = 1
+            x0, x1 = p["range"]
+            c0, c1 = p.get("range_correlated", [0.0, 0.0])
+            if dist == "gaussian":
+                if op_type == "additive":
+                    x0, x1, c0, c1 = x0 * s, x1 * s, c0 * s, c1 * s
+                elif op_type == "scaling":
+                    x1, x0 = x1 * s, x0 * s + 1.0 * (1.0 - s)
+                    c1, c0 = c1 * s, c0 * s + 1.0 * (1.0 - s)
+                params = {"mu": x0, "var": x1, "mu_corr": c0, "var_corr": c1}
+                kcfg = ops.make_noise_cfg("gaussian", op_type, a=x1, b=x0, a_corr=c1, b_corr=c0)
+            elif dist == "uniform":
+                if op_type == "additive":
+                    x0, x1, c0, c1 = x0 * s, x1 * s, c0 * s, c1 * s
+                elif op_type == "scaling":
+                    x0, x1 = x0 * s + 1.0 * (1.0 - s), x1 * s + 1.0 * (1.0 - s)
+                    c0, c1 = c0 * s + 1.0 * (1.0 - s), c1 * s + 1.0 * (1.0 - s)
+                params = {"lo": x0, "hi": x1, "lo_corr": c0, "hi_corr": c1}
+                kcfg = ops.make_noise_cfg("uniform", op_type, a=x1 - x0, b=x0, a_corr=c1 - c0, b_corr=c0)
+            else:
+                raise ValueError(f"unknown distribution {dist!r}")
+            if op_type not in ("additive", "scaling"):
+                raise ValueError(f"unknown operation {op_type!r}")
+            self._dr_period = getattr(self, "_dr_period", 0) + 1
+            stream_id = (self._dr_period << 1) | (name == "actions")
+
+            def noise_lambda(tensor, param_name=name, kcfg=kcfg, stream_id=stream_id):
+                prm = self.dr_randomizations[param_name]
+                if tensor.device != self.compute_device:
+                    tensor = tensor.to(self.compute_device)
+                tensor = tensor.contiguous()
+                corr = prm.get("corr")
+                if corr is None:                                      # drawn once per randomisation period, like upstream
+                    corr = ops.dr_fill(self._dr_seed, stream_id << 32, torch.empty_like(tensor))
+                    prm["corr"] = corr
+                prm["calls"] = prm.get("calls", 0) + 1
+                out = torch.empty_like(tensor) if param_name == "actions" else tensor      # obs_buf is replaced in place
+                return ops.dr_noise(tensor, kcfg, corr=corr, seed=self._dr_seed, step=(stream_id << 32) + prm["calls"], out=out)
+
+            params["noise_lambda"] = noise_lambda
+            self.dr_randomizations[name] = params
+        self.first_randomization = False
 
     def zero_actions(self) -> torch.Tensor:
         return torch.zeros([self.num_envs, self.num_actions], dtype=torch.float32, device=self.rl_device)

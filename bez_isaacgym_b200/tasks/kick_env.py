@@ -49,8 +49,6 @@ class KickEnv(VecTask):
         env_cfg = cfg["env"]
         self.randomize = cfg["task"]["randomize"]
         self.randomization_params = cfg["task"].get("randomization_params", {})
-        if self.randomize:
-            raise NotImplementedError("domain randomisation drives PhysX property setters: out of scope (SURVEY 8)")
         if fusion not in ("fused", "split"):
             raise ValueError(fusion)
         self.fusion = fusion
@@ -179,6 +177,8 @@ class KickEnv(VecTask):
             self._h_reset = torch.empty(n, dtype=torch.long, **pin); self._h_timeout = torch.empty(n, dtype=torch.long, **pin)
             self._h_actions = torch.empty(n, 18, **pin)
         self._bind()
+        if self.randomize:                                # kick_env.py:248-249: once at start-up, before the first step
+            self.apply_randomizations(self.randomization_params)
         self.reset_idx(torch.arange(n, device=dev))       # kick_env.py:238
 
     # ------------------------------------------------------------------ construction helpers
@@ -288,9 +288,11 @@ class KickEnv(VecTask):
 
     def post_physics_step(self):
         """vec_task.py:331-332 + kick_env.py:426-438 in one launch (two with ``fusion='split'``)."""
-        self._stage_in()
         self._rng_step += 1
-        self._randomize_pending += 1
+        self._randomize_pending += 1                      # randomize_buf += 1 (kick_env.py:430), applied lazily
+        if self.randomize and self._resets_pending():     # reset_idx -> apply_randomizations (kick_env.py:433-435, 781-782)
+            self.apply_randomizations(self.randomization_params)
+        self._stage_in()
         if self.fusion == "fused":
             self._launch_post(_lib.PART_ALL)
         else:
@@ -333,6 +335,8 @@ class KickEnv(VecTask):
         """kick_env.py:779-850 for an explicit id list (the per-step path uses the masked reset inside the fused
         kernel instead, which needs no ``nonzero()``)."""
         env_ids = env_ids.to(device=self.compute_device, dtype=torch.long).contiguous()
+        if self.randomize:                                # kick_env.py:781-782
+            self.apply_randomizations(self.randomization_params)
         self._stage_in()
         if self.TASK == "kick":
             ops.reset_idx(env_ids, self._d_dof, self._d_root, self.initial_root_states, self.progress_buf, self.reset_buf,
@@ -347,6 +351,11 @@ class KickEnv(VecTask):
 
     def _observations_out(self):
         return self.obs_buf if self.obs_clipped_buf is None else self.obs_clipped_buf
+
+    def _resets_pending(self):
+        """``len(reset_buf.nonzero()) > 0`` -- the reference's per-step host sync (kick_env.py:432-434), paid here ONLY when
+        domain randomisation is on (its frequency gate is host logic); the default path never syncs."""
+        return bool(self.reset_buf.any())
 
     # ------------------------------------------------------------------ rollout-storage hooks (SURVEY 8f rows 1-2)
     def set_obs_target(self, tensor):

@@ -270,6 +270,27 @@ int bezk_policy_head(const float* mu, const float* logstd, const float* value_no
  * to the reference's Normal.sample() replacement. */
 int bezk_normal_noise(uint64_t seed, uint64_t step, float* out, int64_t n, void* stream);
 
+/* ---------------------------------------------------------------- domain-randomisation noise ----- */
+
+/* The observation / action noise lambdas VecTask.apply_randomizations builds (ref: tasks/base/vec_task.py:562-618; applied
+ * to the actions at :314-315 and to obs_buf at :338-339; parameters cfg/task/bez_kick.yaml:153-162):
+ *     y = op(x, (corr * a_corr + b_corr) + w * a + b)
+ * gaussian: a = var, b = mu, a_corr = var_corr, b_corr = mu_corr, w ~ N(0,1)
+ * uniform:  a = hi - lo, b = lo, a_corr = hi_corr - lo_corr, b_corr = lo_corr, w ~ U[0,1)   (corr stays N(0,1), as upstream)
+ * (schedule scaling is applied by the host when it fills the struct, as the reference does when it builds the lambda).
+ * x, y (total,) f32 (y may alias x); corr (total,) f32 persistent N(0,1) draw or NULL (= zeros); white (total,) f32 draws or
+ * NULL -> Philox4x32-10 keyed (seed, step, element / 4). */
+typedef struct BezkNoiseCfg {
+    int32_t distribution;   /* 0 = gaussian, 1 = uniform */
+    int32_t operation;      /* 0 = additive, 1 = scaling */
+    float a, b, a_corr, b_corr;
+} BezkNoiseCfg;
+int bezk_dr_noise(const float* x, const float* corr, const float* white, uint64_t seed, uint64_t step,
+                  const BezkNoiseCfg* cfg, float* y, int64_t total, void* stream);
+/* The draws the Philox path of bezk_dr_noise uses for (seed, step): distribution 0 -> N(0,1), 1 -> U[0,1).  Also the way
+ * the host creates `corr`. */
+int bezk_dr_fill(uint64_t seed, uint64_t step, int32_t distribution, float* out, int64_t total, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

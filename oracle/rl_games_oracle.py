@@ -266,3 +266,21 @@ def policy_head(mu: Tensor, logstd: Tensor, value_norm: Tensor, value_rms: Runni
     values = value_rms(value_norm, unnorm=True)
     value_rms.training = was_training
     return dict(actions=actions, neglogpacs=nlp, values=values, mus=mu, sigmas=sigma)
+
+
+# ------------------------------------------------------------------------------------------------
+# Domain-randomisation noise lambdas.  NOT rl_games: restated from the reference's own
+# bez_isaacgym/tasks/base/vec_task.py:562-618 (in tree), kept here with the other elementwise rollout helpers.
+# ------------------------------------------------------------------------------------------------
+def dr_noise_lambda(tensor: Tensor, corr: Tensor, white: Tensor, distribution: str, operation: str, p0: float, p1: float,
+                    c0: float = 0.0, c1: float = 0.0) -> Tensor:
+    """``noise_lambda`` of vec_task.py:586-593 (gaussian: p0 = mu, p1 = var, c0 = mu_corr, c1 = var_corr) and :609-616
+    (uniform: p0 = lo, p1 = hi, c0 = lo_corr, c1 = hi_corr) with the two random draws passed in (``corr`` ~ N(0,1) persistent,
+    ``white`` ~ N(0,1) resp. U[0,1) fresh)."""
+    import operator
+    op = operator.add if operation == "additive" else operator.mul
+    if distribution == "gaussian":
+        corr = corr * c1 + c0
+        return op(tensor, corr + white * p1 + p0)
+    corr = corr * (c1 - c0) + c0
+    return op(tensor, corr + white * (p1 - p0) + p0)

@@ -89,6 +89,20 @@ def main():
                timeit(lambda: ops.post_physics(st.dof_state, st.rigid_body, st.root_states, None, goal, ball_init, None,
                                                reset, progress, None, cfg, None, rew, parts=4), flush=fl), f"n={n}")
         del st
+        if n in (4096, 262144):
+            # sibling tasks: fused step, 432 B/env = R dof 144 + root 52 + imu 40 + feet 24 + goal 8 + reset/progress 16
+            # (+ prev 12) ; W obs 208 + rew 4 + reset/progress/timeout 24 (+ prev 12)
+            for task in ("walk", "orient"):
+                sw = sg.make_state(n, seed=1, device=dev, task=task)
+                cfgw = ops.make_task_cfg(num_bodies=sw.num_bodies, max_episode_length=600, reset_root_states=False)
+                gw = torch.tensor([[2.0, 0.0]], device=dev).repeat(n, 1); ga = torch.full((n,), 1.5708, device=dev)
+                obw = torch.empty(n, 52, device=dev)
+                pw, rw = sg.make_bookkeeping(n, device=dev, max_episode_length=600)
+                report(f"post_physics_fused[{task}]", n, 432,
+                       timeit(lambda: ops.post_physics_task(task, sw.dof_state, sw.rigid_body, sw.root_states, sw.net_contact, gw, None,
+                                                            rw, pw, timeout, cfgw, obw, rew, goal_angle=ga, prev_lin_vel=prev), flush=fl),
+                       f"n={n}")
+                del sw
     # ---- GAE
     for n in (4096, 262144) if args.only in ("all", "learner") else ():
         r, v, d, lv, ld = sg.make_rollout(n, 32, device=dev)
@@ -168,6 +182,10 @@ def main():
             o = [torch.empty(n, 18, device=dev) for _ in range(4)]
             nl = torch.empty(n, device=dev); vo = torch.empty(n, device=dev)
             cfg = ops.make_task_cfg()
+            xa = torch.randn(n, 54, device=dev); ca = torch.randn(n, 54, device=dev)
+            ncfg = ops.make_noise_cfg("gaussian", "additive", a=0.002)
+            report("dr_noise(obs, philox)", n * 54, 12, timeit(lambda: ops.dr_noise(xa, ncfg, corr=ca, seed=1, step=2), flush=flush if n < 262144 else None),
+                   f"n={n}: x + corr read, y written, white noise generated in registers")
             fl2 = flush if n < 262144 else None
             report("policy_head(philox)", n, 372,
                    timeit(lambda: ops.policy_head(mu, logstd, vn, vm, vv, 1e-5, noise=None, seed=1, step=2, actions=o[0], neglogp=nl,
