@@ -141,6 +141,25 @@ int bezk_post_physics(float* dof_state, const float* rigid_body, float* root_sta
     return run_task(parts, a, cfg, stream, "bezk_post_physics");
 }
 
+int bezk_post_physics_chunk(float* dof_state, const float* rigid_body, float* root_states, float* net_contact, float* prev_lin_vel,
+                            const float* goal, const float* ball_init, const float* initial_root_states, const float* uniforms,
+                            uint64_t seed, uint64_t step, int64_t* reset_buf, int64_t* progress_buf, int64_t* timeout_buf,
+                            int64_t* randomize_buf, const BezkTaskCfg* cfg, float* obs, float* obs_clipped, float* rew, int parts,
+                            int64_t n, int64_t env_base, float* dof_state_wb, float* root_states_wb, void* stream) {
+    REQUIRE(parts >= 1 && parts <= 7, "parts must be a non-empty subset of {1,2,4}");
+    REQUIRE(env_base >= 0, "env_base < 0");
+    bezk::TaskArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dof_state = dof_state; a.rigid_body = rigid_body; a.root_states = root_states; a.net_contact = net_contact;
+    a.prev_lin_vel = prev_lin_vel; a.goal = const_cast<float*>(goal); a.ball_init = ball_init; a.initial_root = initial_root_states;
+    a.uniforms = uniforms; a.seed = seed; a.step = step; a.env_base = env_base; a.dof_state_wb = dof_state_wb;
+    a.root_states_wb = root_states_wb;
+    a.reset_in = reset_buf; a.reset_out = reset_buf; a.progress_in = progress_buf; a.progress_out = progress_buf;
+    a.timeout_buf = timeout_buf; a.randomize_buf = randomize_buf;
+    a.obs = obs; a.obs_clipped = obs_clipped; a.rew = rew; a.n = n;
+    return run_task(parts, a, cfg, stream, "bezk_post_physics_chunk");
+}
+
 int bezk_post_physics_task(int task, float* dof_state, const float* rigid_body, float* root_states, float* net_contact,
                            float* prev_lin_vel, float* goal, const float* goal_angle, const float* ball_init,
                            const float* initial_root_states, const float* uniforms, const float* goal_uniforms, uint64_t seed,

@@ -18,6 +18,9 @@ struct TaskArgs {
     const float* initial_root;   // (n*2, 13)
     const float* uniforms;       // (n, 36) or nullptr (Philox)
     uint64_t seed, step;
+    int64_t env_base;            // global id of env 0 of this launch (Philox key) -- non-zero when a step is launched in chunks
+    float* dof_state_wb;         // where reset rows are written back (nullptr: dof_state itself)
+    float* root_states_wb;       // likewise for the root rows (nullptr: root_states itself)
     const int64_t* reset_in;
     int64_t* reset_out;
     const int64_t* progress_in;

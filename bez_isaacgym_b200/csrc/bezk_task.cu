@@ -373,7 +373,8 @@ __device__ __forceinline__ void gather_env(const TaskArgs& a, const BezkTaskCfg&
             // request count matters as much as bytes (profiles/r01_fetch_granularity.md): when the 40-byte span straddles a
             // 64-byte boundary but stays inside one 128-byte line, ONE full-line fill replaces two 64-byte ones
             const uint32_t s128 = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 127u);
-            const bool one_line = a.smart_granule && ((s128 & 63u) + 40u > 64u) && (s128 + 40u <= 128u);
+            const bool one_line = (a.smart_granule == 2 && s128 + 40u <= 128u) ||
+                                  (a.smart_granule && ((s128 & 63u) + 40u > 64u) && (s128 + 40u <= 128u));
             float2 a2; float4 b4, c4;
             if (one_line) {
                 a2 = ldg128B_nc_v2(p + (hi ? 0 : 32)); b4 = ldg128B_nc_v4(p + (hi ? 8 : 0)); c4 = ldg128B_nc_v4(p + (hi ? 24 : 16));
@@ -395,8 +396,8 @@ __device__ __forceinline__ void gather_env(const TaskArgs& a, const BezkTaskCfg&
                 const uint32_t sl = (uint32_t)(reinterpret_cast<uintptr_t>(cf_l) & 127u);
                 const uint32_t sr = (uint32_t)(reinterpret_cast<uintptr_t>(cf_r) & 127u);
                 const bool same_line = ((reinterpret_cast<uintptr_t>(cf_l) ^ (reinterpret_cast<uintptr_t>(cf_r) + 11u)) & ~(uintptr_t)127u) == 0;
-                const bool l_line = a.smart_granule && (same_line || (((sl & 63u) + 12u > 64u) && (sl + 12u <= 128u)));
-                const bool r_line = a.smart_granule && !same_line && (((sr & 63u) + 12u > 64u) && (sr + 12u <= 128u));
+                const bool l_line = a.smart_granule == 2 || (a.smart_granule && (same_line || (((sl & 63u) + 12u > 64u) && (sl + 12u <= 128u))));
+                const bool r_line = a.smart_granule == 2 || (a.smart_granule && !same_line && (((sr & 63u) + 12u > 64u) && (sr + 12u <= 128u)));
                 const float2 l2 = l_line ? ldg128B_v2(cf_l) : ldg64B_v2(cf_l);
                 const float2 r2 = r_line ? ldg128B_v2(cf_r) : ldg64B_v2(cf_r);
                 g.fl[0] = l2.x; g.fl[1] = l2.y; g.fl[2] = ldg64B(cf_l + 2);
@@ -536,7 +537,8 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
 #pragma unroll
                     for (int k = 0; k < 4; ++k) u4[k] = a.uniforms[env * 36 + 4 * lane + k];
                 } else {
-                    const Philox4 x = philox4x32_10((uint32_t)env, (uint32_t)((uint64_t)env >> 32), (uint32_t)a.step,
+                    const int64_t genv = a.env_base + env;         // Philox is keyed by the GLOBAL env id
+                    const Philox4 x = philox4x32_10((uint32_t)genv, (uint32_t)((uint64_t)genv >> 32), (uint32_t)a.step,
                                                     ((uint32_t)(a.step >> 32) << 4) + (uint32_t)lane, (uint32_t)a.seed,
                                                     (uint32_t)(a.seed >> 32));
                     u4[0] = u01(x.x); u4[1] = u01(x.y); u4[2] = u01(x.z); u4[3] = u01(x.w);
@@ -555,16 +557,16 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
             __syncwarp();
             if (lane < 9) {
                 if (a.use_tma) {
-                    reinterpret_cast<float4*>(a.dof_state + env * DOF_ROW)[lane] = reinterpret_cast<const float4*>(s_dof + r * DOF_ROW)[lane];
+                    reinterpret_cast<float4*>(a.dof_state_wb + env * DOF_ROW)[lane] = reinterpret_cast<const float4*>(s_dof + r * DOF_ROW)[lane];
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) a.dof_state[env * DOF_ROW + 4 * lane + k] = s_dof[r * DOF_ROW + 4 * lane + k];
+                    for (int k = 0; k < 4; ++k) a.dof_state_wb[env * DOF_ROW + 4 * lane + k] = s_dof[r * DOF_ROW + 4 * lane + k];
                 }
             }
             if ((cfg.flags & BEZK_F_RESET_ROOT_STATES) && lane < ROOT_ROW) {
                 const float t = a.initial_root[env * ROOT_ROW + lane];
                 s_root[r * ROOT_ROW + lane] = t;
-                a.root_states[env * ROOT_ROW + lane] = t;
+                a.root_states_wb[env * ROOT_ROW + lane] = t;
             }
             __syncwarp();
         }
@@ -838,11 +840,14 @@ cudaError_t launch_goal_uniforms(uint64_t seed, uint64_t step, float* out2, cuda
 }
 
 void fill_alignment(TaskArgs& a, const BezkTaskCfg& cfg) {
-    a.use_tma = aligned16(a.dof_state) && aligned16(a.root_states) && (a.obs == nullptr || aligned16(a.obs)) &&
+    if (a.dof_state_wb == nullptr) a.dof_state_wb = a.dof_state;
+    if (a.root_states_wb == nullptr) a.root_states_wb = a.root_states;
+    a.use_tma = aligned16(a.dof_state) && aligned16(a.root_states) && aligned16(a.dof_state_wb) && (a.obs == nullptr || aligned16(a.obs)) &&
                 (a.obs_clipped == nullptr || aligned16(a.obs_clipped));
     a.rb_vec2 = aligned8(a.rigid_body) && (cfg.num_bodies % 2 == 0) && ((cfg.imu_body * 13 + 3) % 2 == 0);
+    // 0: 64-byte granules only; 1 (default): per-lane 64 / 128-byte choice; 2: full 128-byte lines wherever the span allows
     const char* sg = getenv("BEZK_SMART_GRANULE");
-    a.smart_granule = (sg == nullptr) ? 1 : (sg[0] != '0');
+    a.smart_granule = (sg == nullptr) ? 1 : (sg[0] - '0');
     a.cf_vec2 = a.net_contact != nullptr && aligned8(a.net_contact) && ((cfg.num_bodies * 3) % 2 == 0) &&
                 ((cfg.left_foot_body * 3) % 2 == 0) && ((cfg.right_foot_body * 3) % 2 == 0);
 }

@@ -124,6 +124,21 @@ int bezk_post_physics(float* dof_state, const float* rigid_body, float* root_sta
                       int64_t* randomize_buf, const BezkTaskCfg* cfg, float* obs, float* obs_clipped,
                       float* rew, int parts, int64_t n, void* stream);
 
+/* One CHUNK of a step: the same kernel over envs [env_base, env_base + n) of a larger task, every pointer already offset to
+ * the chunk's first env.  env_base keeps the Philox reset noise keyed by the GLOBAL env id, so a step launched in chunks
+ * (the host pipeline overlaps the DMA of chunk c+1 with the kernel of chunk c) gives the results of one launch.
+ * dof_state_wb / root_states_wb: where the rows of the envs that reset are written back (NULL: dof_state / root_states
+ * themselves) -- with a staged copy of the dense tensors on the device, the reset rows still go to the simulator's own
+ * (pinned host) tensors. */
+int bezk_post_physics_chunk(float* dof_state, const float* rigid_body, float* root_states,
+                            float* net_contact, float* prev_lin_vel, const float* goal,
+                            const float* ball_init, const float* initial_root_states,
+                            const float* uniforms, uint64_t seed, uint64_t step,
+                            int64_t* reset_buf, int64_t* progress_buf, int64_t* timeout_buf,
+                            int64_t* randomize_buf, const BezkTaskCfg* cfg, float* obs, float* obs_clipped,
+                            float* rew, int parts, int64_t n, int64_t env_base, float* dof_state_wb,
+                            float* root_states_wb, void* stream);
+
 /* The dense (n,36) uniforms the Philox path of bezk_post_physics / bezk_reset_idx consumes for
  * (seed, step): lets a checker feed the identical draws to the reference's reset_idx. */
 int bezk_philox_uniforms(uint64_t seed, uint64_t step, float* out, int64_t n, void* stream);

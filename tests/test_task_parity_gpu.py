@@ -439,3 +439,42 @@ def test_host_pipeline_equals_gpu_pipeline(host_mode):
         assert torch.equal(envs["gpu"].root_states.cpu(), envs["host"].root_states)
         assert torch.equal(envs["gpu"].targets.cpu(), envs["host"].targets.cpu())
     assert int(d_g.sum()) > 0
+
+
+def test_chunked_step_equals_one_launch():
+    """``bezk_post_physics_chunk``: a step launched as chunks [env_base, env_base + n) with offset pointers gives, bit for bit,
+    the results of one launch -- the Philox reset noise stays keyed by the GLOBAL env id."""
+    import ctypes as C
+    from bez_isaacgym_b200 import _lib
+    ops = _ops()
+    n = 4099
+    cfg = ops.make_task_cfg()
+    goal, ball_init, default, _, _ = U.constants(n, "cuda")
+    init_root = sg.make_initial_root_states(n, "cuda")
+    outs = []
+    for chunks in (None, [(0, 1280), (1280, 2560), (2560, 4099)]):
+        st = sg.make_state(n, seed=31).to("cuda")
+        progress, reset = sg.make_bookkeeping(n, seed=4, device="cuda", p_reset=0.2)
+        timeout = torch.empty(n, dtype=torch.long, device="cuda")
+        obs = torch.empty(n, 54, device="cuda"); rew = torch.empty(n, device="cuda")
+        prev = torch.zeros(n, 3, device="cuda")
+        if chunks is None:
+            ops.post_physics(st.dof_state, st.rigid_body, st.root_states, st.net_contact, goal, ball_init, init_root, reset, progress,
+                             timeout, cfg, obs, rew, prev_lin_vel=prev, seed=9, step=3)
+        else:
+            lib = _lib.load()
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            p4 = lambda t, k: C.c_void_p(t.data_ptr() + 4 * k)        # noqa: E731
+            p8 = lambda t, k: C.c_void_p(t.data_ptr() + 8 * k)        # noqa: E731
+            for lo, hi in chunks:
+                rc = lib.bezk_post_physics_chunk(p4(st.dof_state, lo * 36), p4(st.rigid_body, lo * 22 * 13), p4(st.root_states, lo * 26),
+                                                 p4(st.net_contact, lo * 66), p4(prev, lo * 3), p4(goal, lo * 2), p4(ball_init, lo * 2),
+                                                 p4(init_root, lo * 26), None, 9, 3, p8(reset, lo), p8(progress, lo), p8(timeout, lo),
+                                                 None, C.byref(cfg), p4(obs, lo * 54), None, p4(rew, lo), 7, hi - lo, lo, None, None,
+                                                 stream)
+                _lib.check(rc, "bezk_post_physics_chunk")
+        torch.cuda.synchronize()
+        outs.append([t.clone() for t in (obs, rew, reset, progress, timeout, st.dof_state, st.root_states, st.net_contact, prev)])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b) or bool(((a == b) | (a.isnan() & b.isnan())).all())
+    assert int(outs[0][2].sum()) > 0
