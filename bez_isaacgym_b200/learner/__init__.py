@@ -6,6 +6,8 @@ from .a2c_common import discount_values, normalize_advantages, shape_rewards, sw
 from .losses import ppo_loss, PPOLossConfig
 from .experience import ExperienceBuffer, PPODataset, SlabDataset
 from .policy_head import policy_head
+from .agent import A2CAgent, A2CNetwork, AdaptiveScheduler
 
 __all__ = ["RunningMeanStd", "discount_values", "normalize_advantages", "shape_rewards", "swap_and_flatten01",
-           "ppo_loss", "PPOLossConfig", "ExperienceBuffer", "PPODataset", "SlabDataset", "policy_head"]
+           "ppo_loss", "PPOLossConfig", "ExperienceBuffer", "PPODataset", "SlabDataset", "policy_head", "A2CAgent", "A2CNetwork",
+           "AdaptiveScheduler"]

@@ -2,6 +2,7 @@
 rl_games A2CAgent would make: RunningMeanStd module (train / eval / unnorm, checkpoint layout), discount_values,
 normalize_advantages and the fused PPO loss as an autograd Function feeding a policy MLP."""
 import json
+import math
 import os
 
 import pytest
@@ -109,3 +110,38 @@ def test_ppo_loss_autograd_through_policy_mlp(bound_form):
     assert abs(info["kl"].item() - o["kl"].item()) < 1e-5 and abs(info["a_loss"].item() - o["a_loss"].item()) < 1e-5
     for a, b in zip(got, ref_grads):
         assert torch.allclose(a.cpu(), b, rtol=2e-3, atol=2e-6), (a.cpu() - b).abs().max()
+
+
+def test_a2c_agent_epoch_reproduces_the_checkpoint_cadence():
+    """Two epochs of ``A2CAgent`` (rollout + dataset + mini-epochs through the kernels): the normaliser counts obey the
+    identities the reference's shipped checkpoint pins -- ``count_obs = 1 + mini_epochs * frame``, ``count_val = 1 + 2 * frame``
+     --, losses are finite, parameters move, the adaptive LR stays inside its bounds, and a checkpoint written
+    with rl_games' keys restores the agent."""
+    from bez_isaacgym_b200 import bez_model as bm
+    from bez_isaacgym_b200 import learner as L
+    from bez_isaacgym_b200.synthetic_sim import SyntheticGym
+    from bez_isaacgym_b200.tasks import KickEnv
+    n = 1024
+    env = KickEnv(bm.default_task_cfg(n), "cuda:0", 0, True, sim=SyntheticGym(n, device="cuda:0", seed=2))
+    agent = L.A2CAgent(env, dict(horizon_length=8, minibatch_size=2048, mini_epochs=5), seed=1)
+    before = [p.detach().clone() for p in agent.model.parameters()]
+    for _ in range(2):
+        info = agent.train_epoch()
+    frame = 2 * n * 8
+    assert agent.frame == frame and agent.epoch_num == 2
+    assert float(agent.running_mean_std.count) == 1 + 5 * frame
+    assert float(agent.value_mean_std.count) == 1 + 2 * frame
+    assert all(math.isfinite(float(info[k])) for k in ("a_loss", "c_loss", "kl")) and 1e-6 <= info["lr"] <= 1e-2
+    assert any(not torch.equal(a, b) for a, b in zip(before, agent.model.parameters()))
+    assert torch.isfinite(agent.running_mean_std.running_var).all() and float(agent.running_mean_std.running_var.min()) >= 0
+    # obs column 52:54 is the constant ball_init (0.175, 0): its running mean converges there and its variance towards 0
+    assert abs(float(agent.running_mean_std.running_mean[52]) - 0.175) < 1e-3
+    ck = agent.get_full_state_weights()
+    assert set(ck) >= {"model", "running_mean_std", "reward_mean_std", "optimizer", "epoch", "frame", "last_mean_rewards"}
+    assert all(k.startswith("a2c_network.") for k in ck["model"])
+    env2 = KickEnv(bm.default_task_cfg(n), "cuda:0", 0, True, sim=SyntheticGym(n, device="cuda:0", seed=2))
+    other = L.A2CAgent(env2, dict(horizon_length=8, minibatch_size=2048, mini_epochs=5), seed=9)
+    other.set_full_state_weights(ck)
+    assert other.frame == frame and float(other.running_mean_std.count) == 1 + 5 * frame
+    for a, b in zip(agent.model.parameters(), other.model.parameters()):
+        assert torch.equal(a, b)

@@ -203,3 +203,23 @@ def test_policy_head_oracle_identities():
     torch.testing.assert_close(out["neglogpacs"], want, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(out["values"], raw, rtol=1e-5, atol=1e-5)
     assert torch.equal(rg.preprocess_actions(torch.tensor([-3.0, -0.5, 0.25, 7.0])), torch.tensor([-1.0, -0.5, 0.25, 1.0]))
+
+
+def test_network_and_normaliser_state_match_the_shipped_checkpoint_layout():
+    """``A2CNetwork`` / ``RunningMeanStd`` state dicts carry exactly the names, shapes and dtypes of the reference's shipped
+    checkpoint (tests/golden/checkpoint_facts.json, App. G), so ``A2CAgent.set_full_state_weights`` can load it."""
+    from bez_isaacgym_b200.learner.agent import A2CNetwork, AdaptiveScheduler
+    from bez_isaacgym_b200.learner.running_mean_std import RunningMeanStd as RMS
+    with open(os.path.join(os.path.dirname(__file__), "golden", "checkpoint_facts.json")) as f:
+        facts = json.load(f)
+    net = A2CNetwork()
+    assert {"a2c_network." + k: list(v.shape) for k, v in net.state_dict().items()} == facts["model_shapes"]
+    for mod, key in ((RMS(54), "obs_rms"), (RMS(1), "val_rms")):
+        sd = mod.state_dict()
+        assert {k: {"shape": list(v.shape), "dtype": str(v.dtype)} for k, v in sd.items()} == facts[key]
+    # the checkpoint's learning rate is 3e-4 / 1.5^4: four net down-steps of the adaptive schedule
+    sched, lr = AdaptiveScheduler(0.008), 3e-4
+    for _ in range(4):
+        lr, _ = sched.update(lr, 0.0, 0, 0, 0.02)
+    assert lr == pytest.approx(facts["lr"])
+    assert sched.update(lr, 0.0, 0, 0, 0.001)[0] == pytest.approx(lr * 1.5) and sched.update(lr, 0.0, 0, 0, 0.008)[0] == lr
