@@ -122,11 +122,11 @@ __device__ __forceinline__ void imu_term(const float (&q)[4], const float (&v)[3
     out[5] = clamp_nan(w[2], -c.imu_max_ang_vel, c.imu_max_ang_vel);
 }
 
-// python-style remainder by a positive modulus (torch.remainder / Tensor.__mod__)
-__device__ __forceinline__ float py_mod(float x, float m) {
-    float r = fmodf(x, m);
-    if (r != 0.0f && r < 0.0f) r += m;
-    return r;
+// torch.remainder(x, 2 pi) (python-style, Tensor.__mod__) for x = atan2f(..) in [-pi, pi]: |x| < 2 pi, so fmod(x, 2 pi) is x
+// itself and the remainder is x (+ 2 pi when x < 0); identical bits to fmodf + sign fix-up, without the fmodf loop.  NaN and
+// -0.0 pass through unchanged, as they do there.
+__device__ __forceinline__ float wrap_2pi(float x) {
+    return (x < 0.0f) ? x + 6.283185307179586f : x;
 }
 
 // compute_off_orn, kick_env.py:941-960 (+ yaw of get_euler_xyz)
@@ -137,8 +137,9 @@ __device__ __forceinline__ void off_orn_term(float px, float py, const float (&q
     const float x = q[0], y = q[1], z = q[2], w = q[3];
     const float siny = 2.0f * (w * z + x * y);
     const float cosy = ((w * w + x * x) - y * y) - z * z;
-    const float yaw = py_mod(atan2f(siny, cosy), 6.283185307179586f);
-    const float hx = cosf(yaw), hy = sinf(yaw);
+    const float yaw = wrap_2pi(atan2f(siny, cosy));
+    float hx, hy;
+    sincosf(yaw, &hy, &hx);                              // one shared range reduction; same values as sinf / cosf
     const float c = hx * ux + hy * uy;
     const float cz = ux * hy - uy * hx;                  // only non-zero component of the 3-D cross
     out[0] = sqrtf((0.0f + 0.0f) + cz * cz);             // linalg.norm of (0, 0, cz)
@@ -161,13 +162,15 @@ __device__ __forceinline__ float yaw_mod_2pi(const float (&q)[4]) {
     const float x = q[0], y = q[1], z = q[2], w = q[3];
     const float siny = 2.0f * (w * z + x * y);
     const float cosy = ((w * w + x * x) - y * y) - z * z;
-    return py_mod(atan2f(siny, cosy), 6.283185307179586f);
+    return wrap_2pi(atan2f(siny, cosy));
 }
 
 // compute_off_angle, orient_env.py:720-733: (cos, sin) of goal_angle - normalize_angle(yaw)
 __device__ __forceinline__ float angle_to_goal(const float (&q)[4], float goal_angle) {
     const float yaw = yaw_mod_2pi(q);
-    const float na = atan2f(sinf(yaw), cosf(yaw));       // normalize_angle
+    float sy, cy;
+    sincosf(yaw, &sy, &cy);
+    const float na = atan2f(sy, cy);                     // normalize_angle
     return goal_angle - na;
 }
 
@@ -353,8 +356,11 @@ __device__ __forceinline__ float ld_f32(const float* p) {
     return v;
 }
 
+// rb: this env's IMU-link slice (10 floats); cf_l / cf_r: its foot (first cleat) force rows.  The caller forms them as a
+// warp-uniform 64-bit base plus a 32-bit lane offset.
 template <bool OBS, bool BOOKREW, bool CLEATS, int TASK>
-__device__ __forceinline__ void gather_env(const TaskArgs& a, const BezkTaskCfg& cfg, int64_t e, bool valid, Gathered<CLEATS>& g) {
+__device__ __forceinline__ void gather_env(const TaskArgs& a, const BezkTaskCfg& cfg, int64_t e, bool valid, const float* rb,
+                                           float* cf_l, float* cf_r, Gathered<CLEATS>& g) {
     constexpr int NFORCE = CLEATS ? 12 : 3;
 #pragma unroll
     for (int k = 0; k < NFORCE; ++k) { g.fl[k] = 0.0f; g.fr[k] = 0.0f; }
@@ -365,7 +371,6 @@ __device__ __forceinline__ void gather_env(const TaskArgs& a, const BezkTaskCfg&
 #pragma unroll
     for (int k = 0; k < 10; ++k) g.raw[k] = 0.0f;
     if (valid) {
-        const float* rb = a.rigid_body + ((e * cfg.num_bodies + cfg.imu_body) * 13 + 3);
         if (a.rb_vec2) {
             // 40 bytes at an 8-byte aligned address: one 8 B + two 16 B loads, order chosen per lane by bit 3
             const char* p = reinterpret_cast<const char*>(rb);
@@ -388,8 +393,6 @@ __device__ __forceinline__ void gather_env(const TaskArgs& a, const BezkTaskCfg&
             for (int k = 0; k < 10; ++k) g.raw[k] = ldg64B_nc(rb + k);
         }
         if (OBS) {
-            float* cf_l = a.net_contact + (e * cfg.num_bodies + cfg.left_foot_body) * 3;
-            float* cf_r = a.net_contact + (e * cfg.num_bodies + cfg.right_foot_body) * 3;
             if (!CLEATS && a.cf_vec2) {
                 // same idea for the feet: a full-line fill when both feet (or a foot straddling a 64-byte boundary) sit
                 // inside one 128-byte line, 64-byte granules otherwise
@@ -431,11 +434,10 @@ __device__ __forceinline__ void gather_env(const TaskArgs& a, const BezkTaskCfg&
 // First use of a gathered set: pin the raw registers behind an (empty) volatile asm so that the compiler cannot
 // hoist the unpacking selects up to the loads (which would stall the warp at issue time), then unpack.
 template <bool CLEATS>
-__device__ __forceinline__ void consume(const TaskArgs& a, const BezkTaskCfg& cfg, int64_t e, Gathered<CLEATS>& g, float (&imu)[10]) {
+__device__ __forceinline__ void consume(const TaskArgs& a, const float* rb, Gathered<CLEATS>& g, float (&imu)[10]) {
     asm volatile("" : "+f"(g.raw[0]), "+f"(g.raw[1]), "+f"(g.raw[2]), "+f"(g.raw[3]), "+f"(g.raw[4]), "+f"(g.raw[5]),
                       "+f"(g.raw[6]), "+f"(g.raw[7]), "+f"(g.raw[8]), "+f"(g.raw[9]));
     asm volatile("" : "+l"(g.reset_prev), "+l"(g.progress));
-    const float* rb = a.rigid_body + ((e * cfg.num_bodies + cfg.imu_body) * 13 + 3);
     // vector path, slice NOT 16-byte aligned (hi): pieces were loaded in memory order (8,16,16) -> raw is already in order;
     // 16-byte aligned: pieces were loaded as (tail 8 B, first 16 B, second 16 B) -> rotate
     const bool rot = a.rb_vec2 && ((reinterpret_cast<uintptr_t>(rb) & 8u) == 0);
@@ -498,11 +500,17 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
     }
 
     // ---- 2. sparse gathers, issued before anyone waits (widest aligned vector loads available) ----
+    // per-env row pointers: warp-uniform 64-bit base + 32-bit lane offset
+    const int nbod = cfg.num_bodies;
+    const float* rb = a.rigid_body + ((e0 * nbod + cfg.imu_body) * 13 + 3) + lane * (nbod * 13);
+    float* cf_env = a.net_contact ? a.net_contact + e0 * nbod * 3 + lane * (nbod * 3) : nullptr;
+    float* cf_l = cf_env ? cf_env + cfg.left_foot_body * 3 : nullptr;
+    float* cf_r = cf_env ? cf_env + cfg.right_foot_body * 3 : nullptr;
     Gathered<CLEATS> g;
-    gather_env<OBS, (BOOK || REW), CLEATS, TASK>(a, cfg, e, valid, g);
+    gather_env<OBS, (BOOK || REW), CLEATS, TASK>(a, cfg, e, valid, rb, cf_l, cf_r, g);
 
     float imu_in[10];
-    consume<CLEATS>(a, cfg, e, g, imu_in);
+    consume<CLEATS>(a, rb, g, imu_in);
     float (&fl)[NFORCE] = g.fl;
     float (&fr)[NFORCE] = g.fr;
     float (&goal)[2] = g.goal;
@@ -510,8 +518,6 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
     float (&prev)[3] = g.prev;
     const int64_t reset_prev = (int64_t)g.reset_prev;
     int64_t progress = (int64_t)g.progress;
-    float* cf_l = a.net_contact ? a.net_contact + (e * cfg.num_bodies + cfg.left_foot_body) * 3 : nullptr;
-    float* cf_r = a.net_contact ? a.net_contact + (e * cfg.num_bodies + cfg.right_foot_body) * 3 : nullptr;
     const float q[4] = {imu_in[0], imu_in[1], imu_in[2], imu_in[3]};
     const float v[3] = {imu_in[4], imu_in[5], imu_in[6]};
     const float w[3] = {imu_in[7], imu_in[8], imu_in[9]};
@@ -622,7 +628,7 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
         }
         if (TASK == BEZK_TASK_ORIENT) {                                    // compute_off_angle, orient_env.py:720-733
             const float d = angle_to_goal(q, g.gang);
-            orn2[0] = cosf(d); orn2[1] = sinf(d);
+            sincosf(d, &orn2[1], &orn2[0]);
         } else {
             off_orn_term(bez[0], bez[1], q, goal[0], goal[1], orn2);
         }

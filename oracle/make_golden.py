@@ -181,8 +181,8 @@ def sibling_constants(task, n):
     return goal, goal_angle, default
 
 
-def function_level_sibling(task, ref, st, prev, progress, reset_in, goal):
-    """The reference walk_env / orient_env jit functions on the state (no cleats)."""
+def function_level_sibling(task, ref, st, prev, progress, reset_in, goal, cleats=False):
+    """The reference walk_env / orient_env jit functions on the state."""
     n = st.num_envs
     st = st.clone()
     root, rb = st.root_states.view(n, 1, 13), st.rigid_body.view(n, -1, 13)
@@ -193,10 +193,14 @@ def function_level_sibling(task, ref, st, prev, progress, reset_in, goal):
     gravity = torch.tensor([[0.0, 0.0, -1.0]]).repeat(n, 1)
     imu6, _ = ref.compute_imu(quat, lin, ang, prev, gravity, 2.0 * 9.81, 8.7266, 0.01667, n)
     heading = ref.compute_off_orn(bez_pos, quat, goal) if task == "walk" else ref.compute_off_angle(quat, goal_angle)
-    args = [torch.tensor([[-1.0] * 4]).repeat(n, 1), torch.ones(1), torch.zeros(1), torch.zeros(3)] + \
-           [torch.tensor(r) for r in _FEET_ROWS]
-    feet = torch.cat((ref.compute_feet_sensors_no_cleats(cf[:, 12, :], *args),
-                      ref.compute_feet_sensors_no_cleats(cf[:, 20, :], *args)), 1)
+    if cleats:                          # walk_env.py:176-181, 388-416
+        feet = ref.compute_feet_sensors_cleats(cf[:, 13:17, :], cf[:, 25:29, :], torch.tensor([[-1.0] * 8]).repeat(n, 1),
+                                               torch.ones(n, 8))
+    else:
+        args = [torch.tensor([[-1.0] * 4]).repeat(n, 1), torch.ones(1), torch.zeros(1), torch.zeros(3)] + \
+               [torch.tensor(r) for r in _FEET_ROWS]
+        feet = torch.cat((ref.compute_feet_sensors_no_cleats(cf[:, 12, :], *args),
+                          ref.compute_feet_sensors_no_cleats(cf[:, 20, :], *args)), 1)
     obs = ref.compute_bez_observations(dof[..., 0], dof[..., 1], imu6, heading, feet)
     up = torch.tensor([[0.0, 0.0, 1.0]]).repeat(n, 1)
     rew, reset = ref.compute_bez_reward(dof[..., 0], default, lin, ang, bez_pos, quat, up, goal if task == "walk" else goal_angle,
@@ -327,6 +331,13 @@ def siblings():
         d = dict(state_arrays(st), in_prev_lin_vel=_np(prev), in_progress=_np(progress), in_reset=_np(reset_in))
         d.update(function_level_sibling(task, ref, st, prev, progress, reset_in, goal))
         np.savez_compressed(os.path.join(OUT, f"fn_{task}_edges.npz"), **d)
+        n = 64                                                       # cleats variant: 29 bodies, 4 + 4 cleat force rows
+        st = sg.make_state(n, seed=3300, task=task, cleats=True)
+        progress, reset_in = sg.make_bookkeeping(n, seed=3, max_episode_length=600)
+        goal = torch.tensor([[2.0, 0.0]]).repeat(n, 1)
+        d = dict(state_arrays(st), in_prev_lin_vel=np.zeros((n, 3), np.float32), in_progress=_np(progress), in_reset=_np(reset_in))
+        d.update(function_level_sibling(task, ref, st, torch.zeros(n, 3), progress, reset_in, goal, cleats=True))
+        np.savez_compressed(os.path.join(OUT, f"fn_{task}_cleats_n64.npz"), **d)
         print(task, "edge resets:", d["ref_reset"][:20], "rew:", np.round(d["ref_rew"][:8], 3))
         tr = step_trace_sibling(task)
         np.savez_compressed(os.path.join(OUT, f"step_trace_{task}_n64.npz"), **tr)
