@@ -12,6 +12,11 @@ namespace bezk {
 // Slab addressing: a batch of m rows read straight out of time-major rollout storage.  Batch row r lives at source row
 // (r / slab_rows) * slab_stride + r % slab_rows of the (already offset) base pointer; slab_rows == m means contiguous.
 __device__ __forceinline__ int64_t slab_src_row(int64_t r, int64_t slab_rows, int64_t slab_stride) {
+    if (slab_stride == slab_rows) return r;                // contiguous (the launchers pass slab_rows = slab_stride = m): no divide
+    if ((uint64_t)(r | slab_rows) >> 32 == 0) {            // 32-bit divide when both fit (always, below 4 G rows)
+        const uint32_t s = (uint32_t)r / (uint32_t)slab_rows;
+        return (int64_t)s * slab_stride + ((uint32_t)r - s * (uint32_t)slab_rows);
+    }
     const int64_t s = r / slab_rows;
     return s * slab_stride + (r - s * slab_rows);
 }
@@ -160,6 +165,7 @@ __global__ void __launch_bounds__(RMS_THREADS) rms_partials_kernel(const float* 
 constexpr int RMS_TR = 64;                      // rows per tile
 constexpr int RMS_STAGES = 4;
 
+template <bool SLABS>       // the contiguous instantiation carries no slab arithmetic (32 registers; with it: 44, and 7 % slower)
 __global__ void __launch_bounds__(RMS_THREADS) rms_partials_tma_kernel(const float* __restrict__ x, const double* __restrict__ pivot,
                                                                        double* __restrict__ partials, int64_t m, int c,
                                                                        int64_t slab_rows, int64_t slab_stride) {
@@ -187,7 +193,8 @@ __global__ void __launch_bounds__(RMS_THREADS) rms_partials_tma_kernel(const flo
         const uint32_t bytes = (uint32_t)(rows * c * 4);
         mbar_arrive_expect_tx(&s_full[stage], bytes);
         // slab mode: slab_rows is a multiple of RMS_TR (checked by the launcher), so a tile never straddles two slabs
-        bulk_g2s(s_tile + (size_t)stage * tile_floats, x + slab_src_row(r0, slab_rows, slab_stride) * c, bytes, &s_full[stage]);
+        const int64_t src = SLABS ? slab_src_row(r0, slab_rows, slab_stride) : r0;
+        bulk_g2s(s_tile + (size_t)stage * tile_floats, x + src * c, bytes, &s_full[stage]);
     };
     // this CTA's tiles: blockIdx.x, +gridDim.x, ...
     int64_t my_tiles = 0;
@@ -318,14 +325,17 @@ __global__ void rms_merge_kernel(const double* __restrict__ acc, const double* _
 }
 
 // K5: normalise / un-normalise
-__global__ void __launch_bounds__(256) rms_normalize_kernel(const float* __restrict__ x, const double* __restrict__ running_mean,
+template <bool SLABS>
+__global__ void __launch_bounds__(256, 8) rms_normalize_kernel(const float* __restrict__ x, const double* __restrict__ running_mean,
                                                             const double* __restrict__ running_var, float eps, int unnorm,
                                                             float* __restrict__ y, int64_t total, int c, int vec4,
                                                             int64_t slab_src_elems) {
     // blockIdx.y = slab: `total` elements of THIS slab, read from x + blockIdx.y * slab_src_elems, written to
     // y + blockIdx.y * total (one slab = the whole array in the contiguous case)
-    x += (int64_t)blockIdx.y * slab_src_elems;
-    y += (int64_t)blockIdx.y * total;
+    if (SLABS) {
+        x += (int64_t)blockIdx.y * slab_src_elems;
+        y += (int64_t)blockIdx.y * total;
+    }
     extern __shared__ float s_stat[];       // [2][c]: mean.float(), sqrt(var.float() + eps)
     for (int j = threadIdx.x; j < c; j += blockDim.x) {
         s_stat[j] = (float)running_mean[j];
@@ -389,7 +399,9 @@ cudaError_t launch_rms_moments(const float* x, const double* pivot, double* acc,
             if (red > smem) smem = red;
             static size_t attr_set = 0;
             if (smem > attr_set) {
-                cudaError_t e2 = cudaFuncSetAttribute(rms_partials_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaError_t e2 = cudaFuncSetAttribute(rms_partials_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e2 == cudaSuccess)
+                    e2 = cudaFuncSetAttribute(rms_partials_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e2 != cudaSuccess) return e2;
                 attr_set = smem;
             }
@@ -399,7 +411,8 @@ cudaError_t launch_rms_moments(const float* x, const double* pivot, double* acc,
             int64_t cap = 148LL * per_sm;
             if (cap > RMS_MAX_BLOCKS) cap = RMS_MAX_BLOCKS;
             nblocks = (int)(ntiles < cap ? ntiles : cap);
-            rms_partials_tma_kernel<<<nblocks, RMS_THREADS, smem, st>>>(x, pivot, partials, m, c, slab_rows, slab_stride);
+            if (slabs) rms_partials_tma_kernel<true><<<nblocks, RMS_THREADS, smem, st>>>(x, pivot, partials, m, c, slab_rows, slab_stride);
+            else rms_partials_tma_kernel<false><<<nblocks, RMS_THREADS, smem, st>>>(x, pivot, partials, m, c, m, m);
             cudaError_t err = cudaGetLastError();
             if (err != cudaSuccess) return err;
             moments_finalize_kernel<<<(2 * c + 7) / 8, 256, 0, st>>>(partials, nblocks, c, m, acc);
@@ -441,8 +454,12 @@ cudaError_t launch_rms_normalize(const float* x, const double* running_mean, con
     int blocks = stream_blocks(vec4 ? total / 4 : total, 256, 8);
     const int per_slab_cap = (int)((148 * 8 + nslabs - 1) / nslabs);
     if (blocks > per_slab_cap) blocks = per_slab_cap;
-    rms_normalize_kernel<<<dim3((unsigned)blocks, (unsigned)nslabs), 256, 2 * c * sizeof(float), st>>>(
-        x, running_mean, running_var, eps, unnorm, y, total, c, vec4, slab_stride * c);
+    if (nslabs > 1)
+        rms_normalize_kernel<true><<<dim3((unsigned)blocks, (unsigned)nslabs), 256, 2 * c * sizeof(float), st>>>(
+            x, running_mean, running_var, eps, unnorm, y, total, c, vec4, slab_stride * c);
+    else
+        rms_normalize_kernel<false><<<blocks, 256, 2 * c * sizeof(float), st>>>(x, running_mean, running_var, eps, unnorm, y, total, c,
+                                                                                vec4, 0);
     return cudaGetLastError();
 }
 
