@@ -348,6 +348,12 @@ int bezk_dr_fill(uint64_t seed, uint64_t step, int32_t distribution, float* out,
     return cuda_rc(bezk::launch_dr_fill(seed, step, distribution, out, total, (cudaStream_t)stream), "bezk_dr_fill");
 }
 
+int bezk_selftest_fastmath(uint64_t pairs, uint64_t seed, uint64_t* counts, void* stream) {
+    REQUIRE(counts, "counts NULL");
+    return cuda_rc(bezk::launch_selftest_fastmath(pairs, seed, reinterpret_cast<unsigned long long*>(counts), (cudaStream_t)stream),
+                   "bezk_selftest_fastmath");
+}
+
 int bezk_normal_noise(uint64_t seed, uint64_t step, float* out, int64_t n, void* stream) {
     REQUIRE(n >= 0, "n < 0");
     if (n == 0) return 0;

@@ -361,3 +361,78 @@ cudaError_t launch_dr_fill(uint64_t seed, uint64_t step, int distribution, float
 }
 
 }  // namespace bezk
+
+// ------------------------------------------------------------------------------------------------
+// Self-test of Mth<true> (bezk_common.cuh) against the built-in IEEE operators.
+//   sqrt: every 2^32 bit pattern.   div: `pairs` Philox-random (a, b) bit patterns, a quarter of them drawn from the
+//   2^-70 .. 2^70 exponent window the task math lives in, plus an exhaustive cross of special values (0, -0, denormals, the
+//   guard-range edges, FLT_MAX, inf, NaN).  Wherever the fast path reports `!bad` its bits must equal the operator's.
+// counts[0] = sqrt mismatches, [1] = div mismatches, [2] = sqrt inputs accepted by the fast path, [3] = div pairs accepted.
+// ------------------------------------------------------------------------------------------------
+namespace bezk {
+
+__device__ __forceinline__ bool same_bits(float a, float b) {
+    return __float_as_uint(a) == __float_as_uint(b) || (a != a && b != b);
+}
+
+__global__ void __launch_bounds__(256) selftest_sqrt_kernel(unsigned long long* counts) {
+    unsigned long long bad_cnt = 0, ok_cnt = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32); i += stride) {
+        const float x = __uint_as_float((uint32_t)i);
+        Mth<true> m;
+        const float f = m.sqr(x);
+        if (!m.bad) { ++ok_cnt; if (!same_bits(f, sqrtf(x))) ++bad_cnt; }
+    }
+    if (bad_cnt) atomicAdd(&counts[0], bad_cnt);
+    atomicAdd(&counts[2], ok_cnt);
+}
+
+__device__ __forceinline__ float special_value(int k) {
+    const uint32_t v[] = {0x00000000u, 0x80000000u, 0x00000001u, 0x007FFFFFu, 0x00800000u, 0x21800000u, 0x217FFFFFu, 0x5D800000u,
+                          0x5D800001u, 0x3F800000u, 0xBF800000u, 0x3F7FFFFFu, 0x3F800001u, 0x7F7FFFFFu, 0x7F800000u, 0xFF800000u,
+                          0x7FC00000u, 0x3C888889u /* ~dt */, 0x40000000u, 0x34000000u, 0x4B800000u, 0x3FFFFFFFu, 0x00FFFFFFu, 0xDD800000u};
+    return __uint_as_float(v[k]);
+}
+
+__global__ void __launch_bounds__(256) selftest_div_kernel(uint64_t pairs, uint64_t seed, unsigned long long* counts) {
+    unsigned long long bad_cnt = 0, ok_cnt = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint64_t i = tid; i < pairs / 2; i += stride) {
+        const Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0x5E1F7E57u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+        uint32_t w[4] = {r.x, r.y, r.z, r.w};
+        if ((i & 3) == 0) {              // squeeze the exponents into 2^-70 .. 2^70 so that most pairs take the fast path
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t e = 57u + ((w[k] >> 23) & 0xFFu) % 141u;
+                w[k] = (w[k] & 0x807FFFFFu) | (e << 23);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float a = __uint_as_float(w[2 * k]), b = __uint_as_float(w[2 * k + 1]);
+            Mth<true> m;
+            const float f = m.div(a, b);
+            if (!m.bad) { ++ok_cnt; if (!same_bits(f, a / b)) ++bad_cnt; }
+        }
+    }
+    if (tid < 24 * 24) {
+        const float a = special_value((int)(tid / 24)), b = special_value((int)(tid % 24));
+        Mth<true> m;
+        const float f = m.div(a, b);
+        if (!m.bad) { ++ok_cnt; if (!same_bits(f, a / b)) ++bad_cnt; }
+    }
+    if (bad_cnt) atomicAdd(&counts[1], bad_cnt);
+    atomicAdd(&counts[3], ok_cnt);
+}
+
+cudaError_t launch_selftest_fastmath(uint64_t pairs, uint64_t seed, unsigned long long* counts, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(counts, 0, 4 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    selftest_sqrt_kernel<<<148 * 8, 256, 0, st>>>(counts);
+    selftest_div_kernel<<<148 * 8, 256, 0, st>>>(pairs, seed, counts);
+    return cudaGetLastError();
+}
+
+}  // namespace bezk

@@ -100,14 +100,15 @@ __global__ void __launch_bounds__(K0_THREADS) pre_physics_kernel(const float* __
 
 // compute_imu, kick_env.py:918-930, with quaternion_to_matrix (:857-885) applied to the xyzw
 // quaternion as if it were real-first: (r,i,j,k) = (x,y,z,w).
+template <bool F>
 __device__ __forceinline__ void imu_term(const float (&q)[4], const float (&v)[3], const float (&w)[3],
-                                         const float (&prev)[3], const BezkTaskCfg& c, float (&out)[6]) {
+                                         const float (&prev)[3], const BezkTaskCfg& c, float (&out)[6], Mth<F>& m) {
     float a[3];
-    a[0] = (v[0] - prev[0]) / c.dt - 0.0f;
-    a[1] = (v[1] - prev[1]) / c.dt - 0.0f;
-    a[2] = (v[2] - prev[2]) / c.dt - (-1.0f);            // gravity_vec = (0,0,-1), :217
+    a[0] = m.div(v[0] - prev[0], c.dt) - 0.0f;
+    a[1] = m.div(v[1] - prev[1], c.dt) - 0.0f;
+    a[2] = m.div(v[2] - prev[2], c.dt) - (-1.0f);        // gravity_vec = (0,0,-1), :217
     const float r = q[0], i = q[1], j = q[2], k = q[3];
-    const float two_s = 2.0f / (((r * r + i * i) + j * j) + k * k);
+    const float two_s = m.div(2.0f, ((r * r + i * i) + j * j) + k * k);
     const float m00 = 1.0f - two_s * (j * j + k * k), m01 = two_s * (i * j - k * r), m02 = two_s * (i * k + j * r);
     const float m10 = two_s * (i * j + k * r), m11 = 1.0f - two_s * (i * i + k * k), m12 = two_s * (j * k - i * r);
     const float m20 = two_s * (i * k - j * r), m21 = two_s * (j * k + i * r), m22 = 1.0f - two_s * (i * i + j * j);
@@ -130,10 +131,11 @@ __device__ __forceinline__ float wrap_2pi(float x) {
 }
 
 // compute_off_orn, kick_env.py:941-960 (+ yaw of get_euler_xyz)
-__device__ __forceinline__ void off_orn_term(float px, float py, const float (&q)[4], float gx, float gy, float (&out)[2]) {
+template <bool F>
+__device__ __forceinline__ void off_orn_term(float px, float py, const float (&q)[4], float gx, float gy, float (&out)[2], Mth<F>& m) {
     const float dx = gx - px, dy = gy - py;
-    const float nrm = sqrtf(dx * dx + dy * dy);
-    const float ux = dx / nrm, uy = dy / nrm;
+    const float nrm = m.sqr(dx * dx + dy * dy);
+    const float ux = m.div(dx, nrm), uy = m.div(dy, nrm);
     const float x = q[0], y = q[1], z = q[2], w = q[3];
     const float siny = 2.0f * (w * z + x * y);
     const float cosy = ((w * w + x * x) - y * y) - z * z;
@@ -142,7 +144,7 @@ __device__ __forceinline__ void off_orn_term(float px, float py, const float (&q
     sincosf(yaw, &hy, &hx);                              // one shared range reduction; same values as sinf / cosf
     const float c = hx * ux + hy * uy;
     const float cz = ux * hy - uy * hx;                  // only non-zero component of the 3-D cross
-    out[0] = sqrtf((0.0f + 0.0f) + cz * cz);             // linalg.norm of (0, 0, cz)
+    out[0] = m.sqr((0.0f + 0.0f) + cz * cz);             // linalg.norm of (0, 0, cz)
     out[1] = -c;
 }
 
@@ -176,7 +178,8 @@ __device__ __forceinline__ float angle_to_goal(const float (&q)[4], float goal_a
 
 // quantities walk_env.py:849-876 / orient_env.py:875-897 share
 struct WalkTerms { float up_proj, vel6, vel_lin, vel_ang, pos; };
-__device__ __forceinline__ WalkTerms walk_terms(const float (&q)[4], const float (&v)[3], const float (&w)[3], float pos_sq) {
+template <bool F>
+__device__ __forceinline__ WalkTerms walk_terms(const float (&q)[4], const float (&v)[3], const float (&w)[3], float pos_sq, Mth<F>& m) {
     WalkTerms t;
     // get_basis_vector(q, (0,0,1))[2] = quat_rotate z component: a + b + c
     const float qx = q[0], qy = q[1], qz = q[2], qw = q[3];
@@ -188,8 +191,8 @@ __device__ __forceinline__ WalkTerms walk_terms(const float (&q)[4], const float
     float s3 = v[0] * v[0]; s3 += v[1] * v[1]; s3 += v[2] * v[2];
     float a3 = w[0] * w[0]; a3 += w[1] * w[1]; a3 += w[2] * w[2];
     float s6 = s3; s6 += w[0] * w[0]; s6 += w[1] * w[1]; s6 += w[2] * w[2];
-    t.vel6 = sqrtf(s6); t.vel_lin = sqrtf(s3); t.vel_ang = sqrtf(a3);
-    t.pos = sqrtf(pos_sq);
+    t.vel6 = m.sqr(s6); t.vel_lin = m.sqr(s3); t.vel_ang = m.sqr(a3);
+    t.pos = m.sqr(pos_sq);
     return t;
 }
 
@@ -213,14 +216,15 @@ __device__ __forceinline__ void walk_tail(const WalkTerms& t, bool close, float 
 }
 
 // compute_bez_reward of tasks/walk_env.py:827-997 (debug prints and dead terms dropped)
+template <bool F>
 __device__ __forceinline__ void reward_walk(const float (&bez)[3], const float (&q)[4], const float (&v)[3], const float (&w)[3],
                                             float pos_sq, const float (&goal)[2], const BezkTaskCfg& c, int64_t progress,
-                                            int64_t reset_cur, float* rew_out, int64_t* reset_out) {
+                                            int64_t reset_cur, float* rew_out, int64_t* reset_out, Mth<F>& m) {
     const float dx = goal[0] - bez[0], dy = goal[1] - bez[1];
-    const float n_goal = sqrtf(dx * dx + dy * dy);
-    const float ux = dx / n_goal, uy = dy / n_goal;
+    const float n_goal = m.sqr(dx * dx + dy * dy);
+    const float ux = m.div(dx, n_goal), uy = m.div(dy, n_goal);
     const float vel_fwd = ux * v[0] + uy * v[1];
-    const WalkTerms t = walk_terms(q, v, w, pos_sq);
+    const WalkTerms t = walk_terms(q, v, w, pos_sq, m);
     const float dist_h = fabsf(1.0f - t.up_proj);
     const float vel_s = t.vel6 * 0.05f, pos_s = t.pos * 0.05f;
     const float height_vel_pos = -((vel_s + pos_s) + dist_h);
@@ -229,19 +233,20 @@ __device__ __forceinline__ void reward_walk(const float (&bez)[3], const float (
     const float rew = close ? height_vel_pos : vel_height;
     // out of bound: angle between (goal - (0,0)) and (goal - bez_xy)   (walk_env.py:966-989; bez_init_state is zeroed in place)
     const float ix = goal[0] - 0.0f, iy = goal[1] - 0.0f;
-    const float n_i = sqrtf(ix * ix + iy * iy);
+    const float n_i = m.sqr(ix * ix + iy * iy);
     const float ang_now = atan2f(uy, ux);
-    const float ang_init = atan2f(iy / n_i, ix / n_i);
+    const float ang_init = atan2f(m.div(iy, n_i), m.div(ix, n_i));
     const bool out = fabsf(ang_init - ang_now) > 1.5708f;
     walk_tail(t, close, rew, out, -100.0f, c, progress, reset_cur, rew_out, reset_out);
 }
 
 // compute_bez_reward of tasks/orient_env.py:845-1014
+template <bool F>
 __device__ __forceinline__ void reward_orient(const float (&bez)[3], const float (&q)[4], const float (&v)[3], const float (&w)[3],
                                               float pos_sq, float goal_angle, const BezkTaskCfg& c, int64_t progress,
-                                              int64_t reset_cur, float* rew_out, int64_t* reset_out) {
+                                              int64_t reset_cur, float* rew_out, int64_t* reset_out, Mth<F>& m) {
     const float ang = angle_to_goal(q, goal_angle);
-    const WalkTerms t = walk_terms(q, v, w, pos_sq);
+    const WalkTerms t = walk_terms(q, v, w, pos_sq, m);
     const float dist_h = fabsf(1.0f - t.up_proj);
     const float vel_s = t.vel6 * 0.05f, pos_s = t.pos * 0.05f;
     const float height_vel_pos = -((vel_s + pos_s) + dist_h);
@@ -249,7 +254,7 @@ __device__ __forceinline__ void reward_orient(const float (&bez)[3], const float
     const bool close = ang < 0.05f;                       // the SIGNED angle, as the reference compares it
     const float rew = close ? height_vel_pos : vel_height;
     const float tx = bez[0] - c.bez_init_xy[0], ty = bez[1] - c.bez_init_xy[1];
-    const bool out = sqrtf(tx * tx + ty * ty) > 0.3f;
+    const bool out = m.sqr(tx * tx + ty * ty) > 0.3f;
     walk_tail(t, close, rew, out, -5.0f, c, progress, reset_cur, rew_out, reset_out);
 }
 
@@ -264,31 +269,32 @@ struct RewardIn {
 };
 
 // compute_bez_reward, kick_env.py:1224-1395.  `progress` is the post-increment value.
+template <bool F>
 __device__ __forceinline__ void reward_term(const RewardIn& s, const BezkTaskCfg& c, int64_t progress,
-                                            int64_t reset_cur, float* rew_out, int64_t* reset_out) {
+                                            int64_t reset_cur, float* rew_out, int64_t* reset_out, Mth<F>& m) {
     const float dbx = s.ball_xy[0] - s.bez[0], dby = s.ball_xy[1] - s.bez[1];
-    const float nbb = sqrtf(dbx * dbx + dby * dby);
-    const float vel_fwd = (dbx / nbb) * s.v[0] + (dby / nbb) * s.v[1];
+    const float nbb = m.sqr(dbx * dbx + dby * dby);
+    const float vel_fwd = m.div(dbx, nbb) * s.v[0] + m.div(dby, nbb) * s.v[1];
 
     const float dgx = s.goal[0] - s.ball_xy[0], dgy = s.goal[1] - s.ball_xy[1];
-    const float n_goal = sqrtf(dgx * dgx + dgy * dgy);
-    const float ugx = dgx / n_goal, ugy = dgy / n_goal;
+    const float n_goal = m.sqr(dgx * dgx + dgy * dgy);
+    const float ugx = m.div(dgx, n_goal), ugy = m.div(dgy, n_goal);
     const float ball_fwd = ugx * s.ball_vxy[0] + ugy * s.ball_vxy[1];
 
     const float dix = s.goal[0] - s.ball_init[0], diy = s.goal[1] - s.ball_init[1];
-    const float n_init = sqrtf(dix * dix + diy * diy);
+    const float n_init = m.sqr(dix * dix + diy * diy);
     const float ang_now = atan2f(ugy, ugx);
-    const float ang_init = atan2f(diy / n_init, dix / n_init);
+    const float ang_init = atan2f(m.div(diy, n_init), m.div(dix, n_init));
     const float angle_diff = fabsf(ang_init - ang_now);
 
     float vs = s.v[0] * s.v[0];
     vs += s.v[1] * s.v[1]; vs += s.v[2] * s.v[2];
     vs += s.w[0] * s.w[0]; vs += s.w[1] * s.w[1]; vs += s.w[2] * s.w[2];
-    const float vel_r = sqrtf(vs) * 0.05f;
-    const float pos_r = sqrtf(s.pos_sq) * 0.05f;
+    const float vel_r = m.sqr(vs) * 0.05f;
+    const float pos_r = m.sqr(s.pos_sq) * 0.05f;
     const float height = fabsf(0.325f - s.bez[2]) * 1.0f;
     const float kx = s.ball_xy[0] - s.ball_init[0], ky = s.ball_xy[1] - s.ball_init[1];
-    const float kicked = sqrtf(kx * kx + ky * ky);
+    const float kicked = m.sqr(kx * kx + ky * ky);
 
     const float far_r = ball_fwd * 0.1f - (height + (vel_r + pos_r));
     const float near_r = ball_fwd * 0.1f + (vel_fwd * 0.05f - height);
@@ -297,7 +303,7 @@ __device__ __forceinline__ void reward_term(const RewardIn& s, const BezkTaskCfg
 
     if (s.bez[2] < 0.275f) { reset = 1; rew = -1.0f; }                                    // rule 1
     const float tx = s.bez[0] - c.bez_init_xy[0], ty = s.bez[1] - c.bez_init_xy[1];
-    if (sqrtf(tx * tx + ty * ty) > 0.5f) { reset = 1; rew = -1.0f; }                      // rule 2
+    if (m.sqr(tx * tx + ty * ty) > 0.5f) { reset = 1; rew = -1.0f; }                      // rule 2
     if (angle_diff > 1.5708f) { reset = 1; rew = -1.0f; }                                 // rule 3
     if (n_goal < 0.05f) {                                                                 // rule 4
         reset = 1;
@@ -621,7 +627,10 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
         float pv[3];
         if (a.prev_lin_vel) { pv[0] = prev[0]; pv[1] = prev[1]; pv[2] = prev[2]; }
         else { pv[0] = v[0]; pv[1] = v[1]; pv[2] = v[2]; }                  // aliasing, kick_env.py:930
-        imu_term(q, v, w, pv, cfg, imu6);
+        // the per-env math runs on the branch-free exact operators (Mth<true>); an env with an operand outside their
+        // validity range is recomputed once with the plain operators -- same bits either way
+        Mth<true> mo;
+        imu_term(q, v, w, pv, cfg, imu6, mo);
         if (a.prev_lin_vel) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) a.prev_lin_vel[e * 3 + k] = v[k];
@@ -630,7 +639,12 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
             const float d = angle_to_goal(q, g.gang);
             sincosf(d, &orn2[1], &orn2[0]);
         } else {
-            off_orn_term(bez[0], bez[1], q, goal[0], goal[1], orn2);
+            off_orn_term(bez[0], bez[1], q, goal[0], goal[1], orn2, mo);
+        }
+        if (mo.bad) {
+            Mth<false> mp;
+            imu_term(q, v, w, pv, cfg, imu6, mp);
+            if (TASK != BEZK_TASK_ORIENT) off_orn_term(bez[0], bez[1], q, goal[0], goal[1], orn2, mp);
         }
         if (CLEATS) {                                                      // kick_env.py:1053-1061
 #pragma unroll
@@ -711,8 +725,14 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
     if (REW && valid && TASK != BEZK_TASK_KICK) {
         float rew;
         int64_t reset;
-        if (TASK == BEZK_TASK_WALK) reward_walk(bez, q, v, w, pos_sq, goal, cfg, progress, reset_cur, &rew, &reset);
-        else reward_orient(bez, q, v, w, pos_sq, g.gang, cfg, progress, reset_cur, &rew, &reset);
+        Mth<true> mr;
+        if (TASK == BEZK_TASK_WALK) reward_walk(bez, q, v, w, pos_sq, goal, cfg, progress, reset_cur, &rew, &reset, mr);
+        else reward_orient(bez, q, v, w, pos_sq, g.gang, cfg, progress, reset_cur, &rew, &reset, mr);
+        if (mr.bad) {
+            Mth<false> mp;
+            if (TASK == BEZK_TASK_WALK) reward_walk(bez, q, v, w, pos_sq, goal, cfg, progress, reset_cur, &rew, &reset, mp);
+            else reward_orient(bez, q, v, w, pos_sq, g.gang, cfg, progress, reset_cur, &rew, &reset, mp);
+        }
         a.rew[e] = rew;
         a.reset_out[e] = reset;
         if (BOOK) a.progress_out[e] = progress;
@@ -729,7 +749,12 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
         s.pos_sq = pos_sq;
         float rew;
         int64_t reset;
-        reward_term(s, cfg, progress, reset_cur, &rew, &reset);
+        Mth<true> mr;
+        reward_term(s, cfg, progress, reset_cur, &rew, &reset, mr);
+        if (mr.bad) {
+            Mth<false> mp;
+            reward_term(s, cfg, progress, reset_cur, &rew, &reset, mp);
+        }
         a.rew[e] = rew;
         a.reset_out[e] = reset;
         if (BOOK) a.progress_out[e] = progress;

@@ -306,6 +306,12 @@ int bezk_dr_noise(const float* x, const float* corr, const float* white, uint64_
  * the host creates `corr`. */
 int bezk_dr_fill(uint64_t seed, uint64_t step, int32_t distribution, float* out, int64_t total, void* stream);
 
+/* Diagnostic: the task kernels evaluate IEEE division and square root through branch-free fast sequences with a sticky
+ * validity flag and a once-per-env precise recomputation (bezk_common.cuh: Mth).  This checks the fast sequences against the
+ * built-in operators over ALL 2^32 radicands and `pairs` random + special quotients.  counts (4,) u64 DEVICE memory:
+ * [0] sqrt mismatches, [1] div mismatches (both must be 0), [2] / [3] how many inputs the fast paths accepted. */
+int bezk_selftest_fastmath(uint64_t pairs, uint64_t seed, uint64_t* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

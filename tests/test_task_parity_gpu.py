@@ -478,3 +478,20 @@ def test_chunked_step_equals_one_launch():
     for a, b in zip(*outs):
         assert torch.equal(a, b) or bool(((a == b) | (a.isnan() & b.isnan())).all())
     assert int(outs[0][2].sum()) > 0
+
+
+def test_branch_free_division_and_sqrt_are_ieee_exact():
+    """The task kernels' division / square root (Mth<true>: NVIDIA's fast sequences with a sticky validity flag instead of a
+    branch per operation) against the built-in IEEE operators: all 2^32 radicands, 2^31 random quotients (a quarter of them in
+    the exponent window the task math lives in) and a 24 x 24 cross of special values -- zero mismatches wherever the fast path
+    accepts its operands."""
+    import ctypes as C
+    from bez_isaacgym_b200 import _lib
+    lib = _lib.load()
+    counts = torch.zeros(4, dtype=torch.int64, device="cuda")
+    _lib.check(lib.bezk_selftest_fastmath(1 << 31, 12345, C.c_void_p(counts.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    sq_bad, div_bad, sq_ok, div_ok = counts.tolist()
+    assert sq_bad == 0 and div_bad == 0, (sq_bad, div_bad)
+    # positive floats in [2^-60, 2^60] + the two zeros; a good share of the random quotients
+    assert sq_ok == 120 * (1 << 23) + 1 + 2 and div_ok > (1 << 27)
