@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(256) selftest_sqrt_kernel(unsigned long long* 
         const float x = __uint_as_float((uint32_t)i);
         Mth<true> m;
         const float f = m.sqr(x);
-        if (!m.bad) { ++ok_cnt; if (!same_bits(f, sqrtf(x))) ++bad_cnt; }
+        if (!m.bad()) { ++ok_cnt; if (!same_bits(f, sqrtf(x))) ++bad_cnt; }
     }
     if (bad_cnt) atomicAdd(&counts[0], bad_cnt);
     atomicAdd(&counts[2], ok_cnt);
@@ -414,14 +414,14 @@ __global__ void __launch_bounds__(256) selftest_div_kernel(uint64_t pairs, uint6
             const float a = __uint_as_float(w[2 * k]), b = __uint_as_float(w[2 * k + 1]);
             Mth<true> m;
             const float f = m.div(a, b);
-            if (!m.bad) { ++ok_cnt; if (!same_bits(f, a / b)) ++bad_cnt; }
+            if (!m.bad()) { ++ok_cnt; if (!same_bits(f, a / b)) ++bad_cnt; }
         }
     }
     if (tid < 24 * 24) {
         const float a = special_value((int)(tid / 24)), b = special_value((int)(tid % 24));
         Mth<true> m;
         const float f = m.div(a, b);
-        if (!m.bad) { ++ok_cnt; if (!same_bits(f, a / b)) ++bad_cnt; }
+        if (!m.bad()) { ++ok_cnt; if (!same_bits(f, a / b)) ++bad_cnt; }
     }
     if (bad_cnt) atomicAdd(&counts[1], bad_cnt);
     atomicAdd(&counts[3], ok_cnt);

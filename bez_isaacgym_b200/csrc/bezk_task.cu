@@ -123,7 +123,7 @@ __device__ __forceinline__ void imu_term(const float (&q)[4], const float (&v)[3
     out[5] = clamp_nan(w[2], -c.imu_max_ang_vel, c.imu_max_ang_vel);
 }
 
-// torch.remainder(x, 2 pi) (python-style, Tensor.__mod__) for x = atan2f(..) in [-pi, pi]: |x| < 2 pi, so fmod(x, 2 pi) is x
+// torch.remainder(x, 2 pi) (python-style, Tensor.__mod__) for x = atan2f_z(..) in [-pi, pi]: |x| < 2 pi, so fmod(x, 2 pi) is x
 // itself and the remainder is x (+ 2 pi when x < 0); identical bits to fmodf + sign fix-up, without the fmodf loop.  NaN and
 // -0.0 pass through unchanged, as they do there.
 __device__ __forceinline__ float wrap_2pi(float x) {
@@ -139,7 +139,7 @@ __device__ __forceinline__ void off_orn_term(float px, float py, const float (&q
     const float x = q[0], y = q[1], z = q[2], w = q[3];
     const float siny = 2.0f * (w * z + x * y);
     const float cosy = ((w * w + x * x) - y * y) - z * z;
-    const float yaw = wrap_2pi(atan2f(siny, cosy));
+    const float yaw = wrap_2pi(atan2f_z(siny, cosy));
     float hx, hy;
     sincosf(yaw, &hy, &hx);                              // one shared range reduction; same values as sinf / cosf
     const float c = hx * ux + hy * uy;
@@ -164,7 +164,7 @@ __device__ __forceinline__ float yaw_mod_2pi(const float (&q)[4]) {
     const float x = q[0], y = q[1], z = q[2], w = q[3];
     const float siny = 2.0f * (w * z + x * y);
     const float cosy = ((w * w + x * x) - y * y) - z * z;
-    return wrap_2pi(atan2f(siny, cosy));
+    return wrap_2pi(atan2f_z(siny, cosy));
 }
 
 // compute_off_angle, orient_env.py:720-733: (cos, sin) of goal_angle - normalize_angle(yaw)
@@ -172,7 +172,7 @@ __device__ __forceinline__ float angle_to_goal(const float (&q)[4], float goal_a
     const float yaw = yaw_mod_2pi(q);
     float sy, cy;
     sincosf(yaw, &sy, &cy);
-    const float na = atan2f(sy, cy);                     // normalize_angle
+    const float na = atan2f_z(sy, cy);                     // normalize_angle
     return goal_angle - na;
 }
 
@@ -234,8 +234,8 @@ __device__ __forceinline__ void reward_walk(const float (&bez)[3], const float (
     // out of bound: angle between (goal - (0,0)) and (goal - bez_xy)   (walk_env.py:966-989; bez_init_state is zeroed in place)
     const float ix = goal[0] - 0.0f, iy = goal[1] - 0.0f;
     const float n_i = m.sqr(ix * ix + iy * iy);
-    const float ang_now = atan2f(uy, ux);
-    const float ang_init = atan2f(m.div(iy, n_i), m.div(ix, n_i));
+    const float ang_now = atan2f_z(uy, ux);
+    const float ang_init = atan2f_z(m.div(iy, n_i), m.div(ix, n_i));
     const bool out = fabsf(ang_init - ang_now) > 1.5708f;
     walk_tail(t, close, rew, out, -100.0f, c, progress, reset_cur, rew_out, reset_out);
 }
@@ -283,8 +283,8 @@ __device__ __forceinline__ void reward_term(const RewardIn& s, const BezkTaskCfg
 
     const float dix = s.goal[0] - s.ball_init[0], diy = s.goal[1] - s.ball_init[1];
     const float n_init = m.sqr(dix * dix + diy * diy);
-    const float ang_now = atan2f(ugy, ugx);
-    const float ang_init = atan2f(m.div(diy, n_init), m.div(dix, n_init));
+    const float ang_now = atan2f_z(ugy, ugx);
+    const float ang_init = atan2f_z(m.div(diy, n_init), m.div(dix, n_init));
     const float angle_diff = fabsf(ang_init - ang_now);
 
     float vs = s.v[0] * s.v[0];
@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
         } else {
             off_orn_term(bez[0], bez[1], q, goal[0], goal[1], orn2, mo);
         }
-        if (mo.bad) {
+        if (mo.bad()) {
             Mth<false> mp;
             imu_term(q, v, w, pv, cfg, imu6, mp);
             if (TASK != BEZK_TASK_ORIENT) off_orn_term(bez[0], bez[1], q, goal[0], goal[1], orn2, mp);
@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
         Mth<true> mr;
         if (TASK == BEZK_TASK_WALK) reward_walk(bez, q, v, w, pos_sq, goal, cfg, progress, reset_cur, &rew, &reset, mr);
         else reward_orient(bez, q, v, w, pos_sq, g.gang, cfg, progress, reset_cur, &rew, &reset, mr);
-        if (mr.bad) {
+        if (mr.bad()) {
             Mth<false> mp;
             if (TASK == BEZK_TASK_WALK) reward_walk(bez, q, v, w, pos_sq, goal, cfg, progress, reset_cur, &rew, &reset, mp);
             else reward_orient(bez, q, v, w, pos_sq, g.gang, cfg, progress, reset_cur, &rew, &reset, mp);
@@ -751,7 +751,7 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
         int64_t reset;
         Mth<true> mr;
         reward_term(s, cfg, progress, reset_cur, &rew, &reset, mr);
-        if (mr.bad) {
+        if (mr.bad()) {
             Mth<false> mp;
             reward_term(s, cfg, progress, reset_cur, &rew, &reset, mp);
         }
