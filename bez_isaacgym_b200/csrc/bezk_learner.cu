@@ -349,12 +349,21 @@ __global__ void __launch_bounds__(256, 8) rms_normalize_kernel(const float* __re
         const float4 t = ldg_stream4(reinterpret_cast<const float4*>(x) + i);
         const float in[4] = {t.x, t.y, t.z, t.w};
         float out[4];
-        int col = (int)((i * 4) % c);
+        const int col0 = (int)((i * 4) % c);
+        int col = col0;
+        Mth<true> mq;                              // exact division without a branch per element (bezk_common.cuh)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float mean = s_stat[col], den = s_stat[c + col];
-            out[k] = unnorm ? (den * clamp_nan(in[k], -5.0f, 5.0f) + mean) : clamp_nan((in[k] - mean) / den, -5.0f, 5.0f);
+            out[k] = unnorm ? (den * clamp_nan(in[k], -5.0f, 5.0f) + mean) : clamp_nan(mq.div(in[k] - mean, den), -5.0f, 5.0f);
             col = (col + 1 == c) ? 0 : col + 1;
+        }
+        if (!unnorm && mq.bad()) {                 // an operand outside the fast sequence's range: plain operator
+            col = col0;
+            for (int k = 0; k < 4; ++k) {
+                out[k] = clamp_nan((in[k] - s_stat[col]) / s_stat[c + col], -5.0f, 5.0f);
+                col = (col + 1 == c) ? 0 : col + 1;
+            }
         }
         __stcs(reinterpret_cast<float4*>(y) + i, make_float4(out[0], out[1], out[2], out[3]));
     }
@@ -613,6 +622,7 @@ __global__ void __launch_bounds__(PPO_TILE, 4) ppo_loss_kernel(const PpoArgs a, 
         if (valid) {
             // ---- neglogp (models.py), bound loss, KL: one sweep over the 18 action dims ----
             float sq = 0.0f, bsum = 0.0f, kl = 0.0f;
+            Mth<true> mk;
             const float2* act2 = reinterpret_cast<const float2*>(s_act + tid * 18);
             const float2* mu2 = reinterpret_cast<const float2*>(s_mu + tid * 18);
             const float2* omu2 = reinterpret_cast<const float2*>(s_omu + tid * 18);
@@ -635,7 +645,17 @@ __global__ void __launch_bounds__(PPO_TILE, 4) ppo_loss_kernel(const PpoArgs a, 
                     bsum += lo * lo + hi * hi;
                     const float c1 = logf(osv[q] * isig[j] + 1e-5f);
                     const float dm = omv[q] - mv[q];
-                    const float c2 = (sig[j] * sig[j] + dm * dm) / (2.0f * (osv[q] * osv[q] + 1e-5f));
+                    const float c2 = mk.div(sig[j] * sig[j] + dm * dm, 2.0f * (osv[q] * osv[q] + 1e-5f));   // exact, no branch per dim
+                    kl += (c1 + c2) + (-0.5f);
+                }
+            }
+            if (mk.bad()) {                    // an operand outside the fast division's range: redo the KL sum with the plain operator
+                kl = 0.0f;
+                for (int j = 0; j < 18; ++j) {
+                    const float m_ = s_mu[tid * 18 + j], om_ = s_omu[tid * 18 + j], os_ = s_osig[tid * 18 + j];
+                    const float c1 = logf(os_ * isig[j] + 1e-5f);
+                    const float dm = om_ - m_;
+                    const float c2 = (sig[j] * sig[j] + dm * dm) / (2.0f * (os_ * os_ + 1e-5f));
                     kl += (c1 + c2) + (-0.5f);
                 }
             }
