@@ -25,11 +25,12 @@
 namespace bezk {
 
 #ifndef BEZK_TILE_CTAS
-#define BEZK_TILE_CTAS 5            // resident one-tile CTAs per SM the register allocation is tuned for
+#define BEZK_TILE_CTAS 4            // resident one-tile CTAs per SM the register allocation is tuned for: 4 (122 registers, no
+                                    // spills, 100 KB left to L1 for the multi-load gathers) beats 5 (96 registers, 28 B of
+                                    // spills) by 2-10 % at every size and 6 (80 registers) loses 22 % -- profiles/r01_kernels.md
 #endif
-// envs per CTA = threads per CTA is a template parameter (TILE).  128 is what ships: 64 was 3 % slower, 6 CTAs/SM (80
-// registers, spilling) 16 % slower, a persistent 2-stage pipelined variant (12 warps/SM) 28 % slower and cross-CTA L2
-// prefetch 15 % slower -- measured, profiles/r01_kernels.md.
+// envs per CTA = threads per CTA is a template parameter (TILE).  128 is what ships: 64 was 3 % slower, a persistent 2-stage
+// pipelined variant (12 warps/SM) 28 % slower and cross-CTA L2 prefetch 15 % slower -- measured, profiles/r01_kernels.md.
 constexpr int DOF_ROW = 36;          // floats per env in dof_state
 // Task variants (tasks/kick_env.py, tasks/walk_env.py, tasks/orient_env.py share one skeleton): BezKick has two actors per env
 // (robot + ball -> 26 root floats) and a 54-wide observation; walk / orient have the robot only (13) and 52 columns.
