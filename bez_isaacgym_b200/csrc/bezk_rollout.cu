@@ -32,19 +32,24 @@ __global__ void __launch_bounds__(256) swap_flatten_kernel(const E* __restrict__
     const int run = ebc * w;                                     // contiguous source elements per timestep
     const int total = tbc * run;
     const int orun = tbc * w;                                    // contiguous destination elements per env
-    const int pitch = orun | 1;                                  // odd row pitch: the transposed placement below walks a column
+    // narrow rows walk a COLUMN of the tile in the placement below: give them an odd row pitch (no bank conflicts).  Wide rows
+    // (observations, actions) keep the dense pitch, so that the tile leaves as one linear run
+    const int pitch = (w * (int)sizeof(E) <= 16) ? (orun | 1) : orun;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
         const int t = idx / run, rem = idx - t * run;
         const int e = rem / w, c = rem - e * w;
         tile[e * pitch + t * w + c] = src[((int64_t)(t0 + t) * n + env0 + eblk0) * w + rem];
     }
     __syncthreads();
-    // with the whole horizon in the tile (tbc == horizon) the eb destination runs are adjacent: one linear run
     E* d = dst + (eblk0 * (int64_t)horizon + t0) * w;
-    const int64_t dpitch = (int64_t)horizon * w;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int e = idx / orun, rem = idx - e * orun;
-        d[e * dpitch + rem] = tile[e * pitch + rem];
+    if (pitch == orun && tbc == horizon) {                       // whole horizon in the tile, dense pitch: one linear run
+        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) d[idx] = tile[idx];
+    } else {
+        const int64_t dpitch = (int64_t)horizon * w;
+        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            const int e = idx / orun, rem = idx - e * orun;
+            d[e * dpitch + rem] = tile[e * pitch + rem];
+        }
     }
 }
 
@@ -55,7 +60,7 @@ static cudaError_t launch_sf(const void* src, void* dst, int horizon, int64_t n,
     if (eb < 1) eb = 1;
     if (eb > 256) eb = 256;
     if (eb > envs) eb = envs;
-    const size_t smem = (size_t)(((int64_t)tb * w) | 1) * eb * sizeof(E);
+    const size_t smem = (size_t)(((int64_t)tb * w) | 1) * eb * sizeof(E);      // covers both pitches
     if (smem > 200 * 1024) return cudaErrorInvalidValue;         // rows wider than 6 KB are not rollout tensors
     static size_t attr_set = 0;
     if (smem > 48 * 1024 && smem > attr_set) {
