@@ -24,6 +24,9 @@
 
 namespace bezk {
 
+#ifndef BEZK_TILE
+#define BEZK_TILE 128               // envs (= threads) per CTA
+#endif
 #ifndef BEZK_TILE_CTAS
 #define BEZK_TILE_CTAS 4            // resident one-tile CTAs per SM the register allocation is tuned for: 4 (122 registers, no
                                     // spills, 100 KB left to L1 for the multi-load gathers) beats 5 (96 registers, 28 B of
@@ -488,13 +491,25 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
     const int64_t e = e0 + lane;
     const bool valid = lane < nv;
 
-    // ---- 1. dense tiles: TMA bulk copies (full sub-tiles) or cooperative coalesced loads (tail) ----
     pdl_launch_dependents();               // the next kernel on the stream may be scheduled as our CTAs retire
     if (full && lane == 0) {
         mbar_init(s_bar, 1);
         fence_mbar_init();
     }
     pdl_wait();                            // nothing above touches global memory
+
+    // ---- 1. sparse gathers first: they are the slow requests (one 64-byte granule each), the dense tiles follow ----
+    // per-env row pointers: warp-uniform 64-bit base + 32-bit lane offset
+    const int nbod = cfg.num_bodies;
+    const float* rb = a.rigid_body + ((e0 * nbod + cfg.imu_body) * 13 + 3) + lane * (nbod * 13);
+    float* cf_env = a.net_contact ? a.net_contact + e0 * nbod * 3 + lane * (nbod * 3) : nullptr;
+    float* cf_l = cf_env ? cf_env + cfg.left_foot_body * 3 : nullptr;
+    float* cf_r = cf_env ? cf_env + cfg.right_foot_body * 3 : nullptr;
+    Gathered<CLEATS> g;
+    gather_env<OBS, (BOOK || REW), CLEATS, TASK>(a, cfg, e, valid, rb, cf_l, cf_r, g);
+
+
+    // ---- 2. dense tiles: TMA bulk copies (full sub-tiles) or cooperative coalesced loads (tail) ----
     if (full) {
         if (lane == 0) {
             mbar_arrive_expect_tx(s_bar, WT * (DOF_ROW + ROOT_ROW) * 4);
@@ -505,16 +520,6 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
         for (int i = lane; i < nv * DOF_ROW; i += WT) s_dof[i] = a.dof_state[e0 * DOF_ROW + i];
         for (int i = lane; i < nv * ROOT_ROW; i += WT) s_root[i] = a.root_states[e0 * ROOT_ROW + i];
     }
-
-    // ---- 2. sparse gathers, issued before anyone waits (widest aligned vector loads available) ----
-    // per-env row pointers: warp-uniform 64-bit base + 32-bit lane offset
-    const int nbod = cfg.num_bodies;
-    const float* rb = a.rigid_body + ((e0 * nbod + cfg.imu_body) * 13 + 3) + lane * (nbod * 13);
-    float* cf_env = a.net_contact ? a.net_contact + e0 * nbod * 3 + lane * (nbod * 3) : nullptr;
-    float* cf_l = cf_env ? cf_env + cfg.left_foot_body * 3 : nullptr;
-    float* cf_r = cf_env ? cf_env + cfg.right_foot_body * 3 : nullptr;
-    Gathered<CLEATS> g;
-    gather_env<OBS, (BOOK || REW), CLEATS, TASK>(a, cfg, e, valid, rb, cf_l, cf_r, g);
 
     float imu_in[10];
     consume<CLEATS>(a, rb, g, imu_in);
@@ -831,7 +836,8 @@ static cudaError_t launch_parts3(const TaskArgs& a, const BezkTaskCfg& cfg, cuda
 
 template <int PARTS, int TASK>
 static cudaError_t launch_parts(const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st) {
-    return (cfg.flags & BEZK_F_CLEATS) ? launch_parts3<PARTS, true, 128, TASK>(a, cfg, st) : launch_parts3<PARTS, false, 128, TASK>(a, cfg, st);
+    return (cfg.flags & BEZK_F_CLEATS) ? launch_parts3<PARTS, true, BEZK_TILE, TASK>(a, cfg, st)
+                                       : launch_parts3<PARTS, false, BEZK_TILE, TASK>(a, cfg, st);
 }
 
 // walk / orient: the fused step (7), the observation kernel (2 or 3) and the reward kernel (4)
