@@ -596,6 +596,9 @@ __global__ void __launch_bounds__(PPO_TILE, 4) ppo_loss_kernel(const PpoArgs a, 
         const int64_t j0 = a.slabs ? slab_src_row(i0, a.slab_rows, a.slab_stride) : i0;
         const int64_t ji = a.slabs ? ((full || !valid) ? j0 + tid : slab_src_row(i, a.slab_rows, a.slab_stride)) : i;
 
+        // per-sample scalars first (five independent loads in flight while thread 0 sets up the bulk copies)
+        float val = 0.f, oval = 0.f, ret = 0.f, onlp = 0.f, adv = 0.f;
+        if (valid) { val = a.values[i]; oval = a.old_values[ji]; ret = a.returns[ji]; onlp = a.old_neglogp[ji]; adv = a.advantages[ji]; }
         if (tid == 0 && store_pending) bulk_wait_read0();          // s_gmu of the previous tile has been read out
         __syncthreads();                                           // everybody is done with the previous tile's rows
         if (full) {
@@ -614,8 +617,6 @@ __global__ void __launch_bounds__(PPO_TILE, 4) ppo_loss_kernel(const PpoArgs a, 
                 s_omu[k] = a.old_mu[jk]; s_osig[k] = a.old_sigma[jk];
             }
         }
-        float val = 0.f, oval = 0.f, ret = 0.f, onlp = 0.f, adv = 0.f;
-        if (valid) { val = a.values[i]; oval = a.old_values[ji]; ret = a.returns[ji]; onlp = a.old_neglogp[ji]; adv = a.advantages[ji]; }
         if (full) { mbar_wait(&s_bar, phase); phase ^= 1u; }
         else __syncthreads();
 
