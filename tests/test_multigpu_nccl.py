@@ -45,6 +45,7 @@ def _worker(rank, world, port, tmp):
         dist.destroy_process_group()
 
 
+@pytest.mark.timeout(180)          # a wedged NCCL rendezvous must fail the test, not hang the GPU box
 def test_sharded_statistics_equal_single_gpu(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
