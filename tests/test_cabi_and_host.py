@@ -115,3 +115,78 @@ def test_model_constants_match_reference_urdf():
         assert mine["env"][key] == ref_cfg["env"][key], key
     assert mine["env"]["clipActions"] == ref_cfg["env"]["clipActions"] and mine["sim"]["dt"] == ref_cfg["sim"]["dt"]
     assert mine["env"]["learn"]["episodeLength_s"] == ref_cfg["env"]["learn"]["episodeLength_s"]
+
+
+# ----------------------------------------------------------------------------------------------- DR schedule / gate logic (CPU)
+def _reference_dr_params(p, last_step):
+    """The parameter arithmetic of the reference's apply_randomizations (tasks/base/vec_task.py:562-618), restated."""
+    dist, op_type = p["distribution"], p["operation"]
+    sched_type = p.get("schedule")
+    sched_step = p.get("schedule_steps")
+    if sched_type == "linear":
+        s = 1.0 / sched_step * min(last_step, sched_step)
+    elif sched_type == "constant":
+        s = 0 if last_step < sched_step else 1
+    else:
+        s = 1
+    if dist == "gaussian":
+        mu, var = p["range"]
+        mu_corr, var_corr = p.get("range_correlated", [0., 0.])
+        if op_type == "additive":
+            mu *= s; var *= s; mu_corr *= s; var_corr *= s
+        elif op_type == "scaling":
+            var = var * s
+            mu = mu * s + 1.0 * (1.0 - s)
+            var_corr = var_corr * s
+            mu_corr = mu_corr * s + 1.0 * (1.0 - s)
+        return {"mu": mu, "var": var, "mu_corr": mu_corr, "var_corr": var_corr}
+    lo, hi = p["range"]
+    lo_corr, hi_corr = p.get("range_correlated", [0., 0.])
+    if op_type == "additive":
+        lo *= s; hi *= s; lo_corr *= s; hi_corr *= s
+    elif op_type == "scaling":
+        lo = lo * s + 1.0 * (1.0 - s); hi = hi * s + 1.0 * (1.0 - s)
+        lo_corr = lo_corr * s + 1.0 * (1.0 - s); hi_corr = hi_corr * s + 1.0 * (1.0 - s)
+    return {"lo": lo, "hi": hi, "lo_corr": lo_corr, "hi_corr": hi_corr}
+
+
+def test_apply_randomizations_gate_and_schedules_match_the_reference_logic():
+    """Host logic of ``VecTask.apply_randomizations`` (frequency gate, first-call rule, linear / constant schedules, additive /
+    scaling, gaussian / uniform) against the restated reference arithmetic -- no kernel runs (the lambdas are only built)."""
+    import types
+    import torch
+    from bez_isaacgym_b200.tasks.base.vec_task import VecTask
+    specs = {
+        "observations": {"range": [0.1, .002], "range_correlated": [0.2, 0.03], "operation": "additive", "distribution": "gaussian",
+                         "schedule": "linear", "schedule_steps": 40},
+        "actions": {"range": [0.9, 1.2], "range_correlated": [0.95, 1.05], "operation": "scaling", "distribution": "uniform",
+                    "schedule": "constant", "schedule_steps": 25},
+    }
+    fake = types.SimpleNamespace(sim=types.SimpleNamespace(frame=0), first_randomization=True, last_step=-1, last_rand_step=-1,
+                                 randomize_buf=torch.zeros(8, dtype=torch.long), reset_buf=torch.ones(8, dtype=torch.long),
+                                 dr_randomizations={}, _dr_seed=1, compute_device=torch.device("cpu"))
+    params = dict(frequency=10, **specs)
+    rebuilt = []
+    last_rand = None
+    for frame in (0, 3, 9, 10, 12, 24, 30, 55):
+        fake.sim.frame = frame
+        fake.randomize_buf += 4
+        before = {k: dict(v) for k, v in fake.dr_randomizations.items()}
+        VecTask.apply_randomizations(fake, params)
+        expect_rebuild = last_rand is None or frame - last_rand >= 10
+        if expect_rebuild:
+            last_rand = frame
+            rebuilt.append(frame)
+            for name, spec in specs.items():
+                want = _reference_dr_params(spec, frame)
+                got = fake.dr_randomizations[name]
+                for k, v in want.items():
+                    assert got[k] == pytest.approx(v, rel=1e-12, abs=1e-15), (frame, name, k)
+                assert callable(got["noise_lambda"]) and "corr" not in got          # the correlated draw is redrawn lazily
+        else:
+            assert {k: {kk: vv for kk, vv in v.items() if kk != "noise_lambda"} for k, v in fake.dr_randomizations.items()} == \
+                   {k: {kk: vv for kk, vv in v.items() if kk != "noise_lambda"} for k, v in before.items()}
+    assert rebuilt == [0, 10, 24, 55]
+    assert fake.first_randomization is False
+    with pytest.raises(NotImplementedError):
+        VecTask.apply_randomizations(fake, {"sim_params": {"gravity": {}}})
