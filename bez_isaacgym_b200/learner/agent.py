@@ -166,8 +166,8 @@ class A2CAgent:
     # ------------------------------------------------------------------ learner
     def calc_gradients(self, input_dict):
         """a2c_continuous.py ``calc_gradients`` on one minibatch (slab views)."""
-        obs = self.running_mean_std(input_dict["obses"]) if self.config["normalize_input"] else \
-            input_dict["obses"].reshape(-1, input_dict["obses"].shape[-1]).contiguous()
+        obs = self.running_mean_std(input_dict["obses"]) if self.config["normalize_input"] else input_dict["obses"]
+        obs = obs.reshape(-1, obs.shape[-1]).contiguous()        # (T*E, obs): a single-minibatch epoch hands over (T, N, obs)
         mu, value = self._forward(obs)
         loss, info = losses.ppo_loss(mu, value, self.model.sigma, input_dict["actions"], input_dict["mus"], input_dict["sigmas"],
                                      input_dict["old_values"], input_dict["returns"], input_dict["neglogpacs"],

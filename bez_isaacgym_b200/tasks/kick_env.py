@@ -361,15 +361,22 @@ class KickEnv(VecTask):
     def set_obs_target(self, tensor):
         """Make the step kernel write its (N,54) observation rows straight into ``tensor`` -- e.g.
         ``experience.slot('obses', t)`` -- instead of a private buffer (rl_games copies ``obs`` into its experience
-        buffer after every step; here the copy never happens).  ``obs_buf`` becomes that tensor."""
+        buffer after every step; here the copy never happens).  ``obs_buf`` (``obs_clipped_buf`` when ``clip_obs`` is finite)
+        becomes that tensor."""
         if self.host_staged:
             raise NotImplementedError("set_obs_target needs the GPU pipeline")
         if tensor.shape != (self.num_envs, self._obs_width) or tensor.dtype != torch.float32 or not tensor.is_contiguous() \
                 or tensor.device != self.compute_device:
             raise ValueError(f"obs target must be a contiguous float32 ({self.num_envs}, {self._obs_width}) tensor on "
                              f"{self.compute_device}")
-        self.obs_buf = tensor
-        self._post_fixed["tail"][5] = _ptr(tensor)
+        if self.obs_clipped_buf is not None:
+            # finite clip_obs: what step() returns -- and what rl_games stores -- is the CLIPPED row (vec_task.py:343); the
+            # raw obs_buf stays private
+            self.obs_clipped_buf = tensor
+            self._post_fixed["tail"][6] = _ptr(tensor)
+        else:
+            self.obs_buf = tensor
+            self._post_fixed["tail"][5] = _ptr(tensor)
 
     def step_precomputed_targets(self, env_actions=None):
         """``step`` for callers whose PD ``targets`` were already written by ``learner.policy_head(..., env=self)`` (the
