@@ -4,6 +4,9 @@ repo's CUDA path vs the reference's torch ops (oracle port) on the SAME GPU and 
 (RunningMeanStd + GAE + advantage normalisation + loss) on the 4096 x 32 rollout.  One JSON line per row.
 
     python tools/sweep.py [--out profiles/r01_sweep.jsonl] [--no-cpu] [--max-envs 1048576]
+
+Measurement tool, not product code: ``oracle/`` is imported here only as the BASELINE BEING TIMED (the same role as
+``bench.py``'s ``cpu_baseline`` leg); every "bezk" row runs the C-ABI kernels and nothing else.
 """
 import argparse
 import json
