@@ -190,3 +190,46 @@ def test_apply_randomizations_gate_and_schedules_match_the_reference_logic():
     assert fake.first_randomization is False
     with pytest.raises(NotImplementedError):
         VecTask.apply_randomizations(fake, {"sim_params": {"gravity": {}}})
+
+
+def test_reference_task_yaml_loads_without_hydra():
+    """``utils.config.load_task_config`` resolves the reference's own cfg/task/*.yaml (Hydra interpolations + the four custom
+    resolvers of train.py:53-58) to what ``bez_model.default_task_cfg`` hard-codes.  Needs /root/reference."""
+    from bez_isaacgym_b200 import bez_model as bm
+    from bez_isaacgym_b200.utils import config as cfgmod
+    root = os.environ.get("BEZ_REFERENCE_ROOT", "/root/reference")
+    path = os.path.join(root, "bez_isaacgym", "cfg", "task", "bez_kick.yaml")
+    if not os.path.isfile(path):
+        pytest.skip("needs /root/reference (authoring container)")
+    cfg = cfgmod.load_task_config(path, num_envs=512)
+    want = bm.default_task_cfg(512)
+    assert cfg["env"]["numEnvs"] == 512 and cfg["physics_engine"] == "physx"
+    assert cfg["sim"]["use_gpu_pipeline"] is True and cfg["sim"]["physx"]["use_gpu"] is True
+    assert cfg["sim"]["physx"]["num_threads"] == 4 and cfg["sim"]["physx"]["num_subscenes"] == 4
+    for key in ("clipActions", "bezInitState", "ballInitState", "goalState", "readyJointAngles"):
+        assert cfg["env"][key] == want["env"][key], key
+    assert cfg["env"]["learn"]["episodeLength_s"] == want["env"]["learn"]["episodeLength_s"]
+    assert cfg["env"]["asset"]["cleats"] == want["env"]["asset"]["cleats"] and cfg["sim"]["dt"] == want["sim"]["dt"]
+    assert cfg["task"]["randomize"] is False and "observations" in cfg["task"]["randomization_params"]
+    # defaults: numEnvs 4096 when num_envs is '' ; CPU pipeline flips both flags
+    assert cfgmod.load_task_config(path)["env"]["numEnvs"] == 4096
+    cpu = cfgmod.load_task_config(path, pipeline="cpu", sim_device="cpu")
+    assert cpu["sim"]["use_gpu_pipeline"] is False and cpu["sim"]["physx"]["use_gpu"] is False
+    for name, goal in (("bez_walk.yaml", [2.0, 0.0]), ("bez_orient.yaml", [2.0, 0.0])):
+        c = cfgmod.load_task_config(os.path.join(root, "bez_isaacgym", "cfg", "task", name), num_envs=64)
+        assert c["env"]["goalState"]["goal"] == goal and c["env"]["learn"]["episodeLength_s"] == 10
+    with pytest.raises(KeyError):
+        cfgmod.load_task_config(path, nonsense=1)
+    # every key the env classes read (tasks/kick_env.py, tasks/base/vec_task.py) is present in the reference's own files
+    for name in ("bez_kick.yaml", "bez_walk.yaml", "bez_orient.yaml"):
+        c = cfgmod.load_task_config(os.path.join(root, "bez_isaacgym", "cfg", "task", name), num_envs=8)
+        env = c["env"]
+        for state in ("bezInitState",) + (("ballInitState",) if name == "bez_kick.yaml" else ()):
+            assert all(len(env[state][k]) == n for k, n in (("pos", 3), ("rot", 4), ("vLinear", 3), ("vAngular", 3)))
+        assert len(env["goalState"]["goal"]) == 2 and isinstance(env["asset"]["cleats"], bool)
+        assert set(bm.DOF_NAMES) <= set(env["readyJointAngles"])
+        assert env["control"]["stiffness"] > 0 and env["control"]["damping"] > 0 and env["learn"]["episodeLength_s"] > 0
+        assert isinstance(c["task"]["randomize"], bool) and c["sim"]["dt"] > 0 and c["sim"]["up_axis"] == "z"
+        assert isinstance(env["debug"]["rewards"], bool) and env["clipActions"] == 3.9 and "clipObservations" not in env
+        if name == "bez_orient.yaml":
+            assert env["goalState"]["goal_angle"] == pytest.approx(1.5708)

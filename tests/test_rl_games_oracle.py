@@ -223,3 +223,33 @@ def test_network_and_normaliser_state_match_the_shipped_checkpoint_layout():
         lr, _ = sched.update(lr, 0.0, 0, 0, 0.02)
     assert lr == pytest.approx(facts["lr"])
     assert sched.update(lr, 0.0, 0, 0, 0.001)[0] == pytest.approx(lr * 1.5) and sched.update(lr, 0.0, 0, 0, 0.008)[0] == lr
+
+
+def test_shipped_reference_checkpoint_loads_strictly():
+    """Where /root/reference exists: the reference's own ``results/Bez_Kick/Normal/Bez_Kick_33.pth`` loads, strict, into
+    ``A2CNetwork`` and the two ``RunningMeanStd`` modules (the layout ``A2CAgent.set_full_state_weights`` relies on), and the
+    restored statistics are the checkpoint's (count = 1 + 5*frame / 1 + 2*frame)."""
+    import numpy
+    from bez_isaacgym_b200.learner.agent import A2CNetwork
+    from bez_isaacgym_b200.learner.running_mean_std import RunningMeanStd as RMS
+    from oracle import reference_loader as rl
+    path = os.path.join(rl.REFERENCE_ROOT, "bez_isaacgym", "results", "Bez_Kick", "Normal", "Bez_Kick_33.pth")
+    if not os.path.isfile(path):
+        pytest.skip("needs /root/reference (authoring container)")
+    allow = [(numpy._core.multiarray.scalar, "numpy.core.multiarray.scalar"), (numpy.dtype, "numpy.dtype")]
+    allow += [getattr(numpy.dtypes, n) for n in dir(numpy.dtypes) if n.endswith("DType")]
+    with torch.serialization.safe_globals(allow):
+        ck = torch.load(path, map_location="cpu", weights_only=True)
+    net, obs_rms, val_rms = A2CNetwork(), RMS(54), RMS(1)
+    net.load_state_dict({k[len("a2c_network."):]: v for k, v in ck["model"].items()}, strict=True)
+    obs_rms.load_state_dict(ck["running_mean_std"], strict=True)
+    val_rms.load_state_dict(ck["reward_mean_std"], strict=True)
+    frame = int(ck["frame"])
+    assert float(obs_rms.count) == 1 + 5 * frame and float(val_rms.count) == 1 + 2 * frame
+    assert obs_rms.running_mean.dtype == torch.float64 and tuple(obs_rms.running_var.shape) == (54,)
+    # the policy runs: ready-pose observation -> finite 18-dim mean action, scalar value
+    x = torch.zeros(1, 54)
+    mu, value = net(x)
+    assert mu.shape == (1, 18) and value.shape == (1, 1) and torch.isfinite(mu).all() and torch.isfinite(value).all()
+    # constant observation columns 52:54 (ball_init) pin the normaliser: mean (0.175, 0), variance -> 0
+    assert abs(float(obs_rms.running_mean[52]) - 0.175) < 1e-6 and float(obs_rms.running_var[52]) < 1e-6
