@@ -15,7 +15,7 @@ TOP_LEVEL_DEFAULTS = dict(num_envs="", seed=42, physics_engine="physx", pipeline
                           graphics_device_id=0, num_threads=4, solver_type=1, num_subscenes=4, test=False, checkpoint="",
                           multi_gpu=False, headless=False, experiment="", max_iterations="")
 
-_REF = re.compile(r"\$\{\.+([A-Za-z_][A-Za-z0-9_]*)\}")             # ${..key}: relative reference to a top-level key
+_REF = re.compile(r"\$\{(\.+)([A-Za-z_][A-Za-z0-9_.]*)\}")         # ${..key} / ${....task.env.numEnvs} / ${.name}
 
 
 def _literal(text):
@@ -43,17 +43,26 @@ def _split_args(body):
     return args
 
 
-def _resolve(value, top):
-    """Resolve one scalar: nested ${resolver:args} / ${..key} expressions, innermost first."""
+def _lookup(dots, path, top, siblings):
+    """``${.name}`` is a sibling of the value being resolved; two or more dots climb to the composed root, where the top-level
+    keys of cfg/config.yaml (and ``task`` for the train files) live."""
+    node = siblings if len(dots) == 1 else top
+    for part in path.split("."):
+        node = node[part]
+    return node
+
+
+def _resolve(value, top, siblings=None):
+    """Resolve one scalar: nested ${resolver:args} / relative ${..key} references, innermost first."""
     if not isinstance(value, str) or "${" not in value:
         return value
     text = value.strip()
     whole = _REF.fullmatch(text)
     if whole:
-        return top[whole.group(1)]
+        return _resolve(_lookup(whole.group(1), whole.group(2), top, siblings or {}), top, siblings)
     if text.startswith("${") and text.endswith("}") and ":" in text:
         name, body = text[2:-1].split(":", 1)
-        args = [_resolve(a.strip(), top) if "${" in a else _literal(a) for a in _split_args(body)]
+        args = [_resolve(a.strip(), top, siblings) if "${" in a else _literal(a) for a in _split_args(body)]
         if name == "eq":                                   # train.py:53  lambda x, y: x.lower() == y.lower()
             return str(args[0]).lower() == str(args[1]).lower()
         if name == "contains":                             # train.py:54  lambda x, y: x.lower() in y.lower()
@@ -66,12 +75,12 @@ def _resolve(value, top):
     raise ValueError(f"cannot resolve {value!r}")
 
 
-def _walk(node, top):
+def _walk(node, top, siblings=None):
     if isinstance(node, dict):
-        return {k: _walk(v, top) for k, v in node.items()}
+        return {k: _walk(v, top, node) for k, v in node.items()}
     if isinstance(node, list):
-        return [_walk(v, top) for v in node]
-    return _resolve(node, top)
+        return [_walk(v, top, siblings) for v in node]
+    return _resolve(node, top, siblings)
 
 
 def load_task_config(path, **overrides):
@@ -89,3 +98,30 @@ def load_task_config(path, **overrides):
     cfg.setdefault("rl_device", top["rl_device"])
     cfg.setdefault("seed", top["seed"])
     return cfg
+
+
+def load_train_config(path, task_cfg, **overrides):
+    """Parse a reference train yaml (``cfg/train/*PPO.yaml``) against the composed root: cfg/config.yaml's top-level keys plus
+    ``task`` (a dict from ``load_task_config``).  Returns the resolved ``params`` dict rl_games' ``Runner.load`` receives
+    (``train.py:100-106``); ``agent_config`` extracts what ``learner.A2CAgent`` consumes."""
+    top = dict(TOP_LEVEL_DEFAULTS)
+    unknown = set(overrides) - set(top)
+    if unknown:
+        raise KeyError(f"unknown top-level config keys: {sorted(unknown)}")
+    top.update(overrides)
+    top["task"] = task_cfg
+    with open(path) as f:
+        raw = yaml.safe_load(f)
+    return _walk(raw, top)
+
+
+#: rl_games ``params.config`` keys that ``learner.A2CAgent`` understands
+AGENT_KEYS = ("gamma", "tau", "learning_rate", "lr_schedule", "kl_threshold", "grad_norm", "truncate_grads", "e_clip", "horizon_length",
+              "minibatch_size", "mini_epochs", "critic_coef", "clip_value", "entropy_coef", "bounds_loss_coef", "normalize_input",
+              "normalize_value", "normalize_advantage", "value_bootstrap", "reward_shaper", "mixed_precision")
+
+
+def agent_config(train_cfg):
+    """``params.config`` of a resolved train yaml -> the ``config`` dict of ``learner.A2CAgent``."""
+    c = train_cfg["params"]["config"]
+    return {k: c[k] for k in AGENT_KEYS if k in c}

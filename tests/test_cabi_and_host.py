@@ -233,3 +233,27 @@ def test_reference_task_yaml_loads_without_hydra():
         assert isinstance(env["debug"]["rewards"], bool) and env["clipActions"] == 3.9 and "clipObservations" not in env
         if name == "bez_orient.yaml":
             assert env["goalState"]["goal_angle"] == pytest.approx(1.5708)
+
+
+def test_reference_train_yaml_pins_the_agent_defaults():
+    """``learner.agent.DEFAULT_CONFIG`` is what the reference's own cfg/train/bez_kickPPO.yaml says (:45-79), read through the
+    Hydra-free loader (``${....task.env.numEnvs}``, ``${.name}``, ``${if:...}``, ``${resolve_default:...}``)."""
+    from bez_isaacgym_b200.learner.agent import DEFAULT_CONFIG
+    from bez_isaacgym_b200.utils import config as cfgmod
+    root = os.environ.get("BEZ_REFERENCE_ROOT", "/root/reference")
+    tpath = os.path.join(root, "bez_isaacgym", "cfg", "task", "bez_kick.yaml")
+    ppath = os.path.join(root, "bez_isaacgym", "cfg", "train", "bez_kickPPO.yaml")
+    if not os.path.isfile(ppath):
+        pytest.skip("needs /root/reference (authoring container)")
+    task = cfgmod.load_task_config(tpath, num_envs=2048)
+    train = cfgmod.load_train_config(ppath, task, checkpoint="")
+    p = train["params"]
+    assert p["seed"] == 42 and p["load_checkpoint"] is False and p["load_path"] == ""
+    assert p["config"]["num_actors"] == 2048 and p["config"]["name"] == "Bez_Kick_36" == p["config"]["full_experiment_name"]
+    assert p["config"]["max_epochs"] == 100000
+    assert p["network"]["mlp"]["units"] == [400, 200, 100] and p["network"]["space"]["continuous"]["fixed_sigma"] is True
+    got = cfgmod.agent_config(train)
+    for k, v in got.items():
+        assert DEFAULT_CONFIG[k] == v, (k, DEFAULT_CONFIG[k], v)
+    assert set(got) == set(cfgmod.AGENT_KEYS)
+    assert cfgmod.load_train_config(ppath, task, checkpoint="runs/x.pth")["params"]["load_checkpoint"] is True
