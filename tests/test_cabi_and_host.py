@@ -257,3 +257,69 @@ def test_reference_train_yaml_pins_the_agent_defaults():
         assert DEFAULT_CONFIG[k] == v, (k, DEFAULT_CONFIG[k], v)
     assert set(got) == set(cfgmod.AGENT_KEYS)
     assert cfgmod.load_train_config(ppath, task, checkpoint="runs/x.pth")["params"]["load_checkpoint"] is True
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Argument COUNT and coarse kind (pointer / integer / floating) of every ctypes signature against the prototype in
+    include/bezk.h -- an ABI drift between the two would corrupt arguments silently on the GPU box."""
+    import ctypes as C
+    import re
+    from bez_isaacgym_b200 import _lib
+    header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "bezk.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = dict(re.findall(r"\b(?:int|int64_t|const char\*)\s+(bezk_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S))
+    assert set(protos) == set(_lib.SIGNATURES)
+
+    def kind_of_param(text):
+        text = " ".join(text.split())
+        if text in ("void", ""):
+            return None
+        if "*" in text:
+            return "ptr"
+        if re.search(r"\b(float|double)\b", text):
+            return "fp"
+        return "int"
+
+    def kind_of_ctype(t):
+        if t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or getattr(t, "_type_", None) is not None and issubclass(t, C._Pointer):
+            return "ptr"
+        if t in (C.c_float, C.c_double):
+            return "fp"
+        return "int"
+
+    for name, params in protos.items():
+        want = [k for k in (kind_of_param(p) for p in params.split(",")) if k is not None]
+        got = [kind_of_ctype(t) for t in _lib.SIGNATURES[name][1]]
+        assert got == want, (name, got, want)
+        # 64-bit integers must be declared 64-bit on the Python side too
+        widths = [("64" in p) for p in params.split(",") if kind_of_param(p) == "int"]
+        cw = [C.sizeof(t) == 8 for t in _lib.SIGNATURES[name][1] if kind_of_ctype(t) == "int"]
+        assert widths == cw, (name, widths, cw)
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of the three by-value config structs, as gcc lays them out from include/bezk.h (which must stay plain
+    C), against the ctypes mirrors in bez_isaacgym_b200/_lib.py."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from bez_isaacgym_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    structs = {"BezkTaskCfg": _lib.BezkTaskCfg, "BezkPpoCfg": _lib.BezkPpoCfg, "BezkNoiseCfg": _lib.BezkNoiseCfg}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "bezk.h"', 'int main(void) {']
+    for sname, st in structs.items():
+        lines.append(f'  printf("{sname} %zu\\n", sizeof({sname}));')
+        for fname, _ in st._fields_:
+            lines.append(f'  printf("{sname}.{fname} %zu\\n", offsetof({sname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for sname, st in structs.items():
+        assert int(out[sname]) == C.sizeof(st), sname
+        for fname, _ in st._fields_:
+            assert int(out[f"{sname}.{fname}"]) == getattr(st, fname).offset, (sname, fname)
