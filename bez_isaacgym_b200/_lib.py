@@ -41,6 +41,10 @@ class BezkNoiseCfg(C.Structure):
                 ("a_corr", C.c_float), ("b_corr", C.c_float)]
 
 
+class BezkRolloutCfg(C.Structure):
+    _fields_ = [("scale_value", C.c_float), ("shift_value", C.c_float), ("gamma", C.c_float), ("value_bootstrap", C.c_int32)]
+
+
 class BezkPpoCfg(C.Structure):
     _fields_ = [
         ("e_clip", C.c_float), ("critic_coef", C.c_float), ("entropy_coef", C.c_float),
@@ -78,15 +82,18 @@ SIGNATURES = {
     "bezk_ppo_loss": (C.c_int, [_P] * 10 + [C.POINTER(BezkPpoCfg)] + [_P] * 6 + [_I64, _P]),
     "bezk_post_physics_task": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U64, _U64, _P, _P, _P, _P,
                                          C.POINTER(BezkTaskCfg), _P, _P, _P, C.c_int, _I64, _P]),
-    "bezk_reset_idx_task": (C.c_int, [C.c_int, _P, _I64, _P, _P, _U64, _U64, _P, _P, _P, _P, _P, _P, C.POINTER(BezkTaskCfg), _I64, _P]),
+    "bezk_post_physics_rollout": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U64, _U64, _P, _P, _P, _P,
+                                            C.POINTER(BezkTaskCfg), _P, _P, _P, C.POINTER(BezkRolloutCfg), _P, _P, _P, _I64, _I64, _P]),
+    "bezk_reset_idx_task": (C.c_int, [C.c_int, _P, _I64, _P, _P, _U64, _U64, _P, _P, _P, _P, _P, _P, C.POINTER(BezkTaskCfg), _I64, _I64,
+                                      _P]),
     "bezk_goal_uniforms": (C.c_int, [_U64, _U64, _P, _P]),
     "bezk_rms_moments_slabs": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _I64, C.c_int32, _P]),
     "bezk_rms_normalize_slabs": (C.c_int, [_P, _I64, _I64, _P, _P, C.c_float, C.c_int, _P, _I64, C.c_int32, _P]),
     "bezk_ppo_loss_slabs": (C.c_int, [_P] * 10 + [_I64, _I64, C.POINTER(BezkPpoCfg)] + [_P] * 6 + [_I64, _P]),
     "bezk_swap_and_flatten01": (C.c_int, [_P, _P, C.c_int32, _I64, _I64, _I64, C.c_int32, _P]),
     "bezk_policy_head": (C.c_int, [_P, _P, _P, _P, _P, C.c_float, _P, _U64, _U64, _P, _P, _P, _P, _P,
-                                   C.POINTER(BezkTaskCfg), _P, _P, _I64, _P]),
-    "bezk_normal_noise": (C.c_int, [_U64, _U64, _P, _I64, _P]),
+                                   C.POINTER(BezkTaskCfg), _P, _P, _I64, _I64, _P]),
+    "bezk_normal_noise": (C.c_int, [_U64, _U64, _P, _I64, _I64, _P]),
     "bezk_dr_noise": (C.c_int, [_P, _P, _P, _U64, _U64, C.POINTER(BezkNoiseCfg), _P, _I64, _P]),
     "bezk_selftest_fastmath": (C.c_int, [_U64, _U64, _P, _P]),
     "bezk_dr_fill": (C.c_int, [_U64, _U64, C.c_int32, _P, _I64, _P]),

@@ -107,21 +107,21 @@ int bezk_reset_idx(const int64_t* env_ids, int64_t k, const float* uniforms, uin
     REQUIRE(env_ids && dof_state && progress && reset, "reset_idx buffers NULL");
     if (cfg->flags & BEZK_F_RESET_ROOT_STATES) REQUIRE(root_states && initial_root_states, "root state buffers NULL");
     return cuda_rc(bezk::launch_reset_idx(env_ids, k, uniforms, seed, step, dof_state, root_states, initial_root_states, progress,
-                                          reset, *cfg, n, BEZK_TASK_KICK, nullptr, nullptr, (cudaStream_t)stream), "bezk_reset_idx");
+                                          reset, *cfg, n, BEZK_TASK_KICK, nullptr, nullptr, 0, (cudaStream_t)stream), "bezk_reset_idx");
 }
 
 int bezk_reset_idx_task(int task, const int64_t* env_ids, int64_t k, const float* uniforms, const float* goal_uniforms, uint64_t seed,
                         uint64_t step, float* dof_state, float* root_states, const float* initial_root_states, float* goal,
-                        int64_t* progress, int64_t* reset, const BezkTaskCfg* cfg, int64_t n, void* stream) {
+                        int64_t* progress, int64_t* reset, const BezkTaskCfg* cfg, int64_t env_base, int64_t n, void* stream) {
     REQUIRE(task == BEZK_TASK_KICK || task == BEZK_TASK_WALK || task == BEZK_TASK_ORIENT, "unknown task");
     if (int rc = check_cfg(cfg)) return rc;
-    REQUIRE(k >= 0 && n >= 0, "k/n < 0");
+    REQUIRE(k >= 0 && n >= 0 && env_base >= 0, "k / n / env_base < 0");
     if (k == 0) return 0;
     REQUIRE(env_ids && dof_state && progress && reset, "reset_idx buffers NULL");
     if (task != BEZK_TASK_KICK) REQUIRE(goal, "goal NULL");
     if (cfg->flags & BEZK_F_RESET_ROOT_STATES) REQUIRE(root_states && initial_root_states, "root state buffers NULL");
     return cuda_rc(bezk::launch_reset_idx(env_ids, k, uniforms, seed, step, dof_state, root_states, initial_root_states, progress,
-                                          reset, *cfg, n, task, goal, goal_uniforms, (cudaStream_t)stream), "bezk_reset_idx_task");
+                                          reset, *cfg, n, task, goal, goal_uniforms, env_base, (cudaStream_t)stream), "bezk_reset_idx_task");
 }
 
 int bezk_post_physics(float* dof_state, const float* rigid_body, float* root_states, float* net_contact, float* prev_lin_vel,
@@ -176,6 +176,34 @@ int bezk_post_physics_task(int task, float* dof_state, const float* rigid_body, 
     a.timeout_buf = timeout_buf; a.randomize_buf = randomize_buf;
     a.obs = obs; a.obs_clipped = obs_clipped; a.rew = rew; a.n = n;
     return run_task(parts, a, cfg, stream, "bezk_post_physics_task", task);
+}
+
+int bezk_post_physics_rollout(int task, float* dof_state, const float* rigid_body, float* root_states, float* net_contact,
+                              float* prev_lin_vel, float* goal, const float* goal_angle, const float* ball_init,
+                              const float* initial_root_states, const float* uniforms, const float* goal_uniforms, uint64_t seed,
+                              uint64_t step, int64_t* reset_buf, int64_t* progress_buf, int64_t* timeout_buf, int64_t* randomize_buf,
+                              const BezkTaskCfg* cfg, float* obs, float* obs_clipped, float* rew, const BezkRolloutCfg* rollout,
+                              const float* values, float* shaped_rewards, uint8_t* dones_u8, int64_t env_base, int64_t n,
+                              void* stream) {
+    REQUIRE(task == BEZK_TASK_KICK || task == BEZK_TASK_WALK || task == BEZK_TASK_ORIENT, "unknown task");
+    REQUIRE(env_base >= 0, "env_base < 0");
+    REQUIRE(!shaped_rewards || rollout, "shaped_rewards requested without a BezkRolloutCfg");
+    REQUIRE(!(shaped_rewards && rollout && rollout->value_bootstrap) || values, "value_bootstrap needs values");
+    bezk::TaskArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dof_state = dof_state; a.rigid_body = rigid_body; a.root_states = root_states; a.net_contact = net_contact;
+    a.prev_lin_vel = prev_lin_vel; a.goal = goal; a.goal_angle = goal_angle; a.goal_uniforms = goal_uniforms; a.ball_init = ball_init;
+    a.initial_root = initial_root_states; a.uniforms = uniforms; a.seed = seed; a.step = step; a.env_base = env_base;
+    a.reset_in = reset_buf; a.reset_out = reset_buf; a.progress_in = progress_buf; a.progress_out = progress_buf;
+    a.timeout_buf = timeout_buf; a.randomize_buf = randomize_buf;
+    a.obs = obs; a.obs_clipped = obs_clipped; a.rew = rew; a.n = n;
+    a.shaped_rew = shaped_rewards; a.dones_u8 = dones_u8;
+    if (shaped_rewards) {
+        a.shp_scale = rollout->scale_value; a.shp_shift = rollout->shift_value; a.shp_gamma = rollout->gamma;
+        a.shp_bootstrap = rollout->value_bootstrap != 0;
+        a.values = a.shp_bootstrap ? values : nullptr;
+    }
+    return run_task(BEZK_PART_BOOKKEEP | BEZK_PART_OBS | BEZK_PART_REWARD, a, cfg, stream, "bezk_post_physics_rollout", task);
 }
 
 int bezk_goal_uniforms(uint64_t seed, uint64_t step, float* out2, void* stream) {
@@ -317,8 +345,8 @@ int bezk_swap_and_flatten01(const void* src, void* dst, int32_t horizon, int64_t
 int bezk_policy_head(const float* mu, const float* logstd, const float* value_norm, const double* value_mean,
                      const double* value_var, float value_eps, const float* noise, uint64_t seed, uint64_t step, float* actions,
                      float* neglogp, float* values, float* mus, float* sigmas, const BezkTaskCfg* task_cfg, float* env_actions,
-                     float* targets, int64_t n, void* stream) {
-    REQUIRE(n >= 0, "n < 0");
+                     float* targets, int64_t env_base, int64_t n, void* stream) {
+    REQUIRE(n >= 0 && env_base >= 0, "n / env_base < 0");
     if (n == 0) return 0;
     REQUIRE(mu && logstd, "mu/logstd NULL");
     REQUIRE(!values || value_norm, "values requested without value_norm");
@@ -327,7 +355,7 @@ int bezk_policy_head(const float* mu, const float* logstd, const float* value_no
     if (task_cfg) { if (int rc = check_cfg(task_cfg)) return rc; }
     REQUIRE(ALIGNED(mu, 8) && (!noise || ALIGNED(noise, 8)), "mu / noise must be 8-byte aligned");
     return cuda_rc(bezk::launch_policy_head(mu, logstd, value_norm, value_mean, value_var, value_eps, noise, seed, step, actions,
-                                            neglogp, values, mus, sigmas, task_cfg, env_actions, targets, n, (cudaStream_t)stream),
+                                            neglogp, values, mus, sigmas, task_cfg, env_actions, targets, env_base, n, (cudaStream_t)stream),
                    "bezk_policy_head");
 }
 
@@ -354,11 +382,11 @@ int bezk_selftest_fastmath(uint64_t pairs, uint64_t seed, uint64_t* counts, void
                    "bezk_selftest_fastmath");
 }
 
-int bezk_normal_noise(uint64_t seed, uint64_t step, float* out, int64_t n, void* stream) {
-    REQUIRE(n >= 0, "n < 0");
+int bezk_normal_noise(uint64_t seed, uint64_t step, float* out, int64_t env_base, int64_t n, void* stream) {
+    REQUIRE(n >= 0 && env_base >= 0, "n / env_base < 0");
     if (n == 0) return 0;
     REQUIRE(out, "out NULL");
-    return cuda_rc(bezk::launch_normal_noise(seed, step, out, n, (cudaStream_t)stream), "bezk_normal_noise");
+    return cuda_rc(bezk::launch_normal_noise(seed, step, out, n, env_base, (cudaStream_t)stream), "bezk_normal_noise");
 }
 
 }  // extern "C"

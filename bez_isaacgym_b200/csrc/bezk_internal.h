@@ -30,6 +30,12 @@ struct TaskArgs {
     float* obs;
     float* obs_clipped;
     float* rew;
+    // rl_games play_steps reward path folded into the reward epilogue (bezk_post_physics_rollout); all optional
+    const float* values;         // (n,) un-normalised critic values of this step (value bootstrap)
+    float* shaped_rew;           // (n,) out: (rew + shift) * scale [+ gamma * value * timeout]
+    uint8_t* dones_u8;           // (n,) out: reset mask as uint8 (the experience buffer's `dones` slot of the NEXT step)
+    float shp_scale, shp_shift, shp_gamma;
+    int shp_bootstrap;
     int64_t n;
     int use_tma;      // all dense bases 16 B aligned
     int rb_vec2;      // IMU-link slice of every env is 8 B aligned
@@ -50,7 +56,7 @@ cudaError_t launch_goal_uniforms(uint64_t seed, uint64_t step, float* out2, cuda
 void fill_alignment(TaskArgs& a, const BezkTaskCfg& cfg);
 cudaError_t launch_pre_physics(const float*, float*, float*, const BezkTaskCfg&, int64_t, cudaStream_t);
 cudaError_t launch_reset_idx(const int64_t*, int64_t, const float*, uint64_t, uint64_t, float*, float*, const float*, int64_t*,
-                             int64_t*, const BezkTaskCfg&, int64_t, int, float*, const float*, cudaStream_t);
+                             int64_t*, const BezkTaskCfg&, int64_t, int, float*, const float*, int64_t, cudaStream_t);
 cudaError_t launch_philox_uniforms(uint64_t, uint64_t, float*, int64_t, cudaStream_t);
 cudaError_t launch_gae(const float*, const float*, const void*, const float*, const void*, int, double, double, float*, float*,
                        int, int64_t, cudaStream_t);
@@ -63,9 +69,9 @@ cudaError_t launch_adv_moments(const float*, const float*, double*, double*, int
 cudaError_t launch_adv_normalize(const float*, const float*, const double*, float*, int, int64_t, cudaStream_t);
 cudaError_t launch_swap_flatten(const void*, void*, int, int64_t, int64_t, int64_t, int, cudaStream_t);
 cudaError_t launch_policy_head(const float*, const float*, const float*, const double*, const double*, float, const float*, uint64_t,
-                               uint64_t, float*, float*, float*, float*, float*, const BezkTaskCfg*, float*, float*, int64_t,
+                               uint64_t, float*, float*, float*, float*, float*, const BezkTaskCfg*, float*, float*, int64_t, int64_t,
                                cudaStream_t);
-cudaError_t launch_normal_noise(uint64_t, uint64_t, float*, int64_t, cudaStream_t);
+cudaError_t launch_normal_noise(uint64_t, uint64_t, float*, int64_t, int64_t, cudaStream_t);
 cudaError_t launch_dr_noise(const float*, const float*, const float*, uint64_t, uint64_t, const BezkNoiseCfg&, float*, int64_t, cudaStream_t);
 cudaError_t launch_dr_fill(uint64_t, uint64_t, int, float*, int64_t, cudaStream_t);
 cudaError_t launch_selftest_fastmath(uint64_t, uint64_t, unsigned long long*, cudaStream_t);

@@ -400,20 +400,16 @@ cudaError_t launch_rms_moments(const float* x, const double* pivot, double* acc,
         if (c > RMS_MAX_C) return cudaErrorInvalidValue;
         // TMA path: every tile start (64 rows) and every tile size must be a multiple of 16 bytes
         const bool tma_ok = aligned16(x) && ((RMS_TR * c * 4) % 16 == 0) && (((m % RMS_TR) * c * 4) % 16 == 0) && m >= 4 * RMS_TR &&
-                            (!slabs || (slab_rows % RMS_TR == 0 && (slab_stride * c * 4) % 16 == 0));
+                            (!slabs || (slab_rows % RMS_TR == 0 && (slab_stride * c * 4) % 16 == 0)) &&
+                            (size_t)RMS_STAGES * RMS_TR * c * sizeof(float) <= 220 * 1024;      // wider rows: the plain-load kernel
         if (tma_ok) {
             const int64_t ntiles = (m + RMS_TR - 1) / RMS_TR;
             size_t smem = (size_t)RMS_STAGES * RMS_TR * c * sizeof(float);
             const size_t red = (size_t)2 * (RMS_THREADS / c) * c * sizeof(double);     // fold buffer aliases the ring
             if (red > smem) smem = red;
-            static size_t attr_set = 0;
-            if (smem > attr_set) {
-                cudaError_t e2 = cudaFuncSetAttribute(rms_partials_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e2 == cudaSuccess)
-                    e2 = cudaFuncSetAttribute(rms_partials_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e2 != cudaSuccess) return e2;
-                attr_set = smem;
-            }
+            static SmemOptIn opt_plain, opt_slabs;       // opt in to the cap once per device; the launch passes the real size
+            if (cudaError_t e2 = opt_plain.ensure(rms_partials_tma_kernel<false>, 220 * 1024)) return e2;
+            if (cudaError_t e2 = opt_slabs.ensure(rms_partials_tma_kernel<true>, 220 * 1024)) return e2;
             int per_sm = (int)((220 * 1024) / (smem + 1024));
             if (per_sm > 8) per_sm = 8;
             if (per_sm < 1) per_sm = 1;

@@ -62,11 +62,9 @@ static cudaError_t launch_sf(const void* src, void* dst, int horizon, int64_t n,
     if (eb > envs) eb = envs;
     const size_t smem = (size_t)(((int64_t)tb * w) | 1) * eb * sizeof(E);      // covers both pitches
     if (smem > 200 * 1024) return cudaErrorInvalidValue;         // rows wider than 6 KB are not rollout tensors
-    static size_t attr_set = 0;
-    if (smem > 48 * 1024 && smem > attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(swap_flatten_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = smem;
+    static SmemOptIn opt_in;                                      // per element type, per device
+    if (smem > 48 * 1024) {
+        if (cudaError_t e = opt_in.ensure(swap_flatten_kernel<E>, 200 * 1024)) return e;
     }
     const dim3 grid((unsigned)((envs + eb - 1) / eb), (unsigned)((horizon + tb - 1) / tb));
     return launch_ex(swap_flatten_kernel<E>, grid, dim3(256), smem, st, (const E*)src, (E*)dst, horizon, n, env0, envs, w, (int)eb, tb);
@@ -124,6 +122,7 @@ struct HeadArgs {
     const double *value_mean, *value_var;
     float value_eps;
     uint64_t seed, step;
+    int64_t env_base;            // global id of row 0 (Philox key): non-zero on env-sharded ranks
     float *actions, *neglogp, *values, *mus, *sigmas, *env_actions, *targets;
     int64_t n;
     int use_tma, has_task;
@@ -165,7 +164,7 @@ __global__ void __launch_bounds__(PH_TILE) policy_head_kernel(const HeadArgs a, 
     float vnorm = 0.0f;
     if (valid && a.value_norm) vnorm = a.value_norm[i];
     float z[18];
-    if (!a.noise && valid) philox_normals18(a.seed, a.step, i, z);       // overlaps the tile load
+    if (!a.noise && valid) philox_normals18(a.seed, a.step, a.env_base + i, z);       // keyed by the GLOBAL env id; overlaps the tile load
     if (full) mbar_wait(&s_bar, 0);
     else __syncthreads();
 
@@ -244,11 +243,11 @@ __global__ void __launch_bounds__(PH_TILE) policy_head_kernel(const HeadArgs a, 
     }
 }
 
-__global__ void normal_noise_kernel(uint64_t seed, uint64_t step, float* out, int64_t n) {
+__global__ void normal_noise_kernel(uint64_t seed, uint64_t step, float* out, int64_t n, int64_t env_base) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     float z[18];
-    philox_normals18(seed, step, e, z);
+    philox_normals18(seed, step, env_base + e, z);
 #pragma unroll
     for (int c = 0; c < 18; ++c) out[e * 18 + c] = z[c];
 }
@@ -258,9 +257,10 @@ static inline bool al16(const void* p) { return p == nullptr || (reinterpret_cas
 cudaError_t launch_policy_head(const float* mu, const float* logstd, const float* value_norm, const double* value_mean,
                                const double* value_var, float value_eps, const float* noise, uint64_t seed, uint64_t step,
                                float* actions, float* neglogp, float* values, float* mus, float* sigmas, const BezkTaskCfg* cfg,
-                               float* env_actions, float* targets, int64_t n, cudaStream_t st) {
+                               float* env_actions, float* targets, int64_t env_base, int64_t n, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     HeadArgs a;
+    a.env_base = env_base;
     a.mu = mu; a.logstd = logstd; a.value_norm = value_norm; a.noise = noise; a.value_mean = value_mean; a.value_var = value_var;
     a.value_eps = value_eps; a.seed = seed; a.step = step; a.actions = actions; a.neglogp = neglogp; a.values = values;
     a.mus = mus; a.sigmas = sigmas; a.env_actions = env_actions; a.targets = cfg ? targets : nullptr; a.n = n;
@@ -271,9 +271,9 @@ cudaError_t launch_policy_head(const float* mu, const float* logstd, const float
     return launch_ex(policy_head_kernel, dim3((unsigned)((n + PH_TILE - 1) / PH_TILE)), dim3(PH_TILE), 0, st, a, c);
 }
 
-cudaError_t launch_normal_noise(uint64_t seed, uint64_t step, float* out, int64_t n, cudaStream_t st) {
+cudaError_t launch_normal_noise(uint64_t seed, uint64_t step, float* out, int64_t n, int64_t env_base, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    normal_noise_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seed, step, out, n);
+    normal_noise_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seed, step, out, n, env_base);
     return cudaGetLastError();
 }
 

@@ -318,6 +318,18 @@ __device__ __forceinline__ void reward_term(const RewardIn& s, const BezkTaskCfg
     *reset_out = reset;
 }
 
+// rl_games play_steps reward path (a2c_common.py play_steps + tr_helpers.DefaultRewardsShaper; cfg/train/bez_kickPPO.yaml:53-56):
+//   shaped = (rew + shift) * scale;  shaped += gamma * values * time_outs.float()   (value_bootstrap)
+// and the uint8 copy of the reset mask that becomes the experience buffer's `dones` slot of the next step.
+__device__ __forceinline__ void rollout_epilogue(const TaskArgs& a, int64_t e, float rew, int64_t reset, int64_t timeout, float value) {
+    if (a.shaped_rew) {
+        float s = (rew + a.shp_shift) * a.shp_scale;
+        if (a.shp_bootstrap) s = s + (a.shp_gamma * value) * (float)timeout;
+        a.shaped_rew[e] = s;
+    }
+    if (a.dones_u8) a.dones_u8[e] = (uint8_t)(reset != 0);
+}
+
 // reset_idx DOF part, kick_env.py:786-791
 __device__ __forceinline__ void reset_dof_row(const float (&u)[36], const BezkTaskCfg& c, float (&row)[36]) {
 #pragma unroll
@@ -347,6 +359,7 @@ struct Gathered {
     float fl[CLEATS ? 12 : 3], fr[CLEATS ? 12 : 3];
     float goal[2], binit[2], prev[3];
     float gang;                          // orient task: goal angle
+    float value;                         // critic value of this step (rollout epilogue only)
     long long reset_prev, progress;
 };
 
@@ -377,6 +390,7 @@ __device__ __forceinline__ void gather_env(const TaskArgs& a, const BezkTaskCfg&
     g.goal[0] = g.goal[1] = g.binit[0] = g.binit[1] = 0.0f;
     g.prev[0] = g.prev[1] = g.prev[2] = 0.0f;
     g.gang = 0.0f;
+    g.value = 0.0f;
     g.reset_prev = 0; g.progress = 0;
 #pragma unroll
     for (int k = 0; k < 10; ++k) g.raw[k] = 0.0f;
@@ -437,6 +451,7 @@ __device__ __forceinline__ void gather_env(const TaskArgs& a, const BezkTaskCfg&
         if (BOOKREW) {
             g.reset_prev = ld_i64(a.reset_in + e);
             g.progress = ld_i64(a.progress_in + e);
+            if (a.values) g.value = ld_f32(a.values + e);
         }
     }
 }
@@ -741,7 +756,7 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
         }
         a.rew[e] = rew;
         a.reset_out[e] = reset;
-        if (BOOK) a.progress_out[e] = progress;
+        if (BOOK) { a.progress_out[e] = progress; rollout_epilogue(a, e, rew, reset, timeout, g.value); }
     }
     if (REW && valid && TASK == BEZK_TASK_KICK) {
         RewardIn s;
@@ -763,7 +778,7 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
         }
         a.rew[e] = rew;
         a.reset_out[e] = reset;
-        if (BOOK) a.progress_out[e] = progress;
+        if (BOOK) { a.progress_out[e] = progress; rollout_epilogue(a, e, rew, reset, timeout, g.value); }
     }
 
     if (OBS && full && lane == 0) bulk_wait_read0();   // shared memory must outlive the bulk store's reads
@@ -776,7 +791,7 @@ __global__ void __launch_bounds__(128) reset_idx_kernel(const int64_t* __restric
                                                         uint64_t seed, uint64_t step, float* dof_state, float* root_states,
                                                         const float* __restrict__ initial_root, int64_t* progress, int64_t* reset,
                                                         const __grid_constant__ BezkTaskCfg cfg, int64_t n, int root_floats,
-                                                        float* goal, const float* __restrict__ goal_uniforms) {
+                                                        float* goal, const float* __restrict__ goal_uniforms, int64_t env_base) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= k) return;
     const int64_t e = env_ids[i];
@@ -786,7 +801,7 @@ __global__ void __launch_bounds__(128) reset_idx_kernel(const int64_t* __restric
 #pragma unroll
         for (int c = 0; c < 36; ++c) u[c] = uniforms[i * 36 + c];
     } else {
-        philox_reset_uniforms(seed, step, e, u);
+        philox_reset_uniforms(seed, step, env_base + e, u);          // keyed by the GLOBAL env id
     }
     reset_dof_row(u, cfg, row);
 #pragma unroll
@@ -823,13 +838,10 @@ static inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>
 template <int PARTS, bool CLEATS, int TILE, int TASK>
 static cudaError_t launch_parts3(const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st) {
     const size_t smem = (size_t)(smem_in_floats(TILE, TASK) + (a.obs_clipped ? smem_obs_floats(TILE, TASK) : 0)) * sizeof(float);
-    static bool attr_set = false;          // per instantiation; opt in to > 48 KB dynamic shared memory once
-    if (!attr_set) {
-        cudaError_t err = cudaFuncSetAttribute(task_tile_kernel<PARTS, CLEATS, TILE, TASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)((smem_in_floats(TILE, TASK) + smem_obs_floats(TILE, TASK)) * sizeof(float)));
-        if (err != cudaSuccess) return err;
-        attr_set = true;
-    }
+    static SmemOptIn opt_in;               // per instantiation, per device
+    if (cudaError_t err = opt_in.ensure(task_tile_kernel<PARTS, CLEATS, TILE, TASK>,
+                                        (smem_in_floats(TILE, TASK) + smem_obs_floats(TILE, TASK)) * sizeof(float)))
+        return err;
     const int64_t tiles = (a.n + TILE - 1) / TILE;
     return launch_ex(task_tile_kernel<PARTS, CLEATS, TILE, TASK>, dim3((unsigned)tiles), dim3(TILE), smem, st, a, cfg);
 }
@@ -883,9 +895,10 @@ void fill_alignment(TaskArgs& a, const BezkTaskCfg& cfg) {
     a.use_tma = aligned16(a.dof_state) && aligned16(a.root_states) && aligned16(a.dof_state_wb) && (a.obs == nullptr || aligned16(a.obs)) &&
                 (a.obs_clipped == nullptr || aligned16(a.obs_clipped));
     a.rb_vec2 = aligned8(a.rigid_body) && (cfg.num_bodies % 2 == 0) && ((cfg.imu_body * 13 + 3) % 2 == 0);
-    // 0: 64-byte granules only; 1 (default): per-lane 64 / 128-byte choice; 2: full 128-byte lines wherever the span allows
-    const char* sg = getenv("BEZK_SMART_GRANULE");
-    a.smart_granule = (sg == nullptr) ? 1 : (sg[0] - '0');
+    // 0: 64-byte granules only; 1 (default): per-lane 64 / 128-byte choice; 2: full 128-byte lines wherever the span allows.
+    // Read ONCE per process (A/B measurement knob, profiles/r01_fetch_granularity.md), never on the launch path.
+    static const int smart_granule = env_int("BEZK_SMART_GRANULE", 1);
+    a.smart_granule = smart_granule;
     a.cf_vec2 = a.net_contact != nullptr && aligned8(a.net_contact) && ((cfg.num_bodies * 3) % 2 == 0) &&
                 ((cfg.left_foot_body * 3) % 2 == 0) && ((cfg.right_foot_body * 3) % 2 == 0);
 }
@@ -903,11 +916,11 @@ cudaError_t launch_pre_physics(const float* actions, float* actions_out, float* 
 cudaError_t launch_reset_idx(const int64_t* env_ids, int64_t k, const float* uniforms, uint64_t seed, uint64_t step,
                              float* dof_state, float* root_states, const float* initial_root, int64_t* progress,
                              int64_t* reset, const BezkTaskCfg& cfg, int64_t n, int task, float* goal, const float* goal_uniforms,
-                             cudaStream_t st) {
+                             int64_t env_base, cudaStream_t st) {
     if (k == 0) return cudaSuccess;
     reset_idx_kernel<<<(unsigned)((k + 127) / 128), 128, 0, st>>>(env_ids, k, uniforms, seed, step, dof_state, root_states,
                                                                   initial_root, progress, reset, cfg, n, root_row(task),
-                                                                  task == BEZK_TASK_KICK ? nullptr : goal, goal_uniforms);
+                                                                  task == BEZK_TASK_KICK ? nullptr : goal, goal_uniforms, env_base);
     return cudaGetLastError();
 }
 

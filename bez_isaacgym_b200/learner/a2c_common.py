@@ -1,9 +1,12 @@
 """Rollout math with rl_games' names (rl_games/common/a2c_common.py, v1.1.3): ``discount_values`` (GAE reverse
-scan), the ``prepare_dataset`` advantage normalisation and the ``play_steps`` reward shaping."""
+scan) and the ``prepare_dataset`` advantage normalisation.  The ``play_steps`` reward shaping / value bootstrap is not a
+function here: it rides in the epilogue of the fused step kernel (``KickEnv.set_rollout_targets`` ->
+``bezk_post_physics_rollout``)."""
 import torch
 
 from .. import dist as bdist
 from .. import ops
+from .experience import swap_and_flatten01  # noqa: F401  (rl_games keeps the helper in a2c_common; the ONE definition is experience's)
 
 
 def discount_values(fdones, last_extrinsic_values, mb_fdones, mb_extrinsic_values, mb_rewards, gamma, tau,
@@ -20,12 +23,6 @@ def discount_values(fdones, last_extrinsic_values, mb_fdones, mb_extrinsic_value
     ops.gae(mb_rewards.contiguous(), mb_extrinsic_values.contiguous(), mb_fdones.contiguous(),
             last_extrinsic_values.contiguous(), fdones.contiguous(), gamma, tau, advs, rets)
     return (advs, rets) if return_returns else advs
-
-
-def swap_and_flatten01(arr: torch.Tensor) -> torch.Tensor:
-    """(T, N, ...) -> (N*T, ...) env-major, as rl_games' helper of the same name: one tiled transposition kernel
-    (``bezk_swap_and_flatten01``).  The ``SlabDataset`` path of ``learner.experience`` avoids the pass altogether."""
-    return ops.swap_and_flatten01(arr.contiguous())
 
 
 class _AdvWorkspace:
@@ -50,12 +47,3 @@ def normalize_advantages(returns, values, normalize=True, process_group=None, ou
         if process_group is not None:
             bdist.allreduce_sum_(acc, process_group)
     return ops.adv_normalize(r, v, acc, adv, normalize=normalize)
-
-
-def shape_rewards(rewards, values, time_outs, gamma, scale_value=0.01, shift_value=0.0, value_bootstrap=True):
-    """``play_steps``: DefaultRewardsShaper then ``+= gamma * values * time_outs`` (cfg/train/bez_kickPPO.yaml:53-56).
-    Three tiny elementwise torch ops on (N,1) tensors; kept in torch (not a hot kernel)."""
-    shaped = (rewards.unsqueeze(1) + shift_value) * scale_value
-    if value_bootstrap:
-        shaped = shaped + gamma * values * time_outs.unsqueeze(1).float()
-    return shaped

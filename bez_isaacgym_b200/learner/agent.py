@@ -68,8 +68,16 @@ DEFAULT_CONFIG = dict(gamma=0.99, tau=0.95, learning_rate=3e-4, lr_schedule="ada
 
 class A2CAgent:
     def __init__(self, env, config=None, process_group=None, seed=0, global_advantage_stats=True):
+        """``process_group``: ONE convention for every exchange of the learner -- ``None`` means "all ranks" (the WORLD group)
+        whenever ``torch.distributed`` is initialised with more than one rank, and single-process otherwise.  Gradients, the
+        KL average, the start-up parameter broadcast, both ``RunningMeanStd`` moment merges and (with
+        ``global_advantage_stats``) the advantage moments all use the same group, so a rank-0 checkpoint carries the
+        statistics of every shard.  Pass ``env.env_base`` = the rank's shard offset (``cfg['env']['envBase']``) so that the
+        reset / exploration noise is keyed by global env ids."""
         cfg = dict(DEFAULT_CONFIG)
         cfg.update(config or {})
+        if process_group is None and bdist.is_distributed(None):
+            process_group = torch.distributed.group.WORLD
         self.config, self.env, self.group = cfg, env, process_group
         self.device = env.compute_device
         self.num_actors, self.horizon_length = env.num_envs, int(cfg["horizon_length"])
@@ -99,6 +107,9 @@ class A2CAgent:
         self.advantages = torch.empty(T, N, **f32)
         self.values_norm, self.returns_norm = torch.empty(T, N, 1, **f32), torch.empty(T, N, 1, **f32)
         self._bucket = torch.empty(sum(p.numel() for p in self.model.parameters()), **f32)
+        # rl_games 1.1.3 autocasts inside calc_gradients only; get_action_values (the rollout forward) runs in fp32, so the
+        # stored neglogpacs / mus / values are fp32-exact.  Here autocast is bf16 (no GradScaler needed) -- a documented
+        # deviation from rl_games' fp16 + GradScaler -- and likewise confined to calc_gradients.
         self._amp = dict(device_type="cuda", dtype=torch.bfloat16, enabled=bool(cfg["mixed_precision"]))
         self.frame = self.epoch_num = 0
         self._head_step = 0
@@ -115,31 +126,45 @@ class A2CAgent:
     def set_train(self):
         self.model.train(); self.running_mean_std.train(); self.value_mean_std.train()
 
-    def _forward(self, obs_norm):
-        with torch.autocast(**self._amp):
-            mu, value = self.model(obs_norm)
-        return mu.float(), value.float()
+    def _forward(self, obs_norm, autocast=False):
+        if autocast:
+            with torch.autocast(**self._amp):
+                mu, value = self.model(obs_norm)
+            return mu.float(), value.float()
+        return self.model(obs_norm)
+
+    def _norm_obs(self, obs):
+        return self.running_mean_std(obs) if self.config["normalize_input"] else obs
 
     def play_steps(self):
         """a2c_common.py ``play_steps`` + ``discount_values``: returns the batch dict (time-major tensors, nothing flattened)."""
         env, buf, T = self.env, self.experience_buffer, self.horizon_length
+        shaper = self.config["reward_shaper"]
         self.set_eval()
         buf.slot("obses", 0).copy_(self.obs)
+        buf.slot("dones", 0).copy_(self.dones)
         with torch.no_grad():
             for t in range(T):
-                buf.update_data("dones", t, self.dones)
-                mu, value = self._forward(self.running_mean_std(buf.slot("obses", t)))
+                mu, value = self._forward(self._norm_obs(buf.slot("obses", t)))
+                # with action domain randomisation on, the noise precedes the PD targets (vec_task.py:314-317): the head then
+                # leaves K0 to env.step
+                head_targets = not env.dr_randomizations.get("actions", None)
                 res = _policy_head(mu, self.model.sigma, value, self.value_mean_std if self.config["normalize_value"] else None,
-                                     experience=buf, t=t, seed=self._seed, step=self._head_step, env=env)
+                                     experience=buf, t=t, seed=self._seed, step=self._head_step, env=env if head_targets else None,
+                                     env_base=env.env_base)
                 self._head_step += 1
                 env.set_obs_target(buf.slot("obses", t + 1) if t + 1 < T else self.obs)   # next slot written in place
-                _, rew, done, info = env.step_precomputed_targets(res["env_actions"])
-                self.mb_rewards[t] = a2c_common.shape_rewards(rew, res["values"], info["time_outs"], self.gamma,
-                                                              scale_value=self.config["reward_shaper"].get("scale_value", 1.0),
-                                                              shift_value=self.config["reward_shaper"].get("shift_value", 0.0),
-                                                              value_bootstrap=self.config["value_bootstrap"])
-                self.dones = done.to(torch.uint8)
-            _, last_v = self._forward(self.running_mean_std(self.obs))
+                # reward shaping + value bootstrap + the uint8 dones of the NEXT slot ride in the step kernel's epilogue
+                env.set_rollout_targets(values=res["values"], shaped_rewards=self.mb_rewards[t],
+                                        dones_u8=buf.slot("dones", t + 1) if t + 1 < T else self.dones, gamma=self.gamma,
+                                        scale_value=shaper.get("scale_value", 1.0), shift_value=shaper.get("shift_value", 0.0),
+                                        value_bootstrap=self.config["value_bootstrap"])
+                if head_targets:
+                    env.step_precomputed_targets(res["env_actions"])
+                else:
+                    env.step(res["env_actions"])
+            env.set_rollout_targets()
+            _, last_v = self._forward(self._norm_obs(self.obs))
             last_values = self.value_mean_std(last_v, unnorm=True) if self.config["normalize_value"] else last_v
             a2c_common.discount_values(self.dones, last_values, buf.tensor_dict["dones"], buf.tensor_dict["values"], self.mb_rewards,
                                        self.gamma, self.tau, out_advs=self.mb_advs, out_returns=self.mb_returns)
@@ -168,7 +193,7 @@ class A2CAgent:
         """a2c_continuous.py ``calc_gradients`` on one minibatch (slab views)."""
         obs = self.running_mean_std(input_dict["obses"]) if self.config["normalize_input"] else input_dict["obses"]
         obs = obs.reshape(-1, obs.shape[-1]).contiguous()        # (T*E, obs): a single-minibatch epoch hands over (T, N, obs)
-        mu, value = self._forward(obs)
+        mu, value = self._forward(obs, autocast=True)
         loss, info = losses.ppo_loss(mu, value, self.model.sigma, input_dict["actions"], input_dict["mus"], input_dict["sigmas"],
                                      input_dict["old_values"], input_dict["returns"], input_dict["neglogpacs"],
                                      input_dict["advantages"], self.loss_cfg)

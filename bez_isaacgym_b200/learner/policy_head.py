@@ -7,14 +7,17 @@ rl_games/common/a2c_common.py ``get_action_values`` / ``play_steps`` / ``preproc
     experience_buffer.update_data('actions' | 'neglogpacs' | 'values' | 'mus' | 'sigmas', t, ...)      (written in place)
     env actions = rescale_actions(-1, 1, clamp(actions, -1, 1))  ->  KickEnv.pre_physics_step's PD targets
 
-Documented deviation: the N(0,1) draws come from Philox4x32-10 keyed (seed, step, env id) + Box-Muller instead of
-torch's global generator (invariant to sharding); pass ``noise=`` to supply the draws."""
+Documented deviation: the N(0,1) draws come from Philox4x32-10 keyed (seed, step, GLOBAL env id) + Box-Muller instead of
+torch's global generator; the global id is ``env_base + row`` (``env_base`` = the rank's shard offset, taken from
+``env.env_base`` when an env is given), which is what makes the noise invariant to sharding: ranks that share a seed draw
+different noise and their union equals the un-sharded draw.  Pass ``noise=`` to supply the draws."""
 import torch
 
 from .. import ops
 
 
-def policy_head(mu, logstd, value, value_mean_std=None, experience=None, t=None, noise=None, seed=0, step=0, env=None):
+def policy_head(mu, logstd, value, value_mean_std=None, experience=None, t=None, noise=None, seed=0, step=0, env=None,
+                env_base=None):
     """mu (N,18), logstd (18,), value (N,1)/(N,) normalised critic output.  ``experience``/``t``: ExperienceBuffer slot to
     write in place (otherwise fresh tensors).  ``env``: a KickEnv -- its PD ``targets`` are produced by the same launch
     (the caller then skips ``pre_physics_step``'s K0).  Returns rl_games' ``res_dict`` (+ ``env_actions``)."""
@@ -34,7 +37,8 @@ def policy_head(mu, logstd, value, value_mean_std=None, experience=None, t=None,
                     noise=noise, seed=seed, step=step, actions=out["actions"], neglogp=out["neglogpacs"],
                     values=out["values"].view(-1), mus=out["mus"], sigmas=out["sigmas"],
                     task_cfg=env._kcfg if env is not None else None, env_actions=env_actions,
-                    targets=env.targets if env is not None else None)
+                    targets=env.targets if env is not None else None,
+                    env_base=(getattr(env, "env_base", 0) if env_base is None else env_base))
     res = dict(out)
     res["env_actions"] = env_actions
     return res

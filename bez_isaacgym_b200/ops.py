@@ -8,7 +8,7 @@ import torch
 
 from . import _lib
 from . import bez_model as bm
-from ._lib import BezkNoiseCfg, BezkPpoCfg, BezkTaskCfg, BezkError
+from ._lib import BezkNoiseCfg, BezkPpoCfg, BezkRolloutCfg, BezkTaskCfg, BezkError
 
 
 def _stream(t: torch.Tensor):
@@ -176,8 +176,40 @@ def post_physics_task(task, dof_state, rigid_body, root_states, net_contact, goa
         int(parts), n, _stream(dof_state)), "bezk_post_physics_task")
 
 
+def make_rollout_cfg(gamma=0.99, scale_value=0.01, shift_value=0.0, value_bootstrap=True) -> BezkRolloutCfg:
+    """rl_games' per-step reward path (``play_steps``; cfg/train/bez_kickPPO.yaml:53-56) as kernel constants."""
+    c = BezkRolloutCfg()
+    c.scale_value, c.shift_value, c.gamma = float(scale_value), float(shift_value), float(gamma)
+    c.value_bootstrap = int(bool(value_bootstrap))
+    return c
+
+
+def post_physics_rollout(task, dof_state, rigid_body, root_states, net_contact, goal, initial_root_states, reset_buf,
+                         progress_buf, timeout_buf, cfg, obs, rew, rollout_cfg=None, values=None, shaped_rewards=None,
+                         dones_u8=None, goal_angle=None, ball_init=None, prev_lin_vel=None, uniforms=None, goal_uniforms=None,
+                         seed=0, step=0, randomize_buf=None, obs_clipped=None, env_base=0):
+    """The fused step + rl_games' reward shaping / value bootstrap / uint8 dones in its epilogue (``bezk_post_physics_rollout``)."""
+    n = progress_buf.shape[0]
+    nb = cfg.num_bodies
+    actors, _, width = bm.task_dims(task)
+    lib = _lib.load()
+    _lib.check(lib.bezk_post_physics_rollout(
+        _TASK_ID[task], _p(dof_state, F32, "dof_state", n * 36), _p(rigid_body, F32, "rigid_body", n * nb * 13),
+        _p(root_states, F32, "root_states", n * actors * 13), _p(net_contact, F32, "net_contact", n * nb * 3),
+        _p(prev_lin_vel, F32, "prev_lin_vel", n * 3, True), _p(goal, F32, "goal", n * 2),
+        _p(goal_angle, F32, "goal_angle", n, True), _p(ball_init, F32, "ball_init", n * 2, True),
+        _p(initial_root_states, F32, "initial_root_states", n * actors * 13, True),
+        _p(uniforms, F32, "uniforms", n * 36, True), _p(goal_uniforms, F32, "goal_uniforms", 2, True), seed, step,
+        _p(reset_buf, I64, "reset_buf", n), _p(progress_buf, I64, "progress_buf", n),
+        _p(timeout_buf, I64, "timeout_buf", n), _p(randomize_buf, I64, "randomize_buf", n, True), C.byref(cfg),
+        _p(obs, F32, "obs", n * width), _p(obs_clipped, F32, "obs_clipped", n * width, True), _p(rew, F32, "rew", n),
+        C.byref(rollout_cfg) if rollout_cfg is not None else None, _p(values, F32, "values", n, True),
+        _p(shaped_rewards, F32, "shaped_rewards", n, True), _p(dones_u8, U8, "dones_u8", n, True), int(env_base), n,
+        _stream(dof_state)), "bezk_post_physics_rollout")
+
+
 def reset_idx_task(task, env_ids, dof_state, root_states, initial_root_states, goal, progress, reset, cfg, uniforms=None,
-                   goal_uniforms=None, seed=0, step=0):
+                   goal_uniforms=None, seed=0, step=0, env_base=0):
     k = int(env_ids.numel())
     n = progress.shape[0]
     actors = bm.task_dims(task)[0]
@@ -187,7 +219,8 @@ def reset_idx_task(task, env_ids, dof_state, root_states, initial_root_states, g
         _p(goal_uniforms, F32, "goal_uniforms", 2, True), seed, step, _p(dof_state, F32, "dof_state", n * 36),
         _p(root_states, F32, "root_states", n * actors * 13, True),
         _p(initial_root_states, F32, "initial_root_states", n * actors * 13, True), _p(goal, F32, "goal", n * 2, True),
-        _p(progress, I64, "progress", n), _p(reset, I64, "reset", n), C.byref(cfg), n, _stream(progress)), "bezk_reset_idx_task")
+        _p(progress, I64, "progress", n), _p(reset, I64, "reset", n), C.byref(cfg), int(env_base), n, _stream(progress)),
+        "bezk_reset_idx_task")
 
 
 def goal_uniforms(seed, step, out=None, device="cuda"):
@@ -400,8 +433,10 @@ def swap_and_flatten01(src, out=None, env0=0, envs=None):
 
 
 def policy_head(mu, logstd, value_norm=None, value_mean=None, value_var=None, value_eps=1e-5, noise=None, seed=0, step=0,
-                actions=None, neglogp=None, values=None, mus=None, sigmas=None, task_cfg=None, env_actions=None, targets=None):
-    """Sampling / neglogp / value un-normalisation / experience-slot writes / clamp / K0 in one launch (see bezk.h)."""
+                actions=None, neglogp=None, values=None, mus=None, sigmas=None, task_cfg=None, env_actions=None, targets=None,
+                env_base=0):
+    """Sampling / neglogp / value un-normalisation / experience-slot writes / clamp / K0 in one launch (see bezk.h).
+    ``env_base``: global id of row 0 (the rank's shard offset), the Philox key of the exploration noise."""
     n = mu.shape[0]
     lib = _lib.load()
     _lib.check(lib.bezk_policy_head(
@@ -410,14 +445,15 @@ def policy_head(mu, logstd, value_norm=None, value_mean=None, value_var=None, va
         _p(noise, F32, "noise", n * 18, True), int(seed), int(step), _p(actions, F32, "actions", n * 18, True),
         _p(neglogp, F32, "neglogp", n, True), _p(values, F32, "values", n, True), _p(mus, F32, "mus", n * 18, True),
         _p(sigmas, F32, "sigmas", n * 18, True), C.byref(task_cfg) if task_cfg is not None else None,
-        _p(env_actions, F32, "env_actions", n * 18, True), _p(targets, F32, "targets", n * 18, True), n, _stream(mu)),
-        "bezk_policy_head")
+        _p(env_actions, F32, "env_actions", n * 18, True), _p(targets, F32, "targets", n * 18, True), int(env_base), n,
+        _stream(mu)), "bezk_policy_head")
 
 
-def normal_noise(seed, step, out):
+def normal_noise(seed, step, out, env_base=0):
     n = out.shape[0]
     lib = _lib.load()
-    _lib.check(lib.bezk_normal_noise(int(seed), int(step), _p(out, F32, "out", n * 18), n, _stream(out)), "bezk_normal_noise")
+    _lib.check(lib.bezk_normal_noise(int(seed), int(step), _p(out, F32, "out", n * 18), int(env_base), n, _stream(out)),
+               "bezk_normal_noise")
     return out
 
 

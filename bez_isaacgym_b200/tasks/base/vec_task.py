@@ -172,16 +172,20 @@ class VecTask(Env):
         # timeout_buf (vec_task.py:331-332) is produced by the fused post-physics kernel from the
         # pre-increment progress_buf
         self.post_physics_step()
-        if self.dr_randomizations.get("observations", None):
-            self.obs_buf = self.dr_randomizations["observations"]["noise_lambda"](self.obs_buf)
-            clipped = getattr(self, "obs_clipped_buf", None)
-            if clipped is not None:       # the kernel clipped the noise-free rows; the reference clamps AFTER the noise (:343)
-                torch.clamp(self.obs_buf, -self.clip_obs, self.clip_obs, out=clipped)
+        self._apply_obs_randomization()
         self.extras["time_outs"] = self.timeout_buf.to(self.rl_device)
         self.obs_dict["obs"] = self._observations_out().to(self.rl_device)
         if self.num_states > 0:
             self.obs_dict["states"] = self.get_state()
         return self.obs_dict, self.rew_buf.to(self.rl_device), self.reset_buf.to(self.rl_device), self.extras
+
+    def _apply_obs_randomization(self):
+        """vec_task.py:338-339: the observation noise lambda after post_physics_step, then the clamp of :343."""
+        if self.dr_randomizations.get("observations", None):
+            self.obs_buf = self.dr_randomizations["observations"]["noise_lambda"](self.obs_buf)
+            clipped = getattr(self, "obs_clipped_buf", None)
+            if clipped is not None:       # the kernel clipped the noise-free rows; the reference clamps AFTER the noise (:343)
+                torch.clamp(self.obs_buf, -self.clip_obs, self.clip_obs, out=clipped)
 
     # ------------------------------------------------------------------ domain randomisation: the tensor-path part
     def apply_randomizations(self, dr_params):

@@ -76,6 +76,11 @@ class KickEnv(VecTask):
         self._sim_arg = sim
         self._seed = int(cfg.get("seed", 42))
         self._alias_prev = bool(env_cfg.get("imuPrevVelAliasing", True))
+        #: global id of this instance's env 0 -- the shard offset when num_envs is partitioned over ranks (dist.shard_range).
+        #: Keys the Philox reset noise (and, through A2CAgent, the exploration noise) so that results do not depend on sharding.
+        self.env_base = int(env_cfg.get("envBase", 0))
+        if self.env_base and fusion != "fused":
+            raise ValueError("env.envBase needs fusion='fused'")
 
         super().__init__(config=cfg, sim_device=sim_device, graphics_device_id=graphics_device_id, headless=headless)
 
@@ -170,6 +175,7 @@ class KickEnv(VecTask):
             if self.obs_clipped_buf is not None:
                 self.obs_clipped_buf = torch.zeros(n, 54, dtype=torch.float32).pin_memory()
         self._rng_step = 0
+        self._rollout = None                # (BezkRolloutCfg, values, shaped_rewards, dones_u8) set by set_rollout_targets
         self._lib = _lib.load()
         if self.host_staged:
             pin = dict(pin_memory=True)
@@ -215,6 +221,17 @@ class KickEnv(VecTask):
     def _launch_post(self, parts):
         f = self._post_fixed
         prev = None if self._prev_is_view else _ptr(self._prev_buf)
+        if parts == _lib.PART_ALL:
+            # the whole step, with rl_games' per-step reward path in the epilogue when set_rollout_targets() armed it
+            ro = self._rollout
+            tail = ([C.byref(ro[0]), _ptr(ro[1]), _ptr(ro[2]), _ptr(ro[3])] if ro is not None else [None, None, None, None])
+            t = f["tail"]
+            rc = self._lib.bezk_post_physics_rollout(ops._TASK_ID[self.TASK], *f["head"], prev, *f["mid_task"], self._seed,
+                                                     self._rng_step, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], *tail,
+                                                     self.env_base, self.num_envs, self._stream())
+            if rc:
+                _lib.check(rc, "bezk_post_physics_rollout")
+            return
         if self.TASK == "kick":
             rc = self._lib.bezk_post_physics(*f["head"], prev, *f["mid"], self._seed, self._rng_step, *f["tail"], parts,
                                              self.num_envs, self._stream())
@@ -338,12 +355,9 @@ class KickEnv(VecTask):
         if self.randomize:                                # kick_env.py:781-782
             self.apply_randomizations(self.randomization_params)
         self._stage_in()
-        if self.TASK == "kick":
-            ops.reset_idx(env_ids, self._d_dof, self._d_root, self.initial_root_states, self.progress_buf, self.reset_buf,
-                          self._kcfg, uniforms=None, seed=self._seed, step=self._rng_step)
-        else:
-            ops.reset_idx_task(self.TASK, env_ids, self._d_dof, self._d_root, self.initial_root_states, self.goal,
-                               self.progress_buf, self.reset_buf, self._kcfg, seed=self._seed, step=self._rng_step)
+        ops.reset_idx_task(self.TASK, env_ids, self._d_dof, self._d_root, self.initial_root_states,
+                           None if self.TASK == "kick" else self.goal, self.progress_buf, self.reset_buf, self._kcfg,
+                           seed=self._seed, step=self._rng_step, env_base=self.env_base)
         if self.host_mode == "staged":
             self.dof_state.copy_(self._d_dof)
             if self._kcfg.flags & _lib.F_RESET_ROOT_STATES:
@@ -378,12 +392,41 @@ class KickEnv(VecTask):
             self.obs_buf = tensor
             self._post_fixed["tail"][5] = _ptr(tensor)
 
+    def set_rollout_targets(self, values=None, shaped_rewards=None, dones_u8=None, gamma=0.99, scale_value=0.01, shift_value=0.0,
+                            value_bootstrap=True):
+        """Arm the reward epilogue of the fused step (rl_games ``play_steps``): the NEXT steps also write
+        ``shaped_rewards = (rew + shift) * scale + gamma * values * time_outs`` (e.g. ``mb_rewards[t]``) and the uint8 reset
+        mask ``dones_u8`` (e.g. the experience buffer's ``dones`` slot ``t + 1``).  ``values``: the (N,)/(N,1) un-normalised
+        critic values of the step (what ``policy_head`` wrote).  Call with no arguments to disarm."""
+        if self.host_staged or self.fusion != "fused":
+            raise NotImplementedError("the reward epilogue rides in the fused GPU-pipeline step")
+        if shaped_rewards is None and dones_u8 is None:
+            self._rollout = None
+            return
+        n, dev = self.num_envs, self.compute_device
+
+        def chk(t, dtype, name):
+            if t is None:
+                return None
+            if t.dtype != dtype or t.numel() != n or not t.is_contiguous() or t.device != dev:
+                raise ValueError(f"{name} must be a contiguous {dtype} tensor with {n} elements on {dev}")
+            return t
+
+        if shaped_rewards is not None and value_bootstrap and values is None:
+            raise ValueError("value_bootstrap needs the step's critic values")
+        self._rollout = (ops.make_rollout_cfg(gamma, scale_value, shift_value, value_bootstrap), chk(values, torch.float32, "values"),
+                         chk(shaped_rewards, torch.float32, "shaped_rewards"), chk(dones_u8, torch.uint8, "dones_u8"))
+
     def step_precomputed_targets(self, env_actions=None):
         """``step`` for callers whose PD ``targets`` were already written by ``learner.policy_head(..., env=self)`` (the
         policy-head kernel runs K0 in its epilogue): simulate + post-physics only.  ``env_actions``: what ``self.actions``
         should report (the clamped actions the head produced)."""
         if self.host_staged:
             raise NotImplementedError("step_precomputed_targets needs the GPU pipeline")
+        if self.dr_randomizations.get("actions", None):
+            # vec_task.py:314-315 perturbs the actions BEFORE pre_physics_step; the targets handed over here were computed from
+            # the noise-free actions, so this path would silently drop the action noise
+            raise RuntimeError("action domain randomisation is active: use env.step(actions) (the noise precedes the PD targets)")
         if env_actions is not None:
             self._actions_cache = None
             self._actions_src = env_actions
@@ -391,6 +434,7 @@ class KickEnv(VecTask):
         for _ in range(self.control_freq_inv):
             self.sim.simulate()
         self.post_physics_step()
+        self._apply_obs_randomization()                   # vec_task.py:338-339, 343
         self.extras["time_outs"] = self.timeout_buf.to(self.rl_device)
         self.obs_dict["obs"] = self._observations_out().to(self.rl_device)
         return self.obs_dict, self.rew_buf.to(self.rl_device), self.reset_buf.to(self.rl_device), self.extras

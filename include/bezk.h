@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BEZK_VERSION 110          /* 0.1.1 */
+#define BEZK_VERSION 120          /* 0.1.2 */
 #define BEZK_NUM_DOF 18
 #define BEZK_NUM_OBS 54
 
@@ -228,11 +228,38 @@ int bezk_post_physics_task(int task, float* dof_state, const float* rigid_body, 
                            int64_t* reset_buf, int64_t* progress_buf, int64_t* timeout_buf,
                            int64_t* randomize_buf, const BezkTaskCfg* cfg, float* obs, float* obs_clipped,
                            float* rew, int parts, int64_t n, void* stream);
-/* bezk_reset_idx for any task: root rows are 13 floats for walk / orient, and their goal (n,2) rows are redrawn. */
+/* The fused step with rl_games' per-step reward path in its epilogue.
+ * ref: rl_games/common/a2c_common.py play_steps -- `shaped_rewards = self.rewards_shaper(rewards)`;
+ * `shaped_rewards += self.gamma * res_dict['values'] * self.cast_obs(infos['time_outs']).unsqueeze(1).float()` (value_bootstrap);
+ * `self.dones = dones.byte()` -- with rl_games/common/tr_helpers.py DefaultRewardsShaper ((r + shift_value) * scale_value),
+ * configured by cfg/train/bez_kickPPO.yaml:53-56 (value_bootstrap: True, reward_shaper.scale_value: 0.01).
+ *   values         (n,) f32 in : un-normalised critic values of this step (what bezk_policy_head wrote); needed when
+ *                                value_bootstrap != 0
+ *   shaped_rewards (n,) f32 out: (rew + shift) * scale + (gamma * value) * (float)timeout   -> experience slot mb_rewards[t]
+ *   dones_u8       (n,) u8  out: reset_buf != 0                                             -> experience slot dones[t+1]
+ * Each of shaped_rewards / dones_u8 may be NULL.  rew / reset_buf / timeout_buf are written as by bezk_post_physics_task.
+ * Always the whole step (parts = 7).  env_base: global id of env 0 of this launch (Philox key of the reset noise; 0 for an
+ * un-sharded task) -- env-sharded ranks pass their shard offset so that the noise does not depend on the sharding. */
+typedef struct BezkRolloutCfg {
+    float scale_value;        /* 0.01 */
+    float shift_value;        /* 0    */
+    float gamma;              /* (float)0.99 -- torch multiplies the fp32 tensor by the Python double cast to fp32 */
+    int32_t value_bootstrap;  /* 1 */
+} BezkRolloutCfg;
+int bezk_post_physics_rollout(int task, float* dof_state, const float* rigid_body, float* root_states,
+                              float* net_contact, float* prev_lin_vel, float* goal, const float* goal_angle,
+                              const float* ball_init, const float* initial_root_states,
+                              const float* uniforms, const float* goal_uniforms, uint64_t seed, uint64_t step,
+                              int64_t* reset_buf, int64_t* progress_buf, int64_t* timeout_buf,
+                              int64_t* randomize_buf, const BezkTaskCfg* cfg, float* obs, float* obs_clipped,
+                              float* rew, const BezkRolloutCfg* rollout, const float* values,
+                              float* shaped_rewards, uint8_t* dones_u8, int64_t env_base, int64_t n, void* stream);
+/* bezk_reset_idx for any task: root rows are 13 floats for walk / orient, and their goal (n,2) rows are redrawn.
+ * env_base: global id of local env 0 (Philox key = env_base + env id), as in bezk_post_physics_rollout. */
 int bezk_reset_idx_task(int task, const int64_t* env_ids, int64_t k, const float* uniforms, const float* goal_uniforms,
                         uint64_t seed, uint64_t step, float* dof_state, float* root_states,
                         const float* initial_root_states, float* goal, int64_t* progress, int64_t* reset,
-                        const BezkTaskCfg* cfg, int64_t n, void* stream);
+                        const BezkTaskCfg* cfg, int64_t env_base, int64_t n, void* stream);
 /* The (2,) uniforms the Philox path uses for the goal draw of (seed, step). */
 int bezk_goal_uniforms(uint64_t seed, uint64_t step, float* out2, void* stream);
 
@@ -274,16 +301,19 @@ int bezk_swap_and_flatten01(const void* src, void* dst, int32_t horizon, int64_t
  * play_steps (experience_buffer.update_data of actions / neglogpacs / values / mus / sigmas), preprocess_actions
  * (clamp(-1,1) + rescale_actions; cf. the in-tree fork utils/players.py:11-15,63-64) and KickEnv.pre_physics_step.
  *   mu (n,18), logstd (18,), value_norm (n,) [NULL: no values]; value_mean/value_var: () f64 running stats [NULL: copy]
- *   noise (n,18) N(0,1) draws, or NULL -> Philox4x32-10 keyed (seed, step, env id) + Box-Muller
+ *   noise (n,18) N(0,1) draws, or NULL -> Philox4x32-10 keyed (seed, step, env_base + row) + Box-Muller; env_base = global id of
+ *   row 0 (the rank's shard offset under env-sharded multi-GPU training, 0 otherwise), so that ranks sharing one seed
+ *   draw DIFFERENT noise and the union over ranks equals the un-sharded draw
  *   outputs (each may be NULL): actions (n,18), neglogp (n,), values (n,), mus (n,18), sigmas (n,18),
  *   env_actions (n,18) = clamp(actions,-1,1); targets (n,18) = K0(env_actions) when task_cfg != NULL. */
 int bezk_policy_head(const float* mu, const float* logstd, const float* value_norm, const double* value_mean,
                      const double* value_var, float value_eps, const float* noise, uint64_t seed, uint64_t step,
                      float* actions, float* neglogp, float* values, float* mus, float* sigmas,
-                     const BezkTaskCfg* task_cfg, float* env_actions, float* targets, int64_t n, void* stream);
-/* The (n,18) normals the Philox path of bezk_policy_head uses for (seed, step): lets a checker feed identical noise
- * to the reference's Normal.sample() replacement. */
-int bezk_normal_noise(uint64_t seed, uint64_t step, float* out, int64_t n, void* stream);
+                     const BezkTaskCfg* task_cfg, float* env_actions, float* targets, int64_t env_base, int64_t n,
+                     void* stream);
+/* The (n,18) normals the Philox path of bezk_policy_head uses for (seed, step) and rows env_base .. env_base + n - 1: lets a
+ * checker feed identical noise to the reference's Normal.sample() replacement. */
+int bezk_normal_noise(uint64_t seed, uint64_t step, float* out, int64_t env_base, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------- domain-randomisation noise ----- */
 

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/bezk.h but not exported by libbezk.so"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in bez_isaacgym_b200/_lib.py"
     assert sorted(_lib.SIGNATURES) == declared, "ctypes table and header disagree"
-    assert lib.bezk_version() == 110
+    assert lib.bezk_version() == 120
 
 
 def test_struct_layout_matches_header():
@@ -307,7 +307,8 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     if shutil.which("gcc") is None:
         pytest.skip("no gcc")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    structs = {"BezkTaskCfg": _lib.BezkTaskCfg, "BezkPpoCfg": _lib.BezkPpoCfg, "BezkNoiseCfg": _lib.BezkNoiseCfg}
+    structs = {"BezkTaskCfg": _lib.BezkTaskCfg, "BezkPpoCfg": _lib.BezkPpoCfg, "BezkNoiseCfg": _lib.BezkNoiseCfg,
+               "BezkRolloutCfg": _lib.BezkRolloutCfg}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "bezk.h"', 'int main(void) {']
     for sname, st in structs.items():
         lines.append(f'  printf("{sname} %zu\\n", sizeof({sname}));')

@@ -306,12 +306,17 @@ def test_play_steps_and_mini_epoch_through_the_api():
         assert torch.equal(env.targets, want_targets)
         if t + 1 < T:
             env.set_obs_target(buf.slot("obses", t + 1))        # the step kernel writes the next slot directly
+        # reward shaping + value bootstrap + uint8 dones ride in the step kernel's epilogue
+        env.set_rollout_targets(values=res["values"], shaped_rewards=rewards[t], dones_u8=dones, gamma=0.99, scale_value=0.01)
         o, rew, done, info = env.step_precomputed_targets(res["env_actions"])
         if t + 1 < T:
             assert o["obs"].data_ptr() == buf.slot("obses", t + 1).data_ptr()
         obs = o["obs"]
-        rewards[t] = L.shape_rewards(rew, res["values"], info["time_outs"], 0.99)
-        dones = done.to(torch.uint8)
+        from oracle import rl_games_oracle as rgo
+        want_shaped = rgo.shape_rewards(rew.cpu(), res["values"].cpu(), info["time_outs"].cpu(), 0.99)
+        assert torch.equal(rewards[t].cpu(), want_shaped), "play_steps reward shaping / value bootstrap (bit-exact)"
+        assert torch.equal(dones.cpu(), done.cpu().to(torch.uint8))
+        dones = dones.clone()
     last_values = torch.randn(N, 1, device=dev)
     advs, rets = L.discount_values(dones, last_values, buf.tensor_dict["dones"], buf.tensor_dict["values"], rewards, 0.99, 0.95,
                                    return_returns=True)

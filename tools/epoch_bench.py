@@ -140,9 +140,8 @@ def main():
                 env.set_obs_target(buf.slot("obses", t + 1))          # the step kernel writes the next slot in place
             else:
                 env.set_obs_target(obs)
+            env.set_rollout_targets(values=res["values"], shaped_rewards=rewards[t], dones_u8=dones, gamma=0.99, scale_value=0.01)
             o, rew, done, info = env.step_precomputed_targets(res["env_actions"])
-            rewards[t] = L.shape_rewards(rew, res["values"], info["time_outs"], 0.99)
-            dones = done.to(torch.uint8)
         with torch.no_grad(), torch.autocast(**amp):
             _, last_v = model(obs_rms(obs))
         last_values = val_rms(last_v.float(), unnorm=True)
