@@ -28,7 +28,7 @@ def _run(task, n, seed, rollout_kw=None, values=None, env_base=0, want_shaped=Tr
     goal_angle = torch.full((n,), 1.5708, device="cuda") if task == "orient" else None
     init_root = sg.make_initial_root_states(n, "cuda", task=task)
     progress, reset = sg.make_bookkeeping(n, seed=seed + 1, device="cuda", p_reset=0.1)
-    progress[: min(n, 4)] = torch.tensor([897, 898, 899, 900], device="cuda")[: min(n, 4)]
+    progress[: min(n, 4)] = torch.tensor([899, 900, 897, 898], device="cuda")[: min(n, 4)]
     timeout = torch.empty(n, dtype=torch.long, device="cuda")
     obs = torch.empty(n, width, device="cuda"); rew = torch.empty(n, device="cuda")
     prev = torch.zeros(n, 3, device="cuda")
@@ -66,7 +66,7 @@ def test_reward_shaping_epilogue_is_bit_exact(task, n, kw):
     cfg = ops.make_task_cfg(num_bodies=nb)
     goal = torch.tensor([[1.5, 0.0]] if task == "kick" else [[2.0, 0.0]], device="cuda").repeat(n, 1)
     progress, reset2 = sg.make_bookkeeping(n, seed=41 + n, device="cuda", p_reset=0.1)
-    progress[: min(n, 4)] = torch.tensor([897, 898, 899, 900], device="cuda")[: min(n, 4)]
+    progress[: min(n, 4)] = torch.tensor([899, 900, 897, 898], device="cuda")[: min(n, 4)]
     timeout2 = torch.empty(n, dtype=torch.long, device="cuda")
     obs2 = torch.empty(n, width, device="cuda"); rew2 = torch.empty(n, device="cuda")
     ops.post_physics_task(task, st.dof_state, st.rigid_body, st.root_states, st.net_contact, goal,
@@ -112,7 +112,7 @@ def test_reset_noise_is_keyed_by_global_env_id():
         cfg = ops.make_task_cfg()
         goal, ball_init, _, _, _ = U.constants(m, "cuda")
         progress, reset = sg.make_bookkeeping(n, seed=10, device="cuda", p_reset=0.1)
-        progress[:4] = torch.tensor([897, 898, 899, 900], device="cuda")
+        progress[:4] = torch.tensor([899, 900, 897, 898], device="cuda")
         progress, reset = progress[lo:hi].contiguous(), reset[lo:hi].contiguous()
         timeout = torch.empty(m, dtype=torch.long, device="cuda")
         obs = torch.empty(m, 54, device="cuda"); rew = torch.empty(m, device="cuda")
