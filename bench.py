@@ -1,14 +1,22 @@
 #!/usr/bin/env python
-"""BezKick hot-path benchmark: task step (K0 + fused post-physics kernel) x horizon + one GAE scan.
+"""BezKick hot-path benchmark: one rollout segment = horizon x (K0 + fused post-physics step with rl_games' reward shaping in
+its epilogue) + one GAE scan, at 262 144 envs per GPU (BASELINE configs[3] shard size).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
-    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference torch path on the host CPU
+    python bench.py --gpus N --steps K --warmup W                    # this repo's CUDA path (one process per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference torch path on the host CPU, same config
 
-A "step" is one rollout segment of the hot path on one batch of synthetic Isaac-Gym-layout state:
-``horizon`` (32) env steps through ``KickEnv.step`` (2 kernel launches each) followed by one GAE scan over the
-(32, envs) rollout.  ``value`` = env-steps/s over all ranks with everything resident in HBM; ``e2e`` = the same
-metric through ``KickEnv.step`` in host-pipeline mode (simulator tensors and actions in pinned HOST memory,
-H2D/D2H copies inside the timed region).  Prints ONE JSON line (rank 0).
+Legs of the B200 arm (ONE JSON line, rank 0):
+  value / roofline   the rollout with everything resident in HBM, replayed as one CUDA graph; the fused kernel's duration is read
+                     from timing events recorded INSIDE the timed graph (external event nodes around 4 of its 32 launches) and,
+                     next to it, from per-launch events of an eager timed pass (roofline.eager)
+  e2e                the same rollout through ``KickEnv.step`` with HOST buffers (simulator tensors, actions, targets, results in
+                     pinned host memory; copies inside the timed region), same envs per GPU
+  learner            BASELINE configs[2]/[3]: the PPO epoch math on a 4096 x 32 rollout per GPU -- GAE, advantage moments, value
+                     RunningMeanStd x2, then mini_epochs x minibatches x (obs RunningMeanStd moments -> all-reduce -> merge ->
+                     normalise, fused PPO loss fwd+bwd, flat 124 237-float gradient bucket all-reduce), no MLP; with its own
+                     roofline and the collectives' cost (with-collectives minus without)
+  cpu_baseline       the reference torch ops (oracle port) on the host cores, bounded sample of the same workload (N=1 only)
+  gpu_torch_baseline the same port with CUDA tensors on the same B200 (the torch-eager op sequence is the bar)
 """
 import argparse
 import json
@@ -24,31 +32,40 @@ import torch  # noqa: E402
 
 METRIC = "task+GAE env-steps/s"
 UNIT = "env-steps/s"
-TASK_BYTES_PER_ENV_STEP = 680          # K0 144 + post-physics 536 (prev_lin_vel buffer mode)
-K0_BYTES = 144
-POST_BYTES = 536
+K0_BYTES = 144                         # actions 72 R + targets 72 W
+POST_BYTES = 536 + 9                   # fused post-physics (prev_lin_vel buffer mode) + epilogue: value 4 R, shaped reward 4 W, done 1 W
 GAE_BYTES_PER_SAMPLE = 17
+POLICY_PARAMS = 124237                 # 54-400-200-100 ELU MLP + mu(18) + value(1) + sigma(18), cfg/train/bez_kickPPO.yaml:10-32
 
 
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=50)
+    p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--envs-per-gpu", type=int, default=262144)
     p.add_argument("--horizon", type=int, default=32)
-    p.add_argument("--e2e-envs", type=int, default=65536, help="envs per GPU for the host-pipeline (e2e) leg")
-    p.add_argument("--e2e-mode", default="zero_copy", choices=["zero_copy", "staged"])
-    p.add_argument("--e2e-steps", type=int, default=5)
-    p.add_argument("--cpu-sample-envs", type=int, default=65536)
-    p.add_argument("--cpu-rollouts", type=int, default=24, help="rollouts of the bounded CPU-baseline sample (~10-30 s)")
+    p.add_argument("--e2e-mode", default="auto", choices=["auto", "zero_copy", "staged", "staged_ce"])
+    p.add_argument("--e2e-steps", type=int, default=0, help="rollouts of the e2e leg (0: min(--steps, 10))")
+    p.add_argument("--cpu-rollouts", type=int, default=8, help="rollouts of the bounded CPU-baseline sample (~10-30 s)")
+    p.add_argument("--learner-envs", type=int, default=4096, help="envs per GPU of the learner leg (configs[2]: 4096 x 32)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-gpu-torch-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-learner", action="store_true")
     p.add_argument("--fusion", default="fused", choices=["fused", "split"])
     p.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay of the step")
-    p.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity hint (0 = leave default)")
     return p.parse_args()
+
+
+def workload_config(args):
+    """The `config` object: IDENTICAL in both arms (the driver compares them)."""
+    n, T = args.envs_per_gpu, args.horizon
+    return {"workload": f"bez_kick {n} envs/GPU (BASELINE configs[3] shard size): {T} x (pre-physics K0 + post-physics step with "
+                        f"reward shaping / value bootstrap) + 1 GAE scan per rollout",
+            "envs_per_gpu": n, "horizon": T, "gamma": 0.99, "tau": 0.95, "reward_scale": 0.01, "value_bootstrap": True,
+            "imu_prev_lin_vel": "buffer", "cleats": False}
 
 
 class ClockSampler(threading.Thread):
@@ -100,38 +117,50 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
-def cpu_reference_rate(n, horizon, rollouts, threads=None):
-    """The reference torch path on the host CPU (oracle port of the reference's own functions, op for op):
-    `rollouts` x (horizon task steps + one GAE scan) at n envs.  Returns (env-steps/s, seconds, threads)."""
+def torch_port_rollouts(n, horizon, rollouts, device="cpu", threads=None, warmup=1):
+    """The reference torch path (oracle port of the reference's own functions, op for op; rl_games' play_steps reward path
+    and discount_values as restated) on `device`: `rollouts` x (horizon task steps with reward shaping + one GAE scan) at n
+    envs.  Returns (env-steps/s, seconds, threads).  device="cpu": the reference arm / cpu_baseline; a CUDA device: the same
+    torch-eager op sequence on the GPU (gpu_torch_baseline)."""
     from bez_isaacgym_b200 import synthetic_gym as sg
     from oracle import rl_games_oracle as rg
     from oracle import task_oracle as to
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
-    st = sg.make_state(n, seed=1234, filler=False)
-    goal, ball_init, default, lower, upper = sg.make_constants(n)
-    init_root = torch.zeros(n * 2, 13)
+    on_cpu = torch.device(device).type == "cpu"
+    if on_cpu:
+        threads = threads or os.cpu_count()
+        torch.set_num_threads(threads)
+    st = sg.make_state(n, seed=1234, filler=False, device=device)
+    goal, ball_init, default, lower, upper = sg.make_constants(n, device)
     orc = to.KickStepOracle(n, st.root_states, st.dof_state, st.rigid_body, st.net_contact, default, lower, upper,
-                            goal, ball_init, torch.tensor([0.0, 0.0]), init_root.clone(), alias_prev_lin_vel=False)
-    orc.initial_root_states = st.root_states.clone()      # a real simulator owns the root reset: rows are unchanged
-    orc.prev_lin_vel = torch.zeros(n, 3)
-    progress, reset = sg.make_bookkeeping(n, seed=99)
+                            goal, ball_init, torch.tensor([0.0, 0.0], device=device), st.root_states.clone(), alias_prev_lin_vel=False)
+    orc.prev_lin_vel = torch.zeros(n, 3, device=device)      # a real simulator owns the root reset: rows are unchanged
+    progress, reset = sg.make_bookkeeping(n, seed=99, device=device)
     orc.progress_buf[:] = progress
     orc.reset_buf[:] = reset
-    actions = sg.make_actions(n)
-    rewards, values, dones, last_values, last_dones = sg.make_rollout(n, horizon, seed=7)
+    actions = sg.make_actions(n, device=device)
+    rewards, values, dones, last_values, _ = sg.make_rollout(n, horizon, seed=7, device=device)
+    fdones = dones.float()
 
     def rollout():
-        for _ in range(horizon):
+        cur = fdones[0]
+        for t in range(horizon):
+            fdones[t] = cur
             orc.pre_physics_step(actions)
-            orc.post_physics_step()
-        adv = rg.discount_values(last_dones.float(), last_values, dones.float(), values, rewards, 0.99, 0.95)
+            _, rew, reset_buf, time_outs = orc.post_physics_step()
+            rewards[t] = rg.shape_rewards(rew, values[t], time_outs, 0.99)
+            cur = reset_buf.float()
+        adv = rg.discount_values(cur, last_values, fdones, values, rewards, 0.99, 0.95)
         return adv + values
 
-    orc.pre_physics_step(actions); orc.post_physics_step()         # warm-up (jit / allocator)
+    for _ in range(warmup):
+        rollout()
+    if not on_cpu:
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(rollouts):
         rollout()
+    if not on_cpu:
+        torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     return n * horizon * rollouts / dt, dt, threads
 
@@ -140,22 +169,369 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.cpu_sample_envs
-    rate, secs, threads = cpu_reference_rate(n, args.horizon, 1)              # warm-up rollout
-    t0 = time.perf_counter()
-    rate, secs, threads = cpu_reference_rate(n, args.horizon, max(1, args.steps))
-    sample = f"{max(1, args.steps)} rollouts of {args.horizon} task steps + GAE at {n} envs on the host CPU"
+    n, T, K = args.envs_per_gpu, args.horizon, max(1, args.steps)
+    rate, secs, threads = torch_port_rollouts(n, T, K, warmup=max(1, args.warmup))
+    sample = (f"{K} rollouts of {T} task steps (reward shaping included) + GAE at {n} envs on the host CPU, after {max(1, args.warmup)} "
+              f"warm-up rollouts; the oracle port of the reference's torch functions (/root/reference is absent on the GPU box), "
+              f"torch.set_num_threads({threads})")
     out = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"bez_kick task step x{args.horizon} + GAE, reference torch ops on CPU (oracle port)",
-                      "envs": n, "horizon": args.horizon},
+           "warmup": args.warmup, "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-           "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+           "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
     print(json.dumps(out))
 
 
-# ----------------------------------------------------------------------------------------------- B200 arm
+# ----------------------------------------------------------------------------------------------- B200 arm: helpers
+def _barrier(world, dev):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+
+
+def _max_over_ranks(x, world, dev):
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return x
+
+
+def rollout_leg(args, world, rank, dev):
+    """value + roofline: the HBM-resident rollout."""
+    from bez_isaacgym_b200 import bez_model as bm, ops, synthetic_gym as sg
+    from bez_isaacgym_b200.synthetic_sim import SyntheticGym
+    from bez_isaacgym_b200.tasks.kick_env import KickEnv
+
+    n, T = args.envs_per_gpu, args.horizon
+    cfg = bm.default_task_cfg(n, rl_device=str(dev))
+    cfg["env"]["imuPrevVelAliasing"] = False                # the general (680 B/env-step) path with a prev_lin_vel buffer
+    cfg["env"]["envBase"] = rank * n                        # global env ids: the Philox reset noise does not depend on sharding
+    cfg["seed"] = 42
+
+    class OwnedRootSim(SyntheticGym):
+        owns_root_reset = True                              # as with Isaac Gym: the simulator restores root states
+
+    sim = OwnedRootSim(n, device=str(dev), seed=1234 + rank, filler=True)
+    env = KickEnv(cfg, str(dev), 0, True, sim=sim, fusion=args.fusion)
+    progress, reset = sg.make_bookkeeping(n, seed=99 + rank, device=dev)
+    env.progress_buf.copy_(progress); env.reset_buf.copy_(reset)
+    actions = sg.make_actions(n, seed=4321 + rank, device=dev)
+    rewards, values, _, last_values, _ = sg.make_rollout(n, T, seed=7 + rank, device=dev)
+    dones = torch.zeros(T + 1, n, dtype=torch.uint8, device=dev)     # slot t = dones at the START of step t; slot T = after the last
+    advs, rets = torch.empty_like(rewards), torch.empty_like(rewards)
+    stream = torch.cuda.current_stream(dev)
+    fused = args.fusion == "fused"
+    launches_per_step = T * (2 if fused else 3) + 1
+    ev_pairs = []                                           # (start, end) around single post-physics launches
+
+    def bench_step(mark=(), external=False):
+        dones[0].copy_(dones[T])                            # the dones carried over from the previous rollout (torch copy, N bytes)
+        for t in range(T):
+            env.pre_physics_step(actions)
+            env.sim.simulate()
+            if fused:                                       # a16: shaped reward -> rewards[t], uint8 done -> dones[t+1], in the epilogue
+                env.set_rollout_targets(values=values[t], shaped_rewards=rewards[t], dones_u8=dones[t + 1], gamma=0.99,
+                                        scale_value=0.01)
+            if t in mark:
+                e0 = torch.cuda.Event(enable_timing=True, external=external)
+                e1 = torch.cuda.Event(enable_timing=True, external=external)
+                e0.record(stream)
+                env.post_physics_step()
+                e1.record(stream)
+                ev_pairs.append((e0, e1))
+            else:
+                env.post_physics_step()
+        ops.gae(rewards, values, dones[:T], last_values, dones[T], 0.99, 0.95, advs, rets)
+
+    W = max(3, args.warmup)
+    for _ in range(W):
+        bench_step()
+    _barrier(world, dev)
+    graph, in_graph_events = None, False
+    marks = tuple(range(3, T, 8))                           # 4 of the 32 launches carry timing events inside the graph
+    if not args.no_graph:
+        # the step is 65 dependent launches of 7..45 us kernels: replaying it as ONE CUDA graph removes the CPU-side
+        # launch cost and most of the inter-kernel gaps (the kernels, arguments and work are identical)
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                bench_step(mark=marks, external=True)
+            in_graph_events = True
+        except Exception:                                   # noqa: BLE001  (external event nodes unsupported: plain capture)
+            del ev_pairs[:]
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                bench_step()
+        stream = torch.cuda.current_stream(dev)
+        graph.replay()
+    _barrier(world, dev)
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _barrier(world, dev)
+    start.record(stream)
+    for _ in range(args.steps):
+        if graph is not None:
+            graph.replay()
+        else:
+            bench_step(mark=range(T))
+    end.record(stream)
+    _barrier(world, dev)
+    ms = start.elapsed_time(end)
+    sampler.stop_flag = True
+    sampler.join()
+    post_graph_ms = post_eager_ms = eager_step_ms = None
+    if graph is not None and in_graph_events:
+        try:
+            post_graph_ms = sum(a.elapsed_time(b) for a, b in ev_pairs) / len(ev_pairs)     # the LAST replay of the timed region
+        except Exception:                                   # noqa: BLE001
+            post_graph_ms = None
+    del ev_pairs[:]
+    if graph is not None:
+        # eager timed pass: the same steps launched one by one, per-launch events around every post-physics launch
+        ke = min(args.steps, 10)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _barrier(world, dev)
+        e0.record(stream)
+        for _ in range(ke):
+            bench_step(mark=range(T))
+        e1.record(stream)
+        _barrier(world, dev)
+        eager_step_ms = e0.elapsed_time(e1) / ke
+    post_eager_ms = sum(a.elapsed_time(b) for a, b in ev_pairs) / len(ev_pairs)
+    if post_graph_ms is None and graph is not None:
+        # fallback: a graph holding only the T post-physics launches, replayed between two events after the timed region
+        pg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(pg):
+            for _ in range(T):
+                env.post_physics_step()
+        pg.replay()
+        _barrier(world, dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(10):
+            pg.replay()
+        e1.record(stream)
+        _barrier(world, dev)
+        post_graph_ms = e0.elapsed_time(e1) / (10 * T)
+    reset_rate = float(env.reset_buf.float().mean())
+    ms = _max_over_ranks(ms, world, dev)
+    value = n * world * T * args.steps / (ms * 1e-3)
+
+    peak, peak_src = peaks()
+    post_ms = post_graph_ms if graph is not None else post_eager_ms
+    achieved = POST_BYTES * n / (post_ms * 1e-3) / 1e9
+    eager_gbs = POST_BYTES * n / (post_eager_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "bezk::task_tile_kernel<7> (fused post-physics + reward-shaping epilogue)" if fused
+                else "bezk::task_tile_kernel<3>+<4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_env": POST_BYTES, "envs_per_launch": n,
+                "avg_launch_ms": post_ms, "peak_source": peak_src,
+                "timing": ("CUDA timing events recorded as external event nodes INSIDE the replayed graph of the timed region, around "
+                           f"the post-physics launches of env steps {list(marks)} (read after the last timed replay)") if in_graph_events
+                else ("events around a replayed graph of the step's post-physics launches, after the timed region" if graph is not None
+                      else "per-launch CUDA events inside the eager timed region"),
+                "eager": {"avg_launch_ms": post_eager_ms, "achieved": eager_gbs, "frac": eager_gbs / peak,
+                          "timing": "per-launch CUDA events around every post-physics launch of an eager (no graph) timed pass"},
+                "whole_step_gbs": ((K0_BYTES + POST_BYTES) * n * T + GAE_BYTES_PER_SAMPLE * n * T) * args.steps / (ms * 1e-3) / 1e9}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as f:
+            roofline["traffic"] = json.load(f).get("post_physics_bytes_per_launch")
+    run = {"launch": "cuda_graph_replay" if graph is not None else "eager", "fusion": args.fusion,
+           "l2": "inputs larger than L2 (state footprint ~%.0f MB/GPU, 126 MB L2)" % (n * 4 * (26 + 36 + 16 * bm.BODIES_NO_CLEATS) / 1e6),
+           "ms_per_step_eager_with_events": eager_step_ms, "reset_rate_per_step": reset_rate,
+           "parallelism": f"env-sharded x{world}, no data-path collective (the exchanges are in the learner leg)"}
+    out = dict(value=value, ms_per_step=ms / args.steps, warmup=W, roofline=roofline, run=run, clocks=sampler.summary(),
+               gpu_launches=launches_per_step * args.steps)
+    del env, sim, graph
+    torch.cuda.empty_cache()
+    return out
+
+
+def e2e_leg(args, world, rank, dev):
+    """The same rollout through the reference-facing call with HOST buffers."""
+    from bez_isaacgym_b200 import bez_model as bm, ops, synthetic_gym as sg
+    from bez_isaacgym_b200.synthetic_sim import SyntheticGym
+    from bez_isaacgym_b200.tasks.kick_env import KickEnv
+
+    class OwnedRootSim(SyntheticGym):
+        owns_root_reset = True
+
+    n, T = args.envs_per_gpu, args.horizon
+    steps = args.e2e_steps or min(args.steps, 10)
+    mode = args.e2e_mode
+    if mode == "auto":
+        mode = "staged_ce" if "staged_ce" in KickEnv.HOST_PIPELINES else "zero_copy"
+    hcfg = bm.default_task_cfg(n, use_gpu_pipeline=False, rl_device="cpu")
+    hcfg["env"]["imuPrevVelAliasing"] = False
+    hcfg["env"]["hostPipeline"] = mode
+    hcfg["env"]["envBase"] = rank * n
+    hsim = OwnedRootSim(n, device=str(dev), seed=1234 + rank, host=True, filler=True)
+    henv = KickEnv(hcfg, str(dev), 0, True, sim=hsim, fusion=args.fusion)
+    hact = sg.make_actions(n, seed=1).pin_memory()
+    hr, hv, hd, hlv, hld = [t.pin_memory() for t in sg.make_rollout(n, T, seed=3)]
+    d_r, d_v, d_d, d_lv, d_ld = [torch.empty_like(t, device=dev) for t in (hr, hv, hd, hlv, hld)]
+    d_adv, d_ret = torch.empty_like(d_r), torch.empty_like(d_r)
+    h_adv, h_ret = torch.empty_like(hr).pin_memory(), torch.empty_like(hr).pin_memory()
+    gae_h2d = sum(t.numel() * t.element_size() for t in (hr, hv, hd, hlv, hld))
+    gae_d2h = sum(t.numel() * t.element_size() for t in (h_adv, h_ret))
+
+    def e2e_step():
+        for _ in range(T):
+            henv.step(hact)
+        for d, h in ((d_r, hr), (d_v, hv), (d_d, hd), (d_lv, hlv), (d_ld, hld)):
+            d.copy_(h, non_blocking=True)
+        ops.gae(d_r, d_v, d_d, d_lv, d_ld, 0.99, 0.95, d_adv, d_ret)
+        h_adv.copy_(d_adv, non_blocking=True); h_ret.copy_(d_ret, non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    e2e_step()
+    henv.reset_link_counters()
+    _barrier(world, dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    _barrier(world, dev)
+    dt = _max_over_ranks(time.perf_counter() - t0, world, dev)
+    link = henv.link_counters()
+    out = {"value": n * world * T * steps / dt, "unit": UNIT,
+           "h2d_bytes_per_step": link["h2d_bytes"] // steps + gae_h2d, "d2h_bytes_per_step": link["d2h_bytes"] // steps + gae_d2h,
+           "envs_per_gpu": n, "steps": steps, "ms_per_step": 1e3 * dt / steps, "host_pipeline": mode, "byte_count": link["how"],
+           "note": "KickEnv.step with use_gpu_pipeline=False: simulator tensors, actions and PD targets in pinned HOST memory, "
+                   "obs / rew / reset / time_outs handed back on the host every env step (one stream sync per step); rollout tensors "
+                   "H2D + advantages / returns D2H per GAE scan; bytes per step = per rollout, this rank"}
+    del henv, hsim
+    torch.cuda.empty_cache()
+    return out
+
+
+def learner_leg(args, world, rank, dev):
+    """BASELINE configs[2]/[3]: PPO epoch math on an (T x envs) rollout per GPU with the path's collectives, no MLP."""
+    import torch.distributed as dist
+    from bez_isaacgym_b200 import learner as L, ops, synthetic_gym as sg
+    n, T, mbs, mini_epochs = args.learner_envs, args.horizon, 32768, 5
+    M = n * T
+    if M % mbs:
+        mbs = M
+    E = mbs // T
+    nmb = M // mbs
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    rewards, values, dones, last_values, last_dones = sg.make_rollout(n, T, seed=21 + rank, device=dev)
+    obses = torch.randn(T, n, 54, generator=g, device=dev) * 2 + 0.5
+    mb = {k: v.to(dev) for k, v in sg.make_minibatch(M, seed=5 + rank).items()}
+    tm = lambda x, w: x.view(T, n, w) if w > 1 else x.view(T, n)          # noqa: E731  (time-major rollout storage)
+    actions, old_mu, old_sigma = tm(mb["actions"], 18), tm(mb["old_mu"], 18), tm(mb["old_sigma"], 18)
+    old_neglogp = tm(mb["old_neglogp"], 1)
+    mu_net, val_net, logstd = mb["mu"][:mbs].contiguous(), mb["values"].view(-1)[:mbs].contiguous(), mb["logstd"]
+    advs, rets = torch.empty_like(rewards), torch.empty_like(rewards)
+    adv_n = torch.empty(T, n, device=dev)
+    vals_n, rets_n = torch.empty_like(values), torch.empty_like(values)
+    norm_obs = torch.empty(mbs, 54, device=dev)
+    bucket = torch.randn(POLICY_PARAMS + 1, generator=g, device=dev)       # flat gradient bucket (+ the KL scalar for the shared LR)
+    stats = torch.empty(8, dtype=torch.float64, device=dev)
+    part = torch.empty(ops.ppo_scratch_doubles(), dtype=torch.float64, device=dev)
+    kc = ops.make_ppo_cfg()
+    gmu, gv, gls = torch.empty(mbs, 18, device=dev), torch.empty(mbs, device=dev), torch.empty(18, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def make_epoch(group):
+        obs_rms = L.RunningMeanStd(54, process_group=group).to(dev)
+        val_rms = L.RunningMeanStd(1, process_group=group).to(dev)
+        counters = {"collectives": 0, "bytes": 0}
+
+        def epoch():
+            ops.gae(rewards, values, dones, last_values, last_dones, 0.99, 0.95, advs, rets)
+            L.normalize_advantages(rets, values, process_group=group, out=adv_n.view(-1))       # moments -> all-reduce -> normalise
+            val_rms(values, out=vals_n); val_rms(rets, out=rets_n)                               # two train-mode updates per epoch
+            for _ in range(mini_epochs):
+                for i in range(nmb):
+                    sl = slice(i * E, (i + 1) * E)
+                    obs_rms(obses[:, sl], out=norm_obs)                                        # moments -> all-reduce -> merge -> normalise
+                    ops.ppo_loss_slabs(actions[:, sl], mu_net, logstd, old_mu[:, sl], old_sigma[:, sl], val_net, vals_n[:, sl],
+                                       rets_n[:, sl], old_neglogp[:, sl], adv_n[:, sl], kc, stats, part, grad_mu=gmu,
+                                       grad_values=gv, grad_logstd=gls)
+                    if group is not None:
+                        dist.all_reduce(bucket, group=group)                                   # PPO gradients (+ KL), one flat bucket
+        if group is not None:
+            counters["collectives"] = 3 + 2 * mini_epochs * nmb
+            counters["bytes"] = 8 * (3 + 2 * 3) + mini_epochs * nmb * (8 * 109 + 4 * (POLICY_PARAMS + 1))
+        return epoch, counters
+
+    def timed(epoch, iters):
+        for _ in range(2):
+            epoch()
+        _barrier(world, dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(iters):
+            epoch()
+        b.record(stream)
+        _barrier(world, dev)
+        return _max_over_ranks(a.elapsed_time(b) / iters, world, dev)
+
+    iters = max(3, min(args.steps, 20))
+    local_epoch, _ = make_epoch(None)
+    ms_local = timed(local_epoch, iters)
+    ms_graph = None
+    try:                                                    # the collective-free chain also as one CUDA graph (launch-bound sizes)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            local_epoch()
+        ms_graph = timed(gr.replay, iters)
+    except Exception:                                       # noqa: BLE001
+        ms_graph = None
+    ms_dist, counters = ms_local, {"collectives": 0, "bytes": 0}
+    if world > 1:
+        dist_epoch, counters = make_epoch(dist.group.WORLD)
+        ms_dist = timed(dist_epoch, iters)
+    # per-kernel timings at the minibatch size (graph-replayed x20) for the leg's roofline: the kernel furthest below peak
+    def ktime(fn, reps=20):
+        for _ in range(3):
+            fn()
+        gk = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gk):
+            for _ in range(reps):
+                fn()
+        gk.replay()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(5):
+            gk.replay()
+        b.record(stream)
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / (5 * reps)
+    rms = L.RunningMeanStd(54).to(dev)
+    sl = slice(0, E)
+    k_rms = ktime(lambda: rms(obses[:, sl], out=norm_obs))
+    k_ppo = ktime(lambda: ops.ppo_loss_slabs(actions[:, sl], mu_net, logstd, old_mu[:, sl], old_sigma[:, sl], val_net, vals_n[:, sl],
+                                             rets_n[:, sl], old_neglogp[:, sl], adv_n[:, sl], kc, stats, part, grad_mu=gmu,
+                                             grad_values=gv, grad_logstd=gls))
+    k_gae = ktime(lambda: ops.gae(rewards, values, dones, last_values, last_dones, 0.99, 0.95, advs, rets))
+    peak, _ = peaks()
+    kernels = {"rms_train_forward": {"ms": k_rms, "bytes": 432 * mbs}, "ppo_loss_fwd_bwd": {"ms": k_ppo, "bytes": 384 * mbs},
+               "gae": {"ms": k_gae, "bytes": GAE_BYTES_PER_SAMPLE * M}}
+    for k in kernels.values():
+        k["gbs"] = k["bytes"] / (k["ms"] * 1e-3) / 1e9
+        k["frac"] = k["gbs"] / peak
+    worst = min(kernels, key=lambda k: kernels[k]["frac"])
+    return {"workload": f"PPO epoch math per GPU on a {T} x {n} rollout: GAE, advantage moments + normalise, value RunningMeanStd x2, "
+                        f"{mini_epochs} x {nmb} minibatches of {mbs} x (obs RunningMeanStd train forward on slab views, fused PPO loss "
+                        f"fwd+bwd, {POLICY_PARAMS}-float gradient bucket all-reduce); no MLP",
+            "envs_per_gpu": n, "horizon": T, "minibatch": mbs, "mini_epochs": mini_epochs, "n_gpus": world,
+            "ms_per_epoch": ms_dist, "ms_per_epoch_no_collectives": ms_local, "ms_per_epoch_graph_no_collectives": ms_graph,
+            "collective_us_per_epoch": (ms_dist - ms_local) * 1e3, "collectives_per_epoch": counters["collectives"],
+            "collective_bytes_per_epoch": counters["bytes"], "samples_per_s": M * world / (ms_dist * 1e-3),
+            "env_steps_per_s": M * world / (ms_dist * 1e-3), "timing": "CUDA events, eager launches, max over ranks",
+            "roofline": {"bound": "hbm (launch-latency-bound at this size)", "kernel": worst, "achieved": kernels[worst]["gbs"],
+                         "peak": peak, "unit": "GB/s", "frac": kernels[worst]["frac"], "per_kernel": kernels,
+                         "timing": "each kernel chain graph-replayed x20 between CUDA events, minibatch = 32768 samples"}}
+
+
 def run_b200(args):
     import torch.distributed as dist
     import __graft_entry__ as ge
@@ -167,208 +543,39 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # keep stdout to the ONE JSON line: this image exports NCCL_DEBUG=VERSION, which prints a banner on rank 0
-        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")
+        # stdout carries the ONE JSON line: NCCL's own log lines (whatever NCCL_DEBUG level the caller chose -- it is NOT
+        # touched here) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     ge.build()
-    from bez_isaacgym_b200 import bez_model as bm, ops, synthetic_gym as sg
-    from bez_isaacgym_b200.synthetic_sim import SyntheticGym
-    from bez_isaacgym_b200.tasks.kick_env import KickEnv
 
+    roll = rollout_leg(args, world, rank, dev)
+    e2e = None if args.no_e2e else e2e_leg(args, world, rank, dev)
+    learner = None if args.no_learner else learner_leg(args, world, rank, dev)
+
+    cpu_baseline = gpu_torch = None
     n, T = args.envs_per_gpu, args.horizon
-    l2_fetch = ops.set_l2_fetch_granularity(args.l2_fetch) if args.l2_fetch else None
-    cfg = bm.default_task_cfg(n, rl_device=str(dev))
-    cfg["env"]["imuPrevVelAliasing"] = False                # the general (680 B/env-step) path with a prev_lin_vel buffer
-    cfg["seed"] = 42 + rank
-
-    class OwnedRootSim(SyntheticGym):
-        owns_root_reset = True                              # as with Isaac Gym: the simulator restores root states
-
-    sim = OwnedRootSim(n, device=str(dev), seed=1234 + rank, filler=True)
-    env = KickEnv(cfg, str(dev), 0, True, sim=sim, fusion=args.fusion)
-    progress, reset = sg.make_bookkeeping(n, seed=99 + rank, device=dev)
-    env.progress_buf.copy_(progress); env.reset_buf.copy_(reset)
-    actions = sg.make_actions(n, seed=4321 + rank, device=dev)
-    rewards, values, dones, last_values, last_dones = sg.make_rollout(n, T, seed=7 + rank, device=dev)
-    advs, rets = torch.empty_like(rewards), torch.empty_like(rewards)
-    stream = torch.cuda.current_stream(dev)
-    launches_per_step = T * (2 if args.fusion == "fused" else 3) + 1
-
-    post_events = []
-
-    def bench_step(record):
-        for _ in range(T):
-            env.pre_physics_step(actions)
-            env.sim.simulate()
-            if record:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                env.post_physics_step()
-                e1.record(stream)
-                post_events.append((e0, e1))
-            else:
-                env.post_physics_step()
-        ops.gae(rewards, values, dones, last_values, last_dones, 0.99, 0.95, advs, rets)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    for _ in range(max(3, args.warmup)):
-        bench_step(False)
-    barrier()
-    graph = None
-    if not args.no_graph:
-        # the step is 65 dependent launches of 7..45 us kernels: replaying it as ONE CUDA graph removes the CPU-side
-        # launch cost and most of the inter-kernel gaps (the kernels, arguments and work are identical)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            bench_step(False)
-        stream = torch.cuda.current_stream(dev)
-        graph.replay()
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    start.record(stream)
-    for _ in range(args.steps):
-        if graph is not None:
-            graph.replay()
-        else:
-            bench_step(True)
-    end.record(stream)
-    barrier()
-    ms = start.elapsed_time(end)
-    # Duration of the dominant kernel.  Eager timed region: per-launch CUDA events recorded inside it.  Graph-replayed timed
-    # region (default): events cannot be read back from inside a replayed graph, so right after it (a) the same steps run
-    # eagerly with per-launch events (includes the event-record gaps) and (b) a graph holding only the T post-physics
-    # launches of one step is replayed between two events (back-to-back launch duration); (b) is what `achieved` uses.
-    eager_ms = None
-    post_graph_ms = None
-    if graph is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record(stream)
-        for _ in range(min(args.steps, 10)):
-            bench_step(True)
-        e1.record(stream)
-        barrier()
-        eager_ms = e0.elapsed_time(e1) / min(args.steps, 10)
-        pg = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(pg):
-            for _ in range(T):
-                env.post_physics_step()
-        pg.replay()
-        barrier()
-        e0.record(stream)
-        for _ in range(min(args.steps, 10)):
-            pg.replay()
-        e1.record(stream)
-        barrier()
-        post_graph_ms = e0.elapsed_time(e1) / (min(args.steps, 10) * T)
-    sampler.stop_flag = True
-    sampler.join()
-    reset_rate = float(env.reset_buf.float().mean())
-    post_events_ms = sum(a.elapsed_time(b) for a, b in post_events) / len(post_events)
-    post_ms = post_graph_ms if post_graph_ms is not None else post_events_ms
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    env_steps = n * world * T * args.steps
-    value = env_steps / (ms * 1e-3)
-
-    peak, peak_src = peaks()
-    achieved = POST_BYTES * n / (post_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "bezk::task_tile_kernel<7> (fused post-physics)" if args.fusion == "fused"
-                else "bezk::task_tile_kernel<3>+<4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_env": POST_BYTES, "envs_per_launch": n,
-                "avg_launch_ms": post_ms, "peak_source": peak_src,
-                "avg_launch_ms_eager_events": post_events_ms,
-                "timing": "CUDA events around a replayed graph of the step's 32 post-physics launches, taken right after the "
-                          "graph-replayed timed region (avg_launch_ms); per-launch events of an eager pass in avg_launch_ms_eager_events"
-                if graph is not None else "per-launch CUDA events inside the (eager) timed region",
-                "whole_step_gbs": (TASK_BYTES_PER_ENV_STEP * n * T + GAE_BYTES_PER_SAMPLE * n * T) * args.steps / (ms * 1e-3) / 1e9}
-    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_file):
-        with open(traffic_file) as f:
-            roofline["traffic"] = json.load(f).get("post_physics_bytes_per_launch")
-
-    # ---- e2e: host pipeline (simulator tensors + actions in pinned host memory) through KickEnv.step ----
-    e2e = None
-    if not args.no_e2e:
-        ne = args.e2e_envs
-        hcfg = bm.default_task_cfg(ne, use_gpu_pipeline=False, rl_device="cpu")
-        hcfg["env"]["imuPrevVelAliasing"] = False
-        hcfg["env"]["hostPipeline"] = args.e2e_mode
-        hsim = OwnedRootSim(ne, device=str(dev), seed=1234 + rank, host=True, filler=True)
-        henv = KickEnv(hcfg, f"cuda:{local}", 0, True, sim=hsim, fusion=args.fusion)
-        hact = sg.make_actions(ne, seed=1).pin_memory()
-        hr, hv, hd, hlv, hld = [t.pin_memory() for t in sg.make_rollout(ne, T, seed=3)]
-        d_r, d_v, d_d, d_lv, d_ld = [torch.empty_like(t, device=dev) for t in (hr, hv, hd, hlv, hld)]
-        d_adv, d_ret = torch.empty_like(d_r), torch.empty_like(d_r)
-        h_adv, h_ret = torch.empty_like(hr).pin_memory(), torch.empty_like(hr).pin_memory()
-
-        def e2e_step():
-            for _ in range(T):
-                henv.step(hact)
-            for d, h in ((d_r, hr), (d_v, hv), (d_d, hd), (d_lv, hlv), (d_ld, hld)):
-                d.copy_(h, non_blocking=True)
-            ops.gae(d_r, d_v, d_d, d_lv, d_ld, 0.99, 0.95, d_adv, d_ret)
-            h_adv.copy_(d_adv, non_blocking=True); h_ret.copy_(d_ret, non_blocking=True)
-            torch.cuda.synchronize(dev)
-
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        nb = hsim.num_bodies
-        if args.e2e_mode == "staged":
-            h2d_env = 4 * (26 + 36 + 13 * nb + 3 * nb + 18)       # all four simulator tensors + actions copied
-            d2h_env = 4 * 54 + 4 + 8 + 8 + 4 * 36 + 4 * 18        # obs, rew, reset, timeouts, dof_state back, targets
-        else:
-            # zero-copy: the kernels gather over PCIe -- dense dof_state + root_states + actions, and the sparse
-            # rows at the 64 B fetch granularity (IMU link ~96 B, two feet ~144 B, measured: profiles/r01_fetch_granularity.md)
-            h2d_env = 4 * (26 + 36 + 18) + 96 + 144
-            d2h_env = 4 * 54 + 4 + 8 + 8 + 4 * 18                 # obs, rew, reset, timeouts, targets (+ rare reset rows)
-        e2e = {"value": ne * world * T * args.e2e_steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": (h2d_env * T + 9 * T + 5) * ne, "d2h_bytes_per_step": (d2h_env * T + 8 * T) * ne,
-               "envs_per_gpu": ne, "host_pipeline": args.e2e_mode,
-               "note": "KickEnv.step with use_gpu_pipeline=False (simulator tensors, actions, targets in pinned HOST memory; "
-                       "obs/rew/reset/timeouts returned on the host every env step); rollout H2D + adv/returns D2H per GAE"}
-
-    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_gpu_torch_baseline:
+        rate, secs, _ = torch_port_rollouts(n, T, 2, device=str(dev))
+        gpu_torch = {"value": rate, "unit": UNIT, "kind": "port", "device": torch.cuda.get_device_name(dev),
+                     "sample": f"2 rollouts of {T} task steps + GAE at {n} envs ({secs:.2f} s): the reference's torch-eager op "
+                               f"sequence (oracle port) with CUDA tensors on the same GPU"}
+        torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cn = args.cpu_sample_envs
-        rate, secs, threads = cpu_reference_rate(cn, T, args.cpu_rollouts)
+        rate, secs, threads = torch_port_rollouts(n, T, args.cpu_rollouts)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"{args.cpu_rollouts} rollouts of {T} task steps + GAE at {cn} envs ({secs:.1f} s), reference torch ops "
-                                  f"(oracle port) with torch.set_num_threads({threads})"}
+                        "sample": f"{args.cpu_rollouts} rollouts of {T} task steps + GAE at {n} envs ({secs:.1f} s), reference torch ops "
+                                  f"(oracle port; /root/reference is absent on the GPU box) with torch.set_num_threads({threads})"}
 
     if rank == 0:
-        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-               "data": "synthetic",
-               "config": {"workload": f"bez_kick {n} envs/GPU: {T} x (K0 pre-physics + fused post-physics) + 1 GAE scan "
-                                      f"(BASELINE configs[3] shard size; configs[1] is the 4096-env case)",
-                          "envs_per_gpu": n, "horizon": T, "parallelism": f"env-sharded x{world}, no data-path collective",
-                          "fusion": args.fusion, "l2": "inputs larger than L2 (state footprint ~%.0f MB/GPU)" % (
-                              n * 4 * (26 + 36 + 16 * bm.BODIES_NO_CLEATS) / 1e6),
-                          "launch": "cuda_graph_replay" if graph is not None else "eager", "ms_per_step_eager_with_events": eager_ms,
-                          "reset_rate_per_step": reset_rate, "l2_fetch_granularity": l2_fetch, "imu_prev_lin_vel": "buffer (680 B/env-step path)"},
-               "clocks": sampler.summary(), "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
-               "e2e": e2e, "cpu_baseline": cpu_baseline}
+        out = {"metric": METRIC, "value": roll["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": roll["warmup"],
+               "ms_per_step": roll["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic", "config": workload_config(args), "run": roll["run"], "clocks": roll["clocks"],
+               "gpu_launches": roll["gpu_launches"], "roofline": roll["roofline"], "e2e": e2e, "learner": learner,
+               "cpu_baseline": cpu_baseline, "gpu_torch_baseline": gpu_torch}
         print(json.dumps(out))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -43,6 +43,8 @@ class KickEnv(VecTask):
     #: "kick" here; the sibling tasks (tasks/walk_env.py, tasks/orient_env.py) subclass this with "walk" / "orient": same
     #: skeleton, one actor per env, 52-wide observation, their own heading term / reward / goal randomisation (bezk.h)
     TASK = "kick"
+    #: host pipelines (``sim.use_gpu_pipeline: False``), selected by ``env.hostPipeline``
+    HOST_PIPELINES = ("zero_copy", "staged")
 
     def __init__(self, cfg, sim_device, graphics_device_id, headless, sim: SimBackend = None, fusion="fused"):
         self.cfg = cfg
@@ -97,8 +99,8 @@ class KickEnv(VecTask):
         self.host_mode = env_cfg.get("hostPipeline", "zero_copy") if self.host_staged else None
         if self.host_staged and self.TASK != "kick":
             raise NotImplementedError("the host pipeline is implemented for BezKick only; walk / orient need the GPU pipeline")
-        if self.host_mode not in (None, "zero_copy", "staged"):
-            raise ValueError(f"env.hostPipeline must be 'zero_copy' or 'staged', got {self.host_mode}")
+        if self.host_mode is not None and self.host_mode not in self.HOST_PIPELINES:
+            raise ValueError(f"env.hostPipeline must be one of {self.HOST_PIPELINES}, got {self.host_mode}")
         if self.host_staged and self.host_mode == "zero_copy" and not all(
                 t.is_pinned() for t in (self.root_states, self.dof_state, self.rigid_body, self.net_contact)):
             raise ValueError("hostPipeline='zero_copy' needs the simulator tensors in pinned (page-locked) host memory")
@@ -183,6 +185,8 @@ class KickEnv(VecTask):
             self._h_reset = torch.empty(n, dtype=torch.long, **pin); self._h_timeout = torch.empty(n, dtype=torch.long, **pin)
             self._h_actions = torch.empty(n, 18, **pin)
         self._bind()
+        self._link = {"h2d_bytes": 0, "d2h_bytes": 0}
+        self._link_per_step = self._host_link_bytes_per_step() if self.host_staged else (0, 0)
         if self.randomize:                                # kick_env.py:248-249: once at start-up, before the first step
             self.apply_randomizations(self.randomization_params)
         self.reset_idx(torch.arange(n, device=dev))       # kick_env.py:238
@@ -240,6 +244,48 @@ class KickEnv(VecTask):
                                                   self._rng_step, *f["tail"], parts, self.num_envs, self._stream())
         if rc:
             _lib.check(rc, "bezk_post_physics")
+
+    # ------------------------------------------------------------------ host-link accounting (bench.py's e2e byte counts)
+    def _host_link_bytes_per_step(self):
+        """Bytes one ``step`` moves over the host link, from the tensors / address ranges involved (not a formula per env):
+        staged = the sizes of the tensors copied; zero_copy = the dense tensors the kernels read / write in pinned memory
+        whole, plus the sparse AoS rows counted as the DISTINCT 64-byte granules their address ranges touch."""
+        n, nb = self.num_envs, self.sim.num_bodies
+        nbytes = lambda t: t.numel() * t.element_size()      # noqa: E731
+        outs = nbytes(self._observations_out()) + nbytes(self.rew_buf) + nbytes(self.timeout_buf) + nbytes(self.reset_buf) \
+            + nbytes(self.targets)
+        if self.host_mode == "staged":
+            h2d = sum(nbytes(t) for t in (self.root_states, self.dof_state, self.rigid_body, self.net_contact)) + n * 18 * 4
+            d2h = outs + nbytes(self.dof_state)
+            if self._kcfg.flags & _lib.F_WRITE_CONTACT_FILTER:
+                d2h += nbytes(self.net_contact)
+            if self._kcfg.flags & _lib.F_RESET_ROOT_STATES:
+                d2h += nbytes(self.root_states)
+            return h2d, d2h
+        e = np.arange(n, dtype=np.int64)
+
+        def granules(base, stride, off, width):               # distinct 64-byte granules of [a, a + width) per env
+            a = base + e * stride + off
+            return int(((a + width - 1) // 64 - a // 64 + 1).sum()) * 64
+        sparse = granules(self.rigid_body.data_ptr(), nb * 52, (bm.IMU_BODY * 13 + 3) * 4, 40)
+        if self.cleats:
+            sparse += granules(self.net_contact.data_ptr(), nb * 12, self._kcfg.left_foot_body * 12, 48)
+            sparse += granules(self.net_contact.data_ptr(), nb * 12, self._kcfg.right_foot_body * 12, 48)
+        else:
+            sparse += granules(self.net_contact.data_ptr(), nb * 12, self._kcfg.left_foot_body * 12, 12)
+            sparse += granules(self.net_contact.data_ptr(), nb * 12, self._kcfg.right_foot_body * 12, 12)
+        h2d = nbytes(self.dof_state) + nbytes(self.root_states) + n * 18 * 4 + sparse
+        return h2d, outs
+
+    def reset_link_counters(self):
+        self._link = {"h2d_bytes": 0, "d2h_bytes": 0}
+
+    def link_counters(self):
+        how = {"staged": "sizes of the tensors copied by cudaMemcpyAsync each step",
+               "zero_copy": "address ranges the kernels dereference in pinned host memory each step: dense tensors whole, sparse AoS rows as "
+                            "distinct 64-byte granules (+ the rare reset rows written back, not counted)",
+               None: "GPU pipeline: nothing crosses the host link"}[self.host_mode]
+        return dict(self._link, how=how)
 
     # ------------------------------------------------------------------ reference-named attributes
     @property
@@ -443,6 +489,8 @@ class KickEnv(VecTask):
         if not self.host_staged:
             return super().step(actions)
         # host pipeline: same sequence, results leave through pinned buffers with ONE stream sync
+        self._link["h2d_bytes"] += self._link_per_step[0]
+        self._link["d2h_bytes"] += self._link_per_step[1]
         self.pre_physics_step(actions)
         for _ in range(self.control_freq_inv):
             self.sim.simulate()
