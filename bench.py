@@ -237,11 +237,12 @@ def rollout_leg(args, world, rank, dev):
                 env.set_rollout_targets(values=values[t], shaped_rewards=rewards[t], dones_u8=dones[t + 1], gamma=0.99,
                                         scale_value=0.01)
             if t in mark:
+                cur = torch.cuda.current_stream(dev)        # the capture stream while a graph is being recorded
                 e0 = torch.cuda.Event(enable_timing=True, external=external)
                 e1 = torch.cuda.Event(enable_timing=True, external=external)
-                e0.record(stream)
+                e0.record(cur)
                 env.post_physics_step()
-                e1.record(stream)
+                e1.record(cur)
                 ev_pairs.append((e0, e1))
             else:
                 env.post_physics_step()
@@ -252,7 +253,7 @@ def rollout_leg(args, world, rank, dev):
         bench_step()
     _barrier(world, dev)
     graph, in_graph_events = None, False
-    marks = tuple(range(3, T, 8))                           # 4 of the 32 launches carry timing events inside the graph
+    marks = (T // 3, 2 * T // 3)                            # 2 of the 32 launches carry timing events inside the graph
     if not args.no_graph:
         # the step is 65 dependent launches of 7..45 us kernels: replaying it as ONE CUDA graph removes the CPU-side
         # launch cost and most of the inter-kernel gaps (the kernels, arguments and work are identical)
@@ -261,7 +262,8 @@ def rollout_leg(args, world, rank, dev):
             with torch.cuda.graph(graph):
                 bench_step(mark=marks, external=True)
             in_graph_events = True
-        except Exception:                                   # noqa: BLE001  (external event nodes unsupported: plain capture)
+        except Exception as exc:                            # noqa: BLE001  (external event nodes unsupported: plain capture)
+            print(f"bench: in-graph timing events unavailable ({exc!r}); falling back", file=sys.stderr)
             del ev_pairs[:]
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
@@ -284,12 +286,12 @@ def rollout_leg(args, world, rank, dev):
     ms = start.elapsed_time(end)
     sampler.stop_flag = True
     sampler.join()
-    post_graph_ms = post_eager_ms = eager_step_ms = None
+    post_graph_ms = post_eager_ms = eager_step_ms = in_region_ms = None
     if graph is not None and in_graph_events:
         try:
-            post_graph_ms = sum(a.elapsed_time(b) for a, b in ev_pairs) / len(ev_pairs)     # the LAST replay of the timed region
+            in_region_ms = sum(a.elapsed_time(b) for a, b in ev_pairs) / len(ev_pairs)     # the LAST replay of the timed region
         except Exception:                                   # noqa: BLE001
-            post_graph_ms = None
+            in_region_ms = None
     del ev_pairs[:]
     if graph is not None:
         # eager timed pass: the same steps launched one by one, per-launch events around every post-physics launch
@@ -303,8 +305,10 @@ def rollout_leg(args, world, rank, dev):
         _barrier(world, dev)
         eager_step_ms = e0.elapsed_time(e1) / ke
     post_eager_ms = sum(a.elapsed_time(b) for a, b in ev_pairs) / len(ev_pairs)
-    if post_graph_ms is None and graph is not None:
-        # fallback: a graph holding only the T post-physics launches, replayed between two events after the timed region
+    if graph is not None:
+        # back-to-back duration: a graph holding only the T post-physics launches of one rollout, replayed between two events
+        # right after the timed region.  An event pair around ONE launch (in_region / eager) also times the launch latency the
+        # event nodes expose (no programmatic-dependent-launch overlap across an event node): ~7 us on a 36 us kernel.
         pg = torch.cuda.CUDAGraph()
         with torch.cuda.graph(pg):
             for _ in range(T):
@@ -330,10 +334,14 @@ def rollout_leg(args, world, rank, dev):
                 else "bezk::task_tile_kernel<3>+<4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_env": POST_BYTES, "envs_per_launch": n,
                 "avg_launch_ms": post_ms, "peak_source": peak_src,
-                "timing": ("CUDA timing events recorded as external event nodes INSIDE the replayed graph of the timed region, around "
-                           f"the post-physics launches of env steps {list(marks)} (read after the last timed replay)") if in_graph_events
-                else ("events around a replayed graph of the step's post-physics launches, after the timed region" if graph is not None
-                      else "per-launch CUDA events inside the eager timed region"),
+                "timing": ("CUDA events around a replayed graph of one rollout's 32 post-physics launches (back to back, as in the timed "
+                           "graph), taken right after the timed region; in_region / eager = event pairs around single launches")
+                if graph is not None else "per-launch CUDA events inside the eager timed region",
+                "in_region": None if in_region_ms is None else {
+                    "avg_launch_ms": in_region_ms, "frac": POST_BYTES * n / (in_region_ms * 1e-3) / 1e9 / peak,
+                    "timing": f"timing events recorded as external event nodes INSIDE the replayed graph of the timed region, around the "
+                              f"post-physics launches of env steps {list(marks)}, read after the last timed replay (each pair also "
+                              f"times the launch latency its event nodes expose)"},
                 "eager": {"avg_launch_ms": post_eager_ms, "achieved": eager_gbs, "frac": eager_gbs / peak,
                           "timing": "per-launch CUDA events around every post-physics launch of an eager (no graph) timed pass"},
                 "whole_step_gbs": ((K0_BYTES + POST_BYTES) * n * T + GAE_BYTES_PER_SAMPLE * n * T) * args.steps / (ms * 1e-3) / 1e9}

@@ -160,6 +160,43 @@ int bezk_post_physics_chunk(float* dof_state, const float* rigid_body, float* ro
     return run_task(parts, a, cfg, stream, "bezk_post_physics_chunk");
 }
 
+int bezk_stage_sparse_rows(const float* rigid_body_host, const float* net_contact_host, const BezkTaskCfg* cfg, float* imu_stage,
+                           float* feet_stage, int64_t env0, int64_t n, void* stream) {
+    if (int rc = check_cfg(cfg)) return rc;
+    REQUIRE(env0 >= 0 && n >= 0, "env0 / n < 0");
+    if (n == 0) return 0;
+    REQUIRE(rigid_body_host && net_contact_host && imu_stage && feet_stage, "staging buffers NULL");
+    return cuda_rc(bezk::stage_sparse_rows(rigid_body_host, net_contact_host, *cfg, imu_stage, feet_stage, env0, n,
+                                           (cudaStream_t)stream), "bezk_stage_sparse_rows");
+}
+
+int bezk_post_physics_staged(int task, float* dof_state, const float* imu_stage, float* root_states, float* feet_stage,
+                             float* prev_lin_vel, float* goal, const float* goal_angle, const float* ball_init,
+                             const float* initial_root_states, const float* uniforms, const float* goal_uniforms, uint64_t seed,
+                             uint64_t step, int64_t* reset_buf, int64_t* progress_buf, int64_t* timeout_buf, int64_t* randomize_buf,
+                             const BezkTaskCfg* cfg, float* obs, float* obs_clipped, float* rew, int parts, int64_t n,
+                             int64_t env_base, float* dof_state_wb, float* root_states_wb, void* stream) {
+    REQUIRE(task == BEZK_TASK_KICK || task == BEZK_TASK_WALK || task == BEZK_TASK_ORIENT, "unknown task");
+    REQUIRE(parts >= 1 && parts <= 7, "parts must be a non-empty subset of {1,2,4}");
+    REQUIRE(env_base >= 0, "env_base < 0");
+    REQUIRE(cfg, "cfg is NULL");
+    REQUIRE(!(cfg->flags & BEZK_F_WRITE_CONTACT_FILTER), "the contact-filter write-back would land in the staging buffer: clear BEZK_F_WRITE_CONTACT_FILTER");
+    bezk::TaskArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dof_state = dof_state; a.rigid_body = imu_stage; a.root_states = root_states; a.net_contact = feet_stage;
+    a.prev_lin_vel = prev_lin_vel; a.goal = goal; a.goal_angle = goal_angle; a.goal_uniforms = goal_uniforms; a.ball_init = ball_init;
+    a.initial_root = initial_root_states;
+    a.uniforms = uniforms; a.seed = seed; a.step = step; a.env_base = env_base; a.dof_state_wb = dof_state_wb;
+    a.root_states_wb = root_states_wb;
+    a.reset_in = reset_buf; a.reset_out = reset_buf; a.progress_in = progress_buf; a.progress_out = progress_buf;
+    a.timeout_buf = timeout_buf; a.randomize_buf = randomize_buf;
+    a.obs = obs; a.obs_clipped = obs_clipped; a.rew = rew; a.n = n;
+    const bool cleats = (cfg->flags & BEZK_F_CLEATS) != 0;
+    a.rb_stride = 10; a.rb_off = 0;
+    a.cf_stride = cleats ? 24 : 8; a.cf_l_off = 0; a.cf_r_off = cleats ? 12 : 4;
+    return run_task(parts, a, cfg, stream, "bezk_post_physics_staged", task);
+}
+
 int bezk_post_physics_task(int task, float* dof_state, const float* rigid_body, float* root_states, float* net_contact,
                            float* prev_lin_vel, float* goal, const float* goal_angle, const float* ball_init,
                            const float* initial_root_states, const float* uniforms, const float* goal_uniforms, uint64_t seed,

@@ -36,6 +36,11 @@ struct TaskArgs {
     uint8_t* dones_u8;           // (n,) out: reset mask as uint8 (the experience buffer's `dones` slot of the NEXT step)
     float shp_scale, shp_shift, shp_gamma;
     int shp_bootstrap;
+    // Layout of the two sparse inputs, in floats.  0 = Isaac Gym's AoS layout derived from BezkTaskCfg (env stride
+    // num_bodies * 13 resp. * 3; the IMU-link slice at (imu_body * 13 + 3), the foot rows at body * 3); the host pipeline's
+    // compact staging buffers (bezk_stage_sparse_rows) set them explicitly.
+    int rb_stride, rb_off;       // rigid_body: floats per env, offset of the 10-float IMU-link slice
+    int cf_stride, cf_l_off, cf_r_off;   // net_contact: floats per env, offsets of the left / right foot (first cleat) rows
     int64_t n;
     int use_tma;      // all dense bases 16 B aligned
     int rb_vec2;      // IMU-link slice of every env is 8 B aligned
@@ -54,6 +59,7 @@ struct PpoArgs {
 cudaError_t launch_task(int task, int parts, const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st);
 cudaError_t launch_goal_uniforms(uint64_t seed, uint64_t step, float* out2, cudaStream_t st);
 void fill_alignment(TaskArgs& a, const BezkTaskCfg& cfg);
+cudaError_t stage_sparse_rows(const float*, const float*, const BezkTaskCfg&, float*, float*, int64_t, int64_t, cudaStream_t);
 cudaError_t launch_pre_physics(const float*, float*, float*, const BezkTaskCfg&, int64_t, cudaStream_t);
 cudaError_t launch_reset_idx(const int64_t*, int64_t, const float*, uint64_t, uint64_t, float*, float*, const float*, int64_t*,
                              int64_t*, const BezkTaskCfg&, int64_t, int, float*, const float*, int64_t, cudaStream_t);

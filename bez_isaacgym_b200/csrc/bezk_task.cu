@@ -515,11 +515,10 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
 
     // ---- 1. sparse gathers first: they are the slow requests (one 64-byte granule each), the dense tiles follow ----
     // per-env row pointers: warp-uniform 64-bit base + 32-bit lane offset
-    const int nbod = cfg.num_bodies;
-    const float* rb = a.rigid_body + ((e0 * nbod + cfg.imu_body) * 13 + 3) + lane * (nbod * 13);
-    float* cf_env = a.net_contact ? a.net_contact + e0 * nbod * 3 + lane * (nbod * 3) : nullptr;
-    float* cf_l = cf_env ? cf_env + cfg.left_foot_body * 3 : nullptr;
-    float* cf_r = cf_env ? cf_env + cfg.right_foot_body * 3 : nullptr;
+    const float* rb = a.rigid_body + (e0 * a.rb_stride + a.rb_off) + lane * a.rb_stride;
+    float* cf_env = a.net_contact ? a.net_contact + e0 * a.cf_stride + lane * a.cf_stride : nullptr;
+    float* cf_l = cf_env ? cf_env + a.cf_l_off : nullptr;
+    float* cf_r = cf_env ? cf_env + a.cf_r_off : nullptr;
     Gathered<CLEATS> g;
     gather_env<OBS, (BOOK || REW), CLEATS, TASK>(a, cfg, e, valid, rb, cf_l, cf_r, g);
 
@@ -894,13 +893,37 @@ void fill_alignment(TaskArgs& a, const BezkTaskCfg& cfg) {
     if (a.root_states_wb == nullptr) a.root_states_wb = a.root_states;
     a.use_tma = aligned16(a.dof_state) && aligned16(a.root_states) && aligned16(a.dof_state_wb) && (a.obs == nullptr || aligned16(a.obs)) &&
                 (a.obs_clipped == nullptr || aligned16(a.obs_clipped));
-    a.rb_vec2 = aligned8(a.rigid_body) && (cfg.num_bodies % 2 == 0) && ((cfg.imu_body * 13 + 3) % 2 == 0);
+    if (a.rb_stride == 0) { a.rb_stride = cfg.num_bodies * 13; a.rb_off = cfg.imu_body * 13 + 3; }
+    if (a.cf_stride == 0) { a.cf_stride = cfg.num_bodies * 3; a.cf_l_off = cfg.left_foot_body * 3; a.cf_r_off = cfg.right_foot_body * 3; }
+    a.rb_vec2 = aligned8(a.rigid_body) && (a.rb_stride % 2 == 0) && (a.rb_off % 2 == 0);
     // 0: 64-byte granules only; 1 (default): per-lane 64 / 128-byte choice; 2: full 128-byte lines wherever the span allows.
     // Read ONCE per process (A/B measurement knob, profiles/r01_fetch_granularity.md), never on the launch path.
     static const int smart_granule = env_int("BEZK_SMART_GRANULE", 1);
     a.smart_granule = smart_granule;
-    a.cf_vec2 = a.net_contact != nullptr && aligned8(a.net_contact) && ((cfg.num_bodies * 3) % 2 == 0) &&
-                ((cfg.left_foot_body * 3) % 2 == 0) && ((cfg.right_foot_body * 3) % 2 == 0);
+    a.cf_vec2 = a.net_contact != nullptr && aligned8(a.net_contact) && (a.cf_stride % 2 == 0) && (a.cf_l_off % 2 == 0) &&
+                (a.cf_r_off % 2 == 0);
+}
+
+// Host pipeline: the sparse Isaac Gym rows leave PINNED HOST memory through the copy engines -- strided cudaMemcpy2DAsync
+// pulls into compact device staging -- instead of 64-byte zero-copy reads issued by the SMs (profiles/r02_host_link.md).
+//   imu_stage  (n, 10)                    <- rigid_body row (env, imu_body), floats 3..12                       (40 B of 52 * num_bodies)
+//   feet_stage (n, 8)  [l xyz _ r xyz _]  <- net_contact rows (env, left_foot_body), (env, right_foot_body)     (2 x 12 B of 12 * num_bodies)
+//   cleats:    (n, 24) [l 12, r 12]       <- the two runs of 4 cleat bodies                                     (2 x 48 B)
+cudaError_t stage_sparse_rows(const float* rigid_body, const float* net_contact, const BezkTaskCfg& cfg, float* imu_stage,
+                              float* feet_stage, int64_t env0, int64_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const size_t rb_pitch = (size_t)cfg.num_bodies * 13 * sizeof(float), cf_pitch = (size_t)cfg.num_bodies * 3 * sizeof(float);
+    const bool cleats = (cfg.flags & BEZK_F_CLEATS) != 0;
+    const size_t fw = cleats ? 48 : 12, fpitch = cleats ? 96 : 32, roff = cleats ? 48 : 16;
+    cudaError_t e = cudaMemcpy2DAsync(imu_stage + env0 * 10, 40, rigid_body + (env0 * cfg.num_bodies + cfg.imu_body) * 13 + 3, rb_pitch,
+                                      40, (size_t)n, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    char* fs = reinterpret_cast<char*>(feet_stage) + env0 * fpitch;
+    e = cudaMemcpy2DAsync(fs, fpitch, net_contact + (env0 * cfg.num_bodies + cfg.left_foot_body) * 3, cf_pitch, fw, (size_t)n,
+                          cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy2DAsync(fs + roff, fpitch, net_contact + (env0 * cfg.num_bodies + cfg.right_foot_body) * 3, cf_pitch, fw, (size_t)n,
+                             cudaMemcpyHostToDevice, st);
 }
 
 cudaError_t launch_pre_physics(const float* actions, float* actions_out, float* targets, const BezkTaskCfg& cfg,

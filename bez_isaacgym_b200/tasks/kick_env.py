@@ -44,7 +44,7 @@ class KickEnv(VecTask):
     #: skeleton, one actor per env, 52-wide observation, their own heading term / reward / goal randomisation (bezk.h)
     TASK = "kick"
     #: host pipelines (``sim.use_gpu_pipeline: False``), selected by ``env.hostPipeline``
-    HOST_PIPELINES = ("zero_copy", "staged")
+    HOST_PIPELINES = ("zero_copy", "staged", "staged_ce")
 
     def __init__(self, cfg, sim_device, graphics_device_id, headless, sim: SimBackend = None, fusion="fused"):
         self.cfg = cfg
@@ -94,17 +94,21 @@ class KickEnv(VecTask):
         # simulator tensors (borrowed) and their device images
         self.root_states, self.dof_state = self.sim.root_states, self.sim.dof_state
         self.rigid_body, self.net_contact = self.sim.rigid_body, self.sim.net_contact
-        # host pipeline: "zero_copy" (default) hands the PINNED host tensors straight to the kernels -- they gather the
-        # few bytes they need over PCIe and write resets back in place; "staged" copies all four tensors to HBM first
+        # host pipelines (every task): "zero_copy" (default) hands the PINNED host tensors straight to the kernels -- they gather
+        # the few bytes they need over PCIe and write resets back in place; "staged" copies all four tensors to HBM first;
+        # "staged_ce" moves everything with the copy engines in a chunked three-stream pipeline (dense tensors by
+        # cudaMemcpyAsync, the sparse AoS rows by strided cudaMemcpy2DAsync pulls, results back by cudaMemcpyAsync)
         self.host_mode = env_cfg.get("hostPipeline", "zero_copy") if self.host_staged else None
-        if self.host_staged and self.TASK != "kick":
-            raise NotImplementedError("the host pipeline is implemented for BezKick only; walk / orient need the GPU pipeline")
         if self.host_mode is not None and self.host_mode not in self.HOST_PIPELINES:
             raise ValueError(f"env.hostPipeline must be one of {self.HOST_PIPELINES}, got {self.host_mode}")
-        if self.host_staged and self.host_mode == "zero_copy" and not all(
+        if self.host_staged and self.host_mode in ("zero_copy", "staged_ce") and not all(
                 t.is_pinned() for t in (self.root_states, self.dof_state, self.rigid_body, self.net_contact)):
-            raise ValueError("hostPipeline='zero_copy' needs the simulator tensors in pinned (page-locked) host memory")
-        if self.host_mode == "staged":
+            raise ValueError(f"hostPipeline='{self.host_mode}' needs the simulator tensors in pinned (page-locked) host memory")
+        if self.host_mode == "staged_ce":
+            self._d_root, self._d_dof = (torch.empty_like(t, device=dev) for t in (self.root_states, self.dof_state))
+            self._d_rb = torch.zeros(n, 10, **f32)                                    # IMU-link slices (bezk_stage_sparse_rows)
+            self._d_cf = torch.zeros(n, 24 if self.cleats else 8, **f32)              # foot / cleat force rows
+        elif self.host_mode == "staged":
             self._d_root, self._d_dof = (torch.empty_like(t, device=dev) for t in (self.root_states, self.dof_state))
             self._d_rb, self._d_cf = (torch.empty_like(t, device=dev) for t in (self.rigid_body, self.net_contact))
         else:
@@ -155,15 +159,16 @@ class KickEnv(VecTask):
             num_bodies=self.sim.num_bodies, cleats=self.cleats, dt=self.dt, max_episode_length=self.max_episode_length,
             clip_actions=float(self.clip_actions), clip_obs=float(self.clip_obs), default_dof_pos=ready,
             bez_init_xy=tuple(self.bez_init_state[0:2]),
-            write_contact_filter=bool(env_cfg.get("writeContactFilter", not self.host_staged)),
+            write_contact_filter=bool(env_cfg.get("writeContactFilter", not self.host_staged)) and self.host_mode != "staged_ce",
             reset_root_states=not self.sim.owns_root_reset)
 
         # persistent task state
         self._prev_buf = torch.zeros(n, 3, **f32)       # the reference's int64 zeros, promoted (kick_env.py:183)
         self._prev_is_view = False
         # PD targets go to the simulator: pinned host memory (written by K0 over PCIe) when the simulator lives on the host
-        self.targets = torch.zeros(n, 18, dtype=torch.float32).pin_memory() if self.host_mode == "zero_copy" \
+        self.targets = torch.zeros(n, 18, dtype=torch.float32).pin_memory() if self.host_mode in ("zero_copy", "staged_ce") \
             else torch.zeros(n, 18, **f32)
+        self._d_targets = torch.zeros(n, 18, **f32) if self.host_mode == "staged_ce" else self.targets
         self._actions_in = torch.zeros(n, 18, **f32)      # staging buffer for actions arriving from another device
         self._actions_src = self._actions_in
         self._actions_cache = None
@@ -171,19 +176,32 @@ class KickEnv(VecTask):
         if self.host_mode == "zero_copy":
             # write-only outputs live in pinned host memory: the kernel's stores (TMA bulk store for the obs tile) cross
             # PCIe while its gathers come the other way (full duplex), and step() needs no D2H copies for them
-            self.obs_buf = torch.zeros(n, 54, dtype=torch.float32).pin_memory()
+            self.obs_buf = torch.zeros(n, self._obs_width, dtype=torch.float32).pin_memory()
             self.rew_buf = torch.zeros(n, dtype=torch.float32).pin_memory()
             self.timeout_buf = torch.zeros(n, dtype=torch.long).pin_memory()
             if self.obs_clipped_buf is not None:
-                self.obs_clipped_buf = torch.zeros(n, 54, dtype=torch.float32).pin_memory()
+                self.obs_clipped_buf = torch.zeros(n, self._obs_width, dtype=torch.float32).pin_memory()
         self._rng_step = 0
+        self._ce_copy_out = False
         self._rollout = None                # (BezkRolloutCfg, values, shaped_rewards, dones_u8) set by set_rollout_targets
         self._lib = _lib.load()
         if self.host_staged:
             pin = dict(pin_memory=True)
-            self._h_obs = torch.empty(n, 54, **pin); self._h_rew = torch.empty(n, **pin)
+            self._h_obs = torch.empty(n, self._obs_width, **pin); self._h_rew = torch.empty(n, **pin)
             self._h_reset = torch.empty(n, dtype=torch.long, **pin); self._h_timeout = torch.empty(n, dtype=torch.long, **pin)
             self._h_actions = torch.empty(n, 18, **pin)
+        if self.host_mode == "staged_ce":
+            if self.fusion != "fused":
+                raise ValueError("hostPipeline='staged_ce' runs the fused step (fusion='fused')")
+            if self._kcfg.flags & _lib.F_WRITE_CONTACT_FILTER:
+                raise ValueError("hostPipeline='staged_ce' cannot write the contact filter back (env.writeContactFilter must be False)")
+            self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            chunks = max(1, int(env_cfg.get("hostPipelineChunks", 4)))
+            step_sz = max(128, -(-n // chunks) // 128 * 128)           # chunk starts stay multiples of 128 envs (TMA alignment)
+            self._ce_chunks = [(lo, min(n, lo + step_sz)) for lo in range(0, n, step_sz)]
+            mk = lambda: torch.cuda.Event()                            # noqa: E731
+            self._ev_in, self._ev_k = [mk() for _ in self._ce_chunks], [mk() for _ in self._ce_chunks]
+            self._ev_tgt = mk()
         self._bind()
         self._link = {"h2d_bytes": 0, "d2h_bytes": 0}
         self._link_per_step = self._host_link_bytes_per_step() if self.host_staged else (0, 0)
@@ -222,7 +240,59 @@ class KickEnv(VecTask):
     def _stream(self):
         return _P(torch.cuda.current_stream(self.compute_device).cuda_stream)
 
+    def _launch_staged(self, parts, lo=0, hi=None):
+        """``bezk_post_physics_staged`` over envs [lo, hi) of the staged_ce host pipeline (device staging in, device results
+        out, reset rows written straight back into the simulator's pinned host tensors)."""
+        n = self.num_envs
+        hi = n if hi is None else hi
+        rw, ow = 13 * self._actors, self._obs_width
+        off = lambda t, k: None if t is None else _P(t.data_ptr() + k * t.element_size())      # noqa: E731
+        clip = self.obs_clipped_buf
+        rc = self._lib.bezk_post_physics_staged(
+            ops._TASK_ID[self.TASK], off(self._d_dof, lo * 36), off(self._d_rb, lo * 10), off(self._d_root, lo * rw),
+            off(self._d_cf, lo * self._d_cf.shape[1]), None if self._prev_is_view else off(self._prev_buf, lo * 3),
+            off(self.goal, lo * 2), off(self.goal_angle, lo), off(self.ball_init, lo * 2), off(self.initial_root_states, lo * rw),
+            None, None, self._seed, self._rng_step, off(self.reset_buf, lo), off(self.progress_buf, lo), off(self.timeout_buf, lo),
+            None, C.byref(self._kcfg), off(self.obs_buf, lo * ow), off(clip, lo * ow), off(self.rew_buf, lo), parts, hi - lo,
+            self.env_base + lo, off(self.dof_state, lo * 36), off(self.root_states, lo * rw), self._stream())
+        if rc:
+            _lib.check(rc, "bezk_post_physics_staged")
+
+    def _post_staged_ce(self, copy_out):
+        """One post-physics step of the copy-engine host pipeline, chunked so that chunk c's transfers overlap chunk c-1's kernel
+        and chunk c-2's results going back: [s_in] dense cudaMemcpyAsync + strided cudaMemcpy2DAsync pulls of the sparse rows ->
+        [current stream] fused kernel on device staging -> [s_out] results to the pinned host buffers."""
+        cur = torch.cuda.current_stream(self.compute_device)
+        rw, ow = 13 * self._actors, self._obs_width
+        root_h, root_d = self.root_states.view(-1, rw), self._d_root.view(-1, rw)
+        dof_h, dof_d = self.dof_state.view(-1, 36), self._d_dof.view(-1, 36)
+        kc = C.byref(self._kcfg)
+        self._s_in.wait_stream(cur)                       # staging buffers are free again (previous step's kernels are done)
+        s_in_h = _P(self._s_in.cuda_stream)
+        out = self._observations_out()
+        for c, (lo, hi) in enumerate(self._ce_chunks):
+            with torch.cuda.stream(self._s_in):
+                dof_d[lo:hi].copy_(dof_h[lo:hi], non_blocking=True)
+                root_d[lo:hi].copy_(root_h[lo:hi], non_blocking=True)
+                rc = self._lib.bezk_stage_sparse_rows(_ptr(self.rigid_body), _ptr(self.net_contact), kc, _ptr(self._d_rb),
+                                                      _ptr(self._d_cf), lo, hi - lo, s_in_h)
+                if rc:
+                    _lib.check(rc, "bezk_stage_sparse_rows")
+                self._ev_in[c].record(self._s_in)
+            cur.wait_event(self._ev_in[c])
+            self._launch_staged(_lib.PART_ALL, lo, hi)
+            if copy_out:
+                self._ev_k[c].record(cur)
+                with torch.cuda.stream(self._s_out):
+                    self._s_out.wait_event(self._ev_k[c])
+                    self._h_obs[lo:hi].copy_(out[lo:hi], non_blocking=True)
+                    self._h_rew[lo:hi].copy_(self.rew_buf[lo:hi], non_blocking=True)
+                    self._h_reset[lo:hi].copy_(self.reset_buf[lo:hi], non_blocking=True)
+                    self._h_timeout[lo:hi].copy_(self.timeout_buf[lo:hi], non_blocking=True)
+
     def _launch_post(self, parts):
+        if self.host_mode == "staged_ce":
+            return self._launch_staged(parts)
         f = self._post_fixed
         prev = None if self._prev_is_view else _ptr(self._prev_buf)
         if parts == _lib.PART_ALL:
@@ -254,6 +324,9 @@ class KickEnv(VecTask):
         nbytes = lambda t: t.numel() * t.element_size()      # noqa: E731
         outs = nbytes(self._observations_out()) + nbytes(self.rew_buf) + nbytes(self.timeout_buf) + nbytes(self.reset_buf) \
             + nbytes(self.targets)
+        if self.host_mode == "staged_ce":                 # the arguments of the copies issued each step
+            sparse = n * (40 + (96 if self.cleats else 24))
+            return nbytes(self.dof_state) + nbytes(self.root_states) + n * 18 * 4 + sparse, outs
         if self.host_mode == "staged":
             h2d = sum(nbytes(t) for t in (self.root_states, self.dof_state, self.rigid_body, self.net_contact)) + n * 18 * 4
             d2h = outs + nbytes(self.dof_state)
@@ -282,6 +355,8 @@ class KickEnv(VecTask):
 
     def link_counters(self):
         how = {"staged": "sizes of the tensors copied by cudaMemcpyAsync each step",
+               "staged_ce": "byte counts of the cudaMemcpyAsync / cudaMemcpy2DAsync (width x rows) calls issued each step (+ the rare reset "
+                            "rows the kernel writes back into the simulator's host tensors, not counted)",
                "zero_copy": "address ranges the kernels dereference in pinned host memory each step: dense tensors whole, sparse AoS rows as "
                             "distinct 64-byte granules (+ the rare reset rows written back, not counted)",
                None: "GPU pipeline: nothing crosses the host link"}[self.host_mode]
@@ -325,11 +400,20 @@ class KickEnv(VecTask):
             for d, h in ((self._d_root, self.root_states), (self._d_dof, self.dof_state), (self._d_rb, self.rigid_body),
                          (self._d_cf, self.net_contact)):
                 d.copy_(h, non_blocking=True)
+        elif self.host_mode == "staged_ce":                # unchunked, on the current stream: the stand-alone calls
+            self._d_root.copy_(self.root_states, non_blocking=True)
+            self._d_dof.copy_(self.dof_state, non_blocking=True)
+            rc = self._lib.bezk_stage_sparse_rows(_ptr(self.rigid_body), _ptr(self.net_contact), C.byref(self._kcfg), _ptr(self._d_rb),
+                                                  _ptr(self._d_cf), 0, self.num_envs, self._stream())
+            if rc:
+                _lib.check(rc, "bezk_stage_sparse_rows")
 
     def pre_physics_step(self, actions):
         """kick_env.py:410-419 (+ the clamp of vec_task.py:317): one K0 launch."""
         if actions.shape != (self.num_envs, 18) or actions.dtype != torch.float32:
             raise ValueError(f"actions must be float32 of shape ({self.num_envs}, 18)")
+        if self.host_mode == "staged_ce":
+            return self._pre_physics_staged_ce(actions)
         if actions.device != self.compute_device:
             if self.host_staged and actions.device.type == "cpu" and not actions.is_pinned():
                 self._h_actions.copy_(actions)
@@ -349,12 +433,48 @@ class KickEnv(VecTask):
             _lib.check(rc, "bezk_pre_physics")
         self.sim.set_dof_position_targets(self.targets)
 
+    def _pre_physics_staged_ce(self, actions):
+        """actions H2D [s_in] -> K0 [current stream] -> PD targets D2H into the simulator's pinned ``targets`` [s_out], in the
+        same chunks as the post-physics pipeline so that the two directions of the link overlap."""
+        cur = torch.cuda.current_stream(self.compute_device)
+        if actions.device.type == "cpu" and not actions.is_pinned():
+            self._h_actions.copy_(actions)
+            actions = self._h_actions
+        self._actions_cache = None
+        on_device = actions.device == self.compute_device
+        src = (actions if actions.is_contiguous() else actions.contiguous()) if on_device else self._actions_in
+        self._actions_src = src
+        kc = C.byref(self._kcfg)
+        if not on_device:
+            self._s_in.wait_stream(cur)
+        for c, (lo, hi) in enumerate(self._ce_chunks):
+            if not on_device:
+                with torch.cuda.stream(self._s_in):
+                    self._actions_in[lo:hi].copy_(actions[lo:hi], non_blocking=True)
+                    self._ev_in[c].record(self._s_in)
+                cur.wait_event(self._ev_in[c])
+            rc = self._lib.bezk_pre_physics(_P(src.data_ptr() + lo * 72), None, _P(self._d_targets.data_ptr() + lo * 72), kc, hi - lo,
+                                            self._stream())
+            if rc:
+                _lib.check(rc, "bezk_pre_physics")
+            self._ev_k[c].record(cur)
+            with torch.cuda.stream(self._s_out):
+                self._s_out.wait_event(self._ev_k[c])
+                self.targets[lo:hi].copy_(self._d_targets[lo:hi], non_blocking=True)
+        self._ev_tgt.record(self._s_out)
+        self.sim.set_dof_position_targets(self.targets)
+
     def post_physics_step(self):
         """vec_task.py:331-332 + kick_env.py:426-438 in one launch (two with ``fusion='split'``)."""
         self._rng_step += 1
         self._randomize_pending += 1                      # randomize_buf += 1 (kick_env.py:430), applied lazily
         if self.randomize and self._resets_pending():     # reset_idx -> apply_randomizations (kick_env.py:433-435, 781-782)
             self.apply_randomizations(self.randomization_params)
+        if self.host_mode == "staged_ce" and self.fusion == "fused":
+            self._post_staged_ce(copy_out=self._ce_copy_out)
+            if self._alias_prev:
+                self._prev_is_view = True
+            return
         self._stage_in()
         if self.fusion == "fused":
             self._launch_post(_lib.PART_ALL)
@@ -374,7 +494,9 @@ class KickEnv(VecTask):
         """kick_env.py:749-777 as a stand-alone call (observation kernel only, no bookkeeping)."""
         self._stage_in()
         prev = None if self._prev_is_view else self._prev_buf
-        if self.TASK == "kick":
+        if self.host_mode == "staged_ce":
+            self._launch_staged(_lib.PART_OBS)
+        elif self.TASK == "kick":
             ops.compute_observations(self._d_dof, self._d_rb, self._d_root, self._d_cf, self.goal, self.ball_init, self._kcfg,
                                      self.obs_buf, prev_lin_vel=prev, obs_clipped=self.obs_clipped_buf)
         else:
@@ -386,7 +508,10 @@ class KickEnv(VecTask):
 
     def compute_reward(self, actions=None):
         """kick_env.py:724-747 as a stand-alone call (reward / termination kernel only)."""
-        if self.TASK == "kick":
+        if self.host_mode == "staged_ce":
+            self._stage_in()
+            self._launch_staged(_lib.PART_REWARD)
+        elif self.TASK == "kick":
             ops.compute_reward(self._d_dof, self._d_rb, self._d_root, self.goal, self.ball_init, self.reset_buf,
                                self.progress_buf, self._kcfg, self.rew_buf, self.reset_buf)
         else:
@@ -404,7 +529,7 @@ class KickEnv(VecTask):
         ops.reset_idx_task(self.TASK, env_ids, self._d_dof, self._d_root, self.initial_root_states,
                            None if self.TASK == "kick" else self.goal, self.progress_buf, self.reset_buf, self._kcfg,
                            seed=self._seed, step=self._rng_step, env_base=self.env_base)
-        if self.host_mode == "staged":
+        if self.host_mode in ("staged", "staged_ce"):
             self.dof_state.copy_(self._d_dof)
             if self._kcfg.flags & _lib.F_RESET_ROOT_STATES:
                 self.root_states.copy_(self._d_root)
@@ -492,8 +617,29 @@ class KickEnv(VecTask):
         self._link["h2d_bytes"] += self._link_per_step[0]
         self._link["d2h_bytes"] += self._link_per_step[1]
         self.pre_physics_step(actions)
+        # a simulator on the host reads the PD targets now: they must have landed in its memory
+        if self.host_mode == "staged_ce":
+            self._ev_tgt.synchronize()
+        else:
+            torch.cuda.current_stream(self.compute_device).synchronize()
         for _ in range(self.control_freq_inv):
             self.sim.simulate()
+        if self.host_mode == "staged_ce":
+            self._ce_copy_out = True
+            try:
+                self.post_physics_step()
+            finally:
+                self._ce_copy_out = False
+            self._s_out.synchronize()
+            torch.cuda.current_stream(self.compute_device).wait_stream(self._s_out)
+            rl = torch.device(self.rl_device)
+            if rl.type == "cpu":
+                self.extras["time_outs"] = self._h_timeout
+                self.obs_dict["obs"] = self._h_obs
+                return self.obs_dict, self._h_rew, self._h_reset, self.extras
+            self.extras["time_outs"] = self.timeout_buf.to(rl)
+            self.obs_dict["obs"] = self._observations_out().to(rl)
+            return self.obs_dict, self.rew_buf.to(rl), self.reset_buf.to(rl), self.extras
         self.post_physics_step()
         self._h_reset.copy_(self.reset_buf, non_blocking=True)
         if self.host_mode == "zero_copy":

@@ -139,6 +139,26 @@ int bezk_post_physics_chunk(float* dof_state, const float* rigid_body, float* ro
                             float* rew, int parts, int64_t n, int64_t env_base, float* dof_state_wb,
                             float* root_states_wb, void* stream);
 
+/* Host pipeline (sim_device=cpu / use_gpu_pipeline: False; ref: tasks/base/vec_task.py:51-98 device selection): the simulator
+ * tensors live in PINNED HOST memory.  bezk_stage_sparse_rows pulls the few bytes per env the step needs out of the two sparse
+ * AoS tensors with strided copy-engine transfers (cudaMemcpy2DAsync) into compact DEVICE staging, for envs [env0, env0 + n):
+ *   imu_stage  (N,10) f32  <- rigid_body row (env, imu_body), floats 3..12 (quaternion, linear and angular velocity)
+ *   feet_stage (N,8)  f32  <- [left foot xyz, pad, right foot xyz, pad]        (cleats: (N,24) = [4 left cleat rows, 4 right])
+ * (pointers are the tensor BASES; env0 selects the chunk).  bezk_post_physics_staged is bezk_post_physics_chunk reading those
+ * staging buffers in place of rigid_body / net_contact, for any task (arguments as bezk_post_physics_task); everything else
+ * (dense dof_state / root_states staging copies, the write-back pointers into the simulator's own host tensors, env_base) as
+ * documented there.  BEZK_F_WRITE_CONTACT_FILTER must be
+ * clear (the filtered forces would land in the staging buffer, not in the simulator's tensor). */
+int bezk_stage_sparse_rows(const float* rigid_body_host, const float* net_contact_host, const BezkTaskCfg* cfg,
+                           float* imu_stage, float* feet_stage, int64_t env0, int64_t n, void* stream);
+int bezk_post_physics_staged(int task, float* dof_state, const float* imu_stage, float* root_states, float* feet_stage,
+                             float* prev_lin_vel, float* goal, const float* goal_angle, const float* ball_init,
+                             const float* initial_root_states, const float* uniforms, const float* goal_uniforms,
+                             uint64_t seed, uint64_t step, int64_t* reset_buf, int64_t* progress_buf,
+                             int64_t* timeout_buf, int64_t* randomize_buf, const BezkTaskCfg* cfg, float* obs,
+                             float* obs_clipped, float* rew, int parts, int64_t n, int64_t env_base,
+                             float* dof_state_wb, float* root_states_wb, void* stream);
+
 /* The dense (n,36) uniforms the Philox path of bezk_post_physics / bezk_reset_idx consumes for
  * (seed, step): lets a checker feed the identical draws to the reference's reset_idx. */
 int bezk_philox_uniforms(uint64_t seed, uint64_t step, float* out, int64_t n, void* stream);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Host-pipeline (e2e) experiment: KickEnv.step with the simulator tensors in pinned host memory, per-step wall time and the
-device time of K0 / the post-physics kernel, for the zero-copy and the staged pipelines.  Knobs come from the environment
-(BEZK_SMART_GRANULE=0|1|2).   python tools/exp_e2e.py [--envs 65536]"""
+"""Host-pipeline (e2e) experiment: KickEnv.step with the simulator tensors in pinned host memory -- wall time per env step
+(one stream sync per step, results on the host) for the zero-copy, staged and copy-engine (staged_ce, by chunk count)
+pipelines.  One JSON line per configuration.   python tools/exp_e2e.py [--envs 262144] [--steps 64]"""
 import argparse
 import json
 import os
@@ -19,21 +19,25 @@ from bez_isaacgym_b200.tasks.kick_env import KickEnv  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--envs", type=int, default=65536)
+    ap.add_argument("--envs", type=int, default=262144)
     ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--modes", default="zero_copy,staged_ce:1,staged_ce:2,staged_ce:4,staged_ce:8,staged_ce:16,staged")
     args = ap.parse_args()
     n = args.envs
-    out = {"envs": n, "smart_granule": os.environ.get("BEZK_SMART_GRANULE", "1")}
 
     class OwnedRootSim(SyntheticGym):
         owns_root_reset = True
 
-    for mode in ("zero_copy", "staged"):
+    sim = OwnedRootSim(n, device="cuda:0", seed=1, host=True, filler=True)
+    act = sg.make_actions(n, seed=1).pin_memory()
+    for spec in args.modes.split(","):
+        mode, _, chunks = spec.partition(":")
         cfg = bm.default_task_cfg(n, use_gpu_pipeline=False, rl_device="cpu")
         cfg["env"]["imuPrevVelAliasing"] = False
         cfg["env"]["hostPipeline"] = mode
-        env = KickEnv(cfg, "cuda:0", 0, True, sim=OwnedRootSim(n, device="cuda:0", seed=1, host=True, filler=True))
-        act = sg.make_actions(n, seed=1).pin_memory()
+        if chunks:
+            cfg["env"]["hostPipelineChunks"] = int(chunks)
+        env = KickEnv(cfg, "cuda:0", 0, True, sim=sim)
         for _ in range(5):
             env.step(act)
         torch.cuda.synchronize()
@@ -41,18 +45,22 @@ def main():
         for _ in range(args.steps):
             env.step(act)
         torch.cuda.synchronize()
-        out[f"{mode}_ms_per_step"] = round(1e3 * (time.perf_counter() - t0) / args.steps, 4)
-        # device time of the two kernels alone
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        k0 = post = 0.0
-        for _ in range(16):
-            ev[0].record(); env.pre_physics_step(act); ev[1].record(); env.post_physics_step(); ev[2].record()
-            torch.cuda.synchronize()
-            k0 += ev[0].elapsed_time(ev[1]); post += ev[1].elapsed_time(ev[2])
-        out[f"{mode}_k0_ms"] = round(k0 / 16, 4)
-        out[f"{mode}_post_ms"] = round(post / 16, 4)
+        ms = 1e3 * (time.perf_counter() - t0) / args.steps
+        # the two halves of a step
+        t_pre = t_post = 0.0
+        for _ in range(8):
+            torch.cuda.synchronize(); a = time.perf_counter()
+            env.pre_physics_step(act)
+            torch.cuda.synchronize(); b = time.perf_counter()
+            env._ce_copy_out = mode == "staged_ce"
+            env.post_physics_step()
+            env._ce_copy_out = False
+            torch.cuda.synchronize(); c = time.perf_counter()
+            t_pre += b - a; t_post += c - b
+        print(json.dumps({"mode": mode, "chunks": int(chunks) if chunks else None, "envs": n, "ms_per_step": round(ms, 4),
+                          "env_steps_per_s_M": round(n / ms / 1e3, 2), "pre_ms": round(1e3 * t_pre / 8, 4),
+                          "post_ms": round(1e3 * t_post / 8, 4)}), flush=True)
         del env
-    print(json.dumps(out))
 
 
 if __name__ == "__main__":
