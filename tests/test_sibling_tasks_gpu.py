@@ -196,7 +196,7 @@ def test_sibling_env_philox_goal_is_one_draw_per_step(task, cls):
     assert int(env.progress_buf[flagged].max()) == 0
 
 
-def test_sibling_rejects_unsupported_parts_and_host_pipeline():
+def test_sibling_rejects_unsupported_parts_and_serves_the_host_pipeline():
     from bez_isaacgym_b200 import ops, tasks
     from bez_isaacgym_b200._lib import BezkError
     n = 8
@@ -211,5 +211,7 @@ def test_sibling_rejects_unsupported_parts_and_host_pipeline():
     with pytest.raises(BezkError):          # orient without goal_angle
         ops.post_physics_task("orient", st.dof_state, st.rigid_body, st.root_states, st.net_contact, goal, None, None, None, None,
                               cfg, torch.empty(n, 52, device="cuda"), None, parts=2)
-    with pytest.raises(NotImplementedError):
-        tasks.WalkEnv(bm.default_task_cfg(n, task="walk", use_gpu_pipeline=False, rl_device="cpu"), "cpu", 0, True)
+    # sim_device="cpu" (the reference's device selection, tasks/base/vec_task.py:51-98) serves every task: host pipeline
+    env = tasks.WalkEnv(bm.default_task_cfg(n, task="walk", use_gpu_pipeline=False, rl_device="cpu"), "cpu", 0, True)
+    o, r, d, e = env.step(torch.zeros(n, 18))
+    assert o["obs"].shape == (n, 52) and o["obs"].device.type == "cpu" and r.device.type == "cpu" and d.dtype == torch.long
