@@ -316,6 +316,41 @@ int bezk_rms_normalize_slabs(const float* x, int64_t slab_rows, int64_t slab_str
                                               (cudaStream_t)stream), "bezk_rms_normalize_slabs");
 }
 
+int bezk_rms_train_forward(const float* x, int64_t slab_rows, int64_t slab_stride, double* running_mean, double* running_var,
+                           double* count, float eps, float* y, double* partials, int64_t m, int32_t c, void* stream) {
+    REQUIRE(m > 0 && c > 0 && c <= 4096, "bad m/c");
+    REQUIRE(x && y && running_mean && running_var && count && partials, "rms buffers NULL");
+    if (int rc = check_slabs(slab_rows, slab_stride, m)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool aligned = (c % 2 != 0) || (ALIGNED(x, 8) && ALIGNED(y, 8));
+    if (aligned && bezk::fused_stats_eligible(m, c))
+        return cuda_rc(bezk::launch_rms_train_forward(x, running_mean, running_var, count, eps, y, partials, m, c, slab_rows, slab_stride,
+                                                      st), "bezk_rms_train_forward");
+    // sizes beyond one shared-memory-resident block per SM: the streaming chain.  pivot / acc live at the tail of `partials`.
+    REQUIRE(m / slab_rows <= 65535, "more than 65535 slabs");
+    double* acc = partials + bezk::rms_scratch_doubles(c) - (1 + 2 * (int64_t)c) - c;
+    double* pivot = acc + 1 + 2 * (int64_t)c;
+    cudaError_t e = cudaMemcpyAsync(pivot, running_mean, sizeof(double) * c, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = bezk::launch_rms_moments(x, pivot, acc, partials, m, c, slab_rows, slab_stride, st);
+    if (e == cudaSuccess) e = bezk::launch_rms_merge(acc, pivot, running_mean, running_var, count, c, st);
+    if (e == cudaSuccess) e = bezk::launch_rms_normalize(x, running_mean, running_var, eps, 0, y, m, c, slab_rows, slab_stride, st);
+    return cuda_rc(e, "bezk_rms_train_forward");
+}
+
+int bezk_adv_normalize_fused(const float* returns, const float* values, float* adv_out, double* partials, int normalize, int64_t m,
+                             void* stream) {
+    REQUIRE(m > 0, "m must be positive");
+    REQUIRE(returns && values && adv_out && partials, "adv buffers NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bezk::fused_stats_eligible(m, 1))
+        return cuda_rc(bezk::launch_adv_fused(returns, values, adv_out, partials, normalize, m, st), "bezk_adv_normalize_fused");
+    double* acc = partials + bezk::rms_scratch_doubles(1) - 4;
+    cudaError_t e = cudaSuccess;
+    if (normalize) e = bezk::launch_adv_moments(returns, values, acc, partials, m, st);
+    if (e == cudaSuccess) e = bezk::launch_adv_normalize(returns, values, acc, adv_out, normalize, m, st);
+    return cuda_rc(e, "bezk_adv_normalize_fused");
+}
+
 int bezk_adv_moments(const float* returns, const float* values, double* acc, double* partials, int64_t m, void* stream) {
     REQUIRE(m > 0, "m must be positive");
     REQUIRE(returns && values && acc && partials, "adv buffers NULL");

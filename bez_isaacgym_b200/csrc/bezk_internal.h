@@ -51,6 +51,9 @@ struct PpoArgs {
     const float *actions, *mu, *logstd, *old_mu, *old_sigma, *values, *old_values, *returns, *old_neglogp, *advantages;
     float *grad_mu, *grad_values, *neglogp_out;
     double* partials;
+    double* stats;             // (8,) loss terms; with fused_finalize CTA 0 writes them after a grid barrier
+    float* grad_logstd;
+    int fused_finalize;
     int64_t m;
     int64_t slab_rows, slab_stride;   // rollout-side tensors as slabs of time-major storage (slab_rows == m: contiguous)
     int slabs;
@@ -83,4 +86,8 @@ cudaError_t launch_dr_fill(uint64_t, uint64_t, int, float*, int64_t, cudaStream_
 cudaError_t launch_selftest_fastmath(uint64_t, uint64_t, unsigned long long*, cudaStream_t);
 int64_t ppo_scratch_doubles();
 cudaError_t launch_ppo_loss(const PpoArgs&, const BezkPpoCfg&, double*, float*, cudaStream_t);
+bool fused_stats_eligible(int64_t m, int c);
+cudaError_t launch_rms_train_forward(const float*, double*, double*, double*, float, float*, double*, int64_t, int, int64_t, int64_t,
+                                     cudaStream_t);
+cudaError_t launch_adv_fused(const float*, const float*, float*, double*, int, int64_t, cudaStream_t);
 }  // namespace bezk

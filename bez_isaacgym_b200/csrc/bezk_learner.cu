@@ -5,6 +5,7 @@
 // finalize), so results are run-to-run deterministic and additive across ranks.
 #include "bezk_common.cuh"
 #include "bezk_internal.h"
+#include <cooperative_groups.h>
 #include <math.h>
 
 namespace bezk {
@@ -384,7 +385,8 @@ static inline int stream_blocks(int64_t work_items, int threads, int per_sm) {
     return (int)(b > cap ? cap : b);
 }
 
-int64_t rms_scratch_doubles(int c) { return (int64_t)RMS_MAX_BLOCKS * 2 * (c > 0 ? c : 1); }
+// per-block partials of the largest grid + room for one (1 + 2c) accumulator and a c-wide pivot (bezk_rms_train_forward's chain)
+int64_t rms_scratch_doubles(int c) { const int64_t cc = c > 0 ? c : 1; return (int64_t)RMS_MAX_BLOCKS * 2 * cc + (1 + 2 * cc) + cc + 4; }
 
 cudaError_t launch_rms_moments(const float* x, const double* pivot, double* acc, double* partials, int64_t m, int c,
                                int64_t slab_rows, int64_t slab_stride, cudaStream_t st) {
@@ -530,6 +532,21 @@ constexpr int PPO_NSTAT = 7;                    // a, c, b, kl, clipped, (spare)
 constexpr int PPO_PART = PPO_NSTAT + 18;        // doubles per block
 constexpr int PPO_FLUSH = 8;                    // tiles between fp32 -> fp64 flushes
 constexpr int PPO_MAX_BLOCKS = 148 * 4;         // persistent grid: every CTA walks tiles blockIdx.x, +gridDim.x, ...
+
+// s_tot: the PPO_PART column totals.  Thread 0 forms the loss terms (means), threads 0..17 the logstd gradients.
+__device__ __forceinline__ void ppo_form_loss(const double* s_tot, int64_t m, const float* __restrict__ logstd, const BezkPpoCfg& cfg,
+                                              double* __restrict__ stats, float* __restrict__ grad_logstd, int tid) {
+    const double inv_m = 1.0 / (double)m;
+    if (tid == 0) {
+        double ent = 0.0;
+        for (int k = 0; k < 18; ++k) ent += (double)((0.5f + 0.9189385332046727f) + logstd[k]);   // 0.5*log(2*pi)
+        const double a_m = s_tot[0] * inv_m, c_m = s_tot[1] * inv_m, b_m = s_tot[2] * inv_m, kl_m = s_tot[3] * inv_m;
+        stats[1] = a_m; stats[2] = c_m; stats[3] = ent; stats[4] = b_m; stats[5] = kl_m; stats[6] = s_tot[4] * inv_m; stats[7] = 0.0;
+        stats[0] = a_m + 0.5 * c_m * (double)cfg.critic_coef - ent * (double)cfg.entropy_coef + b_m * (double)cfg.bounds_loss_coef;
+    }
+    if (grad_logstd && tid < 18)
+        grad_logstd[tid] = (float)(s_tot[PPO_NSTAT + tid] * inv_m - (double)cfg.entropy_coef);
+}
 
 __global__ void __launch_bounds__(PPO_TILE, 4) ppo_loss_kernel(const PpoArgs a, const __grid_constant__ BezkPpoCfg cfg) {
     __shared__ __align__(128) float s_act[PPO_TILE * 18];
@@ -731,6 +748,22 @@ __global__ void __launch_bounds__(PPO_TILE, 4) ppo_loss_kernel(const PpoArgs a, 
         a.partials[(int64_t)blockIdx.x * PPO_PART + tid] = t;
     }
     if (tid == 0 && store_pending) bulk_wait_read0();
+    if (a.fused_finalize) {
+        // single-launch mode (cooperative grid): after a grid-wide barrier CTA 0 folds the partials and forms the loss -- the
+        // separate finalize launch costs more than the whole kernel at the reference's minibatch (32 768 samples)
+        __threadfence();
+        cooperative_groups::this_grid().sync();
+        if (blockIdx.x != 0) return;
+        double* s_tot = &s_red[0][0];
+        for (int j = wid; j < PPO_PART; j += PPO_TILE / 32) {
+            double t = 0.0;
+            for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(a.partials + (int64_t)b * PPO_PART + j);
+            t = warp_sum(t);
+            if (lane == 0) s_tot[j] = t;
+        }
+        __syncthreads();
+        ppo_form_loss(s_tot, a.m, a.logstd, cfg, a.stats, a.grad_logstd, tid);
+    }
 }
 
 // one warp per statistic folds the per-CTA partials (fixed order), thread 0 of warp 0 then forms the loss
@@ -744,17 +777,9 @@ __global__ void __launch_bounds__(1024) ppo_finalize_kernel(const double* __rest
         if (lane == 0) s_tot[j] = t;
     }
     __syncthreads();
-    const double inv_m = 1.0 / (double)m;
-    if (threadIdx.x == 0) {
-        double ent = 0.0;
-        for (int k = 0; k < 18; ++k) ent += (double)((0.5f + 0.9189385332046727f) + logstd[k]);   // 0.5*log(2*pi)
-        const double a_m = s_tot[0] * inv_m, c_m = s_tot[1] * inv_m, b_m = s_tot[2] * inv_m, kl_m = s_tot[3] * inv_m;
-        stats[1] = a_m; stats[2] = c_m; stats[3] = ent; stats[4] = b_m; stats[5] = kl_m; stats[6] = s_tot[4] * inv_m; stats[7] = 0.0;
-        stats[0] = a_m + 0.5 * c_m * (double)cfg.critic_coef - ent * (double)cfg.entropy_coef + b_m * (double)cfg.bounds_loss_coef;
-    }
-    if (grad_logstd && threadIdx.x < 18)
-        grad_logstd[threadIdx.x] = (float)(s_tot[PPO_NSTAT + threadIdx.x] * inv_m - (double)cfg.entropy_coef);
+    ppo_form_loss(s_tot, m, logstd, cfg, stats, grad_logstd, (int)threadIdx.x);
 }
+
 
 int64_t ppo_scratch_doubles() { return (int64_t)PPO_MAX_BLOCKS * PPO_PART; }
 
@@ -769,6 +794,21 @@ cudaError_t launch_ppo_loss(const PpoArgs& args, const BezkPpoCfg& cfg, double* 
     a.use_tma = aligned16(a.actions) && aligned16(a.mu) && aligned16(a.old_mu) && aligned16(a.old_sigma) &&
                 (a.grad_mu == nullptr || aligned16(a.grad_mu)) &&
                 (!a.slabs || (a.slab_rows % PPO_TILE == 0 && (a.slab_stride * 18 * 4) % 16 == 0));
+    a.stats = stats; a.grad_logstd = grad_logstd;
+    // the grid never exceeds 4 resident CTAs per SM (PPO_MAX_BLOCKS), so it can always be launched cooperatively: ONE launch,
+    // CTA 0 finalizes after a grid barrier.  BEZK_PPO_SINGLE_LAUNCH=0 keeps the two-kernel form (A/B measurements).
+    static const int single = env_int("BEZK_PPO_SINGLE_LAUNCH", 1);
+    if (single) {
+        a.fused_finalize = 1;
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)nblocks); lc.blockDim = dim3(PPO_TILE); lc.dynamicSmemBytes = 0; lc.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        lc.attrs = attr; lc.numAttrs = 1;
+        return cudaLaunchKernelEx(&lc, ppo_loss_kernel, a, cfg);
+    }
+    a.fused_finalize = 0;
     ppo_loss_kernel<<<(unsigned)nblocks, PPO_TILE, 0, st>>>(a, cfg);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;

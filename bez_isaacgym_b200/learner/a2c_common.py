@@ -37,13 +37,12 @@ def normalize_advantages(returns, values, normalize=True, process_group=None, ou
     r = returns.detach().reshape(-1).contiguous()
     v = values.detach().reshape(-1).contiguous()
     adv = out if out is not None else torch.empty_like(r)
-    acc = None
-    if normalize:
-        ws = _AdvWorkspace
-        if ws.acc is None or ws.acc.device != r.device:
-            ws.acc = torch.empty(3, dtype=torch.float64, device=r.device)
-            ws.scratch = torch.empty(ops.rms_scratch_doubles(1), dtype=torch.float64, device=r.device)
-        acc = ops.adv_moments(r, v, ws.acc, ws.scratch)
-        if process_group is not None:
-            bdist.allreduce_sum_(acc, process_group)
-    return ops.adv_normalize(r, v, acc, adv, normalize=normalize)
+    ws = _AdvWorkspace
+    if ws.acc is None or ws.acc.device != r.device:
+        ws.acc = torch.empty(3, dtype=torch.float64, device=r.device)
+        ws.scratch = torch.empty(ops.rms_scratch_doubles(1), dtype=torch.float64, device=r.device)
+    if not (normalize and process_group is not None and bdist.is_distributed(process_group)):
+        return ops.adv_normalize_fused(r, v, adv, ws.scratch, normalize=normalize)      # one call, one kernel at rollout sizes
+    acc = ops.adv_moments(r, v, ws.acc, ws.scratch)
+    bdist.allreduce_sum_(acc, process_group)
+    return ops.adv_normalize(r, v, acc, adv, normalize=True)

@@ -61,6 +61,15 @@ class RunningMeanStd(nn.Module):
             x = x.contiguous()
         if x.shape[-1] != self.insize and not (self.insize == 1 and x.dim() == 1):
             raise ValueError(f"expected last dim {self.insize}, got {tuple(x.shape)}")
+        local = self.process_group is None or not bdist.is_distributed(self.process_group)
+        if self.training and not unnorm and local:
+            # single-GPU train forward: ONE call -- moments, merge and normalise in one cooperative kernel at minibatch sizes
+            self._workspace(x.device)
+            rows = x.shape[0] * x.shape[1] if slab else x.numel() // self.insize
+            y = out if out is not None else (torch.empty(rows, self.insize, dtype=torch.float32, device=x.device) if slab
+                                             else torch.empty_like(x))
+            ops.rms_train_forward(x, self.running_mean, self.running_var, self.count.view(1), y, self._scratch, eps=self.epsilon)
+            return y
         if self.training:
             self.update(x)
         if slab:

@@ -288,6 +288,33 @@ def rms_normalize(x, running_mean, running_var, y, eps=1e-5, unnorm=False):
     return y
 
 
+def rms_train_forward(x, running_mean, running_var, count, y, partials, eps=1e-5):
+    """The whole train-mode ``RunningMeanStd.forward`` in ONE call (one cooperative kernel at the reference's minibatch sizes):
+    merge the batch moments of ``x`` into the running statistics, then ``y`` = normalise(x) with the updated statistics.
+    ``x``: contiguous (m, c) / (m,) or a slab view ``storage[:, e0:e0+E]``; ``y``: contiguous, m * c elements."""
+    c = running_mean.numel()
+    ptr, rows, stride, m = _slab_view(x, F32, "x", c)
+    if partials.numel() < rms_scratch_doubles(c):
+        raise BezkError("partials scratch too small")
+    lib = _lib.load()
+    _lib.check(lib.bezk_rms_train_forward(ptr, rows, stride, _p(running_mean, F64, "running_mean", c), _p(running_var, F64, "running_var", c),
+                                          _p(count, F64, "count", 1), float(eps), _p(y, F32, "y", m * c), _p(partials, F64, "partials"),
+                                          m, c, _stream(x)), "bezk_rms_train_forward")
+    return y
+
+
+def adv_normalize_fused(returns, values, adv_out, partials, normalize=True):
+    """``adv_out = returns - values`` normalised to zero mean / unit unbiased std, one call (single GPU)."""
+    m = returns.numel()
+    if partials.numel() < rms_scratch_doubles(1):
+        raise BezkError("partials scratch too small")
+    lib = _lib.load()
+    _lib.check(lib.bezk_adv_normalize_fused(_p(returns, F32, "returns", m), _p(values, F32, "values", m), _p(adv_out, F32, "adv_out", m),
+                                            _p(partials, F64, "partials"), int(bool(normalize)), m, _stream(returns)),
+               "bezk_adv_normalize_fused")
+    return adv_out
+
+
 def adv_moments(returns, values, acc, partials):
     m = returns.numel()
     lib = _lib.load()

@@ -191,6 +191,24 @@ int bezk_rms_merge(const double* acc, const double* pivot, double* running_mean,
 int bezk_rms_normalize(const float* x, const double* running_mean, const double* running_var,
                        float eps, int unnorm, float* y, int64_t m, int32_t c, void* stream);
 
+/* K4 + K5 in ONE call: the train-mode forward of RunningMeanStd (update the running statistics with the batch, then normalise
+ * the batch with the UPDATED statistics), what rl_games runs on every minibatch of every mini-epoch.  x may be a
+ * slab view (slab_rows / slab_stride as in bezk_rms_moments_slabs; slab_rows <= 0: contiguous); y (m,c) contiguous.
+ * When one block of rows per SM fits in shared memory (m*c*4 <= ~23 MB: the reference's 32 768 x 54 minibatch is 7 MB) this is
+ * ONE cooperative kernel -- rows are read from HBM once, kept in shared memory across a grid barrier, and written normalised:
+ * 216 B read + 216 B written per 54-wide sample.  Larger batches run the streaming chain (moments, merge, normalise).  Single-GPU
+ * only: with env-sharded ranks the moments are all-reduced between bezk_rms_moments and bezk_rms_merge.
+ * partials: scratch f64, >= bezk_rms_scratch_doubles(c). */
+int bezk_rms_train_forward(const float* x, int64_t slab_rows, int64_t slab_stride, double* running_mean,
+                           double* running_var, double* count, float eps, float* y, double* partials,
+                           int64_t m, int32_t c, void* stream);
+
+/* K7 in ONE call (single GPU): adv_out = returns - values, normalised to zero mean / unit (unbiased) std when normalize != 0.
+ * One cooperative kernel up to ~6 M samples, the bezk_adv_moments / bezk_adv_normalize chain beyond.
+ * partials: scratch f64, >= bezk_rms_scratch_doubles(1). */
+int bezk_adv_normalize_fused(const float* returns, const float* values, float* adv_out, double* partials,
+                             int normalize, int64_t m, void* stream);
+
 /* K7.  ref: a2c_common.py prepare_dataset: adv = returns - values, then (adv - mean)/(std + 1e-8)
  * with the unbiased std.  Step 1 accumulates acc (3,) f64 = [m, sum adv, sum adv^2] (additive across
  * ranks); step 2 normalises.  returns, values (m,) f32; adv_out (m,) f32. */
