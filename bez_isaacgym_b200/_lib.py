@@ -80,6 +80,8 @@ SIGNATURES = {
     "bezk_rms_merge": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P]),
     "bezk_rms_normalize": (C.c_int, [_P, _P, _P, C.c_float, C.c_int, _P, _I64, C.c_int32, _P]),
     "bezk_rms_train_forward": (C.c_int, [_P, _I64, _I64, _P, _P, _P, C.c_float, _P, _P, _I64, C.c_int32, _P]),
+    "bezk_rms_moments_ext": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _P, _P, _I64, C.c_int32, _P]),
+    "bezk_rms_merge_normalize": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _P, C.c_float, _P, _I64, C.c_int32, _P]),
     "bezk_adv_normalize_fused": (C.c_int, [_P, _P, _P, _P, C.c_int, _I64, _P]),
     "bezk_adv_moments": (C.c_int, [_P, _P, _P, _P, _I64, _P]),
     "bezk_adv_normalize": (C.c_int, [_P, _P, _P, _P, C.c_int, _I64, _P]),

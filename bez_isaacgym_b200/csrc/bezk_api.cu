@@ -322,19 +322,38 @@ int bezk_rms_train_forward(const float* x, int64_t slab_rows, int64_t slab_strid
     REQUIRE(x && y && running_mean && running_var && count && partials, "rms buffers NULL");
     if (int rc = check_slabs(slab_rows, slab_stride, m)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool aligned = (c % 2 != 0) || (ALIGNED(x, 8) && ALIGNED(y, 8));
-    if (aligned && bezk::fused_stats_eligible(m, c))
+    // the cooperative single-kernel form wins only where the whole pass is latency (c == 1: 8.3 us vs 12.6 us for the chain at
+    // 131 072 values); for the 54-wide minibatch its three serial phases lose to the chain's wide kernels (27 us vs 12.6 us,
+    // profiles/r02_learner_kernels.md)
+    if (c == 1 && bezk::fused_stats_eligible(m, c))
         return cuda_rc(bezk::launch_rms_train_forward(x, running_mean, running_var, count, eps, y, partials, m, c, slab_rows, slab_stride,
                                                       st), "bezk_rms_train_forward");
-    // sizes beyond one shared-memory-resident block per SM: the streaming chain.  pivot / acc live at the tail of `partials`.
+    // three launches: moments (pivot = the running mean itself, no copy) -> finalize (+ snapshot of the old statistics) ->
+    // merge + normalise.  The extended accumulator lives at the tail of `partials`.
     REQUIRE(m / slab_rows <= 65535, "more than 65535 slabs");
-    double* acc = partials + bezk::rms_scratch_doubles(c) - (1 + 2 * (int64_t)c) - c;
-    double* pivot = acc + 1 + 2 * (int64_t)c;
-    cudaError_t e = cudaMemcpyAsync(pivot, running_mean, sizeof(double) * c, cudaMemcpyDeviceToDevice, st);
-    if (e == cudaSuccess) e = bezk::launch_rms_moments(x, pivot, acc, partials, m, c, slab_rows, slab_stride, st);
-    if (e == cudaSuccess) e = bezk::launch_rms_merge(acc, pivot, running_mean, running_var, count, c, st);
-    if (e == cudaSuccess) e = bezk::launch_rms_normalize(x, running_mean, running_var, eps, 0, y, m, c, slab_rows, slab_stride, st);
+    double* acc = partials + bezk::rms_scratch_doubles(c) - (2 + 4 * (int64_t)c);
+    cudaError_t e = bezk::launch_rms_moments(x, running_mean, acc, partials, m, c, slab_rows, slab_stride, st, running_var, count);
+    if (e == cudaSuccess) e = bezk::launch_rms_merge_normalize(x, acc, running_mean, running_var, count, eps, y, m, c, slab_rows, slab_stride, st);
     return cuda_rc(e, "bezk_rms_train_forward");
+}
+
+int bezk_rms_moments_ext(const float* x, int64_t slab_rows, int64_t slab_stride, const double* running_mean, const double* running_var,
+                         const double* count, double* acc_ext, double* partials, int64_t m, int32_t c, void* stream) {
+    REQUIRE(m > 0 && c > 0 && c <= 4096, "bad m/c");
+    REQUIRE(x && running_mean && running_var && count && acc_ext && partials, "rms buffers NULL");
+    if (int rc = check_slabs(slab_rows, slab_stride, m)) return rc;
+    return cuda_rc(bezk::launch_rms_moments(x, running_mean, acc_ext, partials, m, c, slab_rows, slab_stride, (cudaStream_t)stream,
+                                            running_var, count), "bezk_rms_moments_ext");
+}
+
+int bezk_rms_merge_normalize(const float* x, int64_t slab_rows, int64_t slab_stride, const double* acc_ext, double* running_mean,
+                             double* running_var, double* count, float eps, float* y, int64_t m, int32_t c, void* stream) {
+    REQUIRE(m > 0 && c > 0 && c <= 4096, "bad m/c");
+    REQUIRE(x && y && acc_ext && running_mean && running_var && count, "rms buffers NULL");
+    if (int rc = check_slabs(slab_rows, slab_stride, m)) return rc;
+    REQUIRE(m / slab_rows <= 65535, "more than 65535 slabs");
+    return cuda_rc(bezk::launch_rms_merge_normalize(x, acc_ext, running_mean, running_var, count, eps, y, m, c, slab_rows, slab_stride,
+                                                    (cudaStream_t)stream), "bezk_rms_merge_normalize");
 }
 
 int bezk_adv_normalize_fused(const float* returns, const float* values, float* adv_out, double* partials, int normalize, int64_t m,

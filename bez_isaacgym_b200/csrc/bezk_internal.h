@@ -70,7 +70,10 @@ cudaError_t launch_philox_uniforms(uint64_t, uint64_t, float*, int64_t, cudaStre
 cudaError_t launch_gae(const float*, const float*, const void*, const float*, const void*, int, double, double, float*, float*,
                        int, int64_t, cudaStream_t);
 int64_t rms_scratch_doubles(int c);
-cudaError_t launch_rms_moments(const float*, const double*, double*, double*, int64_t, int, int64_t, int64_t, cudaStream_t);
+cudaError_t launch_rms_moments(const float*, const double*, double*, double*, int64_t, int, int64_t, int64_t, cudaStream_t,
+                               const double* snap_var = nullptr, const double* snap_count = nullptr);
+cudaError_t launch_rms_merge_normalize(const float*, const double*, double*, double*, double*, float, float*, int64_t, int, int64_t,
+                                       int64_t, cudaStream_t);
 cudaError_t launch_rms_merge(const double*, const double*, double*, double*, double*, int, cudaStream_t);
 cudaError_t launch_rms_normalize(const float*, const double*, const double*, float, int, float*, int64_t, int, int64_t, int64_t,
                                  cudaStream_t);

@@ -178,7 +178,6 @@ __global__ void __launch_bounds__(RMS_THREADS) rms_partials_tma_kernel(const flo
     const int rpb = RMS_THREADS / c;                                          // row groups per block (>= 1)
     const int rg = tid / c, col = tid - rg * c;
     const bool active = rg < rpb;
-    const double pv = (pivot && active) ? pivot[col] : 0.0;
     const int64_t ntiles = (m + RMS_TR - 1) / RMS_TR;
     const int tile_floats = RMS_TR * c;
     if (tid == 0) {
@@ -186,6 +185,9 @@ __global__ void __launch_bounds__(RMS_THREADS) rms_partials_tma_kernel(const flo
         for (int s = 0; s < RMS_STAGES; ++s) mbar_init(&s_full[s], 1);
         fence_mbar_init();
     }
+    pdl_wait();                                          // the prologue above overlaps the previous kernel's tail
+    pdl_launch_dependents();
+    const double pv = (pivot && active) ? pivot[col] : 0.0;
     __syncthreads();
 
     auto issue = [&](int64_t tile, int stage) {          // thread 0 only
@@ -289,10 +291,20 @@ __device__ __forceinline__ double fold_column(const double* __restrict__ partial
 }
 
 // acc = [m, sums(c), sumsqs(c)]
+// With snap_mean != nullptr the OLD running statistics are appended: acc[1+2c ..] = [mean(c), var(c), count] -- the snapshot
+// rms_merge_normalize_kernel merges from, so that it never reads running_* while its CTA 0 overwrites them.
 __global__ void __launch_bounds__(256) moments_finalize_kernel(const double* __restrict__ partials, int nblocks, int c, int64_t m,
-                                                               double* __restrict__ acc) {
+                                                               double* __restrict__ acc, const double* __restrict__ snap_mean = nullptr,
+                                                               const double* __restrict__ snap_var = nullptr,
+                                                               const double* __restrict__ snap_count = nullptr) {
+    pdl_wait();                 // programmatic dependent launch: everything below may read the previous kernel's output
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (snap_mean && blockIdx.x == 0) {
+        for (int k = threadIdx.x; k < c; k += blockDim.x) { acc[1 + 2 * c + k] = snap_mean[k]; acc[1 + 3 * c + k] = snap_var[k]; }
+        if (threadIdx.x == 0) acc[1 + 4 * c] = snap_count[0];
+    }
     if (j == 0 && lane == 0) acc[0] = (double)m;
     if (j >= 2 * c) return;
     const double t = fold_column(partials, nblocks, 2 * c, j, lane);
@@ -375,6 +387,70 @@ __global__ void __launch_bounds__(256, 8) rms_normalize_kernel(const float* __re
     }
 }
 
+// K4b + K5 in one launch: every CTA merges acc_ext = [B, S(c), SS(c), old mean(c), old var(c), old count] (the batch moments,
+// possibly all-reduced over ranks, and the snapshot of the running statistics moments_finalize_kernel appended) with the
+// reference's parallel-variance update -- identical arithmetic in every CTA -- then normalises its share of x with the UPDATED
+// statistics; CTA (0,0) writes running_mean / running_var / count back.  Nothing reads running_* here, so there is no race.
+template <bool SLABS>
+__global__ void __launch_bounds__(256, 8) rms_merge_normalize_kernel(const float* __restrict__ x, const double* __restrict__ acc,
+                                                                  double* running_mean, double* running_var, double* count, float eps,
+                                                                  float* __restrict__ y, int64_t total, int c, int vec4,
+                                                                  int64_t slab_src_elems) {
+    pdl_wait();                 // programmatic dependent launch: everything below may read the previous kernel's output
+    pdl_launch_dependents();
+    if (SLABS) {
+        x += (int64_t)blockIdx.y * slab_src_elems;
+        y += (int64_t)blockIdx.y * total;
+    }
+    extern __shared__ float s_stat[];       // [2][c]: mean.float(), sqrt(var.float() + eps)
+    const double B = acc[0], cnt = acc[1 + 4 * c], tot = cnt + B;
+    const bool writer = (blockIdx.x == 0 && blockIdx.y == 0);
+    for (int j = threadIdx.x; j < c; j += blockDim.x) {
+        const double S = acc[1 + j], SS = acc[1 + c + j], mean = acc[1 + 2 * c + j], var = acc[1 + 3 * c + j];
+        double new_mean = mean, new_var = var;
+        if (B > 0.0) {
+            const double mean_b = mean + S / B;                         // pivot = the old running mean
+            const double var_b = (SS - S * S / B) / (B - 1.0);          // NaN for B == 1, like torch.var
+            const double delta = mean_b - mean;
+            new_mean = mean + delta * B / tot;
+            new_var = (var * cnt + var_b * B + delta * delta * cnt * B / tot) / tot;
+        }
+        s_stat[j] = (float)new_mean;
+        s_stat[c + j] = sqrtf((float)new_var + eps);
+        if (writer) { running_mean[j] = new_mean; running_var[j] = new_var; }
+    }
+    if (writer && threadIdx.x == 0 && B > 0.0) count[0] = tot;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nvec = vec4 ? (total >> 2) : 0;
+    for (int64_t i = tid; i < nvec; i += stride) {
+        const float4 t = ldg_stream4(reinterpret_cast<const float4*>(x) + i);
+        const float in[4] = {t.x, t.y, t.z, t.w};
+        float out[4];
+        const int col0 = (int)((i * 4) % c);
+        int col = col0;
+        Mth<true> mq;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            out[k] = clamp_nan(mq.div(in[k] - s_stat[col], s_stat[c + col]), -5.0f, 5.0f);
+            col = (col + 1 == c) ? 0 : col + 1;
+        }
+        if (mq.bad()) {
+            col = col0;
+            for (int k = 0; k < 4; ++k) {
+                out[k] = clamp_nan((in[k] - s_stat[col]) / s_stat[c + col], -5.0f, 5.0f);
+                col = (col + 1 == c) ? 0 : col + 1;
+            }
+        }
+        __stcs(reinterpret_cast<float4*>(y) + i, make_float4(out[0], out[1], out[2], out[3]));
+    }
+    for (int64_t i = nvec * 4 + tid; i < total; i += stride) {
+        const int col = (int)(i % c);
+        y[i] = clamp_nan((x[i] - s_stat[col]) / s_stat[c + col], -5.0f, 5.0f);
+    }
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 
@@ -386,10 +462,13 @@ static inline int stream_blocks(int64_t work_items, int threads, int per_sm) {
 }
 
 // per-block partials of the largest grid + room for one (1 + 2c) accumulator and a c-wide pivot (bezk_rms_train_forward's chain)
-int64_t rms_scratch_doubles(int c) { const int64_t cc = c > 0 ? c : 1; return (int64_t)RMS_MAX_BLOCKS * 2 * cc + (1 + 2 * cc) + cc + 4; }
+int64_t rms_scratch_doubles(int c) { const int64_t cc = c > 0 ? c : 1; return (int64_t)RMS_MAX_BLOCKS * 2 * cc + (2 + 4 * cc) + 4; }
 
 cudaError_t launch_rms_moments(const float* x, const double* pivot, double* acc, double* partials, int64_t m, int c,
-                               int64_t slab_rows, int64_t slab_stride, cudaStream_t st) {
+                               int64_t slab_rows, int64_t slab_stride, cudaStream_t st, const double* snap_var,
+                               const double* snap_count) {
+    // snap_var != nullptr: acc is the EXTENDED accumulator (2 + 4c doubles) and also receives [pivot (= old mean), var, count]
+    const double* snap_mean = snap_var ? pivot : nullptr;
     int nblocks;
     if (slab_rows <= 0 || slab_rows >= m) { slab_rows = m; slab_stride = m; }
     if (m % slab_rows != 0) return cudaErrorInvalidValue;
@@ -418,12 +497,13 @@ cudaError_t launch_rms_moments(const float* x, const double* pivot, double* acc,
             int64_t cap = 148LL * per_sm;
             if (cap > RMS_MAX_BLOCKS) cap = RMS_MAX_BLOCKS;
             nblocks = (int)(ntiles < cap ? ntiles : cap);
-            if (slabs) rms_partials_tma_kernel<true><<<nblocks, RMS_THREADS, smem, st>>>(x, pivot, partials, m, c, slab_rows, slab_stride);
-            else rms_partials_tma_kernel<false><<<nblocks, RMS_THREADS, smem, st>>>(x, pivot, partials, m, c, m, m);
-            cudaError_t err = cudaGetLastError();
+            cudaError_t err = slabs ? launch_pdl(learner_pdl(), rms_partials_tma_kernel<true>, dim3((unsigned)nblocks), dim3(RMS_THREADS), smem, st, x, pivot,
+                                                partials, m, c, slab_rows, slab_stride)
+                                    : launch_pdl(learner_pdl(), rms_partials_tma_kernel<false>, dim3((unsigned)nblocks), dim3(RMS_THREADS), smem, st, x, pivot,
+                                                partials, m, c, m, m);
             if (err != cudaSuccess) return err;
-            moments_finalize_kernel<<<(2 * c + 7) / 8, 256, 0, st>>>(partials, nblocks, c, m, acc);
-            return cudaGetLastError();
+            return launch_pdl(learner_pdl(), moments_finalize_kernel, dim3((unsigned)((2 * c + 7) / 8)), dim3(256), 0, st, partials, nblocks, c, m, acc,
+                             snap_mean, snap_var, snap_count);
         }
         const bool v2 = (c % 2 == 0) && aligned8(x);      // rows start at multiples of c floats: even c keeps 8-byte alignment in slab mode too
         const int cg = v2 ? c / 2 : c;
@@ -438,8 +518,27 @@ cudaError_t launch_rms_moments(const float* x, const double* pivot, double* acc,
     }
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
-    moments_finalize_kernel<<<(2 * c + 7) / 8, 256, 0, st>>>(partials, nblocks, c, m, acc);
-    return cudaGetLastError();
+    return launch_pdl(learner_pdl(), moments_finalize_kernel, dim3((unsigned)((2 * c + 7) / 8)), dim3(256), 0, st, partials, nblocks, c, m, acc, snap_mean,
+                     snap_var, snap_count);
+}
+
+cudaError_t launch_rms_merge_normalize(const float* x, const double* acc_ext, double* running_mean, double* running_var, double* count,
+                                       float eps, float* y, int64_t m, int c, int64_t slab_rows, int64_t slab_stride, cudaStream_t st) {
+    if (m * c == 0) return cudaSuccess;
+    if (slab_rows <= 0 || slab_rows >= m) { slab_rows = m; slab_stride = m; }
+    if (m % slab_rows != 0) return cudaErrorInvalidValue;
+    const int64_t nslabs = m / slab_rows;
+    if (nslabs > 65535) return cudaErrorInvalidValue;
+    const int64_t total = slab_rows * c;
+    const int vec4 = aligned16(x) && aligned16(y) && (nslabs == 1 || (total % 4 == 0 && (slab_stride * c) % 4 == 0));
+    int blocks = stream_blocks(vec4 ? total / 4 : total, 256, 8);
+    const int per_slab_cap = (int)((148 * 8 + nslabs - 1) / nslabs);
+    if (blocks > per_slab_cap) blocks = per_slab_cap;
+    if (nslabs > 1)
+        return launch_pdl(learner_pdl(), rms_merge_normalize_kernel<true>, dim3((unsigned)blocks, (unsigned)nslabs), dim3(256), 2 * c * sizeof(float), st, x,
+                         acc_ext, running_mean, running_var, count, eps, y, total, c, vec4, slab_stride * c);
+    return launch_pdl(learner_pdl(), rms_merge_normalize_kernel<false>, dim3((unsigned)blocks), dim3(256), 2 * c * sizeof(float), st, x, acc_ext, running_mean,
+                     running_var, count, eps, y, total, c, vec4, (int64_t)0);
 }
 
 cudaError_t launch_rms_merge(const double* acc, const double* pivot, double* running_mean, double* running_var,
@@ -508,8 +607,8 @@ cudaError_t launch_adv_moments(const float* returns, const float* values, double
     flat_partials_kernel<<<nblocks, RMS_THREADS, 0, st>>>(returns, values, nullptr, partials, m, vec4, m, m);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
-    moments_finalize_kernel<<<1, 256, 0, st>>>(partials, nblocks, 1, m, acc);
-    return cudaGetLastError();
+    return launch_pdl(learner_pdl(), moments_finalize_kernel, dim3(1), dim3(256), 0, st, (const double*)partials, nblocks, 1, m, acc, (const double*)nullptr,
+                     (const double*)nullptr, (const double*)nullptr);
 }
 
 cudaError_t launch_adv_normalize(const float* returns, const float* values, const double* acc, float* adv, int normalize,
@@ -564,6 +663,8 @@ __global__ void __launch_bounds__(PPO_TILE, 4) ppo_loss_kernel(const PpoArgs a, 
     const float inv_m = 1.0f / (float)a.m;
 
     if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+    pdl_wait();
+    pdl_launch_dependents();
     if (tid < 18) { const float ls = a.logstd[tid]; s_logstd[tid] = ls; s_sigma[tid] = expf(ls); }
     __syncthreads();
     // per-column constants.  Divisions by sigma are multiplications by 1/sigma (sigma is one (18,) row for the whole
@@ -755,11 +856,32 @@ __global__ void __launch_bounds__(PPO_TILE, 4) ppo_loss_kernel(const PpoArgs a, 
         cooperative_groups::this_grid().sync();
         if (blockIdx.x != 0) return;
         double* s_tot = &s_red[0][0];
-        for (int j = wid; j < PPO_PART; j += PPO_TILE / 32) {
+        // fixed-order fold with every load of a chunk in flight: thread (column j = tid % 32 < 25, row group q = tid / 32) sums CTAs
+        // q, q + 4, ... (unrolled by 8: independent loads), then the 4 row groups are added in order
+        __shared__ double s_fold[PPO_TILE / 32][32];
+        {
+            const int j = lane, q = wid;
             double t = 0.0;
-            for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(a.partials + (int64_t)b * PPO_PART + j);
-            t = warp_sum(t);
-            if (lane == 0) s_tot[j] = t;
+            if (j < PPO_PART) {
+                int b = q;
+                const int nb = (int)gridDim.x, stride = PPO_TILE / 32;
+                for (; b + 7 * stride < nb; b += 8 * stride) {
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = __ldcg(a.partials + (int64_t)(b + u * stride) * PPO_PART + j);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) t += v[u];
+                }
+                for (; b < nb; b += stride) t += __ldcg(a.partials + (int64_t)b * PPO_PART + j);
+            }
+            s_fold[q][j] = t;
+        }
+        __syncthreads();
+        if (tid < PPO_PART) {
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < PPO_TILE / 32; ++q) t += s_fold[q][tid];
+            s_tot[tid] = t;
         }
         __syncthreads();
         ppo_form_loss(s_tot, a.m, a.logstd, cfg, a.stats, a.grad_logstd, tid);
@@ -771,6 +893,8 @@ __global__ void __launch_bounds__(1024) ppo_finalize_kernel(const double* __rest
                                                             const float* __restrict__ logstd, const __grid_constant__ BezkPpoCfg cfg,
                                                             double* __restrict__ stats, float* __restrict__ grad_logstd) {
     __shared__ double s_tot[PPO_PART];
+    pdl_wait();                 // programmatic dependent launch: everything below may read the previous kernel's output
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
     if (j < PPO_PART) {
         const double t = fold_column(partials, nblocks, PPO_PART, j, lane);
@@ -795,9 +919,10 @@ cudaError_t launch_ppo_loss(const PpoArgs& args, const BezkPpoCfg& cfg, double* 
                 (a.grad_mu == nullptr || aligned16(a.grad_mu)) &&
                 (!a.slabs || (a.slab_rows % PPO_TILE == 0 && (a.slab_stride * 18 * 4) % 16 == 0));
     a.stats = stats; a.grad_logstd = grad_logstd;
-    // the grid never exceeds 4 resident CTAs per SM (PPO_MAX_BLOCKS), so it can always be launched cooperatively: ONE launch,
-    // CTA 0 finalizes after a grid barrier.  BEZK_PPO_SINGLE_LAUNCH=0 keeps the two-kernel form (A/B measurements).
-    static const int single = env_int("BEZK_PPO_SINGLE_LAUNCH", 1);
+    // The grid never exceeds 4 resident CTAs per SM (PPO_MAX_BLOCKS), so it CAN be launched cooperatively with CTA 0 finalizing
+    // after a grid barrier (BEZK_PPO_SINGLE_LAUNCH=1).  Measured at the reference's minibatch (32 768): 11.9 us against 10.7 us
+    // for the two-kernel form -- a cooperative launch + grid barrier costs more than a second launch -- so two kernels ship.
+    static const int single = env_int("BEZK_PPO_SINGLE_LAUNCH", 0);
     if (single) {
         a.fused_finalize = 1;
         cudaLaunchConfig_t lc = {};
@@ -809,11 +934,10 @@ cudaError_t launch_ppo_loss(const PpoArgs& args, const BezkPpoCfg& cfg, double* 
         return cudaLaunchKernelEx(&lc, ppo_loss_kernel, a, cfg);
     }
     a.fused_finalize = 0;
-    ppo_loss_kernel<<<(unsigned)nblocks, PPO_TILE, 0, st>>>(a, cfg);
-    cudaError_t err = cudaGetLastError();
+    cudaError_t err = launch_pdl(learner_pdl(), ppo_loss_kernel, dim3((unsigned)nblocks), dim3(PPO_TILE), 0, st, a, cfg);
     if (err != cudaSuccess) return err;
-    ppo_finalize_kernel<<<1, 32 * PPO_PART, 0, st>>>(a.partials, nblocks, a.m, a.logstd, cfg, stats, grad_logstd);
-    return cudaGetLastError();
+    return launch_pdl(learner_pdl(), ppo_finalize_kernel, dim3(1), dim3(32 * PPO_PART), 0, st, (const double*)a.partials, nblocks, a.m, a.logstd, cfg, stats,
+                     grad_logstd);
 }
 
 }  // namespace bezk

@@ -31,6 +31,7 @@ class RunningMeanStd(nn.Module):
         self._acc = None
         self._scratch = None
         self._pivot = None
+        self._acc_ext = None
 
     def _workspace(self, device):
         if self._acc is None or self._acc.device != device:
@@ -38,6 +39,7 @@ class RunningMeanStd(nn.Module):
             self._acc = torch.empty(1 + 2 * c, dtype=torch.float64, device=device)
             self._scratch = torch.empty(ops.rms_scratch_doubles(c), dtype=torch.float64, device=device)
             self._pivot = torch.empty(c, dtype=torch.float64, device=device)
+            self._acc_ext = torch.empty(2 + 4 * c, dtype=torch.float64, device=device)
 
     def update(self, x: torch.Tensor):
         """Merge the batch moments of ``x`` into the running statistics.  ``x``: (m, insize) contiguous, or a slab view
@@ -62,13 +64,20 @@ class RunningMeanStd(nn.Module):
         if x.shape[-1] != self.insize and not (self.insize == 1 and x.dim() == 1):
             raise ValueError(f"expected last dim {self.insize}, got {tuple(x.shape)}")
         local = self.process_group is None or not bdist.is_distributed(self.process_group)
-        if self.training and not unnorm and local:
-            # single-GPU train forward: ONE call -- moments, merge and normalise in one cooperative kernel at minibatch sizes
+        if self.training and not unnorm:
+            # train forward: moments (pivot = running_mean, in place) -> fold + snapshot -> [SUM all-reduce over ranks] -> merge +
+            # normalise; ONE C call when local
             self._workspace(x.device)
             rows = x.shape[0] * x.shape[1] if slab else x.numel() // self.insize
             y = out if out is not None else (torch.empty(rows, self.insize, dtype=torch.float32, device=x.device) if slab
                                              else torch.empty_like(x))
-            ops.rms_train_forward(x, self.running_mean, self.running_var, self.count.view(1), y, self._scratch, eps=self.epsilon)
+            count = self.count.view(1)
+            if local:
+                ops.rms_train_forward(x, self.running_mean, self.running_var, count, y, self._scratch, eps=self.epsilon)
+            else:
+                ops.rms_moments_ext(x, self.running_mean, self.running_var, count, self._acc_ext, self._scratch)
+                bdist.allreduce_sum_(self._acc_ext[:1 + 2 * self.insize], self.process_group)
+                ops.rms_merge_normalize(x, self._acc_ext, self.running_mean, self.running_var, count, y, eps=self.epsilon)
             return y
         if self.training:
             self.update(x)

@@ -303,6 +303,31 @@ def rms_train_forward(x, running_mean, running_var, count, y, partials, eps=1e-5
     return y
 
 
+def rms_moments_ext(x, running_mean, running_var, count, acc_ext, partials):
+    """Distributed half 1 of the train-mode forward: ``acc_ext`` (2 + 4c,) = pivoted batch moments + snapshot of the running
+    statistics; all-reduce ``acc_ext[:1 + 2c]`` (SUM) before ``rms_merge_normalize``."""
+    c = running_mean.numel()
+    ptr, rows, stride, m = _slab_view(x, F32, "x", c)
+    if partials.numel() < rms_scratch_doubles(c):
+        raise BezkError("partials scratch too small")
+    lib = _lib.load()
+    _lib.check(lib.bezk_rms_moments_ext(ptr, rows, stride, _p(running_mean, F64, "running_mean", c), _p(running_var, F64, "running_var", c),
+                                        _p(count, F64, "count", 1), _p(acc_ext, F64, "acc_ext", 2 + 4 * c), _p(partials, F64, "partials"),
+                                        m, c, _stream(x)), "bezk_rms_moments_ext")
+    return acc_ext
+
+
+def rms_merge_normalize(x, acc_ext, running_mean, running_var, count, y, eps=1e-5):
+    """Distributed half 2: merge + normalise in one launch."""
+    c = running_mean.numel()
+    ptr, rows, stride, m = _slab_view(x, F32, "x", c)
+    lib = _lib.load()
+    _lib.check(lib.bezk_rms_merge_normalize(ptr, rows, stride, _p(acc_ext, F64, "acc_ext", 2 + 4 * c), _p(running_mean, F64, "running_mean", c),
+                                            _p(running_var, F64, "running_var", c), _p(count, F64, "count", 1), float(eps),
+                                            _p(y, F32, "y", m * c), m, c, _stream(x)), "bezk_rms_merge_normalize")
+    return y
+
+
 def adv_normalize_fused(returns, values, adv_out, partials, normalize=True):
     """``adv_out = returns - values`` normalised to zero mean / unit unbiased std, one call (single GPU)."""
     m = returns.numel()

@@ -194,14 +194,23 @@ int bezk_rms_normalize(const float* x, const double* running_mean, const double*
 /* K4 + K5 in ONE call: the train-mode forward of RunningMeanStd (update the running statistics with the batch, then normalise
  * the batch with the UPDATED statistics), what rl_games runs on every minibatch of every mini-epoch.  x may be a
  * slab view (slab_rows / slab_stride as in bezk_rms_moments_slabs; slab_rows <= 0: contiguous); y (m,c) contiguous.
- * When one block of rows per SM fits in shared memory (m*c*4 <= ~23 MB: the reference's 32 768 x 54 minibatch is 7 MB) this is
- * ONE cooperative kernel -- rows are read from HBM once, kept in shared memory across a grid barrier, and written normalised:
- * 216 B read + 216 B written per 54-wide sample.  Larger batches run the streaming chain (moments, merge, normalise).  Single-GPU
- * only: with env-sharded ranks the moments are all-reduced between bezk_rms_moments and bezk_rms_merge.
+ * Three launches (moments with pivot = running_mean read in place; fold + snapshot of the old statistics; merge + normalise in
+ * one kernel), against five for the separate entries; c == 1 (value normaliser) runs as ONE cooperative kernel.
+ * Single-GPU form; env-sharded ranks use the two halves below with one SUM all-reduce of acc_ext[0 : 1 + 2c] in between.
  * partials: scratch f64, >= bezk_rms_scratch_doubles(c). */
 int bezk_rms_train_forward(const float* x, int64_t slab_rows, int64_t slab_stride, double* running_mean,
                            double* running_var, double* count, float eps, float* y, double* partials,
                            int64_t m, int32_t c, void* stream);
+/* acc_ext (2 + 4c,) f64 = [m, sum_j(x - mean), sum_j(x - mean)^2, old mean(c), old var(c), old count]: the pivoted batch moments
+ * (pivot = running_mean, identical on every rank) followed by a snapshot of the running statistics. */
+int bezk_rms_moments_ext(const float* x, int64_t slab_rows, int64_t slab_stride, const double* running_mean,
+                         const double* running_var, const double* count, double* acc_ext, double* partials,
+                         int64_t m, int32_t c, void* stream);
+/* Merge acc_ext (its first 1 + 2c entries possibly all-reduced) into running_mean / running_var / count and write
+ * y = clamp((x - mean') / sqrt(var' + eps), -5, 5) with the updated statistics, one launch. */
+int bezk_rms_merge_normalize(const float* x, int64_t slab_rows, int64_t slab_stride, const double* acc_ext,
+                             double* running_mean, double* running_var, double* count, float eps, float* y,
+                             int64_t m, int32_t c, void* stream);
 
 /* K7 in ONE call (single GPU): adv_out = returns - values, normalised to zero mean / unit (unbiased) std when normalize != 0.
  * One cooperative kernel up to ~6 M samples, the bezk_adv_moments / bezk_adv_normalize chain beyond.
