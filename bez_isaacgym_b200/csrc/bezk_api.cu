@@ -73,6 +73,8 @@ static int run_task(int parts, bezk::TaskArgs& a, const BezkTaskCfg* cfg, void* 
         if (cfg->flags & BEZK_F_RESET_ROOT_STATES) REQUIRE(a.initial_root, "initial_root_states NULL");
     }
     bezk::fill_alignment(a, *cfg);
+    if (bezk::persist_eligible(task, parts, a, *cfg))          // the persistent pipelined kernel (bezk_task_persist.cu)
+        return cuda_rc(bezk::launch_task_persist(a, *cfg, (cudaStream_t)stream), where);
     return cuda_rc(bezk::launch_task(task, parts, a, *cfg, (cudaStream_t)stream), where);
 }
 

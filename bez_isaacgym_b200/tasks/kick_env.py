@@ -59,9 +59,9 @@ class KickEnv(VecTask):
             s = env_cfg[key]
             return list(s["pos"]) + list(s["rot"]) + list(s["vLinear"]) + list(s["vAngular"])
 
+        self._state13 = state13
         self.bez_init_state = state13("bezInitState")
-        if self.TASK == "kick":
-            self.ball_init_state = state13("ballInitState")
+        self._read_task_cfg(env_cfg)
         goal = env_cfg["goalState"]["goal"]
         self._actors, _, self._obs_width = bm.task_dims(self.TASK)
         self.cleats = env_cfg["asset"]["cleats"]
@@ -121,16 +121,8 @@ class KickEnv(VecTask):
 
         self.goal = torch.tensor([goal], **f32).repeat((n, 1))
         self.bez_init_xy = torch.tensor(self.bez_init_state[0:2], **f32)
-        if self.TASK == "kick":
-            self.ball_init = torch.tensor([self.ball_init_state[0:2]], **f32).repeat((n, 1))
-            self.initial_root_states = torch.tensor([self.bez_init_state, self.ball_init_state], **f32).repeat((n, 1))
-        else:
-            self.ball_init = None
-            self.initial_root_states = torch.tensor([self.bez_init_state], **f32).repeat((n, 1))      # walk_env.py:146-149
-            if self.TASK == "walk":
-                self.bez_init_xy.zero_()                # compute_bez_reward zeroes it in place, walk_env.py:966-967
-        self.goal_angle = torch.tensor([[float(env_cfg["goalState"]["goal_angle"])]], **f32).repeat((n, 1)) \
-            if self.TASK == "orient" else None          # orient_env.py:145
+        self.ball_init = self.goal_angle = None
+        self._init_task_tensors(env_cfg, n, f32)          # initial_root_states (+ ball_init / goal_angle): per task
         self.initial_root_states[:, 7:13] = 0
         self.num_dof = bm.NUM_DOF
         self.num_dofs = bm.NUM_DOF
@@ -143,10 +135,7 @@ class KickEnv(VecTask):
         self.root_orient_bez = self.rigid_body.view(n, -1, 13)[..., bm.IMU_BODY, 3:7]
         self.root_vel_bez = self.rigid_body.view(n, -1, 13)[..., bm.IMU_BODY, 7:10]
         self.root_ang_bez = self.rigid_body.view(n, -1, 13)[..., bm.IMU_BODY, 10:13]
-        if self.TASK == "kick":
-            self.root_pos_ball = self.root_states.view(n, -1, 13)[..., 1, 0:3]
-            self.root_orient_ball = self.root_states.view(n, -1, 13)[..., 1, 3:7]
-            self.root_vel_ball = self.root_states.view(n, -1, 13)[..., 1, 7:10]
+        self._init_task_views(n)
 
         ready = [float(self.named_default_joint_angles[name]) for name in bm.DOF_NAMES]
         self.default_dof_pos = torch.tensor(ready, **f32).repeat((n, 1))
@@ -208,6 +197,26 @@ class KickEnv(VecTask):
         if self.randomize:                                # kick_env.py:248-249: once at start-up, before the first step
             self.apply_randomizations(self.randomization_params)
         self.reset_idx(torch.arange(n, device=dev))       # kick_env.py:238
+
+    # ------------------------------------------------------------------ per-task pieces (overridden by WalkEnv / OrientEnv)
+    def _read_task_cfg(self, env_cfg):
+        """BezKick has a second actor, the ball (kick_env.py:161-166)."""
+        self.ball_init_state = self._state13("ballInitState")
+
+    def _init_task_tensors(self, env_cfg, n, f32):
+        """kick_env.py:159-166, 213: the constant ``ball_init`` rows of the observation and the two-actor reset rows."""
+        self.ball_init = torch.tensor([self.ball_init_state[0:2]], **f32).repeat((n, 1))
+        self.initial_root_states = torch.tensor([self.bez_init_state, self.ball_init_state], **f32).repeat((n, 1))
+
+    def _init_task_views(self, n):
+        """kick_env.py:179-181: the ball's views of the root-state tensor."""
+        self.root_pos_ball = self.root_states.view(n, -1, 13)[..., 1, 0:3]
+        self.root_orient_ball = self.root_states.view(n, -1, 13)[..., 1, 3:7]
+        self.root_vel_ball = self.root_states.view(n, -1, 13)[..., 1, 7:10]
+
+    def _reset_goal_tensor(self):
+        """The tensor ``reset_idx`` redraws on reset: none for BezKick (its goal is fixed)."""
+        return None
 
     # ------------------------------------------------------------------ construction helpers
     def create_sim(self):
@@ -527,7 +536,7 @@ class KickEnv(VecTask):
             self.apply_randomizations(self.randomization_params)
         self._stage_in()
         ops.reset_idx_task(self.TASK, env_ids, self._d_dof, self._d_root, self.initial_root_states,
-                           None if self.TASK == "kick" else self.goal, self.progress_buf, self.reset_buf, self._kcfg,
+                           self._reset_goal_tensor(), self.progress_buf, self.reset_buf, self._kcfg,
                            seed=self._seed, step=self._rng_step, env_base=self.env_base)
         if self.host_mode in ("staged", "staged_ce"):
             self.dof_state.copy_(self._d_dof)
