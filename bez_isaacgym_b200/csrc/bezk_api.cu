@@ -459,7 +459,18 @@ int bezk_dr_noise(const float* x, const float* corr, const float* white, uint64_
     REQUIRE((cfg->distribution == 0 || cfg->distribution == 1) && (cfg->operation == 0 || cfg->operation == 1), "bad distribution / operation");
     if (total == 0) return 0;
     REQUIRE(x && y, "x / y NULL");
-    return cuda_rc(bezk::launch_dr_noise(x, corr, white, seed, step, *cfg, y, total, (cudaStream_t)stream), "bezk_dr_noise");
+    return cuda_rc(bezk::launch_dr_noise(x, corr, white, seed, step, *cfg, y, nullptr, 0.0f, total, (cudaStream_t)stream), "bezk_dr_noise");
+}
+
+int bezk_dr_noise_clip(const float* x, const float* corr, const float* white, uint64_t seed, uint64_t step, const BezkNoiseCfg* cfg,
+                       float* y, float* y_clipped, float clip, int64_t total, void* stream) {
+    REQUIRE(cfg, "cfg NULL");
+    REQUIRE(total >= 0, "total < 0");
+    REQUIRE((cfg->distribution == 0 || cfg->distribution == 1) && (cfg->operation == 0 || cfg->operation == 1), "bad distribution / operation");
+    if (total == 0) return 0;
+    REQUIRE(x && y && y_clipped, "x / y / y_clipped NULL");
+    return cuda_rc(bezk::launch_dr_noise(x, corr, white, seed, step, *cfg, y, y_clipped, clip, total, (cudaStream_t)stream),
+                   "bezk_dr_noise_clip");
 }
 
 int bezk_dr_fill(uint64_t seed, uint64_t step, int32_t distribution, float* out, int64_t total, void* stream) {

@@ -295,39 +295,63 @@ __device__ __forceinline__ float dr_one(float x, float corr, float w, const Bezk
     return c.operation == 0 ? x + nz : x * nz;
 }
 
+// One quad (4 consecutive elements, one Philox counter).  FULL: all four exist and the pointers are 16-byte aligned -> float4
+// accesses.  Otherwise every element is handled by fully unrolled, predicated scalar code: no array is ever indexed with a
+// run-time value, so nothing lives in local memory (round 1's ragged-tail loops cost 77 STL in the SASS).
+template <bool FULL>
+__device__ __forceinline__ void dr_quad(const float* __restrict__ x, const float* __restrict__ corr, const float* __restrict__ white,
+                                        uint64_t seed, uint64_t step, const BezkNoiseCfg& cfg, float* __restrict__ y,
+                                        float* __restrict__ y_clip, float clip, int64_t q, int64_t total) {
+    const int64_t i0 = q * 4;
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, w0, w1, w2, w3;
+    const bool e1 = FULL || i0 + 1 < total, e2 = FULL || i0 + 2 < total, e3 = FULL || i0 + 3 < total;
+    if (FULL) {
+        const float4 t = ldg_stream4(reinterpret_cast<const float4*>(x) + q);
+        x0 = t.x; x1 = t.y; x2 = t.z; x3 = t.w;
+        if (corr) { const float4 u = ldg_stream4(reinterpret_cast<const float4*>(corr) + q); c0 = u.x; c1 = u.y; c2 = u.z; c3 = u.w; }
+    } else {
+        x0 = x[i0]; if (e1) x1 = x[i0 + 1]; if (e2) x2 = x[i0 + 2]; if (e3) x3 = x[i0 + 3];
+        if (corr) { c0 = corr[i0]; if (e1) c1 = corr[i0 + 1]; if (e2) c2 = corr[i0 + 2]; if (e3) c3 = corr[i0 + 3]; }
+    }
+    if (white) {
+        if (FULL) { const float4 t = ldg_stream4(reinterpret_cast<const float4*>(white) + q); w0 = t.x; w1 = t.y; w2 = t.z; w3 = t.w; }
+        else { w0 = white[i0]; w1 = e1 ? white[i0 + 1] : 0.f; w2 = e2 ? white[i0 + 2] : 0.f; w3 = e3 ? white[i0 + 3] : 0.f; }
+    } else {
+        const Philox4 r = philox4x32_10((uint32_t)q, (uint32_t)((uint64_t)q >> 32), (uint32_t)step, (uint32_t)(step >> 32),
+                                        (uint32_t)seed ^ 0x2545F491u, (uint32_t)(seed >> 32));
+        if (cfg.distribution == 0) { box_muller(r.x, r.y, &w0, &w1); box_muller(r.z, r.w, &w2, &w3); }
+        else { w0 = u01(r.x); w1 = u01(r.y); w2 = u01(r.z); w3 = u01(r.w); }
+    }
+    const float o0 = dr_one(x0, c0, w0, cfg), o1 = dr_one(x1, c1, w1, cfg), o2 = dr_one(x2, c2, w2, cfg), o3 = dr_one(x3, c3, w3, cfg);
+    if (FULL) {
+        __stcs(reinterpret_cast<float4*>(y) + q, make_float4(o0, o1, o2, o3));
+        if (y_clip) __stcs(reinterpret_cast<float4*>(y_clip) + q, make_float4(clamp_nan(o0, -clip, clip), clamp_nan(o1, -clip, clip),
+                                                                              clamp_nan(o2, -clip, clip), clamp_nan(o3, -clip, clip)));
+    } else {
+        y[i0] = o0; if (e1) y[i0 + 1] = o1; if (e2) y[i0 + 2] = o2; if (e3) y[i0 + 3] = o3;
+        if (y_clip) {
+            y_clip[i0] = clamp_nan(o0, -clip, clip);
+            if (e1) y_clip[i0 + 1] = clamp_nan(o1, -clip, clip);
+            if (e2) y_clip[i0 + 2] = clamp_nan(o2, -clip, clip);
+            if (e3) y_clip[i0 + 3] = clamp_nan(o3, -clip, clip);
+        }
+    }
+}
+
+// y_clip != nullptr: also write clamp(y, -clip, clip) -- VecTask.step clamps the observations AFTER the noise (vec_task.py:338-343),
+// so the clipped copy the step kernel produced from the noise-free rows is refreshed in the same pass.
 __global__ void __launch_bounds__(256) dr_noise_kernel(const float* __restrict__ x, const float* __restrict__ corr,
                                                        const float* __restrict__ white, uint64_t seed, uint64_t step,
-                                                       const __grid_constant__ BezkNoiseCfg cfg, float* __restrict__ y, int64_t total,
-                                                       int vec4) {
+                                                       const __grid_constant__ BezkNoiseCfg cfg, float* __restrict__ y,
+                                                       float* __restrict__ y_clip, float clip, int64_t total, int vec4) {
     pdl_launch_dependents();
     pdl_wait();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t nq = (total + 3) >> 2;                         // quads of elements; quad q owns Philox counter q
+    const int64_t nfull = vec4 ? (total >> 2) : 0;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
-        const int64_t i0 = q * 4;
-        const int cnt = (int)((total - i0) < 4 ? (total - i0) : 4);
-        float xv[4] = {0.f, 0.f, 0.f, 0.f}, cv[4] = {0.f, 0.f, 0.f, 0.f}, wv[4];
-        if (vec4 && cnt == 4) {
-            const float4 t = ldg_stream4(reinterpret_cast<const float4*>(x) + q);
-            xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
-            if (corr) { const float4 u = ldg_stream4(reinterpret_cast<const float4*>(corr) + q); cv[0] = u.x; cv[1] = u.y; cv[2] = u.z; cv[3] = u.w; }
-        } else {
-            for (int k = 0; k < cnt; ++k) { xv[k] = x[i0 + k]; if (corr) cv[k] = corr[i0 + k]; }
-        }
-        if (white) {
-            for (int k = 0; k < cnt; ++k) wv[k] = white[i0 + k];
-            for (int k = cnt; k < 4; ++k) wv[k] = 0.0f;
-        } else {
-            const Philox4 r = philox4x32_10((uint32_t)q, (uint32_t)((uint64_t)q >> 32), (uint32_t)step, (uint32_t)(step >> 32),
-                                            (uint32_t)seed ^ 0x2545F491u, (uint32_t)(seed >> 32));
-            if (cfg.distribution == 0) { box_muller(r.x, r.y, &wv[0], &wv[1]); box_muller(r.z, r.w, &wv[2], &wv[3]); }
-            else { wv[0] = u01(r.x); wv[1] = u01(r.y); wv[2] = u01(r.z); wv[3] = u01(r.w); }
-        }
-        float o[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) o[k] = dr_one(xv[k], cv[k], wv[k], cfg);
-        if (vec4 && cnt == 4) __stcs(reinterpret_cast<float4*>(y) + q, make_float4(o[0], o[1], o[2], o[3]));
-        else for (int k = 0; k < cnt; ++k) y[i0 + k] = o[k];
+        if (q < nfull) dr_quad<true>(x, corr, white, seed, step, cfg, y, y_clip, clip, q, total);
+        else dr_quad<false>(x, corr, white, seed, step, cfg, y, y_clip, clip, q, total);
     }
 }
 
@@ -353,10 +377,11 @@ static inline int dr_blocks(int64_t total) {
 }
 
 cudaError_t launch_dr_noise(const float* x, const float* corr, const float* white, uint64_t seed, uint64_t step,
-                            const BezkNoiseCfg& cfg, float* y, int64_t total, cudaStream_t st) {
+                            const BezkNoiseCfg& cfg, float* y, float* y_clip, float clip, int64_t total, cudaStream_t st) {
     if (total == 0) return cudaSuccess;
-    const int vec4 = al16(x) && al16(corr) && al16(y);
-    return launch_ex(dr_noise_kernel, dim3((unsigned)dr_blocks(total)), dim3(256), 0, st, x, corr, white, seed, step, cfg, y, total, vec4);
+    const int vec4 = al16(x) && al16(corr) && al16(white) && al16(y) && al16(y_clip);
+    return launch_ex(dr_noise_kernel, dim3((unsigned)dr_blocks(total)), dim3(256), 0, st, x, corr, white, seed, step, cfg, y, y_clip, clip,
+                     total, vec4);
 }
 
 cudaError_t launch_dr_fill(uint64_t seed, uint64_t step, int distribution, float* out, int64_t total, cudaStream_t st) {

@@ -19,6 +19,16 @@ def is_distributed(group=None) -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
 
 
+def resolve_group(group=None):
+    """The learner's ONE convention (``learner.A2CAgent``): ``group=None`` means "every rank" -- the WORLD group -- whenever
+    ``torch.distributed`` runs with more than one rank, and "single process" otherwise.  The low-level helpers below keep the
+    explicit meaning (``allreduce_sum_(acc, None)`` is local), so the agent resolves its argument ONCE through this function and
+    hands the result to gradients, KL average, parameter broadcast, both RunningMeanStd normalisers and the advantage moments."""
+    if group is None and is_distributed(None):
+        return dist.group.WORLD
+    return group
+
+
 def shard_range(num_envs: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous block [lo, hi) of global env ids owned by ``rank`` (remainder spread over the first ranks)."""
     if not (0 <= rank < world):

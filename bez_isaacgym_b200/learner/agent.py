@@ -76,8 +76,7 @@ class A2CAgent:
         reset / exploration noise is keyed by global env ids."""
         cfg = dict(DEFAULT_CONFIG)
         cfg.update(config or {})
-        if process_group is None and bdist.is_distributed(None):
-            process_group = torch.distributed.group.WORLD
+        process_group = bdist.resolve_group(process_group)
         self.config, self.env, self.group = cfg, env, process_group
         self.device = env.compute_device
         self.num_actors, self.horizon_length = env.num_envs, int(cfg["horizon_length"])

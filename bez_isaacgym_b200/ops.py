@@ -519,10 +519,16 @@ def make_noise_cfg(distribution="gaussian", operation="additive", a=0.0, b=0.0, 
     return c
 
 
-def dr_noise(x, cfg: BezkNoiseCfg, corr=None, white=None, seed=0, step=0, out=None):
+def dr_noise(x, cfg: BezkNoiseCfg, corr=None, white=None, seed=0, step=0, out=None, out_clipped=None, clip=None):
+    """``out_clipped`` / ``clip``: also write ``clamp(y, -clip, clip)`` in the same pass (``bezk_dr_noise_clip``)."""
     total = x.numel()
     y = x if out is None else out
     lib = _lib.load()
+    if out_clipped is not None:
+        _lib.check(lib.bezk_dr_noise_clip(_p(x, F32, "x"), _p(corr, F32, "corr", total, True), _p(white, F32, "white", total, True),
+                                          int(seed), int(step), C.byref(cfg), _p(y, F32, "y", total),
+                                          _p(out_clipped, F32, "out_clipped", total), float(clip), total, _stream(x)), "bezk_dr_noise_clip")
+        return y
     _lib.check(lib.bezk_dr_noise(_p(x, F32, "x"), _p(corr, F32, "corr", total, True), _p(white, F32, "white", total, True),
                                  int(seed), int(step), C.byref(cfg), _p(y, F32, "y", total), total, _stream(x)), "bezk_dr_noise")
     return y

@@ -182,10 +182,10 @@ class VecTask(Env):
     def _apply_obs_randomization(self):
         """vec_task.py:338-339: the observation noise lambda after post_physics_step, then the clamp of :343."""
         if self.dr_randomizations.get("observations", None):
-            self.obs_buf = self.dr_randomizations["observations"]["noise_lambda"](self.obs_buf)
-            clipped = getattr(self, "obs_clipped_buf", None)
-            if clipped is not None:       # the kernel clipped the noise-free rows; the reference clamps AFTER the noise (:343)
-                torch.clamp(self.obs_buf, -self.clip_obs, self.clip_obs, out=clipped)
+            # the step kernel clipped the noise-free rows; the reference clamps AFTER the noise (:343): the noise kernel refreshes
+            # the clipped copy in the same pass
+            self.obs_buf = self.dr_randomizations["observations"]["noise_lambda"](
+                self.obs_buf, out_clipped=getattr(self, "obs_clipped_buf", None))
 
     # ------------------------------------------------------------------ domain randomisation: the tensor-path part
     def apply_randomizations(self, dr_params):
@@ -247,7 +247,7 @@ class VecTask(Env):
             self._dr_period = getattr(self, "_dr_period", 0) + 1
             stream_id = (self._dr_period << 1) | (name == "actions")
 
-            def noise_lambda(tensor, param_name=name, kcfg=kcfg, stream_id=stream_id):
+            def noise_lambda(tensor, param_name=name, kcfg=kcfg, stream_id=stream_id, out_clipped=None):
                 prm = self.dr_randomizations[param_name]
                 if tensor.device != self.compute_device:
                     tensor = tensor.to(self.compute_device)
@@ -258,7 +258,8 @@ class VecTask(Env):
                     prm["corr"] = corr
                 prm["calls"] = prm.get("calls", 0) + 1
                 out = torch.empty_like(tensor) if param_name == "actions" else tensor      # obs_buf is replaced in place
-                return ops.dr_noise(tensor, kcfg, corr=corr, seed=self._dr_seed, step=(stream_id << 32) + prm["calls"], out=out)
+                return ops.dr_noise(tensor, kcfg, corr=corr, seed=self._dr_seed, step=(stream_id << 32) + prm["calls"], out=out,
+                                    out_clipped=out_clipped, clip=float(self.clip_obs) if out_clipped is not None else None)
 
             params["noise_lambda"] = noise_lambda
             self.dr_randomizations[name] = params

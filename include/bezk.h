@@ -379,6 +379,10 @@ typedef struct BezkNoiseCfg {
 } BezkNoiseCfg;
 int bezk_dr_noise(const float* x, const float* corr, const float* white, uint64_t seed, uint64_t step,
                   const BezkNoiseCfg* cfg, float* y, int64_t total, void* stream);
+/* bezk_dr_noise that ALSO writes y_clipped = clamp(y, -clip, clip): VecTask.step clamps the observations after the noise lambda
+ * (ref: tasks/base/vec_task.py:338-343), so with a finite clip_obs the clipped copy is refreshed in the same pass. */
+int bezk_dr_noise_clip(const float* x, const float* corr, const float* white, uint64_t seed, uint64_t step,
+                       const BezkNoiseCfg* cfg, float* y, float* y_clipped, float clip, int64_t total, void* stream);
 /* The draws the Philox path of bezk_dr_noise uses for (seed, step): distribution 0 -> N(0,1), 1 -> U[0,1).  Also the way
  * the host creates `corr`. */
 int bezk_dr_fill(uint64_t seed, uint64_t step, int32_t distribution, float* out, int64_t total, void* stream);

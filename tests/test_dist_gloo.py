@@ -80,6 +80,16 @@ def _worker(rank, world, port, tmp):
             both = [torch.empty_like(l) for _ in range(world)]
             dist.all_gather(both, l)
             assert torch.allclose(p.grad, (both[0] + both[1]) / 2, rtol=1e-6, atol=1e-7)
+        # the learner's group convention: None resolves to WORLD under torchrun, so statistics are shared exactly like
+        # the gradients; the low-level helper keeps "None = local"
+        assert bdist.resolve_group(None) is dist.group.WORLD and bdist.resolve_group(dist.group.WORLD) is dist.group.WORLD
+        shared = acc.clone()
+        bdist.allreduce_sum_(shared, bdist.resolve_group(None))
+        assert torch.allclose(shared, whole, rtol=1e-13, atol=1e-9)
+        # env-sharded ranks key their Philox noise by global env ids: shard offsets tile [0, n) without gaps
+        bases = [torch.zeros(1, dtype=torch.long) for _ in range(world)]
+        dist.all_gather(bases, torch.tensor([lo]))
+        assert [int(b) for b in bases] == [bdist.shard_range(n_envs, r, world)[0] for r in range(world)]
         with open(os.path.join(tmp, f"ok{rank}"), "w") as f:
             f.write("ok")
     finally:
@@ -105,6 +115,7 @@ def test_shard_range_partitions_exactly():
 
 
 def test_single_process_collectives_are_noops():
+    assert bdist.resolve_group(None) is None                 # no process group: the learner stays single-process
     t = torch.arange(5, dtype=torch.float64)
     assert torch.equal(bdist.allreduce_sum_(t.clone()), t)
     flat, views = bdist.pack([torch.ones(3, dtype=torch.float64), torch.zeros((), dtype=torch.float64)])
