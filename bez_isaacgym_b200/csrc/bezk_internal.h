@@ -44,6 +44,7 @@ struct TaskArgs {
     int64_t n;
     int use_tma;      // all dense bases 16 B aligned
     int rb_vec2;      // IMU-link slice of every env is 8 B aligned
+    int rb_win;       // slice only 4 B aligned, but the 16-byte aligned window around it is readable: 3-4 vector loads
     int cf_vec2;      // both foot force rows of every env are 8 B aligned
     int smart_granule;  // per-lane 64 B / 128 B fill choice for the sparse gathers (env BEZK_SMART_GRANULE=0 disables)
 };

@@ -110,6 +110,7 @@ template <bool CLEATS>
 struct Gathered {
     // raw load results: NOTHING depends on them until consume(), so issuing gather_env() never stalls the warp
     float raw[10];                       // the 40-byte IMU-link slice in LOAD order (vector path: 8 B, 16 B, 16 B pieces)
+    float win[6];                        // window path only: floats 10..15 of the 16-byte aligned window around the slice
     float fl[CLEATS ? 12 : 3], fr[CLEATS ? 12 : 3];
     float goal[2], binit[2], prev[3];
     float gang;                          // orient task: goal angle
@@ -148,6 +149,8 @@ __device__ __forceinline__ void gather_env(const TaskArgs& a, const BezkTaskCfg&
     g.reset_prev = 0; g.progress = 0;
 #pragma unroll
     for (int k = 0; k < 10; ++k) g.raw[k] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g.win[k] = 0.0f;
     if (valid) {
         if (a.rb_vec2) {
             // 40 bytes at an 8-byte aligned address: one 8 B + two 16 B loads, order chosen per lane by bit 3
@@ -166,6 +169,17 @@ __device__ __forceinline__ void gather_env(const TaskArgs& a, const BezkTaskCfg&
             }
             g.raw[0] = a2.x; g.raw[1] = a2.y; g.raw[2] = b4.x; g.raw[3] = b4.y; g.raw[4] = b4.z; g.raw[5] = b4.w;
             g.raw[6] = c4.x; g.raw[7] = c4.y; g.raw[8] = c4.z; g.raw[9] = c4.w;
+        } else if (TASK != BEZK_TASK_KICK && a.rb_win) {       // BezKick's 22-body rows are 8-byte aligned: the branch is compiled out
+            // slice only 4-byte aligned (21-body walk / orient rows): 3 (4 when the slice starts at +12) aligned 16-byte loads
+            // of the window around it instead of 10 scalar loads; consume() rotates by the start offset
+            const char* p = reinterpret_cast<const char*>(rb);
+            const uint32_t o = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u);
+            const float4 c0 = ldg64B_nc_v4(p - o), c1 = ldg64B_nc_v4(p - o + 16), c2 = ldg64B_nc_v4(p - o + 32);
+            float4 c3 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (o == 12u) c3 = ldg64B_nc_v4(p - o + 48);
+            g.raw[0] = c0.x; g.raw[1] = c0.y; g.raw[2] = c0.z; g.raw[3] = c0.w; g.raw[4] = c1.x; g.raw[5] = c1.y; g.raw[6] = c1.z;
+            g.raw[7] = c1.w; g.raw[8] = c2.x; g.raw[9] = c2.y;
+            g.win[0] = c2.z; g.win[1] = c2.w; g.win[2] = c3.x; g.win[3] = c3.y; g.win[4] = c3.z; g.win[5] = c3.w;
         } else {
 #pragma unroll
             for (int k = 0; k < 10; ++k) g.raw[k] = ldg64B_nc(rb + k);
@@ -212,13 +226,27 @@ __device__ __forceinline__ void gather_env(const TaskArgs& a, const BezkTaskCfg&
 
 // First use of a gathered set: pin the raw registers behind an (empty) volatile asm so that the compiler cannot
 // hoist the unpacking selects up to the loads (which would stall the warp at issue time), then unpack.
-template <bool CLEATS>
+template <bool CLEATS, int TASK>
 __device__ __forceinline__ void consume(const TaskArgs& a, const float* rb, Gathered<CLEATS>& g, float (&imu)[10]) {
     asm volatile("" : "+f"(g.raw[0]), "+f"(g.raw[1]), "+f"(g.raw[2]), "+f"(g.raw[3]), "+f"(g.raw[4]), "+f"(g.raw[5]),
                       "+f"(g.raw[6]), "+f"(g.raw[7]), "+f"(g.raw[8]), "+f"(g.raw[9]));
     asm volatile("" : "+l"(g.reset_prev), "+l"(g.progress));
     // vector path, slice NOT 16-byte aligned (hi): pieces were loaded in memory order (8,16,16) -> raw is already in order;
     // 16-byte aligned: pieces were loaded as (tail 8 B, first 16 B, second 16 B) -> rotate
+    if (TASK != BEZK_TASK_KICK && !a.rb_vec2 && a.rb_win) {
+        asm volatile("" : "+f"(g.win[0]), "+f"(g.win[1]), "+f"(g.win[2]), "+f"(g.win[3]), "+f"(g.win[4]), "+f"(g.win[5]));
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(rb) & 15u) >> 2;     // slice starts at window float 0..3
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            // window float k + sh, statically indexed: floats 0..9 live in raw, 10..15 in win
+            const float w0 = g.raw[k];
+            const float w1 = (k + 1 < 10) ? g.raw[k + 1] : g.win[k + 1 - 10];
+            const float w2 = (k + 2 < 10) ? g.raw[k + 2] : g.win[k + 2 - 10];
+            const float w3 = (k + 3 < 10) ? g.raw[k + 3] : g.win[k + 3 - 10];
+            imu[k] = sh == 0 ? w0 : (sh == 1 ? w1 : (sh == 2 ? w2 : w3));
+        }
+        return;
+    }
     const bool rot = a.rb_vec2 && ((reinterpret_cast<uintptr_t>(rb) & 8u) == 0);
 #pragma unroll
     for (int k = 0; k < 10; ++k) imu[k] = rot ? g.raw[(k + 2) % 10] : g.raw[k];
@@ -290,7 +318,7 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
     }
 
     float imu_in[10];
-    consume<CLEATS>(a, rb, g, imu_in);
+    consume<CLEATS, TASK>(a, rb, g, imu_in);
     float (&fl)[NFORCE] = g.fl;
     float (&fr)[NFORCE] = g.fr;
     float (&goal)[2] = g.goal;
@@ -395,6 +423,29 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
         }
     }
 
+    // ---- 5b. the dof half of the observation row leaves the registers NOW: pos_sq (the only other use of the 36 dof values) is
+    // formed first, then -- once every lane has read its rows -- the de-interleaved [pos 18, vel 18] columns are written into the
+    // aliased output tile, so the long dependent chains below (IMU, heading, reward) run without 36 live registers ----
+    float pos_sq = 0.0f;
+    if (REW && valid) {
+#pragma unroll
+        for (int j = 0; j < 18; ++j) {
+            const float d = cfg.default_dof_pos[j] - row[2 * j];
+            pos_sq += d * d;
+        }
+    }
+    if (OBS) {
+        __syncwarp();                      // every lane has finished reading its s_dof / s_root rows
+        if (valid) {
+            float2* o2 = reinterpret_cast<float2*>(s_obs + lane * OBS_ROW);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {  // dof_pos 0:18, dof_vel 18:36 (de-interleave of [pos, vel] pairs)
+                o2[k] = make_float2(row[4 * k], row[4 * k + 2]);
+                o2[9 + k] = make_float2(row[4 * k + 1], row[4 * k + 3]);
+            }
+        }
+    }
+
     // ---- 6. observations (kick_env.py:749-777) ----
     float imu6[6], orn2[2], feet[8];
     if (OBS && valid) {
@@ -446,24 +497,10 @@ __global__ void __launch_bounds__(TILE, BEZK_TILE_CTAS * 128 / TILE) task_tile_k
         }
     }
 
-    // ---- 7. observation rows -> shared (aliasing the input tiles) -> one bulk store ----
-    float pos_sq = 0.0f;
-    if (REW && valid) {
-#pragma unroll
-        for (int j = 0; j < 18; ++j) {
-            const float d = cfg.default_dof_pos[j] - row[2 * j];
-            pos_sq += d * d;
-        }
-    }
+    // ---- 7. remaining observation columns -> shared (aliasing the input tiles) -> one bulk store ----
     if (OBS) {
-        __syncwarp();                      // every lane has finished reading its s_dof / s_root rows
         if (valid) {
             float2* o2 = reinterpret_cast<float2*>(s_obs + lane * OBS_ROW);
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {  // dof_pos 0:18, dof_vel 18:36 (de-interleave of [pos, vel] pairs)
-                o2[k] = make_float2(row[4 * k], row[4 * k + 2]);
-                o2[9 + k] = make_float2(row[4 * k + 1], row[4 * k + 3]);
-            }
             o2[18] = make_float2(imu6[0], imu6[1]); o2[19] = make_float2(imu6[2], imu6[3]); o2[20] = make_float2(imu6[4], imu6[5]);
             o2[21] = make_float2(orn2[0], orn2[1]);
             o2[22] = make_float2(feet[0], feet[1]); o2[23] = make_float2(feet[2], feet[3]);
@@ -650,6 +687,10 @@ void fill_alignment(TaskArgs& a, const BezkTaskCfg& cfg) {
     if (a.rb_stride == 0) { a.rb_stride = cfg.num_bodies * 13; a.rb_off = cfg.imu_body * 13 + 3; }
     if (a.cf_stride == 0) { a.cf_stride = cfg.num_bodies * 3; a.cf_l_off = cfg.left_foot_body * 3; a.cf_r_off = cfg.right_foot_body * 3; }
     a.rb_vec2 = aligned8(a.rigid_body) && (a.rb_stride % 2 == 0) && (a.rb_off % 2 == 0);
+    // window path for slices that are only 4-byte aligned: needs a 16-byte aligned base and 12 readable bytes either side of
+    // the slice inside the tensor (the slice starts >= 3 floats into its body row; it must not sit in the last body)
+    a.rb_win = !a.rb_vec2 && aligned16(a.rigid_body) && a.rb_off >= 3 && a.rb_stride == cfg.num_bodies * 13 &&
+               cfg.imu_body + 1 < cfg.num_bodies;
     // 0: 64-byte granules only; 1 (default): per-lane 64 / 128-byte choice; 2: full 128-byte lines wherever the span allows.
     // Read ONCE per process (A/B measurement knob, profiles/r01_fetch_granularity.md), never on the launch path.
     static const int smart_granule = env_int("BEZK_SMART_GRANULE", 1);

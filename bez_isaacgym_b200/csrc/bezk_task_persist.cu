@@ -306,7 +306,10 @@ __global__ void __launch_bounds__(PK_THREADS, 1) task_persist_kernel(const TaskA
 }
 
 bool persist_eligible(int task, int parts, const TaskArgs& a, const BezkTaskCfg& cfg) {
-    static const int mode = env_int("BEZK_PERSIST", 1);     // 0: never (A/B against the one-shot kernel)
+    // OPT-IN (BEZK_PERSIST=1): measured on B200 (profiles/r02_persist.md) the one-shot tile kernel is as fast or faster at every
+    // size -- the step is bound by the per-env dependent instruction chain times the warps an SM can hold (16 there, <= 11 here
+    // because of shared memory), not by the latency of its loads -- so the one-shot kernel ships and this one stays as the A/B.
+    static const int mode = env_int("BEZK_PERSIST", 0);
     if (!mode) return false;
     if (task != BEZK_TASK_KICK || parts != (BEZK_PART_BOOKKEEP | BEZK_PART_OBS | BEZK_PART_REWARD)) return false;
     if ((cfg.flags & BEZK_F_CLEATS) || a.obs_clipped || !a.use_tma || !a.rb_vec2 || !a.cf_vec2) return false;
