@@ -667,9 +667,8 @@ __global__ void __launch_bounds__(PPO_TILE, 4) ppo_loss_kernel(const PpoArgs a, 
     pdl_launch_dependents();
     if (tid < 18) { const float ls = a.logstd[tid]; s_logstd[tid] = ls; s_sigma[tid] = expf(ls); }
     __syncthreads();
-    // per-column constants.  Divisions by sigma are multiplications by 1/sigma (sigma is one (18,) row for the whole
-    // minibatch): 3 IEEE divides per sample-dimension become 2 multiplies + 1 divide, ~25 % fewer instructions; the
-    // extra rounding (<= 1 ulp) is far inside the fp32 tolerance of the loss.
+    // per-column constants.  The FORWARD quantities (neglogp, KL) divide by sigma exactly as the reference does (branch-free IEEE
+    // division, Mth); only the hand-derived GRADIENT sweep below multiplies by 1/sigma (it has no reference op order to follow).
     // (the 2 x 18 constants are read from shared memory -- broadcast loads -- instead of living in 36 registers)
     if (tid < 18) s_isig[tid] = 1.0f / s_sigma[tid];
     __syncthreads();
@@ -749,7 +748,7 @@ __global__ void __launch_bounds__(PPO_TILE, 4) ppo_loss_kernel(const PpoArgs a, 
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const int j = 2 * h + q;
-                    const float zz = (av[q] - mv[q]) * isig[j];
+                    const float zz = mk.div(av[q] - mv[q], sig[j]);      // the reference DIVIDES by sigma (models.py neglogp): exact
                     sq += zz * zz;
                     float hi, lo;
                     if (cfg.bound_form == 0) {          // rl_games 1.1.3 as recalled
@@ -758,17 +757,19 @@ __global__ void __launch_bounds__(PPO_TILE, 4) ppo_loss_kernel(const PpoArgs a, 
                         hi = fmaxf(mv[q] - cfg.soft_bound, 0.0f); lo = fminf(mv[q] + cfg.soft_bound, 0.0f);
                     }
                     bsum += lo * lo + hi * hi;
-                    const float c1 = logf(osv[q] * isig[j] + 1e-5f);
+                    const float c1 = logf(mk.div(osv[q], sig[j]) + 1e-5f);       // torch_ext.policy_kl: log(p1_sigma / p0_sigma + 1e-5)
                     const float dm = omv[q] - mv[q];
                     const float c2 = mk.div(sig[j] * sig[j] + dm * dm, 2.0f * (osv[q] * osv[q] + 1e-5f));   // exact, no branch per dim
                     kl += (c1 + c2) + (-0.5f);
                 }
             }
-            if (mk.bad()) {                    // an operand outside the fast division's range: redo the KL sum with the plain operator
-                kl = 0.0f;
+            if (mk.bad()) {                    // an operand outside the fast division's range: redo both sums with the plain operator
+                kl = 0.0f; sq = 0.0f;
                 for (int j = 0; j < 18; ++j) {
-                    const float m_ = s_mu[tid * 18 + j], om_ = s_omu[tid * 18 + j], os_ = s_osig[tid * 18 + j];
-                    const float c1 = logf(os_ * isig[j] + 1e-5f);
+                    const float a_ = s_act[tid * 18 + j], m_ = s_mu[tid * 18 + j], om_ = s_omu[tid * 18 + j], os_ = s_osig[tid * 18 + j];
+                    const float zz = (a_ - m_) / sig[j];
+                    sq += zz * zz;
+                    const float c1 = logf(os_ / sig[j] + 1e-5f);
                     const float dm = om_ - m_;
                     const float c2 = (sig[j] * sig[j] + dm * dm) / (2.0f * (os_ * os_ + 1e-5f));
                     kl += (c1 + c2) + (-0.5f);

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(PH_TILE) policy_head_kernel(const HeadArgs a, 
     __shared__ __align__(128) float s_act[PH_TILE * 18];
     __shared__ __align__(128) float s_tgt[PH_TILE * 18];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ float s_sigma[18], s_logstd[18], s_isig[18];
+    __shared__ float s_sigma[18], s_logstd[18];
     const int tid = threadIdx.x;
     constexpr uint32_t TILE_BYTES = PH_TILE * 18 * 4;
     const int64_t i0 = (int64_t)blockIdx.x * PH_TILE;
@@ -146,8 +146,7 @@ __global__ void __launch_bounds__(PH_TILE) policy_head_kernel(const HeadArgs a, 
     pdl_launch_dependents();
     if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
     pdl_wait();
-    // 1/sigma once per CTA: (a - mu) / sigma becomes a multiply (<= 1 ulp from the reference's divide, as in the PPO-loss kernel)
-    if (tid < 18) { const float ls = a.logstd[tid]; s_logstd[tid] = ls; const float sg = expf(ls); s_sigma[tid] = sg; s_isig[tid] = 1.0f / sg; }
+    if (tid < 18) { const float ls = a.logstd[tid]; s_logstd[tid] = ls; s_sigma[tid] = expf(ls); }
     __syncthreads();
     if (full) {
         if (tid == 0) {
@@ -173,6 +172,7 @@ __global__ void __launch_bounds__(PH_TILE) policy_head_kernel(const HeadArgs a, 
 #pragma unroll
         for (int j = 0; j < 18; ++j) lsum += s_logstd[j];
         float sq = 0.0f;
+        Mth<true> mq;                                                    // exact division without a branch per dimension
         float2* mu2 = reinterpret_cast<float2*>(s_mu + tid * 18);
         float2* eps2 = reinterpret_cast<float2*>(s_eps + tid * 18);
         float2* act2 = reinterpret_cast<float2*>(s_act + tid * 18);
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(PH_TILE) policy_head_kernel(const HeadArgs a, 
                 const int j = 2 * h + q;
                 const float sg = s_sigma[j];
                 av[q] = mv[q] + sg * ev[q];                              // Normal(mu, sigma).sample()
-                const float zz = (av[q] - mv[q]) * s_isig[j];            // models.py neglogp
+                const float zz = mq.div(av[q] - mv[q], sg);              // models.py neglogp: the reference divides by sigma
                 sq += zz * zz;
                 cv[q] = clamp_nan(av[q], -1.0f, 1.0f) * 1.0f + 0.0f;     // preprocess_actions: clamp, rescale_actions(-1, 1)
                 float stored;
@@ -199,6 +199,13 @@ __global__ void __launch_bounds__(PH_TILE) policy_head_kernel(const HeadArgs a, 
             act2[h] = make_float2(av[0], av[1]);
             eps2[h] = make_float2(cv[0], cv[1]);                         // s_eps now holds the env actions
             tgt2[h] = make_float2(tv[0], tv[1]);
+        }
+        if (mq.bad()) {                                                  // operands outside the fast sequence's range: plain operator
+            sq = 0.0f;
+            for (int j = 0; j < 18; ++j) {
+                const float zz = (s_act[tid * 18 + j] - s_mu[tid * 18 + j]) / s_sigma[j];
+                sq += zz * zz;
+            }
         }
         if (a.neglogp) a.neglogp[i] = (0.5f * sq + (float)(0.5 * 1.8378770664093453 * 18.0)) + lsum;
         if (a.values) {

@@ -67,11 +67,10 @@ def test_learner_and_rollout_kernels_use_tma(sass):
 
 
 def test_no_local_memory_in_the_streaming_kernels(sass):
-    """No spills / local arrays in the streaming kernels.  (Known exceptions, not listed: ``dr_noise_kernel`` keeps its ragged-tail
-    arrays and the ``sincosf`` slow path in local memory -- DESIGN 7 -- and K0's scalar fallback indexes the constant block
-    dynamically.)"""
+    """No spills / local arrays in the streaming kernels (``dr_noise_kernel`` included since round 2: its ragged tail is fully
+    unrolled, predicated scalar code).  Known exception, not listed: K0's scalar fallback indexes the constant block dynamically."""
     for frag in ("gae_kernelIhLi8", "gae_kernelIfLi8", "rms_normalize_kernelILb0", "rms_partials_tma_kernelILb0", "swap_flatten_kernelIm",
-                 "adv_normalize_kernel", "flat_partials_kernel"):
+                 "adv_normalize_kernel", "flat_partials_kernel", "dr_noise_kernel"):
         for name in _find(sass, frag):
             assert "STL" not in sass[name] and "LDL" not in sass[name], name
 
@@ -82,3 +81,27 @@ def test_fused_kernel_divides_without_a_branch_per_operation(sass):
     body = sass[_find(sass, "task_tile_kernelILi7ELb0ELi128ELi0E")[0]]
     assert body.count("MUFU.RCP") >= 10 and body.count("MUFU.RSQ") >= 6
     assert body.count("FCHK") <= 24            # 3 inside atan2f + the fallback copies; the first version had 16 on the MAIN path
+
+
+def test_fused_kernel_fits_five_ctas_worth_of_registers(sass):
+    """Round 2: the dof half of the observation row is written before the long dependent chains, so the fused BezKick step needs
+    ~101 registers instead of 126 (cuobjdump -res-usage)."""
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    out = subprocess.check_output([exe, "-res-usage", LIB], text=True)
+    m = re.search(r"Function _ZN4bezk16task_tile_kernelILi7ELb0ELi128ELi0EE[^\n]*\n\s*REG:(\d+)", out)
+    assert m, "resource usage of the fused kernel not found"
+    assert int(m.group(1)) <= 104, m.group(1)
+
+
+def test_persistent_variant_gathers_with_cp_async_and_tma(sass):
+    """The opt-in persistent variant (bezk_task_persist.cu): bulk copies for the dense sub-tiles, LDGSTS (cp.async, L1 bypassed)
+    for the sparse rows, mbarrier waits, one bulk store per tile."""
+    body = sass[_find(sass, "task_persist_kernel")[0]]
+    assert "UBLKCP.S.G" in body and "UBLKCP.G.S" in body and "SYNCS" in body
+    assert "LDGSTS" in body, "sparse rows arrive by cp.async"
+    assert "BAR.SYNC" not in body
+
+
+def test_cooperative_statistics_kernel_has_a_grid_barrier(sass):
+    body = sass[_find(sass, "fused_stats_kernelILi1E")[0]]
+    assert "STL" not in body and "LDL" not in body
