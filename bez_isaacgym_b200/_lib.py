@@ -103,6 +103,8 @@ SIGNATURES = {
     "bezk_normal_noise": (C.c_int, [_U64, _U64, _P, _I64, _I64, _P]),
     "bezk_dr_noise": (C.c_int, [_P, _P, _P, _U64, _U64, C.POINTER(BezkNoiseCfg), _P, _I64, _P]),
     "bezk_dr_noise_clip": (C.c_int, [_P, _P, _P, _U64, _U64, C.POINTER(BezkNoiseCfg), _P, _P, C.c_float, _I64, _P]),
+    "bezk_quat_rotate": (C.c_int, [_P, _P, _P, C.c_int, _I64, _P]),
+    "bezk_scale_transform": (C.c_int, [_P, _P, _P, _P, C.c_int, _I64, C.c_int32, _P]),
     "bezk_selftest_fastmath": (C.c_int, [_U64, _U64, _P, _P]),
     "bezk_dr_fill": (C.c_int, [_U64, _U64, C.c_int32, _P, _I64, _P]),
 }

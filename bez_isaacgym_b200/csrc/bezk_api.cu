@@ -480,6 +480,22 @@ int bezk_dr_fill(uint64_t seed, uint64_t step, int32_t distribution, float* out,
     return cuda_rc(bezk::launch_dr_fill(seed, step, distribution, out, total, (cudaStream_t)stream), "bezk_dr_fill");
 }
 
+int bezk_quat_rotate(const float* q, const float* v, float* out, int inverse, int64_t n, void* stream) {
+    REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return 0;
+    REQUIRE(q && v && out, "q / v / out NULL");
+    return cuda_rc(bezk::launch_quat_rotate(q, v, out, inverse != 0, n, (cudaStream_t)stream), "bezk_quat_rotate");
+}
+
+int bezk_scale_transform(const float* x, const float* lower, const float* upper, float* y, int mode, int64_t n, int32_t dims,
+                         void* stream) {
+    REQUIRE(n >= 0 && dims >= 0, "n / dims < 0");
+    REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (scale), 1 (unscale) or 2 (saturate)");
+    if (n == 0 || dims == 0) return 0;
+    REQUIRE(x && lower && upper && y, "x / lower / upper / y NULL");
+    return cuda_rc(bezk::launch_scale_transform(x, lower, upper, y, mode, n, dims, (cudaStream_t)stream), "bezk_scale_transform");
+}
+
 int bezk_selftest_fastmath(uint64_t pairs, uint64_t seed, uint64_t* counts, void* stream) {
     REQUIRE(counts, "counts NULL");
     return cuda_rc(bezk::launch_selftest_fastmath(pairs, seed, reinterpret_cast<unsigned long long*>(counts), (cudaStream_t)stream),

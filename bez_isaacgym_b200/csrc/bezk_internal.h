@@ -93,6 +93,8 @@ cudaError_t launch_dr_fill(uint64_t, uint64_t, int, float*, int64_t, cudaStream_
 cudaError_t launch_selftest_fastmath(uint64_t, uint64_t, unsigned long long*, cudaStream_t);
 int64_t ppo_scratch_doubles();
 cudaError_t launch_ppo_loss(const PpoArgs&, const BezkPpoCfg&, double*, float*, cudaStream_t);
+cudaError_t launch_quat_rotate(const float*, const float*, float*, int, int64_t, cudaStream_t);
+cudaError_t launch_scale_transform(const float*, const float*, const float*, float*, int, int64_t, int, cudaStream_t);
 bool fused_stats_eligible(int64_t m, int c);
 cudaError_t launch_rms_train_forward(const float*, double*, double*, double*, float, float*, double*, int64_t, int, int64_t, int64_t,
                                      cudaStream_t);

@@ -539,3 +539,24 @@ def dr_fill(seed, step, out, distribution="gaussian"):
     _lib.check(lib.bezk_dr_fill(int(seed), int(step), {"gaussian": 0, "uniform": 1}[distribution], _p(out, F32, "out"),
                                 out.numel(), _stream(out)), "bezk_dr_fill")
     return out
+
+
+# ------------------------------------------------------------------------------------------- generic jit helpers
+def quat_rotate(q, v, out=None, inverse=False):
+    """isaacgym.torch_utils ``quat_rotate`` / ``quat_rotate_inverse`` (xyzw): q (n,4), v (n,3) -> (n,3)."""
+    n = q.shape[0]
+    out = torch.empty(n, 3, dtype=F32, device=q.device) if out is None else out
+    _lib.check(_lib.load().bezk_quat_rotate(_p(q, F32, "q", n * 4), _p(v, F32, "v", n * 3), _p(out, F32, "out", n * 3), int(bool(inverse)),
+                                            n, _stream(q)), "bezk_quat_rotate")
+    return out
+
+
+def scale_transform(x, lower, upper, out=None, mode="scale"):
+    """``utils/torch_jit_utils.py`` ``scale_transform`` / ``unscale_transform`` / ``saturate`` on x (n, dims)."""
+    dims = lower.numel()
+    n = x.numel() // max(dims, 1)
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(_lib.load().bezk_scale_transform(_p(x, F32, "x", n * dims), _p(lower, F32, "lower", dims), _p(upper, F32, "upper", dims),
+                                                _p(out, F32, "out", n * dims), {"scale": 0, "unscale": 1, "saturate": 2}[mode], n, dims,
+                                                _stream(x)), "bezk_scale_transform")
+    return out

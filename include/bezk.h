@@ -387,6 +387,17 @@ int bezk_dr_noise_clip(const float* x, const float* corr, const float* white, ui
  * the host creates `corr`. */
 int bezk_dr_fill(uint64_t seed, uint64_t step, int32_t distribution, float* out, int64_t total, void* stream);
 
+/* ---------------------------------------------------------------- generic jit helpers (north_star: quat_rotate_inverse, projected gravity, scaling) ----- */
+
+/* ref: isaacgym.torch_utils quat_rotate / quat_rotate_inverse (star-imported by utils/torch_jit_utils.py:31, used by
+ * compute_rot :52-63; projected gravity = quat_rotate_inverse(q, gravity_vec)).  q (n,4) xyzw, v (n,3) -> out (n,3).
+ * The reference's KickEnv does not call them (its calls are commented out, tasks/kick_env.py:905-908). */
+int bezk_quat_rotate(const float* q, const float* v, float* out, int inverse, int64_t n, void* stream);
+/* ref: utils/torch_jit_utils.py scale_transform :78-96 (mode 0), unscale_transform :99-117 (mode 1), saturate :119-134 (mode 2).
+ * x, y (n,dims) f32 (y may alias x); lower, upper (dims,). */
+int bezk_scale_transform(const float* x, const float* lower, const float* upper, float* y, int mode, int64_t n,
+                         int32_t dims, void* stream);
+
 /* Diagnostic: the task kernels evaluate IEEE division and square root through branch-free fast sequences with a sticky
  * validity flag and a once-per-env precise recomputation (bezk_common.cuh: Mth).  This checks the fast sequences against the
  * built-in operators over ALL 2^32 radicands and `pairs` random + special quotients.  counts (4,) u64 DEVICE memory:

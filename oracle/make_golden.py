@@ -371,11 +371,42 @@ def checkpoint_facts():
         json.dump(facts, f, indent=1)
 
 
+def jit_utils():
+    """Outputs of the reference's OWN ``utils/torch_jit_utils.py`` helpers (executed from /root/reference over the isaacgym stubs):
+    ``scale_transform`` / ``unscale_transform`` / ``saturate`` are defined in that file; ``quat_rotate`` / ``quat_rotate_inverse``
+    reach it through ``from isaacgym.torch_utils import *`` (restated, parity unpinned) and are exercised through its
+    ``compute_rot`` (``vel_loc = quat_rotate_inverse(torso_quat, velocity)``)."""
+    import importlib
+    rl.install_stubs()
+    pkg_dir = os.path.join(rl.REFERENCE_ROOT, "bez_isaacgym")
+    if pkg_dir not in sys.path:
+        sys.path.insert(0, pkg_dir)
+    tj = importlib.import_module("utils.torch_jit_utils")
+    g = torch.Generator().manual_seed(77)
+    n, dims = 257, 18
+    x = 3.0 * torch.randn(n, dims, generator=g)
+    x.view(-1)[::31] = float("nan"); x.view(-1)[5::37] = float("inf")
+    lower = -1.0 - torch.rand(dims, generator=g) * 2
+    upper = 0.5 + torch.rand(dims, generator=g) * 3
+    q = torch.randn(n, 4, generator=g); q = q / q.norm(dim=1, keepdim=True)
+    q[0] = torch.tensor([0.0, 0.0, 0.0, 1.0]); q[1] = torch.tensor([1.0, 0.0, 0.0, 0.0]); q[2] = 2.5 * q[2]       # identity, 180 deg, non-unit
+    v = torch.randn(n, 3, generator=g); w = torch.randn(n, 3, generator=g)
+    targets, pos = torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g)
+    vel_loc, angvel_loc, *_ = tj.compute_rot(q, v, w, targets, pos)
+    np.savez_compressed(os.path.join(OUT, "fn_jit_utils.npz"), in_x=_np(x), in_lower=_np(lower), in_upper=_np(upper), in_q=_np(q),
+                        in_v=_np(v), in_w=_np(w), ref_scale=_np(tj.scale_transform(x, lower, upper)),
+                        ref_unscale=_np(tj.unscale_transform(x, lower, upper)), ref_saturate=_np(tj.saturate(x, lower, upper)),
+                        ref_vel_loc=_np(vel_loc), ref_angvel_loc=_np(angvel_loc), ref_quat_axis2=_np(tj.quat_axis(q, 2)))
+
+
 def main():
     warnings.simplefilter("ignore")
     if not rl.reference_available():
         raise SystemExit("needs /root/reference")
     os.makedirs(OUT, exist_ok=True)
+    if "--jit-utils-only" in sys.argv:
+        jit_utils()
+        return
     if "--siblings-only" in sys.argv:
         siblings()
         return
@@ -403,6 +434,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "step_trace_n64.npz"), **tr)
     print("resets per step in the trace:", tr["meta_resets_per_step"])
     siblings()
+    jit_utils()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 
