@@ -121,3 +121,29 @@ def test_physx_randomisation_keys_are_refused():
     cfg["task"] = {"randomize": True, "randomization_params": {"sim_params": {"gravity": {"range": [0, 0.4]}}}}
     with pytest.raises(NotImplementedError):
         KickEnv(cfg, "cuda:0", 0, True)
+
+
+def test_observation_noise_with_finite_clip_obs_refreshes_the_clipped_copy_in_the_same_pass():
+    """vec_task.py:338-343: the clamp follows the noise.  With ``clipObservations`` finite the noise kernel also writes
+    ``clamp(noised, -clip, clip)`` (``bezk_dr_noise_clip``): what ``step`` returns equals clamp(obs_buf) bit for bit."""
+    from bez_isaacgym_b200.synthetic_sim import SyntheticGym
+    from bez_isaacgym_b200.tasks import KickEnv
+    ops = _ops()
+    n = 1023                                                            # odd size: the ragged-tail path of the kernel
+    cfg = bm.default_task_cfg(n)
+    cfg["env"]["clipObservations"] = 1.5
+    cfg["task"] = {"randomize": True, "randomization_params": {
+        "frequency": 1, "observations": {"range": [0, .5], "operation": "additive", "distribution": "gaussian"}}}
+    env = KickEnv(cfg, "cuda:0", 0, True, sim=SyntheticGym(n, device="cuda:0", seed=9))
+    out, *_ = env.step(torch.zeros(n, 18, device="cuda"))
+    got = out["obs"]
+    assert got.data_ptr() == env.obs_clipped_buf.data_ptr()
+    assert torch.equal(torch.nan_to_num(got, nan=7.0), torch.nan_to_num(torch.clamp(env.obs_buf, -1.5, 1.5), nan=7.0))
+    assert float(got.abs().max()) <= 1.5 and float(env.obs_buf.abs().max()) > 1.5
+    # the stand-alone entry: y and its clipped copy from one launch, ragged total
+    x = torch.randn(4099, device="cuda") * 3
+    y, yc = torch.empty_like(x), torch.empty_like(x)
+    kc = ops.make_noise_cfg("uniform", "scaling", a=0.5, b=0.75)
+    ops.dr_noise(x, kc, seed=3, step=4, out=y, out_clipped=yc, clip=2.0)
+    y2 = ops.dr_noise(x, kc, seed=3, step=4, out=torch.empty_like(x))
+    assert torch.equal(y, y2) and torch.equal(yc, torch.clamp(y, -2.0, 2.0))
