@@ -493,9 +493,23 @@ def learner_leg(args, world, rank, dev):
     except Exception:                                       # noqa: BLE001
         ms_graph = None
     ms_dist, counters = ms_local, {"collectives": 0, "bytes": 0}
+    ms_dist_graph = None
     if world > 1:
         dist_epoch, counters = make_epoch(dist.group.WORLD)
         ms_dist = timed(dist_epoch, iters)
+        # the same epoch, collectives included, replayed as ONE CUDA graph: eager launches expose every rank's Python jitter at each of
+        # the 43 collectives (the slowest rank sets the pace); a graph leaves only the NCCL kernels' own latency
+        try:
+            gd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gd, capture_error_mode="thread_local"):
+                dist_epoch()
+            ms_dist_graph = timed(gd.replay, iters)
+        except Exception as exc:                            # noqa: BLE001
+            print(f"bench: NCCL graph capture of the learner epoch unavailable ({exc!r})", file=sys.stderr)
+            ms_dist_graph = None
+    graph_ms = ms_dist_graph if world > 1 else ms_graph
+    best, best_how = (graph_ms, "cuda_graph_replay (NCCL collectives captured)" if world > 1 else "cuda_graph_replay") \
+        if graph_ms is not None else (ms_dist, "eager")
     # per-kernel timings at the minibatch size (graph-replayed x20) for the leg's roofline: the kernel furthest below peak
     def ktime(fn, reps=20):
         for _ in range(3):
@@ -531,10 +545,15 @@ def learner_leg(args, world, rank, dev):
                         f"{mini_epochs} x {nmb} minibatches of {mbs} x (obs RunningMeanStd train forward on slab views, fused PPO loss "
                         f"fwd+bwd, {POLICY_PARAMS}-float gradient bucket all-reduce); no MLP",
             "envs_per_gpu": n, "horizon": T, "minibatch": mbs, "mini_epochs": mini_epochs, "n_gpus": world,
-            "ms_per_epoch": ms_dist, "ms_per_epoch_no_collectives": ms_local, "ms_per_epoch_graph_no_collectives": ms_graph,
-            "collective_us_per_epoch": (ms_dist - ms_local) * 1e3, "collectives_per_epoch": counters["collectives"],
-            "collective_bytes_per_epoch": counters["bytes"], "samples_per_s": M * world / (ms_dist * 1e-3),
-            "env_steps_per_s": M * world / (ms_dist * 1e-3), "timing": "CUDA events, eager launches, max over ranks",
+            "ms_per_epoch": best, "launch": best_how,
+            "ms_per_epoch_eager": ms_dist, "ms_per_epoch_eager_no_collectives": ms_local,
+            "ms_per_epoch_graph": ms_dist_graph if world > 1 else ms_graph, "ms_per_epoch_graph_no_collectives": ms_graph,
+            "collective_us_per_epoch_eager": (ms_dist - ms_local) * 1e3,
+            "collective_us_per_epoch_graph": None if (ms_dist_graph is None or ms_graph is None) else (ms_dist_graph - ms_graph) * 1e3,
+            "collectives_per_epoch": counters["collectives"],
+            "collective_bytes_per_epoch": counters["bytes"], "samples_per_s": M * world / (best * 1e-3),
+            "env_steps_per_s": M * world / (best * 1e-3),
+            "timing": "CUDA events around `iters` epochs after 2 warm-up epochs, max over ranks; collective cost = with - without",
             "roofline": {"bound": "hbm (launch-latency-bound at this size)", "kernel": worst, "achieved": kernels[worst]["gbs"],
                          "peak": peak, "unit": "GB/s", "frac": kernels[worst]["frac"], "per_kernel": kernels,
                          "timing": "each kernel chain graph-replayed x20 between CUDA events, minibatch = 32768 samples"}}
