@@ -63,7 +63,7 @@ DEFAULT_CONFIG = dict(gamma=0.99, tau=0.95, learning_rate=3e-4, lr_schedule="ada
                       truncate_grads=True, e_clip=0.2, horizon_length=32, minibatch_size=32768, mini_epochs=5, critic_coef=2.0,
                       clip_value=True, entropy_coef=0.0, bounds_loss_coef=0.001, normalize_input=True, normalize_value=True,
                       normalize_advantage=True, value_bootstrap=True, reward_shaper=dict(scale_value=0.01), mixed_precision=True,
-                      bound_form="v1.1.3")
+                      bound_form="v1.1.3", cuda_graph=False)
 
 
 class A2CAgent:
@@ -91,7 +91,13 @@ class A2CAgent:
         torch.manual_seed(seed)
         self.model = A2CNetwork(env.num_obs, env.num_acts).to(self.device)
         bdist.broadcast_parameters(self.model, 0, process_group)
-        self.optimizer = torch.optim.Adam(self.model.parameters(), self.last_lr, eps=1e-08, weight_decay=0.0)
+        # the learning rate lives on the device (a tensor the capturable Adam reads): the adaptive-KL schedule can then run inside
+        # a CUDA graph with no host round trip per minibatch (``cuda_graph: True``); eager mode fills the same tensor
+        self._lr_t = torch.tensor(self.last_lr, dtype=torch.float32, device=self.device)
+        self.optimizer = torch.optim.Adam(self.model.parameters(), self._lr_t, eps=1e-08, weight_decay=0.0, capturable=True)
+        self._learn_graph = None
+        self._learn_last = None
+        self._epochs_eager = 0
         self.running_mean_std = RunningMeanStd(env.num_obs, process_group=process_group).to(self.device)
         self.value_mean_std = RunningMeanStd(1, process_group=process_group).to(self.device)
         self.adv_group = process_group if global_advantage_stats else None
@@ -205,8 +211,62 @@ class A2CAgent:
         return info
 
     def update_lr(self, lr):
-        for g in self.optimizer.param_groups:
-            g["lr"] = lr
+        self.last_lr = float(lr)
+        self._lr_t.fill_(self.last_lr)
+
+    def _mean_kl(self, kl):
+        """rl_games averages the KL over ranks before the adaptive schedule (HorovodWrapper.average_value)."""
+        kl = kl.clone()
+        if bdist.is_distributed(self.group):
+            torch.distributed.all_reduce(kl, group=self.group)
+            kl /= torch.distributed.get_world_size(self.group)
+        return kl
+
+    def _learn_eager(self):
+        last = None
+        for _ in range(self.mini_epochs_num):
+            for i in range(len(self.dataset)):
+                last = self.calc_gradients(self.dataset[i])
+                if self.scheduler is not None:
+                    kl = self._mean_kl(last["kl"])
+                    lr, _ = self.scheduler.update(self.last_lr, self.config["entropy_coef"], self.epoch_num, 0, float(kl))
+                    self.update_lr(lr)
+        return last
+
+    def _learn_device_schedule(self):
+        """The same loop with the adaptive-KL schedule evaluated ON THE DEVICE (schedulers.AdaptiveScheduler.update as two
+        ``torch.where``): no host synchronisation, so the whole learner phase can be captured into one CUDA graph."""
+        last = None
+        sch = self.scheduler
+        for _ in range(self.mini_epochs_num):
+            for i in range(len(self.dataset)):
+                last = self.calc_gradients(self.dataset[i])
+                if sch is not None:
+                    kl = self._mean_kl(last["kl"]).float()
+                    lr = self._lr_t
+                    down = torch.clamp(lr / 1.5, min=sch.min_lr)
+                    up = torch.clamp(lr * 1.5, max=sch.max_lr)
+                    self._lr_t.copy_(torch.where(kl > 2.0 * sch.kl_threshold, down, torch.where(kl < 0.5 * sch.kl_threshold, up, lr)))
+        return last
+
+    def _learn_graphed(self):
+        """mini_epochs x minibatches of ``calc_gradients`` (obs RunningMeanStd, MLP forward / backward, fused PPO loss, gradient
+        all-reduce, clip, Adam, adaptive LR) replayed as ONE CUDA graph.  Every input is a persistent buffer (the time-major
+        rollout tensors, ``advantages``, ``values_norm`` / ``returns_norm``), so the graph captured on the second epoch stays valid."""
+        if self._learn_graph is None:
+            if self._epochs_eager < 1:                      # first epoch eagerly: allocator / workspaces / Adam state warm-up
+                self._epochs_eager += 1
+                last = self._learn_device_schedule()
+                self.last_lr = float(self._lr_t)
+                return last
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._learn_last = self._learn_device_schedule()
+            self._learn_graph = g
+        self._learn_graph.replay()
+        self.last_lr = float(self._lr_t)                    # ONE host read per epoch (reporting only)
+        return self._learn_last
 
     def train_epoch(self):
         """One epoch: play_steps -> prepare_dataset -> mini_epochs x minibatches of calc_gradients (+ adaptive LR on the KL,
@@ -214,17 +274,7 @@ class A2CAgent:
         batch = self.play_steps()
         self.set_train()
         self.prepare_dataset(batch)
-        last = None
-        for _ in range(self.mini_epochs_num):
-            for i in range(len(self.dataset)):
-                last = self.calc_gradients(self.dataset[i])
-                if self.scheduler is not None:
-                    kl = last["kl"].clone()
-                    if bdist.is_distributed(self.group):
-                        torch.distributed.all_reduce(kl, group=self.group)
-                        kl /= torch.distributed.get_world_size(self.group)
-                    self.last_lr, _ = self.scheduler.update(self.last_lr, self.config["entropy_coef"], self.epoch_num, 0, float(kl))
-                    self.update_lr(self.last_lr)
+        last = self._learn_graphed() if self.config["cuda_graph"] else self._learn_eager()
         self.epoch_num += 1
         return dict(a_loss=last["a_loss"], c_loss=last["c_loss"], kl=last["kl"], lr=self.last_lr)
 
@@ -241,5 +291,10 @@ class A2CAgent:
         self.value_mean_std.load_state_dict(weights["reward_mean_std"])
         if "optimizer" in weights:
             self.optimizer.load_state_dict(weights["optimizer"])
+            for g in self.optimizer.param_groups:           # keep the learning rate on the device tensor the graph reads
+                self.last_lr = float(g["lr"])
+                g["lr"] = self._lr_t
+            self._lr_t.fill_(self.last_lr)
+            self._learn_graph = None
         self.epoch_num, self.frame = int(weights.get("epoch", 0)), int(weights.get("frame", 0))
         self.last_mean_rewards = weights.get("last_mean_rewards", self.last_mean_rewards)

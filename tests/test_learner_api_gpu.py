@@ -143,3 +143,28 @@ def test_a2c_agent_epoch_reproduces_the_checkpoint_cadence():
     assert other.frame == frame and float(other.running_mean_std.count) == 1 + 5 * frame
     for a, b in zip(agent.model.parameters(), other.model.parameters()):
         assert torch.equal(a, b)
+
+
+def test_a2c_agent_cuda_graph_learner_phase_equals_eager():
+    """``cuda_graph: True``: the mini-epoch loop (obs RunningMeanStd, MLP forward / backward, fused PPO loss, clip, Adam, adaptive-KL
+    schedule evaluated on the device) replayed as ONE CUDA graph from the third epoch on.  Same kernels in the same order as the
+    eager loop: parameters, normaliser statistics and the learning rate agree after four epochs."""
+    from bez_isaacgym_b200 import bez_model as bm
+    from bez_isaacgym_b200 import learner as L
+    from bez_isaacgym_b200.synthetic_sim import SyntheticGym
+    from bez_isaacgym_b200.tasks import KickEnv
+    n = 1024
+    agents = []
+    for graph in (False, True):
+        env = KickEnv(bm.default_task_cfg(n), "cuda:0", 0, True, sim=SyntheticGym(n, device="cuda:0", seed=2))
+        agents.append(L.A2CAgent(env, dict(horizon_length=8, minibatch_size=2048, mini_epochs=3, mixed_precision=False,
+                                           cuda_graph=graph), seed=1))
+    infos = [[ag.train_epoch() for _ in range(4)] for ag in agents]
+    eager, graphed = agents
+    assert graphed._learn_graph is not None, "the learner phase was captured"
+    assert float(eager.running_mean_std.count) == float(graphed.running_mean_std.count) == 1 + 3 * 4 * n * 8
+    torch.testing.assert_close(eager.running_mean_std.running_mean, graphed.running_mean_std.running_mean, rtol=1e-6, atol=1e-9)
+    for a, b in zip(eager.model.parameters(), graphed.model.parameters()):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-6)
+    assert infos[0][-1]["lr"] == pytest.approx(infos[1][-1]["lr"], rel=1e-5)
+    assert float(infos[0][-1]["kl"]) == pytest.approx(float(infos[1][-1]["kl"]), rel=1e-3, abs=1e-7)
