@@ -172,6 +172,17 @@ int bezk_stage_sparse_rows(const float* rigid_body_host, const float* net_contac
                                            (cudaStream_t)stream), "bezk_stage_sparse_rows");
 }
 
+int bezk_stage_sparse_rows_split(const float* rigid_body_host, const float* net_contact_host, const BezkTaskCfg* cfg, float* imu_stage,
+                                 float* feet_stage, int64_t env0, int64_t n, void* copy_stream, void* gather_stream) {
+    if (int rc = check_cfg(cfg)) return rc;
+    REQUIRE(env0 >= 0 && n >= 0, "env0 / n < 0");
+    if (n == 0) return 0;
+    REQUIRE(rigid_body_host && net_contact_host && imu_stage && feet_stage, "staging buffers NULL");
+    cudaError_t e = bezk::stage_imu_rows(rigid_body_host, *cfg, imu_stage, env0, n, (cudaStream_t)copy_stream);
+    if (e == cudaSuccess) e = bezk::stage_feet_gather(net_contact_host, *cfg, feet_stage, env0, n, (cudaStream_t)gather_stream);
+    return cuda_rc(e, "bezk_stage_sparse_rows_split");
+}
+
 int bezk_post_physics_staged(int task, float* dof_state, const float* imu_stage, float* root_states, float* feet_stage,
                              float* prev_lin_vel, float* goal, const float* goal_angle, const float* ball_init,
                              const float* initial_root_states, const float* uniforms, const float* goal_uniforms, uint64_t seed,

@@ -65,6 +65,8 @@ cudaError_t launch_goal_uniforms(uint64_t seed, uint64_t step, float* out2, cuda
 void fill_alignment(TaskArgs& a, const BezkTaskCfg& cfg);
 bool persist_eligible(int task, int parts, const TaskArgs& a, const BezkTaskCfg& cfg);
 cudaError_t launch_task_persist(const TaskArgs& a, const BezkTaskCfg& cfg, cudaStream_t st);
+cudaError_t stage_feet_gather(const float*, const BezkTaskCfg&, float*, int64_t, int64_t, cudaStream_t);
+cudaError_t stage_imu_rows(const float*, const BezkTaskCfg&, float*, int64_t, int64_t, cudaStream_t);
 cudaError_t stage_sparse_rows(const float*, const float*, const BezkTaskCfg&, float*, float*, int64_t, int64_t, cudaStream_t);
 cudaError_t launch_pre_physics(const float*, float*, float*, const BezkTaskCfg&, int64_t, cudaStream_t);
 cudaError_t launch_reset_idx(const int64_t*, int64_t, const float*, uint64_t, uint64_t, float*, float*, const float*, int64_t*,

@@ -721,6 +721,36 @@ cudaError_t stage_sparse_rows(const float* rigid_body, const float* net_contact,
                              cudaMemcpyHostToDevice, st);
 }
 
+// The foot rows of bezk_stage_sparse_rows pulled by the SMs instead (zero-copy reads of pinned host memory): the copy engine
+// that serves the H2D direction is row-rate-bound on the strided pulls (1.4 ns per row), so letting a small gather kernel fetch
+// the two foot rows over PCIe WHILE the engine moves the dense tensors and the IMU slices shortens the H2D critical path.
+__global__ void __launch_bounds__(256) stage_feet_kernel(const float* __restrict__ net_contact, float* __restrict__ feet_stage,
+                                                         const __grid_constant__ BezkTaskCfg cfg, int64_t env0, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t e = env0 + i;
+    const bool cleats = (cfg.flags & BEZK_F_CLEATS) != 0;
+    const int w = cleats ? 12 : 3, pitch = cleats ? 24 : 8, roff = cleats ? 12 : 4;
+    const float* l = net_contact + (e * cfg.num_bodies + cfg.left_foot_body) * 3;
+    const float* r = net_contact + (e * cfg.num_bodies + cfg.right_foot_body) * 3;
+    float* d = feet_stage + e * pitch;
+    for (int k = 0; k < w; ++k) { d[k] = ldg64B_nc(l + k); d[roff + k] = ldg64B_nc(r + k); }
+}
+
+cudaError_t stage_feet_gather(const float* net_contact, const BezkTaskCfg& cfg, float* feet_stage, int64_t env0, int64_t n,
+                              cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    stage_feet_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(net_contact, feet_stage, cfg, env0, n);
+    return cudaGetLastError();
+}
+
+cudaError_t stage_imu_rows(const float* rigid_body, const BezkTaskCfg& cfg, float* imu_stage, int64_t env0, int64_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const size_t rb_pitch = (size_t)cfg.num_bodies * 13 * sizeof(float);
+    return cudaMemcpy2DAsync(imu_stage + env0 * 10, 40, rigid_body + (env0 * cfg.num_bodies + cfg.imu_body) * 13 + 3, rb_pitch, 40,
+                             (size_t)n, cudaMemcpyHostToDevice, st);
+}
+
 cudaError_t launch_pre_physics(const float* actions, float* actions_out, float* targets, const BezkTaskCfg& cfg,
                                int64_t n, cudaStream_t st) {
     const int vec2 = aligned8(actions) && aligned8(targets) && (actions_out == nullptr || aligned8(actions_out));

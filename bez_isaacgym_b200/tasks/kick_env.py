@@ -185,6 +185,7 @@ class KickEnv(VecTask):
             if self._kcfg.flags & _lib.F_WRITE_CONTACT_FILTER:
                 raise ValueError("hostPipeline='staged_ce' cannot write the contact filter back (env.writeContactFilter must be False)")
             self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self._ce_split = bool(env_cfg.get("hostPipelineSplitSparse", True))
             chunks = max(1, int(env_cfg.get("hostPipelineChunks", 4)))
             step_sz = max(128, -(-n // chunks) // 128 * 128)           # chunk starts stay multiples of 128 envs (TMA alignment)
             self._ce_chunks = [(lo, min(n, lo + step_sz)) for lo in range(0, n, step_sz)]
@@ -283,8 +284,12 @@ class KickEnv(VecTask):
             with torch.cuda.stream(self._s_in):
                 dof_d[lo:hi].copy_(dof_h[lo:hi], non_blocking=True)
                 root_d[lo:hi].copy_(root_h[lo:hi], non_blocking=True)
-                rc = self._lib.bezk_stage_sparse_rows(_ptr(self.rigid_body), _ptr(self.net_contact), kc, _ptr(self._d_rb),
-                                                      _ptr(self._d_cf), lo, hi - lo, s_in_h)
+                if self._ce_split:       # IMU slices by the copy engine, foot rows by an SM gather kernel on the compute stream
+                    rc = self._lib.bezk_stage_sparse_rows_split(_ptr(self.rigid_body), _ptr(self.net_contact), kc, _ptr(self._d_rb),
+                                                                _ptr(self._d_cf), lo, hi - lo, s_in_h, _P(cur.cuda_stream))
+                else:
+                    rc = self._lib.bezk_stage_sparse_rows(_ptr(self.rigid_body), _ptr(self.net_contact), kc, _ptr(self._d_rb),
+                                                          _ptr(self._d_cf), lo, hi - lo, s_in_h)
                 if rc:
                     _lib.check(rc, "bezk_stage_sparse_rows")
                 self._ev_in[c].record(self._s_in)
@@ -333,9 +338,19 @@ class KickEnv(VecTask):
         nbytes = lambda t: t.numel() * t.element_size()      # noqa: E731
         outs = nbytes(self._observations_out()) + nbytes(self.rew_buf) + nbytes(self.timeout_buf) + nbytes(self.reset_buf) \
             + nbytes(self.targets)
+        e = np.arange(n, dtype=np.int64)
+
+        def granules(base, stride, off, width):               # distinct 64-byte granules of [a, a + width) per env
+            a = base + e * stride + off
+            return int(((a + width - 1) // 64 - a // 64 + 1).sum()) * 64
+        fw = 48 if self.cleats else 12
         if self.host_mode == "staged_ce":                 # the arguments of the copies issued each step
-            sparse = n * (40 + (96 if self.cleats else 24))
-            return nbytes(self.dof_state) + nbytes(self.root_states) + n * 18 * 4 + sparse, outs
+            if self._ce_split:                            # foot rows: zero-copy reads of the gather kernel, as 64-byte granules
+                feet = granules(self.net_contact.data_ptr(), nb * 12, self._kcfg.left_foot_body * 12, fw) + \
+                    granules(self.net_contact.data_ptr(), nb * 12, self._kcfg.right_foot_body * 12, fw)
+            else:
+                feet = n * 2 * fw
+            return nbytes(self.dof_state) + nbytes(self.root_states) + n * 18 * 4 + n * 40 + feet, outs
         if self.host_mode == "staged":
             h2d = sum(nbytes(t) for t in (self.root_states, self.dof_state, self.rigid_body, self.net_contact)) + n * 18 * 4
             d2h = outs + nbytes(self.dof_state)
@@ -344,18 +359,9 @@ class KickEnv(VecTask):
             if self._kcfg.flags & _lib.F_RESET_ROOT_STATES:
                 d2h += nbytes(self.root_states)
             return h2d, d2h
-        e = np.arange(n, dtype=np.int64)
-
-        def granules(base, stride, off, width):               # distinct 64-byte granules of [a, a + width) per env
-            a = base + e * stride + off
-            return int(((a + width - 1) // 64 - a // 64 + 1).sum()) * 64
         sparse = granules(self.rigid_body.data_ptr(), nb * 52, (bm.IMU_BODY * 13 + 3) * 4, 40)
-        if self.cleats:
-            sparse += granules(self.net_contact.data_ptr(), nb * 12, self._kcfg.left_foot_body * 12, 48)
-            sparse += granules(self.net_contact.data_ptr(), nb * 12, self._kcfg.right_foot_body * 12, 48)
-        else:
-            sparse += granules(self.net_contact.data_ptr(), nb * 12, self._kcfg.left_foot_body * 12, 12)
-            sparse += granules(self.net_contact.data_ptr(), nb * 12, self._kcfg.right_foot_body * 12, 12)
+        sparse += granules(self.net_contact.data_ptr(), nb * 12, self._kcfg.left_foot_body * 12, fw)
+        sparse += granules(self.net_contact.data_ptr(), nb * 12, self._kcfg.right_foot_body * 12, fw)
         h2d = nbytes(self.dof_state) + nbytes(self.root_states) + n * 18 * 4 + sparse
         return h2d, outs
 
@@ -364,8 +370,9 @@ class KickEnv(VecTask):
 
     def link_counters(self):
         how = {"staged": "sizes of the tensors copied by cudaMemcpyAsync each step",
-               "staged_ce": "byte counts of the cudaMemcpyAsync / cudaMemcpy2DAsync (width x rows) calls issued each step (+ the rare reset "
-                            "rows the kernel writes back into the simulator's host tensors, not counted)",
+               "staged_ce": "byte counts of the cudaMemcpyAsync / cudaMemcpy2DAsync (width x rows) calls issued each step; with the split "
+                            "sparse staging (default) the foot rows are zero-copy reads of a gather kernel, counted as distinct 64-byte "
+                            "granules (+ the rare reset rows the kernel writes back into the simulator's host tensors, not counted)",
                "zero_copy": "address ranges the kernels dereference in pinned host memory each step: dense tensors whole, sparse AoS rows as "
                             "distinct 64-byte granules (+ the rare reset rows written back, not counted)",
                None: "GPU pipeline: nothing crosses the host link"}[self.host_mode]

@@ -151,6 +151,11 @@ int bezk_post_physics_chunk(float* dof_state, const float* rigid_body, float* ro
  * clear (the filtered forces would land in the staging buffer, not in the simulator's tensor). */
 int bezk_stage_sparse_rows(const float* rigid_body_host, const float* net_contact_host, const BezkTaskCfg* cfg,
                            float* imu_stage, float* feet_stage, int64_t env0, int64_t n, void* stream);
+/* As bezk_stage_sparse_rows, but only the IMU slices go through the copy engine (on copy_stream); the foot rows are fetched by a
+ * small gather kernel on gather_stream that reads the pinned host tensor directly, concurrently with the engine's transfers. */
+int bezk_stage_sparse_rows_split(const float* rigid_body_host, const float* net_contact_host, const BezkTaskCfg* cfg,
+                                 float* imu_stage, float* feet_stage, int64_t env0, int64_t n, void* copy_stream,
+                                 void* gather_stream);
 int bezk_post_physics_staged(int task, float* dof_state, const float* imu_stage, float* root_states, float* feet_stage,
                              float* prev_lin_vel, float* goal, const float* goal_angle, const float* ball_init,
                              const float* initial_root_states, const float* uniforms, const float* goal_uniforms,

@@ -21,7 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=262144)
     ap.add_argument("--steps", type=int, default=64)
-    ap.add_argument("--modes", default="zero_copy,staged_ce:1,staged_ce:2,staged_ce:4,staged_ce:8,staged_ce:16,staged")
+    ap.add_argument("--modes", default="zero_copy,staged_ce:2,staged_ce:4,staged_ce:8,staged_ce:2s,staged_ce:4s,staged_ce:8s")
     args = ap.parse_args()
     n = args.envs
 
@@ -32,11 +32,14 @@ def main():
     act = sg.make_actions(n, seed=1).pin_memory()
     for spec in args.modes.split(","):
         mode, _, chunks = spec.partition(":")
+        split = chunks.endswith("s")
+        chunks = chunks.rstrip("s")
         cfg = bm.default_task_cfg(n, use_gpu_pipeline=False, rl_device="cpu")
         cfg["env"]["imuPrevVelAliasing"] = False
         cfg["env"]["hostPipeline"] = mode
         if chunks:
             cfg["env"]["hostPipelineChunks"] = int(chunks)
+        cfg["env"]["hostPipelineSplitSparse"] = split
         env = KickEnv(cfg, "cuda:0", 0, True, sim=sim)
         for _ in range(5):
             env.step(act)
@@ -57,7 +60,7 @@ def main():
             env._ce_copy_out = False
             torch.cuda.synchronize(); c = time.perf_counter()
             t_pre += b - a; t_post += c - b
-        print(json.dumps({"mode": mode, "chunks": int(chunks) if chunks else None, "envs": n, "ms_per_step": round(ms, 4),
+        print(json.dumps({"mode": mode, "chunks": int(chunks) if chunks else None, "split_sparse": split, "envs": n, "ms_per_step": round(ms, 4),
                           "env_steps_per_s_M": round(n / ms / 1e3, 2), "pre_ms": round(1e3 * t_pre / 8, 4),
                           "post_ms": round(1e3 * t_post / 8, 4)}), flush=True)
         del env
