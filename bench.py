@@ -292,8 +292,8 @@ def rollout_leg(args, world, rank, dev):
             in_region_ms = sum(a.elapsed_time(b) for a, b in ev_pairs) / len(ev_pairs)     # the LAST replay of the timed region
         except Exception:                                   # noqa: BLE001
             in_region_ms = None
-    del ev_pairs[:]
     if graph is not None:
+        del ev_pairs[:]
         # eager timed pass: the same steps launched one by one, per-launch events around every post-physics launch
         ke = min(args.steps, 10)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
