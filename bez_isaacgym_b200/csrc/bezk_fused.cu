@@ -216,7 +216,11 @@ static inline bool f_aligned8(const void* p) { return (reinterpret_cast<uintptr_
 // geometry shared by the eligibility test and the launcher
 static bool fused_geometry(int64_t m, int c, int vec, int* grid, int* rows_per_cta, size_t* smem) {
     if (m < 2 || c < 1 || c > 128 || m >= (1LL << 31)) return false;
-    int g = 148;
+    // one CTA per SM of the CURRENT device (a cooperative grid must be co-resident): 148 on a full B200
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
+        return false;
+    int g = sms < FOLD_MAXB ? sms : FOLD_MAXB;
     int64_t rpc = (m + g - 1) / g;
     rpc = (rpc + 1) & ~1LL;                                 // even: every CTA's output block stays 8-byte aligned
     if (rpc < 2) rpc = 2;

@@ -53,8 +53,37 @@ __global__ void __launch_bounds__(256) swap_flatten_kernel(const E* __restrict__
     }
 }
 
+// One-element rows (values, returns, neglogpacs, rewards, uint8 dones): the classic padded 32 x 128 transposition tile, indexed
+// with shifts and masks only -- the generic kernel's per-element divisions made these the slowest rows (0.30 of the HBM peak).
+constexpr int SFS_EB = 128;               // envs per tile
+template <typename E>
+__global__ void __launch_bounds__(256) swap_flatten_scalar_kernel(const E* __restrict__ src, E* __restrict__ dst, int horizon, int64_t n,
+                                                                  int64_t env0, int64_t envs) {
+    __shared__ E tile[SFS_EB][33];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t eblk0 = (int64_t)blockIdx.x * SFS_EB;
+    const int t0 = blockIdx.y * 32;
+    const int ebc = (int)((envs - eblk0) < (int64_t)SFS_EB ? (envs - eblk0) : (int64_t)SFS_EB);
+    const int tbc = (horizon - t0) < 32 ? (horizon - t0) : 32;
+    for (int i = threadIdx.x; i < 32 * SFS_EB; i += 256) {       // reads: 128 consecutive envs of one timestep per 128 threads
+        const int t = i >> 7, e = i & (SFS_EB - 1);
+        if (t < tbc && e < ebc) tile[e][t] = src[(int64_t)(t0 + t) * n + env0 + eblk0 + e];
+    }
+    __syncthreads();
+    E* d = dst + eblk0 * (int64_t)horizon + t0;
+    for (int i = threadIdx.x; i < 32 * SFS_EB; i += 256) {       // writes: the 32 timesteps of one env per warp
+        const int e = i >> 5, t = i & 31;
+        if (t < tbc && e < ebc) d[(int64_t)e * horizon + t] = tile[e][t];
+    }
+}
+
 template <typename E>
 static cudaError_t launch_sf(const void* src, void* dst, int horizon, int64_t n, int64_t env0, int64_t envs, int w, cudaStream_t st) {
+    if (w == 1) {
+        const dim3 grid((unsigned)((envs + SFS_EB - 1) / SFS_EB), (unsigned)((horizon + 31) / 32));
+        return launch_ex(swap_flatten_scalar_kernel<E>, grid, dim3(256), 0, st, (const E*)src, (E*)dst, horizon, n, env0, envs);
+    }
     const int tb = horizon < 32 ? horizon : 32;
     int64_t eb = 32768 / ((int64_t)tb * w * (int64_t)sizeof(E));
     if (eb < 1) eb = 1;

@@ -12,7 +12,9 @@ PARITY UNPINNED: the reference holds no test or golden vector for this half.  Wh
 the reference's own call sites and hyper-parameters (``cfg/train/bez_kickPPO.yaml:45-79``) and the
 shipped checkpoint's identities (``results/Bez_Kick/Normal/Bez_Kick_33.pth``: fp64 ``running_mean``/
 ``running_var``/``count`` buffers, ``count_obs = 1 + 5*frame``, ``count_val = 1 + 2*frame``), which
-``tests/test_checkpoint_identities.py`` checks against this restatement's update cadence.
+``tests/test_rl_games_oracle.py`` (``test_checkpoint_state_layout``, ``test_checkpoint_update_cadence_identities``) checks against
+this restatement's update cadence.  Because this half is unpinned, the CUDA learner kernels are ALSO checked without it:
+``tests/test_learner_properties_gpu.py`` (closed-form GAE, two-pass fp64 moments, fp64 autograd of the published loss formulas).
 """
 import math
 from typing import Dict, Tuple
