@@ -499,14 +499,19 @@ def learner_leg(args, world, rank, dev):
         ms_dist = timed(dist_epoch, iters)
         # the same epoch, collectives included, replayed as ONE CUDA graph: eager launches expose every rank's Python jitter at each of
         # the 43 collectives (the slowest rank sets the pace); a graph leaves only the NCCL kernels' own latency
+        gd, ok = None, 1
         try:
             gd = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gd, capture_error_mode="thread_local"):
                 dist_epoch()
-            ms_dist_graph = timed(gd.replay, iters)
         except Exception as exc:                            # noqa: BLE001
-            print(f"bench: NCCL graph capture of the learner epoch unavailable ({exc!r})", file=sys.stderr)
-            ms_dist_graph = None
+            print(f"bench: NCCL graph capture of the learner epoch unavailable on rank {rank} ({exc!r})", file=sys.stderr)
+            ok = 0
+        # replay only if EVERY rank captured: a rank that skipped the replays would leave the others waiting in their all-reduces
+        flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            ms_dist_graph = timed(gd.replay, iters)
     graph_ms = ms_dist_graph if world > 1 else ms_graph
     best, best_how = (graph_ms, "cuda_graph_replay (NCCL collectives captured)" if world > 1 else "cuda_graph_replay") \
         if graph_ms is not None else (ms_dist, "eager")

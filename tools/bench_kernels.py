@@ -123,7 +123,9 @@ def main():
             ops.rms_moments(x, mean, acc, scratch)
             ops.rms_merge(acc, mean, mean, var, count)
             ops.rms_normalize(x, mean, var, y)
-        report("rms_train_forward(obs)", m, 432, timeit(rms_train, flush=fl), f"m={m} (moments + merge + normalize, 4 launches)")
+        report("rms_train_forward(obs), separate entries", m, 432, timeit(rms_train, flush=fl), f"m={m} (bezk_rms_moments + merge + normalize, 4 launches)")
+        report("rms_train_forward(obs)", m, 432, timeit(lambda: ops.rms_train_forward(x, mean, var, count, y, scratch), flush=fl),
+               f"m={m} (bezk_rms_train_forward: moments, fold + snapshot, merge + normalise = 3 launches)")
         report("rms_moments(obs)", m, 216, timeit(lambda: ops.rms_moments(x, mean, acc, scratch), flush=fl), f"m={m}")
         report("rms_normalize(obs)", m, 432, timeit(lambda: ops.rms_normalize(x, mean, var, y), flush=fl), f"m={m}")
         del x, y
