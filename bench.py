@@ -46,7 +46,7 @@ def parse():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--envs-per-gpu", type=int, default=262144)
     p.add_argument("--horizon", type=int, default=32)
-    p.add_argument("--e2e-mode", default="auto", choices=["auto", "zero_copy", "staged", "staged_ce"])
+    p.add_argument("--e2e-mode", default="auto", choices=["auto", "zero_copy", "staged", "staged_ce", "staged_pack"])
     p.add_argument("--e2e-steps", type=int, default=0, help="rollouts of the e2e leg (0: min(--steps, 10))")
     p.add_argument("--cpu-rollouts", type=int, default=8, help="rollouts of the bounded CPU-baseline sample (~10-30 s)")
     p.add_argument("--learner-envs", type=int, default=4096, help="envs per GPU of the learner leg (configs[2]: 4096 x 32)")
@@ -373,7 +373,7 @@ def e2e_leg(args, world, rank, dev):
     steps = args.e2e_steps or min(args.steps, 10)
     mode = args.e2e_mode
     if mode == "auto":
-        mode = "staged_ce" if "staged_ce" in KickEnv.HOST_PIPELINES else "zero_copy"
+        mode = "staged_pack"
     hcfg = bm.default_task_cfg(n, use_gpu_pipeline=False, rl_device="cpu")
     hcfg["env"]["imuPrevVelAliasing"] = False
     hcfg["env"]["hostPipeline"] = mode

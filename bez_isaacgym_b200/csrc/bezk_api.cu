@@ -183,6 +183,33 @@ int bezk_stage_sparse_rows_split(const float* rigid_body_host, const float* net_
     return cuda_rc(e, "bezk_stage_sparse_rows_split");
 }
 
+int bezk_host_pack_config(int32_t threads, int32_t spin_us, int32_t pin) {
+    if (threads < 0 || threads > 64) { fail(BEZK_E_BADARG, "threads must be 0 (default) .. 64"); return -BEZK_E_BADARG; }
+    return bezk::host_pack_config(threads, spin_us, pin);
+}
+
+int bezk_host_pack_record_floats(int task, const BezkTaskCfg* cfg) {
+    if (!(task == BEZK_TASK_KICK || task == BEZK_TASK_WALK || task == BEZK_TASK_ORIENT)) { fail(BEZK_E_BADARG, "unknown task"); return -BEZK_E_BADARG; }
+    if (int rc = check_cfg(cfg)) return -rc;
+    return bezk::pack_layout(task, *cfg).stride;
+}
+
+int64_t bezk_host_pack_begin(int task, const float* rigid_body_host, const float* net_contact_host, const float* root_states_host,
+                             const BezkTaskCfg* cfg, float* records, int64_t env0, int64_t n) {
+    if (!(task == BEZK_TASK_KICK || task == BEZK_TASK_WALK || task == BEZK_TASK_ORIENT)) return -(int64_t)fail(BEZK_E_BADARG, "unknown task");
+    if (int rc = check_cfg(cfg)) return -(int64_t)rc;
+    if (env0 < 0 || n < 0) return -(int64_t)fail(BEZK_E_BADARG, "env0 / n < 0");
+    if (n == 0) return 0;
+    if (!(rigid_body_host && net_contact_host && root_states_host && records)) return -(int64_t)fail(BEZK_E_BADARG, "pack buffers NULL");
+    if (!ALIGNED(records, 16)) return -(int64_t)fail(BEZK_E_ALIGN, "records must be 16-byte aligned");
+    return bezk::host_pack_begin(task, rigid_body_host, net_contact_host, root_states_host, *cfg, records, env0, n);
+}
+
+int bezk_host_pack_wait(int64_t ticket) {
+    if (bezk::host_pack_wait(ticket) != 0) return fail(BEZK_E_BADARG, "bezk_host_pack_wait: unknown ticket");
+    return 0;
+}
+
 int bezk_post_physics_staged(int task, float* dof_state, const float* imu_stage, float* root_states, float* feet_stage,
                              float* prev_lin_vel, float* goal, const float* goal_angle, const float* ball_init,
                              const float* initial_root_states, const float* uniforms, const float* goal_uniforms, uint64_t seed,
@@ -208,6 +235,37 @@ int bezk_post_physics_staged(int task, float* dof_state, const float* imu_stage,
     a.rb_stride = 10; a.rb_off = 0;
     a.cf_stride = cleats ? 24 : 8; a.cf_l_off = 0; a.cf_r_off = cleats ? 12 : 4;
     return run_task(parts, a, cfg, stream, "bezk_post_physics_staged", task);
+}
+
+int bezk_post_physics_packed(int task, float* dof_state, const float* records, float* root_states, float* prev_lin_vel, float* goal,
+                             const float* goal_angle, const float* ball_init, const float* initial_root_states, const float* uniforms,
+                             const float* goal_uniforms, uint64_t seed, uint64_t step, int64_t* reset_buf, int64_t* progress_buf,
+                             int64_t* timeout_buf, int64_t* randomize_buf, const BezkTaskCfg* cfg, float* obs, float* obs_clipped,
+                             float* rew, int parts, int64_t n, int64_t env_base, float* dof_state_wb, float* root_states_wb,
+                             void* stream) {
+    REQUIRE(task == BEZK_TASK_KICK || task == BEZK_TASK_WALK || task == BEZK_TASK_ORIENT, "unknown task");
+    REQUIRE(parts >= 1 && parts <= 7, "parts must be a non-empty subset of {1,2,4}");
+    REQUIRE(env_base >= 0 && n >= 0, "env_base / n < 0");
+    if (int rc = check_cfg(cfg)) return rc;
+    if (n == 0) return 0;
+    REQUIRE(records && root_states, "records / root_states NULL");
+    REQUIRE(!(cfg->flags & BEZK_F_WRITE_CONTACT_FILTER), "the contact-filter write-back would land in the records: clear BEZK_F_WRITE_CONTACT_FILTER");
+    const bezk::PackLayout L = bezk::pack_layout(task, *cfg);
+    if (int rc = cuda_rc(bezk::launch_unpack_root(task, records, L, root_states, n, (cudaStream_t)stream), "bezk_post_physics_packed (unpack)"))
+        return rc;
+    bezk::TaskArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dof_state = dof_state; a.rigid_body = records; a.root_states = root_states; a.net_contact = const_cast<float*>(records);
+    a.prev_lin_vel = prev_lin_vel; a.goal = goal; a.goal_angle = goal_angle; a.goal_uniforms = goal_uniforms; a.ball_init = ball_init;
+    a.initial_root = initial_root_states;
+    a.uniforms = uniforms; a.seed = seed; a.step = step; a.env_base = env_base; a.dof_state_wb = dof_state_wb;
+    a.root_states_wb = root_states_wb;
+    a.reset_in = reset_buf; a.reset_out = reset_buf; a.progress_in = progress_buf; a.progress_out = progress_buf;
+    a.timeout_buf = timeout_buf; a.randomize_buf = randomize_buf;
+    a.obs = obs; a.obs_clipped = obs_clipped; a.rew = rew; a.n = n;
+    a.rb_stride = L.stride; a.rb_off = 0;
+    a.cf_stride = L.stride; a.cf_l_off = L.l_off; a.cf_r_off = L.r_off;
+    return run_task(parts, a, cfg, stream, "bezk_post_physics_packed", task);
 }
 
 int bezk_post_physics_task(int task, float* dof_state, const float* rigid_body, float* root_states, float* net_contact,

@@ -68,6 +68,13 @@ cudaError_t launch_task_persist(const TaskArgs& a, const BezkTaskCfg& cfg, cudaS
 cudaError_t stage_feet_gather(const float*, const BezkTaskCfg&, float*, int64_t, int64_t, cudaStream_t);
 cudaError_t stage_imu_rows(const float*, const BezkTaskCfg&, float*, int64_t, int64_t, cudaStream_t);
 cudaError_t stage_sparse_rows(const float*, const float*, const BezkTaskCfg&, float*, float*, int64_t, int64_t, cudaStream_t);
+// layout of the host pipeline's packed per-env record (bezk_host_pack.cu), in floats
+struct PackLayout { int stride, l_off, r_off, feet_w, root_off, root_n; };
+PackLayout pack_layout(int task, const BezkTaskCfg& cfg);
+int host_pack_config(int threads, int spin_us, int pin);
+int64_t host_pack_begin(int task, const float*, const float*, const float*, const BezkTaskCfg&, float*, int64_t, int64_t);
+cudaError_t launch_unpack_root(int task, const float* records, PackLayout L, float* root_states, int64_t n, cudaStream_t st);
+int host_pack_wait(int64_t ticket);
 cudaError_t launch_pre_physics(const float*, float*, float*, const BezkTaskCfg&, int64_t, cudaStream_t);
 cudaError_t launch_reset_idx(const int64_t*, int64_t, const float*, uint64_t, uint64_t, float*, float*, const float*, int64_t*,
                              int64_t*, const BezkTaskCfg&, int64_t, int, float*, const float*, int64_t, cudaStream_t);

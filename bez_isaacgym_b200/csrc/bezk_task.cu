@@ -751,6 +751,25 @@ cudaError_t stage_imu_rows(const float* rigid_body, const BezkTaskCfg& cfg, floa
                              (size_t)n, cudaMemcpyHostToDevice, st);
 }
 
+// Host pipeline, packed records (bezk_host_pack.cu): the 3 (7) root-state floats the step reads travel inside the per-env record;
+// this scatters them into the columns of the device image of root_states the tile kernel's dense bulk copy expects (the other
+// columns are never read).  28 B per env, a few microseconds per chunk.
+__global__ void __launch_bounds__(256) unpack_root_kernel(const float* __restrict__ records, PackLayout L, float* __restrict__ root_states,
+                                                          int root_row_floats, int64_t n) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const float* q = records + e * L.stride + L.root_off;
+    float* r = root_states + e * root_row_floats;
+    r[0] = q[0]; r[1] = q[1]; r[2] = q[2];
+    if (L.root_n == 7) { r[13] = q[3]; r[14] = q[4]; r[20] = q[5]; r[21] = q[6]; }
+}
+
+cudaError_t launch_unpack_root(int task, const float* records, PackLayout L, float* root_states, int64_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    unpack_root_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(records, L, root_states, root_row(task), n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pre_physics(const float* actions, float* actions_out, float* targets, const BezkTaskCfg& cfg,
                                int64_t n, cudaStream_t st) {
     const int vec2 = aligned8(actions) && aligned8(targets) && (actions_out == nullptr || aligned8(actions_out));

@@ -44,7 +44,7 @@ class KickEnv(VecTask):
     #: skeleton, one actor per env, 52-wide observation, their own heading term / reward / goal randomisation (bezk.h)
     TASK = "kick"
     #: host pipelines (``sim.use_gpu_pipeline: False``), selected by ``env.hostPipeline``
-    HOST_PIPELINES = ("zero_copy", "staged", "staged_ce")
+    HOST_PIPELINES = ("zero_copy", "staged", "staged_ce", "staged_pack")
 
     def __init__(self, cfg, sim_device, graphics_device_id, headless, sim: SimBackend = None, fusion="fused"):
         self.cfg = cfg
@@ -97,8 +97,13 @@ class KickEnv(VecTask):
         # host pipelines (every task): "zero_copy" (default) hands the PINNED host tensors straight to the kernels -- they gather
         # the few bytes they need over PCIe and write resets back in place; "staged" copies all four tensors to HBM first;
         # "staged_ce" moves everything with the copy engines in a chunked three-stream pipeline (dense tensors by
-        # cudaMemcpyAsync, the sparse AoS rows by strided cudaMemcpy2DAsync pulls, results back by cudaMemcpyAsync)
+        # cudaMemcpyAsync, the sparse AoS rows by strided cudaMemcpy2DAsync pulls, results back by cudaMemcpyAsync);
+        # "staged_pack" is staged_ce with the sparse rows gathered by HOST worker threads into pinned pack buffers
+        # (bezk_host_pack_begin / _wait) and moved by dense copies -- the engine is row-rate-bound on strided pulls
         self.host_mode = env_cfg.get("hostPipeline", "zero_copy") if self.host_staged else None
+        self._pack = self.host_mode == "staged_pack"
+        if self._pack:
+            self.host_mode = "staged_ce"                  # same pipeline; only the sparse staging differs
         if self.host_mode is not None and self.host_mode not in self.HOST_PIPELINES:
             raise ValueError(f"env.hostPipeline must be one of {self.HOST_PIPELINES}, got {self.host_mode}")
         if self.host_staged and self.host_mode in ("zero_copy", "staged_ce") and not all(
@@ -106,8 +111,12 @@ class KickEnv(VecTask):
             raise ValueError(f"hostPipeline='{self.host_mode}' needs the simulator tensors in pinned (page-locked) host memory")
         if self.host_mode == "staged_ce":
             self._d_root, self._d_dof = (torch.empty_like(t, device=dev) for t in (self.root_states, self.dof_state))
-            self._d_rb = torch.zeros(n, 10, **f32)                                    # IMU-link slices (bezk_stage_sparse_rows)
-            self._d_cf = torch.zeros(n, 24 if self.cleats else 8, **f32)              # foot / cleat force rows
+            if self._pack:                               # per-env records (bezk_host_pack_begin): IMU slice, foot rows, root subset
+                self._d_rb = self._d_cf = None
+                self._d_root.copy_(self.root_states)      # the columns the step reads are refreshed from the records every step
+            else:
+                self._d_rb = torch.zeros(n, 10, **f32)                                # IMU-link slices (bezk_stage_sparse_rows)
+                self._d_cf = torch.zeros(n, 24 if self.cleats else 8, **f32)          # foot / cleat force rows
         elif self.host_mode == "staged":
             self._d_root, self._d_dof = (torch.empty_like(t, device=dev) for t in (self.root_states, self.dof_state))
             self._d_rb, self._d_cf = (torch.empty_like(t, device=dev) for t in (self.rigid_body, self.net_contact))
@@ -189,9 +198,25 @@ class KickEnv(VecTask):
             chunks = max(1, int(env_cfg.get("hostPipelineChunks", 4)))
             step_sz = max(128, -(-n // chunks) // 128 * 128)           # chunk starts stay multiples of 128 envs (TMA alignment)
             self._ce_chunks = [(lo, min(n, lo + step_sz)) for lo in range(0, n, step_sz)]
-            mk = lambda: torch.cuda.Event()                            # noqa: E731
+            #: env.hostPipelineTimeline: timing-enabled events + host stamps of the last step (tools/exp_e2e.py --timeline)
+            self._timeline = bool(env_cfg.get("hostPipelineTimeline", False))
+            mk = lambda: torch.cuda.Event(enable_timing=self._timeline)               # noqa: E731
             self._ev_in, self._ev_k = [mk() for _ in self._ce_chunks], [mk() for _ in self._ce_chunks]
+            self._ev_out, self._ev_t0 = [mk() for _ in self._ce_chunks], mk()
+            self._host_stamps = []
             self._ev_tgt = mk()
+            self._ev_pack = mk()                                       # last H2D that read the pack buffers
+            if self._pack:
+                rs = self._lib.bezk_host_pack_record_floats(ops._TASK_ID[self.TASK], C.byref(self._kcfg))
+                if rs <= 0:
+                    _lib.check(-rs or 1, "bezk_host_pack_record_floats")
+                self._h_rec = torch.zeros(n, rs, dtype=torch.float32).pin_memory()
+                self._d_rec = torch.zeros(n, rs, **f32)
+                k = self._lib.bezk_host_pack_config(int(env_cfg.get("hostPackThreads", 0)), int(env_cfg.get("hostPackSpinUs", -1)),
+                                                    int(env_cfg.get("hostPackPin", -1)))
+                if k <= 0:
+                    _lib.check(-k or 1, "bezk_host_pack_config")
+                self.host_pack_threads = k
         self._bind()
         self._link = {"h2d_bytes": 0, "d2h_bytes": 0}
         self._link_per_step = self._host_link_bytes_per_step() if self.host_staged else (0, 0)
@@ -258,6 +283,17 @@ class KickEnv(VecTask):
         rw, ow = 13 * self._actors, self._obs_width
         off = lambda t, k: None if t is None else _P(t.data_ptr() + k * t.element_size())      # noqa: E731
         clip = self.obs_clipped_buf
+        if self._pack:
+            rc = self._lib.bezk_post_physics_packed(
+                ops._TASK_ID[self.TASK], off(self._d_dof, lo * 36), off(self._d_rec, lo * self._d_rec.shape[1]), off(self._d_root, lo * rw),
+                None if self._prev_is_view else off(self._prev_buf, lo * 3),
+                off(self.goal, lo * 2), off(self.goal_angle, lo), off(self.ball_init, lo * 2), off(self.initial_root_states, lo * rw),
+                None, None, self._seed, self._rng_step, off(self.reset_buf, lo), off(self.progress_buf, lo), off(self.timeout_buf, lo),
+                None, C.byref(self._kcfg), off(self.obs_buf, lo * ow), off(clip, lo * ow), off(self.rew_buf, lo), parts, hi - lo,
+                self.env_base + lo, off(self.dof_state, lo * 36), off(self.root_states, lo * rw), self._stream())
+            if rc:
+                _lib.check(rc, "bezk_post_physics_packed")
+            return
         rc = self._lib.bezk_post_physics_staged(
             ops._TASK_ID[self.TASK], off(self._d_dof, lo * 36), off(self._d_rb, lo * 10), off(self._d_root, lo * rw),
             off(self._d_cf, lo * self._d_cf.shape[1]), None if self._prev_is_view else off(self._prev_buf, lo * 3),
@@ -280,18 +316,35 @@ class KickEnv(VecTask):
         self._s_in.wait_stream(cur)                       # staging buffers are free again (previous step's kernels are done)
         s_in_h = _P(self._s_in.cuda_stream)
         out = self._observations_out()
+        tl = self._timeline
+        if tl:
+            import time
+            self._host_stamps = [("start", time.perf_counter())]
+            self._ev_t0.record(self._s_in)
+        tickets = self._pack_begin(self._ce_chunks) if self._pack else None
+        if tl:
+            self._host_stamps.append(("pack_issued", time.perf_counter()))
         for c, (lo, hi) in enumerate(self._ce_chunks):
             with torch.cuda.stream(self._s_in):
                 dof_d[lo:hi].copy_(dof_h[lo:hi], non_blocking=True)
-                root_d[lo:hi].copy_(root_h[lo:hi], non_blocking=True)
-                if self._ce_split:       # IMU slices by the copy engine, foot rows by an SM gather kernel on the compute stream
-                    rc = self._lib.bezk_stage_sparse_rows_split(_ptr(self.rigid_body), _ptr(self.net_contact), kc, _ptr(self._d_rb),
-                                                                _ptr(self._d_cf), lo, hi - lo, s_in_h, _P(cur.cuda_stream))
+                if self._pack:           # records gathered by the host workers while the engine moved the dense tensor
+                    rc = self._lib.bezk_host_pack_wait(tickets[c])
+                    if tl:
+                        self._host_stamps.append((f"pack_done{c}", time.perf_counter()))
+                    self._d_rec[lo:hi].copy_(self._h_rec[lo:hi], non_blocking=True)
+                    if c == len(self._ce_chunks) - 1:
+                        self._ev_pack.record(self._s_in)
                 else:
-                    rc = self._lib.bezk_stage_sparse_rows(_ptr(self.rigid_body), _ptr(self.net_contact), kc, _ptr(self._d_rb),
-                                                          _ptr(self._d_cf), lo, hi - lo, s_in_h)
+                    root_d[lo:hi].copy_(root_h[lo:hi], non_blocking=True)
+                    if self._ce_split:   # IMU slices by the copy engine, foot rows by an SM gather kernel on the compute stream
+                        rc = self._lib.bezk_stage_sparse_rows_split(_ptr(self.rigid_body), _ptr(self.net_contact), kc,
+                                                                    _ptr(self._d_rb), _ptr(self._d_cf), lo, hi - lo, s_in_h,
+                                                                    _P(cur.cuda_stream))
+                    else:
+                        rc = self._lib.bezk_stage_sparse_rows(_ptr(self.rigid_body), _ptr(self.net_contact), kc, _ptr(self._d_rb),
+                                                              _ptr(self._d_cf), lo, hi - lo, s_in_h)
                 if rc:
-                    _lib.check(rc, "bezk_stage_sparse_rows")
+                    _lib.check(rc, "bezk_host_pack_wait" if self._pack else "bezk_stage_sparse_rows")
                 self._ev_in[c].record(self._s_in)
             cur.wait_event(self._ev_in[c])
             self._launch_staged(_lib.PART_ALL, lo, hi)
@@ -303,6 +356,32 @@ class KickEnv(VecTask):
                     self._h_rew[lo:hi].copy_(self.rew_buf[lo:hi], non_blocking=True)
                     self._h_reset[lo:hi].copy_(self.reset_buf[lo:hi], non_blocking=True)
                     self._h_timeout[lo:hi].copy_(self.timeout_buf[lo:hi], non_blocking=True)
+                    if tl:
+                        self._ev_out[c].record(self._s_out)
+            if tl:
+                self._host_stamps.append((f"issued{c}", time.perf_counter()))
+
+    def host_timeline(self):
+        """After a synchronised ``step`` with ``env.hostPipelineTimeline``: per chunk, when its inputs had landed, its kernel had
+        finished and its results were back (ms after the step's first copy was queued, device clock), and the host stamps."""
+        t0 = self._ev_t0
+        dev = [{"chunk": c, "h2d_done": round(t0.elapsed_time(self._ev_in[c]), 4), "kernel_done": round(t0.elapsed_time(self._ev_k[c]), 4),
+                "d2h_done": round(t0.elapsed_time(self._ev_out[c]), 4)} for c in range(len(self._ce_chunks))]
+        h0 = self._host_stamps[0][1]
+        return {"device_ms": dev, "host_ms": {k: round(1e3 * (v - h0), 4) for k, v in self._host_stamps[1:]}}
+
+    def _pack_begin(self, chunks):
+        """Queue the host-side gather of the sparse rows of ``chunks`` (served in order); returns the tickets."""
+        self._ev_pack.synchronize()                       # the previous step's copies out of the pack buffers are done
+        kc = C.byref(self._kcfg)
+        tickets = []
+        for lo, hi in chunks:
+            t = self._lib.bezk_host_pack_begin(ops._TASK_ID[self.TASK], _ptr(self.rigid_body), _ptr(self.net_contact),
+                                               _ptr(self.root_states), kc, _ptr(self._h_rec), lo, hi - lo)
+            if t < 0:
+                _lib.check(int(-t), "bezk_host_pack_begin")
+            tickets.append(t)
+        return tickets
 
     def _launch_post(self, parts):
         if self.host_mode == "staged_ce":
@@ -345,7 +424,9 @@ class KickEnv(VecTask):
             return int(((a + width - 1) // 64 - a // 64 + 1).sum()) * 64
         fw = 48 if self.cleats else 12
         if self.host_mode == "staged_ce":                 # the arguments of the copies issued each step
-            if self._ce_split:                            # foot rows: zero-copy reads of the gather kernel, as 64-byte granules
+            if self._pack:                                # dense copies: dof_state, the packed records, the actions
+                return nbytes(self.dof_state) + nbytes(self._h_rec) + n * 18 * 4, outs
+            if self._ce_split:                          # foot rows: zero-copy reads of the gather kernel, as 64-byte granules
                 feet = granules(self.net_contact.data_ptr(), nb * 12, self._kcfg.left_foot_body * 12, fw) + \
                     granules(self.net_contact.data_ptr(), nb * 12, self._kcfg.right_foot_body * 12, fw)
             else:
@@ -370,12 +451,15 @@ class KickEnv(VecTask):
 
     def link_counters(self):
         how = {"staged": "sizes of the tensors copied by cudaMemcpyAsync each step",
+               "staged_pack": "byte counts of the cudaMemcpyAsync calls issued each step (dof_state, the per-env records the host worker "
+                              "threads gather the sparse rows and the root-state subset into, actions; results and PD targets back) "
+                              "(+ the rare reset rows the kernel writes back into the simulator's host tensors, not counted)",
                "staged_ce": "byte counts of the cudaMemcpyAsync / cudaMemcpy2DAsync (width x rows) calls issued each step; with the split "
                             "sparse staging (default) the foot rows are zero-copy reads of a gather kernel, counted as distinct 64-byte "
                             "granules (+ the rare reset rows the kernel writes back into the simulator's host tensors, not counted)",
                "zero_copy": "address ranges the kernels dereference in pinned host memory each step: dense tensors whole, sparse AoS rows as "
                             "distinct 64-byte granules (+ the rare reset rows written back, not counted)",
-               None: "GPU pipeline: nothing crosses the host link"}[self.host_mode]
+               None: "GPU pipeline: nothing crosses the host link"}["staged_pack" if self._pack else self.host_mode]
         return dict(self._link, how=how)
 
     # ------------------------------------------------------------------ reference-named attributes
@@ -419,8 +503,13 @@ class KickEnv(VecTask):
         elif self.host_mode == "staged_ce":                # unchunked, on the current stream: the stand-alone calls
             self._d_root.copy_(self.root_states, non_blocking=True)
             self._d_dof.copy_(self.dof_state, non_blocking=True)
-            rc = self._lib.bezk_stage_sparse_rows(_ptr(self.rigid_body), _ptr(self.net_contact), C.byref(self._kcfg), _ptr(self._d_rb),
-                                                  _ptr(self._d_cf), 0, self.num_envs, self._stream())
+            if self._pack:
+                rc = self._lib.bezk_host_pack_wait(self._pack_begin([(0, self.num_envs)])[0])
+                self._d_rec.copy_(self._h_rec, non_blocking=True)
+                self._ev_pack.record(torch.cuda.current_stream(self.compute_device))
+            else:
+                rc = self._lib.bezk_stage_sparse_rows(_ptr(self.rigid_body), _ptr(self.net_contact), C.byref(self._kcfg),
+                                                      _ptr(self._d_rb), _ptr(self._d_cf), 0, self.num_envs, self._stream())
             if rc:
                 _lib.check(rc, "bezk_stage_sparse_rows")
 

@@ -324,3 +324,60 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
         assert int(out[sname]) == C.sizeof(st), sname
         for fname, _ in st._fields_:
             assert int(out[f"{sname}.{fname}"]) == getattr(st, fname).offset, (sname, fname)
+
+
+@pytest.mark.parametrize("task,cleats", [("kick", False), ("kick", True), ("walk", False), ("orient", False)])
+def test_host_pack_gathers_the_sparse_rows(task, cleats):
+    """``bezk_host_pack_begin`` / ``_wait`` (host worker threads, no CUDA call): every env's record holds, bit for bit, the
+    IMU-link slice, the foot (cleat) force rows and the root-state subset of the Isaac Gym AoS tensors -- for ragged chunk sizes, a
+    non-zero env0, more jobs in flight than the ring has slots, and an empty job."""
+    import numpy as np
+    from bez_isaacgym_b200 import _lib, ops
+    lib = _lib.load()
+    assert lib.bezk_host_pack_config(3, 50, -1) >= 3 and lib.bezk_host_pack_config(99, -1, -1) == -10001
+    tid = ops._TASK_ID[task]
+    nb = (30 if cleats else 22) - (0 if task == "kick" else 1)
+    actors = 2 if task == "kick" else 1
+    cfg = ops.make_task_cfg(num_bodies=nb, cleats=cleats)
+    fw = 12 if cleats else 3
+    nroot = 7 if task == "kick" else 3
+    rs = lib.bezk_host_pack_record_floats(tid, ctypes.byref(cfg))
+    assert rs == -(-(10 + 2 * fw + nroot) // 4) * 4 and (rs, task, cleats) != (24, "kick", True)
+    if task == "kick" and not cleats:
+        assert rs == 24                                          # 96 B per env
+    n = 70_001
+    rng = np.random.default_rng(5)
+    rb = rng.standard_normal((n, nb, 13), dtype=np.float32)
+    cf = rng.standard_normal((n, nb, 3), dtype=np.float32)
+    root = rng.standard_normal((n, actors, 13), dtype=np.float32)
+    cf[::7, cfg.left_foot_body] = np.nan                       # NaN forces travel unchanged
+    rec = np.full((n, rs), -7.0, dtype=np.float32)
+    P = lambda a: ctypes.c_void_p(a.ctypes.data)                # noqa: E731
+    # 97 ragged jobs (> 64 ring slots) issued before any wait, covering [0, n) in order
+    edges = sorted(set([0, n] + [int(x) for x in rng.integers(1, n, size=96)]))
+    tickets = [lib.bezk_host_pack_begin(tid, P(rb), P(cf), P(root), ctypes.byref(cfg), P(rec), lo, hi - lo)
+               for lo, hi in zip(edges[:-1], edges[1:])]
+    assert all(t > 0 for t in tickets) and tickets == sorted(tickets)
+    for t in reversed(tickets):
+        assert lib.bezk_host_pack_wait(t) == 0
+    assert lib.bezk_host_pack_wait(tickets[0]) == 0              # waiting twice is fine
+    bits = lambda a: np.ascontiguousarray(a).view(np.uint32)     # noqa: E731
+    assert np.array_equal(bits(rec[:, 0:10]), bits(rb[:, cfg.imu_body, 3:13]))
+    k = fw // 3
+    left = cf[:, cfg.left_foot_body:cfg.left_foot_body + k].reshape(n, -1)
+    right = cf[:, cfg.right_foot_body:cfg.right_foot_body + k].reshape(n, -1)
+    assert np.array_equal(bits(rec[:, 10:10 + fw]), bits(left))
+    assert np.array_equal(bits(rec[:, 10 + fw:10 + 2 * fw]), bits(right))
+    ro = 10 + 2 * fw
+    flat = root.reshape(n, -1)
+    want_root = flat[:, [0, 1, 2, 13, 14, 20, 21]] if task == "kick" else flat[:, 0:3]
+    assert np.array_equal(bits(rec[:, ro:ro + nroot]), bits(want_root))
+    assert (rec[:, ro + nroot:] == 0).all()
+    # empty job, bad arguments
+    assert lib.bezk_host_pack_begin(tid, P(rb), P(cf), P(root), ctypes.byref(cfg), P(rec), 5, 0) == 0
+    assert lib.bezk_host_pack_wait(0) == 0
+    assert lib.bezk_host_pack_begin(tid, None, P(cf), P(root), ctypes.byref(cfg), P(rec), 0, 4) == -10001
+    assert lib.bezk_host_pack_begin(9, P(rb), P(cf), P(root), ctypes.byref(cfg), P(rec), 0, 4) == -10001
+    assert lib.bezk_host_pack_wait(1 << 40) == 10001
+    assert lib.bezk_post_physics_packed(tid, *([None] * 10), 0, 0, *([None] * 4), ctypes.byref(cfg), None, None, None, 7, 4, 0, None, None,
+                                        None) == 10001

@@ -410,12 +410,13 @@ def test_cpu_tensors_raise_no_fallback():
 
 
 @pytest.mark.parametrize("task", ["kick", "walk", "orient"])
-@pytest.mark.parametrize("host_mode", ["zero_copy", "staged", "staged_ce"])
+@pytest.mark.parametrize("host_mode", ["zero_copy", "staged", "staged_ce", "staged_pack"])
 def test_host_pipeline_equals_gpu_pipeline(host_mode, task):
     """``use_gpu_pipeline: False`` (simulator tensors in pinned host memory; BASELINE configs[0] sim_device=cpu pipeline=cpu;
     the reference's device selection ``tasks/base/vec_task.py:51-98`` serves every task): same kernels, so results are
     bit-identical to the GPU pipeline, and resets land in the HOST dof_state.  ``staged_ce`` = chunked copy-engine pipeline
-    (strided cudaMemcpy2DAsync pulls of the sparse rows); it cannot write the contact filter back, so the filter is off there."""
+    (strided cudaMemcpy2DAsync pulls of the sparse rows); it cannot write the contact filter back, so the filter is off there.
+    ``staged_pack`` = the same pipeline with the sparse rows gathered by host worker threads (``bezk_host_pack_*``)."""
     from bez_isaacgym_b200.synthetic_sim import SyntheticGym
     from bez_isaacgym_b200 import tasks as T
     cls = {"kick": T.KickEnv, "walk": T.WalkEnv, "orient": T.OrientEnv}[task]
@@ -427,7 +428,7 @@ def test_host_pipeline_equals_gpu_pipeline(host_mode, task):
         cfg["seed"] = 5
         cfg["env"]["hostPipeline"] = host_mode
         cfg["env"]["hostPipelineChunks"] = 3
-        cfg["env"]["writeContactFilter"] = host_mode != "staged_ce"
+        cfg["env"]["writeContactFilter"] = host_mode not in ("staged_ce", "staged_pack")
         sim = SyntheticGym(n, device="cuda:0", state=st.clone(), host=(kind == "host"), task=task)
         envs[kind] = cls(cfg, "cuda:0", 0, True, sim=sim)
         envs[kind].progress_buf.copy_(torch.arange(n, device="cuda") % envs[kind].max_episode_length)

@@ -21,7 +21,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=262144)
     ap.add_argument("--steps", type=int, default=64)
-    ap.add_argument("--modes", default="zero_copy,staged_ce:2,staged_ce:4,staged_ce:8,staged_ce:2s,staged_ce:4s,staged_ce:8s")
+    ap.add_argument("--modes", default="zero_copy,staged_ce:4,staged_ce:4s,staged_pack:2,staged_pack:4,staged_pack:8")
+    ap.add_argument("--timeline", action="store_true", help="add the per-chunk device / host timeline of one step (staged_ce / staged_pack)")
+    ap.add_argument("--pack-threads", type=int, default=0)
     args = ap.parse_args()
     n = args.envs
 
@@ -40,6 +42,8 @@ def main():
         if chunks:
             cfg["env"]["hostPipelineChunks"] = int(chunks)
         cfg["env"]["hostPipelineSplitSparse"] = split
+        cfg["env"]["hostPipelineTimeline"] = args.timeline and mode in ("staged_ce", "staged_pack")
+        cfg["env"]["hostPackThreads"] = args.pack_threads
         env = KickEnv(cfg, "cuda:0", 0, True, sim=sim)
         for _ in range(5):
             env.step(act)
@@ -55,14 +59,19 @@ def main():
             torch.cuda.synchronize(); a = time.perf_counter()
             env.pre_physics_step(act)
             torch.cuda.synchronize(); b = time.perf_counter()
-            env._ce_copy_out = mode == "staged_ce"
+            env._ce_copy_out = mode in ("staged_ce", "staged_pack")
             env.post_physics_step()
             env._ce_copy_out = False
             torch.cuda.synchronize(); c = time.perf_counter()
             t_pre += b - a; t_post += c - b
+        tl = None
+        if cfg["env"]["hostPipelineTimeline"]:
+            env.step(act)
+            torch.cuda.synchronize()
+            tl = env.host_timeline()
         print(json.dumps({"mode": mode, "chunks": int(chunks) if chunks else None, "split_sparse": split, "envs": n, "ms_per_step": round(ms, 4),
                           "env_steps_per_s_M": round(n / ms / 1e3, 2), "pre_ms": round(1e3 * t_pre / 8, 4),
-                          "post_ms": round(1e3 * t_post / 8, 4)}), flush=True)
+                          "post_ms": round(1e3 * t_post / 8, 4), "timeline": tl}), flush=True)
         del env
 
 
