@@ -74,7 +74,7 @@ SIGNATURES = {
     "bezk_stage_sparse_rows_split": (C.c_int, [_P, _P, C.POINTER(BezkTaskCfg), _P, _P, _I64, _I64, _P, _P]),
     "bezk_host_pack_config": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     "bezk_host_pack_record_floats": (C.c_int, [C.c_int, C.POINTER(BezkTaskCfg)]),
-    "bezk_host_pack_begin": (_I64, [C.c_int, _P, _P, _P, C.POINTER(BezkTaskCfg), _P, _I64, _I64]),
+    "bezk_host_pack_begin": (_I64, [C.c_int, _P, _P, _P, _P, C.POINTER(BezkTaskCfg), _P, _I64, _I64]),
     "bezk_post_physics_packed": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U64, _U64, _P, _P, _P, _P,
                                            C.POINTER(BezkTaskCfg), _P, _P, _P, C.c_int, _I64, _I64, _P, _P, _P]),
     "bezk_host_pack_wait": (C.c_int, [_I64]),

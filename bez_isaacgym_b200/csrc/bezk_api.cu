@@ -195,14 +195,14 @@ int bezk_host_pack_record_floats(int task, const BezkTaskCfg* cfg) {
 }
 
 int64_t bezk_host_pack_begin(int task, const float* rigid_body_host, const float* net_contact_host, const float* root_states_host,
-                             const BezkTaskCfg* cfg, float* records, int64_t env0, int64_t n) {
+                             const float* dof_state_host, const BezkTaskCfg* cfg, float* dst, int64_t env0, int64_t n) {
     if (!(task == BEZK_TASK_KICK || task == BEZK_TASK_WALK || task == BEZK_TASK_ORIENT)) return -(int64_t)fail(BEZK_E_BADARG, "unknown task");
     if (int rc = check_cfg(cfg)) return -(int64_t)rc;
     if (env0 < 0 || n < 0) return -(int64_t)fail(BEZK_E_BADARG, "env0 / n < 0");
     if (n == 0) return 0;
-    if (!(rigid_body_host && net_contact_host && root_states_host && records)) return -(int64_t)fail(BEZK_E_BADARG, "pack buffers NULL");
-    if (!ALIGNED(records, 16)) return -(int64_t)fail(BEZK_E_ALIGN, "records must be 16-byte aligned");
-    return bezk::host_pack_begin(task, rigid_body_host, net_contact_host, root_states_host, *cfg, records, env0, n);
+    if (!(rigid_body_host && net_contact_host && root_states_host && dst)) return -(int64_t)fail(BEZK_E_BADARG, "pack buffers NULL");
+    if (!ALIGNED(dst, 16)) return -(int64_t)fail(BEZK_E_ALIGN, "dst must be 16-byte aligned");
+    return bezk::host_pack_begin(task, rigid_body_host, net_contact_host, root_states_host, dof_state_host, *cfg, dst, env0, n);
 }
 
 int bezk_host_pack_wait(int64_t ticket) {

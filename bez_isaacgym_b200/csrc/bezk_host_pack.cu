@@ -34,7 +34,8 @@ constexpr int64_t kPiece = 1024;      // envs a worker claims at a time
 constexpr int kPrefetchAhead = 12;    // envs; the AoS rows are 1144 / 264 B apart, one or two cache lines each
 
 struct Job {
-    const float* rb; const float* cf; const float* root; float* rec;
+    const float* rb; const float* cf; const float* root; float* rec;        // rec: record of env env0 (the job's own destination)
+    const float* dof; float* dof_dst;                                       // optional: dense dof_state rows copied along
     int64_t rb_stride, rb_off, cf_stride, cf_l, cf_r, root_stride;       // floats
     PackLayout L;
     int64_t env0, n;
@@ -59,7 +60,7 @@ inline void pack_one(const Job& j, const PackLayout& L, const float* rb, const f
     int used = 10 + 2 * fw + 3;
     if (STRIDE == 24 || L.root_n == 7) { q[3] = r[13]; q[4] = r[14]; q[5] = r[20]; q[6] = r[21]; used += 4; }
     for (int k = used; k < stride; ++k) t[k] = 0.0f;
-    float* d = j.rec + e * stride;
+    float* d = j.rec + (e - j.env0) * stride;
 #if defined(__x86_64__)
     for (int k = 0; k < stride; k += 4) _mm_stream_ps(d + k, _mm_load_ps(t + k));
 #else
@@ -85,6 +86,19 @@ void pack_piece(const Job& j, int64_t lo, int64_t hi) {
         __builtin_prefetch(j.root + (e + 2 * kPrefetchAhead) * j.root_stride);
         if (kick24) pack_one<24>(j, L, rb, cl, cr, e);
         else pack_one<0>(j, L, rb, cl, cr, e);
+    }
+    if (j.dof) {                                             // this piece's dof_state rows: one contiguous streaming copy
+        const float* src = j.dof + lo * 36;
+        float* dst = j.dof_dst + (lo - j.env0) * 36;
+        const int64_t nf = (hi - lo) * 36;                   // a multiple of 4 floats
+#if defined(__x86_64__)
+        for (int64_t k = 0; k < nf; k += 4) {
+            if ((k & 15) == 0) __builtin_prefetch(src + k + 256);
+            _mm_stream_ps(dst + k, _mm_loadu_ps(src + k));
+        }
+#else
+        memcpy(dst, src, (size_t)nf * 4);
+#endif
     }
 #if defined(__x86_64__)
     _mm_sfence();                                            // the streamed records are globally visible before the job is marked done
@@ -119,7 +133,7 @@ public:
         // a worker that picked this slot up for its PREVIOUS job may still be about to claim from it: park the claim counter
         // out of range while the fields change, open it (release) only when the job is complete
         j.next.store(INT64_MAX / 2, std::memory_order_relaxed);
-        j.rb = proto.rb; j.cf = proto.cf; j.root = proto.root; j.rec = proto.rec;
+        j.rb = proto.rb; j.cf = proto.cf; j.root = proto.root; j.rec = proto.rec; j.dof = proto.dof; j.dof_dst = proto.dof_dst;
         j.rb_stride = proto.rb_stride; j.rb_off = proto.rb_off; j.cf_stride = proto.cf_stride; j.cf_l = proto.cf_l; j.cf_r = proto.cf_r;
         j.root_stride = proto.root_stride; j.L = proto.L;
         j.env0 = proto.env0; j.n = proto.n;
@@ -264,13 +278,15 @@ PackLayout pack_layout(int task, const BezkTaskCfg& cfg) {
     return L;
 }
 
-int64_t host_pack_begin(int task, const float* rigid_body, const float* net_contact, const float* root_states, const BezkTaskCfg& cfg,
-                        float* records, int64_t env0, int64_t n) {
+int64_t host_pack_begin(int task, const float* rigid_body, const float* net_contact, const float* root_states, const float* dof_state,
+                        const BezkTaskCfg& cfg, float* dst, int64_t env0, int64_t n) {
     if (n <= 0) return 0;
     Pool& p = Pool::get();
     p.ensure_threads(0);
     Job j;
-    j.rb = rigid_body; j.cf = net_contact; j.root = root_states; j.rec = records;
+    j.rb = rigid_body; j.cf = net_contact; j.root = root_states;
+    j.dof = dof_state; j.dof_dst = dof_state ? dst : nullptr;
+    j.rec = dof_state ? dst + n * 36 : dst;                  // [n x 36 dof rows |] n records
     j.rb_stride = (int64_t)cfg.num_bodies * 13; j.rb_off = (int64_t)cfg.imu_body * 13 + 3;
     j.cf_stride = (int64_t)cfg.num_bodies * 3; j.cf_l = (int64_t)cfg.left_foot_body * 3; j.cf_r = (int64_t)cfg.right_foot_body * 3;
     j.root_stride = task == BEZK_TASK_KICK ? 26 : 13;

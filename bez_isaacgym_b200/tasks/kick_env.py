@@ -195,9 +195,18 @@ class KickEnv(VecTask):
                 raise ValueError("hostPipeline='staged_ce' cannot write the contact filter back (env.writeContactFilter must be False)")
             self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
             self._ce_split = bool(env_cfg.get("hostPipelineSplitSparse", True))
-            chunks = max(1, int(env_cfg.get("hostPipelineChunks", 4)))
-            step_sz = max(128, -(-n // chunks) // 128 * 128)           # chunk starts stay multiples of 128 envs (TMA alignment)
-            self._ce_chunks = [(lo, min(n, lo + step_sz)) for lo in range(0, n, step_sz)]
+            # env.hostPipelineChunks: a count (equal chunks) or a list of relative sizes -- a small first chunk shortens the
+            # pipeline's fill (its gather + H2D are exposed), a small last one its drain (its D2H is)
+            chunks = env_cfg.get("hostPipelineChunks", 4)
+            weights = [1.0] * max(1, int(chunks)) if isinstance(chunks, (int, float)) else [float(w) for w in chunks]
+            if not weights or min(weights) <= 0:
+                raise ValueError("env.hostPipelineChunks must be a positive count or a list of positive relative sizes")
+            edges, acc = [0], 0.0
+            for w in weights[:-1]:                                     # chunk starts stay multiples of 128 envs (TMA alignment)
+                acc += w
+                edges.append(min(n, max(edges[-1] + 128, int(round(n * acc / sum(weights) / 128)) * 128)))
+            edges.append(n)
+            self._ce_chunks = [(lo, hi) for lo, hi in zip(edges[:-1], edges[1:]) if hi > lo]
             #: env.hostPipelineTimeline: timing-enabled events + host stamps of the last step (tools/exp_e2e.py --timeline)
             self._timeline = bool(env_cfg.get("hostPipelineTimeline", False))
             mk = lambda: torch.cuda.Event(enable_timing=self._timeline)               # noqa: E731
@@ -210,10 +219,20 @@ class KickEnv(VecTask):
                 rs = self._lib.bezk_host_pack_record_floats(ops._TASK_ID[self.TASK], C.byref(self._kcfg))
                 if rs <= 0:
                     _lib.check(-rs or 1, "bezk_host_pack_record_floats")
-                self._h_rec = torch.zeros(n, rs, dtype=torch.float32).pin_memory()
-                self._d_rec = torch.zeros(n, rs, **f32)
-                k = self._lib.bezk_host_pack_config(int(env_cfg.get("hostPackThreads", 0)), int(env_cfg.get("hostPackSpinUs", -1)),
-                                                    int(env_cfg.get("hostPackPin", -1)))
+                # env.hostPackDof (default off): the workers also copy the chunk's dof_state rows, so that ONE cudaMemcpyAsync per
+                # chunk moves [dof rows | records].  A second H2D call per chunk costs the link ~40 us, but streaming 144 B/env
+                # through the host cores makes the gather the bottleneck: 81 M vs 92 M env-steps/s (profiles/r02_host_pack.md)
+                self._pack_dof = bool(env_cfg.get("hostPackDof", False))
+                self._rs = rs
+                self._pw = rs + (36 if self._pack_dof else 0)            # floats per env in the pack buffers
+                self._h_pack = torch.zeros(n * self._pw, dtype=torch.float32).pin_memory()
+                self._d_pack = torch.zeros(n * self._pw, **f32)
+                threads = int(env_cfg.get("hostPackThreads", 0))
+                if threads <= 0:         # this rank's share of the host cores (one process per GPU), minus the issuing thread
+                    import os
+                    share = (os.cpu_count() or 2) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+                    threads = max(1, min(16, share - 1))
+                k = self._lib.bezk_host_pack_config(threads, int(env_cfg.get("hostPackSpinUs", -1)), int(env_cfg.get("hostPackPin", -1)))
                 if k <= 0:
                     _lib.check(-k or 1, "bezk_host_pack_config")
                 self.host_pack_threads = k
@@ -275,7 +294,7 @@ class KickEnv(VecTask):
     def _stream(self):
         return _P(torch.cuda.current_stream(self.compute_device).cuda_stream)
 
-    def _launch_staged(self, parts, lo=0, hi=None):
+    def _launch_staged(self, parts, lo=0, hi=None, whole_dof=True):
         """``bezk_post_physics_staged`` over envs [lo, hi) of the staged_ce host pipeline (device staging in, device results
         out, reset rows written straight back into the simulator's pinned host tensors)."""
         n = self.num_envs
@@ -284,8 +303,11 @@ class KickEnv(VecTask):
         off = lambda t, k: None if t is None else _P(t.data_ptr() + k * t.element_size())      # noqa: E731
         clip = self.obs_clipped_buf
         if self._pack:
+            # chunk (lo, hi) of the pack buffer: [dof rows (hi - lo) x 36 |] records (hi - lo) x rs
+            d_dof = off(self._d_pack, lo * self._pw) if (self._pack_dof and not whole_dof) else off(self._d_dof, lo * 36)
+            d_rec = off(self._d_pack, lo * self._pw + ((hi - lo) * 36 if self._pack_dof else 0))
             rc = self._lib.bezk_post_physics_packed(
-                ops._TASK_ID[self.TASK], off(self._d_dof, lo * 36), off(self._d_rec, lo * self._d_rec.shape[1]), off(self._d_root, lo * rw),
+                ops._TASK_ID[self.TASK], d_dof, d_rec, off(self._d_root, lo * rw),
                 None if self._prev_is_view else off(self._prev_buf, lo * 3),
                 off(self.goal, lo * 2), off(self.goal_angle, lo), off(self.ball_init, lo * 2), off(self.initial_root_states, lo * rw),
                 None, None, self._seed, self._rng_step, off(self.reset_buf, lo), off(self.progress_buf, lo), off(self.timeout_buf, lo),
@@ -326,15 +348,22 @@ class KickEnv(VecTask):
             self._host_stamps.append(("pack_issued", time.perf_counter()))
         for c, (lo, hi) in enumerate(self._ce_chunks):
             with torch.cuda.stream(self._s_in):
-                dof_d[lo:hi].copy_(dof_h[lo:hi], non_blocking=True)
-                if self._pack:           # records gathered by the host workers while the engine moved the dense tensor
+                if self._pack:           # records gathered by the host workers while the engine moved the previous chunk
+                    if not self._pack_dof and c == 0:
+                        dof_d[lo:hi].copy_(dof_h[lo:hi], non_blocking=True)
                     rc = self._lib.bezk_host_pack_wait(tickets[c])
                     if tl:
                         self._host_stamps.append((f"pack_done{c}", time.perf_counter()))
-                    self._d_rec[lo:hi].copy_(self._h_rec[lo:hi], non_blocking=True)
+                    pw = self._pw
+                    self._d_pack[lo * pw:hi * pw].copy_(self._h_pack[lo * pw:hi * pw], non_blocking=True)
                     if c == len(self._ce_chunks) - 1:
                         self._ev_pack.record(self._s_in)
+                    self._ev_in[c].record(self._s_in)
+                    if not self._pack_dof and c + 1 < len(self._ce_chunks):      # keep the engine fed while this chunk is launched
+                        lo2, hi2 = self._ce_chunks[c + 1]
+                        dof_d[lo2:hi2].copy_(dof_h[lo2:hi2], non_blocking=True)
                 else:
+                    dof_d[lo:hi].copy_(dof_h[lo:hi], non_blocking=True)
                     root_d[lo:hi].copy_(root_h[lo:hi], non_blocking=True)
                     if self._ce_split:   # IMU slices by the copy engine, foot rows by an SM gather kernel on the compute stream
                         rc = self._lib.bezk_stage_sparse_rows_split(_ptr(self.rigid_body), _ptr(self.net_contact), kc,
@@ -345,9 +374,10 @@ class KickEnv(VecTask):
                                                               _ptr(self._d_cf), lo, hi - lo, s_in_h)
                 if rc:
                     _lib.check(rc, "bezk_host_pack_wait" if self._pack else "bezk_stage_sparse_rows")
-                self._ev_in[c].record(self._s_in)
+                if not self._pack:
+                    self._ev_in[c].record(self._s_in)
             cur.wait_event(self._ev_in[c])
-            self._launch_staged(_lib.PART_ALL, lo, hi)
+            self._launch_staged(_lib.PART_ALL, lo, hi, whole_dof=False)
             if copy_out:
                 self._ev_k[c].record(cur)
                 with torch.cuda.stream(self._s_out):
@@ -370,14 +400,18 @@ class KickEnv(VecTask):
         h0 = self._host_stamps[0][1]
         return {"device_ms": dev, "host_ms": {k: round(1e3 * (v - h0), 4) for k, v in self._host_stamps[1:]}}
 
-    def _pack_begin(self, chunks):
-        """Queue the host-side gather of the sparse rows of ``chunks`` (served in order); returns the tickets."""
-        self._ev_pack.synchronize()                       # the previous step's copies out of the pack buffers are done
+    def _pack_begin(self, chunks, with_dof=None):
+        """Queue the host-side gather of ``chunks`` into their regions of the pinned pack buffer (served in order); returns the
+        tickets."""
+        self._ev_pack.synchronize()                       # the previous step's copies out of the pack buffer are done
         kc = C.byref(self._kcfg)
+        with_dof = self._pack_dof if with_dof is None else with_dof
         tickets = []
         for lo, hi in chunks:
+            dst = _P(self._h_pack.data_ptr() + 4 * (lo * self._pw + (0 if with_dof or not self._pack_dof else (hi - lo) * 36)))
             t = self._lib.bezk_host_pack_begin(ops._TASK_ID[self.TASK], _ptr(self.rigid_body), _ptr(self.net_contact),
-                                               _ptr(self.root_states), kc, _ptr(self._h_rec), lo, hi - lo)
+                                               _ptr(self.root_states), _ptr(self.dof_state) if with_dof else None, kc, dst,
+                                               lo, hi - lo)
             if t < 0:
                 _lib.check(int(-t), "bezk_host_pack_begin")
             tickets.append(t)
@@ -425,7 +459,7 @@ class KickEnv(VecTask):
         fw = 48 if self.cleats else 12
         if self.host_mode == "staged_ce":                 # the arguments of the copies issued each step
             if self._pack:                                # dense copies: dof_state, the packed records, the actions
-                return nbytes(self.dof_state) + nbytes(self._h_rec) + n * 18 * 4, outs
+                return (0 if self._pack_dof else nbytes(self.dof_state)) + nbytes(self._h_pack) + n * 18 * 4, outs
             if self._ce_split:                          # foot rows: zero-copy reads of the gather kernel, as 64-byte granules
                 feet = granules(self.net_contact.data_ptr(), nb * 12, self._kcfg.left_foot_body * 12, fw) + \
                     granules(self.net_contact.data_ptr(), nb * 12, self._kcfg.right_foot_body * 12, fw)
@@ -451,8 +485,9 @@ class KickEnv(VecTask):
 
     def link_counters(self):
         how = {"staged": "sizes of the tensors copied by cudaMemcpyAsync each step",
-               "staged_pack": "byte counts of the cudaMemcpyAsync calls issued each step (dof_state, the per-env records the host worker "
-                              "threads gather the sparse rows and the root-state subset into, actions; results and PD targets back) "
+               "staged_pack": "byte counts of the cudaMemcpyAsync calls issued each step (the pack buffer the host worker threads fill: dense "
+                              "dof_state rows + per-env records of the sparse rows and the root-state subset; actions; results and PD "
+                              "targets back) "
                               "(+ the rare reset rows the kernel writes back into the simulator's host tensors, not counted)",
                "staged_ce": "byte counts of the cudaMemcpyAsync / cudaMemcpy2DAsync (width x rows) calls issued each step; with the split "
                             "sparse staging (default) the foot rows are zero-copy reads of a gather kernel, counted as distinct 64-byte "
@@ -503,9 +538,11 @@ class KickEnv(VecTask):
         elif self.host_mode == "staged_ce":                # unchunked, on the current stream: the stand-alone calls
             self._d_root.copy_(self.root_states, non_blocking=True)
             self._d_dof.copy_(self.dof_state, non_blocking=True)
-            if self._pack:
-                rc = self._lib.bezk_host_pack_wait(self._pack_begin([(0, self.num_envs)])[0])
-                self._d_rec.copy_(self._h_rec, non_blocking=True)
+            if self._pack:                                 # the records of "chunk" (0, n); dof_state went dense above
+                n = self.num_envs
+                rc = self._lib.bezk_host_pack_wait(self._pack_begin([(0, n)], with_dof=False)[0])
+                o = n * 36 if self._pack_dof else 0
+                self._d_pack[o:o + n * self._rs].copy_(self._h_pack[o:o + n * self._rs], non_blocking=True)
                 self._ev_pack.record(torch.cuda.current_stream(self.compute_device))
             else:
                 rc = self._lib.bezk_stage_sparse_rows(_ptr(self.rigid_body), _ptr(self.net_contact), C.byref(self._kcfg),

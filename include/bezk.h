@@ -156,30 +156,34 @@ int bezk_stage_sparse_rows(const float* rigid_body_host, const float* net_contac
 int bezk_stage_sparse_rows_split(const float* rigid_body_host, const float* net_contact_host, const BezkTaskCfg* cfg,
                                  float* imu_stage, float* feet_stage, int64_t env0, int64_t n, void* copy_stream,
                                  void* gather_stream);
-/* The same gather done by HOST worker threads instead of the copy engine, into ONE compact record per env in PINNED host memory
- * (records is the buffer BASE, 16-byte aligned, (N, bezk_host_pack_record_floats) f32; the job covers envs [env0, env0 + n)):
+/* The same gather done by HOST worker threads instead of the copy engine, into ONE compact record per env in PINNED host memory.
+ * A job covers envs [env0, env0 + n) of the simulator tensors (passed as tensor BASES) and writes to dst, the job's OWN
+ * destination (16-byte aligned): n records of bezk_host_pack_record_floats floats each,
  *   [ IMU-link q, v, w (10) | left foot row (3; cleats 12) | right foot row | root subset | zero pad to a multiple of 4 floats ]
  * root subset = the only floats of root_states the step reads: robot position xyz, and for BezKick the ball's xy position and xy
  * velocity (7 floats of 26; walk / orient: 3 of 13).  BezKick: 24 floats = 96 B per env instead of 1512 B of AoS rows.
- * The caller moves the chunk's records with one dense cudaMemcpyAsync.  The copy engine serving the H2D direction is
- * row-rate-bound on strided pulls (1.4 ns per row); the simulator's host cores, idle between simulate() calls, gather the rows
- * of chunk c + 1 while the engine streams chunk c (ref: tasks/base/vec_task.py:51-98, the sim_device=cpu pipeline).
+ * With dof_state_host != NULL the job ALSO copies the chunk's dense dof_state rows: dst = [ n x 36 dof floats | n records ], so
+ * that ONE cudaMemcpyAsync moves everything the chunk's kernel reads (every additional H2D call costs the link ~40 us under
+ * bidirectional load, profiles/r02_host_pack.md).
+ * The copy engine serving the H2D direction is row-rate-bound on strided pulls (1.4 ns per row); the simulator's host cores, idle
+ * between simulate() calls, gather the rows of chunk c + 1 while the engine streams chunk c (ref: tasks/base/vec_task.py:51-98,
+ * the sim_device=cpu pipeline).
  * bezk_host_pack_begin is asynchronous: it returns a ticket > 0 (0 for n == 0, -BEZK_E_* on a bad argument);
- * bezk_host_pack_wait(ticket) returns once those records are written (the caller's thread packs too while it waits).
+ * bezk_host_pack_wait(ticket) returns once the job's output is written (the caller's thread packs too while it waits).
  * Jobs are served in issue order.  One thread at a time may issue / wait.  bezk_host_pack_config sizes the pool (threads = 0:
  * hardware threads - 1, at most 16; the pool only grows), sets how long an idle worker polls for the next job before it blocks
  * (spin_us, default 2000; < 0 keeps the current value: a step issues jobs every few milliseconds and a futex wake would sit on its
  * critical path) and whether workers are pinned one per CPU (pin, honoured before the first worker starts; < 0 keeps it); it
  * returns the worker count (-BEZK_E_BADARG on a bad thread count).  No CUDA call is made by these four.
  * bezk_post_physics_packed is bezk_post_physics_chunk for a chunk whose records are on the DEVICE (pointer already offset to the
- * chunk's first env, like every other argument): it scatters the root subset into the chunk's rows of root_states (a device
+ * chunk's first record, like every other argument): it scatters the root subset into the chunk's rows of root_states (a device
  * image of the simulator tensor; its other columns are never read) and runs the step reading the IMU slice and the foot rows
  * straight out of the records.  BEZK_F_WRITE_CONTACT_FILTER must be clear. */
 int bezk_host_pack_config(int32_t threads, int32_t spin_us, int32_t pin);
 int bezk_host_pack_record_floats(int task, const BezkTaskCfg* cfg);
 int64_t bezk_host_pack_begin(int task, const float* rigid_body_host, const float* net_contact_host,
-                             const float* root_states_host, const BezkTaskCfg* cfg, float* records, int64_t env0,
-                             int64_t n);
+                             const float* root_states_host, const float* dof_state_host, const BezkTaskCfg* cfg,
+                             float* dst, int64_t env0, int64_t n);
 int bezk_host_pack_wait(int64_t ticket);
 int bezk_post_physics_packed(int task, float* dof_state, const float* records, float* root_states, float* prev_lin_vel,
                              float* goal, const float* goal_angle, const float* ball_init,

@@ -352,10 +352,11 @@ def test_host_pack_gathers_the_sparse_rows(task, cleats):
     root = rng.standard_normal((n, actors, 13), dtype=np.float32)
     cf[::7, cfg.left_foot_body] = np.nan                       # NaN forces travel unchanged
     rec = np.full((n, rs), -7.0, dtype=np.float32)
-    P = lambda a: ctypes.c_void_p(a.ctypes.data)                # noqa: E731
+    dof = rng.standard_normal((n, 36), dtype=np.float32)
+    P = lambda a, off=0: ctypes.c_void_p(a.ctypes.data + 4 * off)           # noqa: E731
     # 97 ragged jobs (> 64 ring slots) issued before any wait, covering [0, n) in order
     edges = sorted(set([0, n] + [int(x) for x in rng.integers(1, n, size=96)]))
-    tickets = [lib.bezk_host_pack_begin(tid, P(rb), P(cf), P(root), ctypes.byref(cfg), P(rec), lo, hi - lo)
+    tickets = [lib.bezk_host_pack_begin(tid, P(rb), P(cf), P(root), None, ctypes.byref(cfg), P(rec, lo * rs), lo, hi - lo)
                for lo, hi in zip(edges[:-1], edges[1:])]
     assert all(t > 0 for t in tickets) and tickets == sorted(tickets)
     for t in reversed(tickets):
@@ -374,10 +375,17 @@ def test_host_pack_gathers_the_sparse_rows(task, cleats):
     assert np.array_equal(bits(rec[:, ro:ro + nroot]), bits(want_root))
     assert (rec[:, ro + nroot:] == 0).all()
     # empty job, bad arguments
-    assert lib.bezk_host_pack_begin(tid, P(rb), P(cf), P(root), ctypes.byref(cfg), P(rec), 5, 0) == 0
+    # chunk layout with the dense dof_state rows copied along: dst = [k x 36 dof floats | k records]
+    lo, k = 4099, 30_001
+    buf = np.full(k * (36 + rs), -7.0, dtype=np.float32)
+    assert lib.bezk_host_pack_wait(lib.bezk_host_pack_begin(tid, P(rb), P(cf), P(root), P(dof), ctypes.byref(cfg), P(buf), lo, k)) == 0
+    assert np.array_equal(bits(buf[:k * 36].reshape(k, 36)), bits(dof[lo:lo + k]))
+    assert np.array_equal(bits(buf[k * 36:].reshape(k, rs)), bits(rec[lo:lo + k]))
+    assert lib.bezk_host_pack_begin(tid, P(rb), P(cf), P(root), None, ctypes.byref(cfg), P(rec), 5, 0) == 0
     assert lib.bezk_host_pack_wait(0) == 0
-    assert lib.bezk_host_pack_begin(tid, None, P(cf), P(root), ctypes.byref(cfg), P(rec), 0, 4) == -10001
-    assert lib.bezk_host_pack_begin(9, P(rb), P(cf), P(root), ctypes.byref(cfg), P(rec), 0, 4) == -10001
+    assert lib.bezk_host_pack_begin(tid, None, P(cf), P(root), None, ctypes.byref(cfg), P(rec), 0, 4) == -10001
+    assert lib.bezk_host_pack_begin(9, P(rb), P(cf), P(root), None, ctypes.byref(cfg), P(rec), 0, 4) == -10001
+    assert lib.bezk_host_pack_begin(tid, P(rb), P(cf), P(root), None, ctypes.byref(cfg), P(rec, 1), 0, 4) == -10002
     assert lib.bezk_host_pack_wait(1 << 40) == 10001
     assert lib.bezk_post_physics_packed(tid, *([None] * 10), 0, 0, *([None] * 4), ctypes.byref(cfg), None, None, None, 7, 4, 0, None, None,
                                         None) == 10001

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--modes", default="zero_copy,staged_ce:4,staged_ce:4s,staged_pack:2,staged_pack:4,staged_pack:8")
     ap.add_argument("--timeline", action="store_true", help="add the per-chunk device / host timeline of one step (staged_ce / staged_pack)")
     ap.add_argument("--pack-threads", type=int, default=0)
+    ap.add_argument("--pack-dof", type=int, default=0)
     args = ap.parse_args()
     n = args.envs
 
@@ -40,10 +41,11 @@ def main():
         cfg["env"]["imuPrevVelAliasing"] = False
         cfg["env"]["hostPipeline"] = mode
         if chunks:
-            cfg["env"]["hostPipelineChunks"] = int(chunks)
+            cfg["env"]["hostPipelineChunks"] = int(chunks) if chunks.isdigit() else [float(w) for w in chunks.split("-")]
         cfg["env"]["hostPipelineSplitSparse"] = split
         cfg["env"]["hostPipelineTimeline"] = args.timeline and mode in ("staged_ce", "staged_pack")
         cfg["env"]["hostPackThreads"] = args.pack_threads
+        cfg["env"]["hostPackDof"] = bool(args.pack_dof)
         env = KickEnv(cfg, "cuda:0", 0, True, sim=sim)
         for _ in range(5):
             env.step(act)
@@ -69,7 +71,7 @@ def main():
             env.step(act)
             torch.cuda.synchronize()
             tl = env.host_timeline()
-        print(json.dumps({"mode": mode, "chunks": int(chunks) if chunks else None, "split_sparse": split, "envs": n, "ms_per_step": round(ms, 4),
+        print(json.dumps({"mode": mode, "pack_dof": args.pack_dof if mode == "staged_pack" else None, "chunks": chunks or None, "split_sparse": split, "envs": n, "ms_per_step": round(ms, 4),
                           "env_steps_per_s_M": round(n / ms / 1e3, 2), "pre_ms": round(1e3 * t_pre / 8, 4),
                           "post_ms": round(1e3 * t_post / 8, 4), "timeline": tl}), flush=True)
         del env

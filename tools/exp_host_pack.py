@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--spin-us", type=int, default=-1)
     ap.add_argument("--pin", type=int, default=-1)
     ap.add_argument("--reps", type=int, default=6)
+    ap.add_argument("--dof", type=int, default=1, help="copy the dense dof_state rows along (chunk layout [dof rows | records])")
     ap.add_argument("--gap-ms", type=float, default=3.0, help="idle time between two steps (the K0 phase + simulate())")
     args = ap.parse_args()
     lib = _lib.load()
@@ -32,7 +33,10 @@ def main():
     rb = np.random.default_rng(0).standard_normal((n, nb, 13), dtype=np.float32)
     cf = np.random.default_rng(1).standard_normal((n, nb, 3), dtype=np.float32)
     root = np.random.default_rng(2).standard_normal((n, 2, 13), dtype=np.float32)
-    rec = np.zeros((n, lib.bezk_host_pack_record_floats(0, ctypes.byref(cfg))), np.float32)
+    dof = np.random.default_rng(3).standard_normal((n, 36), dtype=np.float32)
+    rs = lib.bezk_host_pack_record_floats(0, ctypes.byref(cfg))
+    pw = rs + (36 if args.dof else 0)
+    rec = np.zeros(n * pw, np.float32)
     P = lambda a: ctypes.c_void_p(a.ctypes.data)              # noqa: E731
     workers = lib.bezk_host_pack_config(args.threads, args.spin_us, args.pin)
     junk = np.zeros((96 << 20) // 4, np.float32)
@@ -46,15 +50,18 @@ def main():
         t0 = time.perf_counter()
         tickets, begins, waits = [], [], []
         for lo in range(0, n, c):
-            tickets.append(lib.bezk_host_pack_begin(0, P(rb), P(cf), P(root), ctypes.byref(cfg), P(rec), lo, min(c, n - lo)))
+            tickets.append(lib.bezk_host_pack_begin(0, P(rb), P(cf), P(root), P(dof) if args.dof else None, ctypes.byref(cfg),
+                                                    ctypes.c_void_p(rec.ctypes.data + 4 * lo * pw), lo, min(c, n - lo)))
             begins.append(round(1e3 * (time.perf_counter() - t0), 3))
         for t in tickets:
             lib.bezk_host_pack_wait(t)
             waits.append(round(1e3 * (time.perf_counter() - t0), 3))
         runs.append({"begin_ms": begins, "wait_ms": waits})
-    assert np.array_equal(rec[:, :10], rb[:, cfg.imu_body, 3:13])
+    k0 = min(c, n)
+    first = rec[(k0 * 36 if args.dof else 0):k0 * pw].reshape(k0, rs)
+    assert np.array_equal(first[:, :10], rb[:k0, cfg.imu_body, 3:13])
     best = min(r["wait_ms"][-1] for r in runs)
-    print(json.dumps({"envs": n, "workers": workers, "chunks": args.chunks, "spin_us": args.spin_us, "pin": args.pin,
+    print(json.dumps({"envs": n, "workers": workers, "chunks": args.chunks, "dof": args.dof, "spin_us": args.spin_us, "pin": args.pin,
                       "cpus": os.cpu_count(), "best_total_ms": best, "runs": runs[1:]}), flush=True)
 
 
