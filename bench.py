@@ -372,8 +372,7 @@ def e2e_leg(args, world, rank, dev):
     n, T = args.envs_per_gpu, args.horizon
     steps = args.e2e_steps or min(args.steps, 10)
     mode = args.e2e_mode
-    if mode == "auto":
-        mode = "staged_pack"
+    # "auto": KickEnv picks staged_pack when this rank has >= 8 host cores to gather with, else staged_ce (copy-engine pulls)
     hcfg = bm.default_task_cfg(n, use_gpu_pipeline=False, rl_device="cpu")
     hcfg["env"]["imuPrevVelAliasing"] = False
     hcfg["env"]["hostPipeline"] = mode
@@ -408,7 +407,8 @@ def e2e_leg(args, world, rank, dev):
     link = henv.link_counters()
     out = {"value": n * world * T * steps / dt, "unit": UNIT,
            "h2d_bytes_per_step": link["h2d_bytes"] // steps + gae_h2d, "d2h_bytes_per_step": link["d2h_bytes"] // steps + gae_d2h,
-           "envs_per_gpu": n, "steps": steps, "ms_per_step": 1e3 * dt / steps, "host_pipeline": mode, "byte_count": link["how"],
+           "envs_per_gpu": n, "steps": steps, "ms_per_step": 1e3 * dt / steps, "host_pipeline": henv.host_pipeline,
+           "host_pack_threads": getattr(henv, "host_pack_threads", None), "byte_count": link["how"],
            "note": "KickEnv.step with use_gpu_pipeline=False: simulator tensors, actions and PD targets in pinned HOST memory, "
                    "obs / rew / reset / time_outs handed back on the host every env step (one stream sync per step); rollout tensors "
                    "H2D + advantages / returns D2H per GAE scan; bytes per step = per rollout, this rank"}

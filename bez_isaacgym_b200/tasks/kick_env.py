@@ -101,10 +101,17 @@ class KickEnv(VecTask):
         # "staged_pack" is staged_ce with the sparse rows gathered by HOST worker threads into pinned pack buffers
         # (bezk_host_pack_begin / _wait) and moved by dense copies -- the engine is row-rate-bound on strided pulls
         self.host_mode = env_cfg.get("hostPipeline", "zero_copy") if self.host_staged else None
+        if self.host_mode == "auto":
+            # the fastest pipeline this host can feed: the packed pipeline needs ~8 worker threads per GPU to stay ahead of the
+            # link (98 vs 69 M env-steps/s on 16 cores / 1 GPU); with 4 cores per GPU (8 ranks on 32 cores) the gather becomes
+            # the bottleneck and the copy-engine pulls win (176 vs 151 M, profiles/r02_host_pack.md)
+            self.host_mode = "staged_pack" if self._host_core_share() - 1 >= 8 else "staged_ce"
+        #: the resolved pipeline name ("staged_pack" runs on the staged_ce machinery: host_mode reads "staged_ce" for both)
+        self.host_pipeline = self.host_mode
         self._pack = self.host_mode == "staged_pack"
         if self._pack:
             self.host_mode = "staged_ce"                  # same pipeline; only the sparse staging differs
-        if self.host_mode is not None and self.host_mode not in self.HOST_PIPELINES:
+        if self.host_mode is not None and self.host_mode not in self.HOST_PIPELINES + ("auto",):
             raise ValueError(f"env.hostPipeline must be one of {self.HOST_PIPELINES}, got {self.host_mode}")
         if self.host_staged and self.host_mode in ("zero_copy", "staged_ce") and not all(
                 t.is_pinned() for t in (self.root_states, self.dof_state, self.rigid_body, self.net_contact)):
@@ -229,9 +236,7 @@ class KickEnv(VecTask):
                 self._d_pack = torch.zeros(n * self._pw, **f32)
                 threads = int(env_cfg.get("hostPackThreads", 0))
                 if threads <= 0:         # this rank's share of the host cores (one process per GPU), minus the issuing thread
-                    import os
-                    share = (os.cpu_count() or 2) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-                    threads = max(1, min(16, share - 1))
+                    threads = max(1, min(16, self._host_core_share() - 1))
                 k = self._lib.bezk_host_pack_config(threads, int(env_cfg.get("hostPackSpinUs", -1)), int(env_cfg.get("hostPackPin", -1)))
                 if k <= 0:
                     _lib.check(-k or 1, "bezk_host_pack_config")
@@ -262,6 +267,17 @@ class KickEnv(VecTask):
     def _reset_goal_tensor(self):
         """The tensor ``reset_idx`` redraws on reset: none for BezKick (its goal is fixed)."""
         return None
+
+    @staticmethod
+    def _host_core_share():
+        """Host cores available to this process: the CPU affinity mask divided among the ranks of the node (torchrun's
+        LOCAL_WORLD_SIZE; one process per GPU)."""
+        import os
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 2
+        return max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
 
     # ------------------------------------------------------------------ construction helpers
     def create_sim(self):

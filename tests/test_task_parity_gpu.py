@@ -410,7 +410,7 @@ def test_cpu_tensors_raise_no_fallback():
 
 
 @pytest.mark.parametrize("task", ["kick", "walk", "orient"])
-@pytest.mark.parametrize("host_mode", ["zero_copy", "staged", "staged_ce", "staged_pack"])
+@pytest.mark.parametrize("host_mode", ["zero_copy", "staged", "staged_ce", "staged_pack", "staged_pack+dof", "staged_pack+cleats", "auto"])
 def test_host_pipeline_equals_gpu_pipeline(host_mode, task):
     """``use_gpu_pipeline: False`` (simulator tensors in pinned host memory; BASELINE configs[0] sim_device=cpu pipeline=cpu;
     the reference's device selection ``tasks/base/vec_task.py:51-98`` serves every task): same kernels, so results are
@@ -421,15 +421,21 @@ def test_host_pipeline_equals_gpu_pipeline(host_mode, task):
     from bez_isaacgym_b200 import tasks as T
     cls = {"kick": T.KickEnv, "walk": T.WalkEnv, "orient": T.OrientEnv}[task]
     n = 4099
-    st = sg.make_state(n, seed=77, task=task)
+    host_mode, _, variant = host_mode.partition("+")
+    cleats = variant == "cleats"
+    if cleats and task != "kick":
+        pytest.skip("cleats variant: BezKick only")
+    st = sg.make_state(n, seed=77, task=task, cleats=cleats)
     envs = {}
     for kind in ("gpu", "host"):
-        cfg = bm.default_task_cfg(n, use_gpu_pipeline=(kind == "gpu"), rl_device="cuda:0" if kind == "gpu" else "cpu", task=task)
+        cfg = bm.default_task_cfg(n, cleats=cleats, use_gpu_pipeline=(kind == "gpu"), rl_device="cuda:0" if kind == "gpu" else "cpu",
+                                  task=task)
         cfg["seed"] = 5
         cfg["env"]["hostPipeline"] = host_mode
-        cfg["env"]["hostPipelineChunks"] = 3
-        cfg["env"]["writeContactFilter"] = host_mode not in ("staged_ce", "staged_pack")
-        sim = SyntheticGym(n, device="cuda:0", state=st.clone(), host=(kind == "host"), task=task)
+        cfg["env"]["hostPipelineChunks"] = [1, 2, 1] if variant == "dof" else 3
+        cfg["env"]["hostPackDof"] = variant == "dof"
+        cfg["env"]["writeContactFilter"] = host_mode not in ("staged_ce", "staged_pack", "auto")
+        sim = SyntheticGym(n, device="cuda:0", cleats=cleats, state=st.clone(), host=(kind == "host"), task=task)
         envs[kind] = cls(cfg, "cuda:0", 0, True, sim=sim)
         envs[kind].progress_buf.copy_(torch.arange(n, device="cuda") % envs[kind].max_episode_length)
     for step in range(4):
@@ -450,6 +456,8 @@ def test_host_pipeline_equals_gpu_pipeline(host_mode, task):
     assert int(d_g.sum()) > 0
     link = envs["host"].link_counters()
     assert link["h2d_bytes"] > 0 and link["d2h_bytes"] > 0
+    if host_mode == "auto":
+        assert envs["host"].host_pipeline in ("staged_pack", "staged_ce")
 
 
 def test_chunked_step_equals_one_launch():

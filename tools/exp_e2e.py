@@ -27,11 +27,20 @@ def main():
     ap.add_argument("--pack-dof", type=int, default=0)
     args = ap.parse_args()
     n = args.envs
+    # under torchrun: one process per GPU, a gloo barrier before each timed loop (all ranks load the host link together)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    dev = f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}"
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
 
     class OwnedRootSim(SyntheticGym):
         owns_root_reset = True
 
-    sim = OwnedRootSim(n, device="cuda:0", seed=1, host=True, filler=True)
+    sim = OwnedRootSim(n, device=dev, seed=1 + rank, host=True, filler=True)
     act = sg.make_actions(n, seed=1).pin_memory()
     for spec in args.modes.split(","):
         mode, _, chunks = spec.partition(":")
@@ -46,15 +55,17 @@ def main():
         cfg["env"]["hostPipelineTimeline"] = args.timeline and mode in ("staged_ce", "staged_pack")
         cfg["env"]["hostPackThreads"] = args.pack_threads
         cfg["env"]["hostPackDof"] = bool(args.pack_dof)
-        env = KickEnv(cfg, "cuda:0", 0, True, sim=sim)
+        env = KickEnv(cfg, dev, 0, True, sim=sim)
         for _ in range(5):
             env.step(act)
         torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             env.step(act)
         torch.cuda.synchronize()
         ms = 1e3 * (time.perf_counter() - t0) / args.steps
+        barrier()
         # the two halves of a step
         t_pre = t_post = 0.0
         for _ in range(8):
@@ -71,7 +82,7 @@ def main():
             env.step(act)
             torch.cuda.synchronize()
             tl = env.host_timeline()
-        print(json.dumps({"mode": mode, "pack_dof": args.pack_dof if mode == "staged_pack" else None, "chunks": chunks or None, "split_sparse": split, "envs": n, "ms_per_step": round(ms, 4),
+        print(json.dumps({"rank": rank, "world": world, "pack_threads": getattr(env, "host_pack_threads", None), "mode": mode, "pack_dof": args.pack_dof if mode == "staged_pack" else None, "chunks": chunks or None, "split_sparse": split, "envs": n, "ms_per_step": round(ms, 4),
                           "env_steps_per_s_M": round(n / ms / 1e3, 2), "pre_ms": round(1e3 * t_pre / 8, 4),
                           "post_ms": round(1e3 * t_post / 8, 4), "timeline": tl}), flush=True)
         del env
