@@ -603,13 +603,14 @@ class KickEnv(VecTask):
         src = (actions if actions.is_contiguous() else actions.contiguous()) if on_device else self._actions_in
         self._actions_src = src
         kc = C.byref(self._kcfg)
-        if not on_device:
-            self._s_in.wait_stream(cur)
-        for c, (lo, hi) in enumerate(self._ce_chunks):
-            if not on_device:
-                with torch.cuda.stream(self._s_in):
+        if not on_device:                                 # every chunk's H2D is queued first: the engine streams them back to back
+            self._s_in.wait_stream(cur)                   # while the launches / D2H copies below are being issued
+            with torch.cuda.stream(self._s_in):
+                for c, (lo, hi) in enumerate(self._ce_chunks):
                     self._actions_in[lo:hi].copy_(actions[lo:hi], non_blocking=True)
                     self._ev_in[c].record(self._s_in)
+        for c, (lo, hi) in enumerate(self._ce_chunks):
+            if not on_device:
                 cur.wait_event(self._ev_in[c])
             rc = self._lib.bezk_pre_physics(_P(src.data_ptr() + lo * 72), None, _P(self._d_targets.data_ptr() + lo * 72), kc, hi - lo,
                                             self._stream())
