@@ -9,8 +9,9 @@ Legs of the B200 arm (ONE JSON line, rank 0):
   value / roofline   the rollout with everything resident in HBM, replayed as one CUDA graph; the fused kernel's duration is read
                      from timing events recorded INSIDE the timed graph (external event nodes around 4 of its 32 launches) and,
                      next to it, from per-launch events of an eager timed pass (roofline.eager)
-  e2e                the same rollout through ``KickEnv.step`` with HOST buffers (simulator tensors, actions, targets, results in
-                     pinned host memory; copies inside the timed region), same envs per GPU
+  e2e                the same rollout through ``KickEnv.step`` with HOST buffers (simulator tensors, actions, targets, results and
+                     the critic values of every step in pinned host memory; copies inside the timed region), same envs per GPU,
+                     the reward shaping / value bootstrap / uint8 dones written by the step's epilogue as in the device leg
   learner            BASELINE configs[2]/[3]: the PPO epoch math on a 4096 x 32 rollout per GPU -- GAE, advantage moments, value
                      RunningMeanStd x2, then mini_epochs x minibatches x (obs RunningMeanStd moments -> all-reduce -> merge ->
                      normalise, fused PPO loss fwd+bwd, flat 124 237-float gradient bucket all-reduce), no MLP; with its own
@@ -380,19 +381,26 @@ def e2e_leg(args, world, rank, dev):
     hsim = OwnedRootSim(n, device=str(dev), seed=1234 + rank, host=True, filler=True)
     henv = KickEnv(hcfg, str(dev), 0, True, sim=hsim, fusion=args.fusion)
     hact = sg.make_actions(n, seed=1).pin_memory()
-    hr, hv, hd, hlv, hld = [t.pin_memory() for t in sg.make_rollout(n, T, seed=3)]
-    d_r, d_v, d_d, d_lv, d_ld = [torch.empty_like(t, device=dev) for t in (hr, hv, hd, hlv, hld)]
+    # host side of the rollout: the critic values of every step and the bootstrap values (the policy lives with the simulator on
+    # the host); device side: the rollout storage the step's reward epilogue and the GAE scan work on
+    _, hv, _, hlv, _ = [t.pin_memory() for t in sg.make_rollout(n, T, seed=3)]
+    d_r, d_v, d_lv = (torch.empty_like(t, device=dev) for t in (hv, hv, hlv))
+    d_d = torch.zeros(T + 1, n, dtype=torch.uint8, device=dev)       # slot t = dones at the START of step t
     d_adv, d_ret = torch.empty_like(d_r), torch.empty_like(d_r)
-    h_adv, h_ret = torch.empty_like(hr).pin_memory(), torch.empty_like(hr).pin_memory()
-    gae_h2d = sum(t.numel() * t.element_size() for t in (hr, hv, hd, hlv, hld))
+    h_adv, h_ret = torch.empty_like(hv).pin_memory(), torch.empty_like(hv).pin_memory()
+    gae_h2d = sum(t.numel() * t.element_size() for t in (hv, hlv))
     gae_d2h = sum(t.numel() * t.element_size() for t in (h_adv, h_ret))
+    vals_in_step = 0 if henv.host_pipeline == "staged_pack" else n * 4      # staged_pack: the values ride inside the records
 
     def e2e_step():
-        for _ in range(T):
+        d_d[0].copy_(d_d[T])
+        for t in range(T):
+            # a16 in the step's epilogue (shaped reward -> d_r[t], uint8 done -> d_d[t + 1]), values arriving from the host
+            henv.set_rollout_targets(values=hv[t].view(-1), shaped_rewards=d_r[t].view(-1), dones_u8=d_d[t + 1], gamma=0.99,
+                                     scale_value=0.01)
             henv.step(hact)
-        for d, h in ((d_r, hr), (d_v, hv), (d_d, hd), (d_lv, hlv), (d_ld, hld)):
-            d.copy_(h, non_blocking=True)
-        ops.gae(d_r, d_v, d_d, d_lv, d_ld, 0.99, 0.95, d_adv, d_ret)
+        d_v.copy_(hv, non_blocking=True); d_lv.copy_(hlv, non_blocking=True)
+        ops.gae(d_r, d_v, d_d[:T], d_lv, d_d[T], 0.99, 0.95, d_adv, d_ret)
         h_adv.copy_(d_adv, non_blocking=True); h_ret.copy_(d_ret, non_blocking=True)
         torch.cuda.synchronize(dev)
 
@@ -406,12 +414,15 @@ def e2e_leg(args, world, rank, dev):
     dt = _max_over_ranks(time.perf_counter() - t0, world, dev)
     link = henv.link_counters()
     out = {"value": n * world * T * steps / dt, "unit": UNIT,
-           "h2d_bytes_per_step": link["h2d_bytes"] // steps + gae_h2d, "d2h_bytes_per_step": link["d2h_bytes"] // steps + gae_d2h,
+           "h2d_bytes_per_step": link["h2d_bytes"] // steps + gae_h2d + T * vals_in_step,
+           "d2h_bytes_per_step": link["d2h_bytes"] // steps + gae_d2h,
            "envs_per_gpu": n, "steps": steps, "ms_per_step": 1e3 * dt / steps, "host_pipeline": henv.host_pipeline,
            "host_pack_threads": getattr(henv, "host_pack_threads", None), "byte_count": link["how"],
            "note": "KickEnv.step with use_gpu_pipeline=False: simulator tensors, actions and PD targets in pinned HOST memory, "
-                   "obs / rew / reset / time_outs handed back on the host every env step (one stream sync per step); rollout tensors "
-                   "H2D + advantages / returns D2H per GAE scan; bytes per step = per rollout, this rank"}
+                   "obs / rew / reset / time_outs handed back on the host every env step (one stream sync per step); the step's "
+                   "critic values come from the host (inside the packed records, or one extra copy per step) and the reward "
+                   "shaping / value bootstrap / uint8 dones are written by the step's epilogue into device rollout storage; "
+                   "values + bootstrap values H2D and advantages / returns D2H per GAE scan; bytes per step = per rollout, this rank"}
     del henv, hsim
     torch.cuda.empty_cache()
     return out

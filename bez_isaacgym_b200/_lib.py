@@ -74,12 +74,14 @@ SIGNATURES = {
     "bezk_stage_sparse_rows_split": (C.c_int, [_P, _P, C.POINTER(BezkTaskCfg), _P, _P, _I64, _I64, _P, _P]),
     "bezk_host_pack_config": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     "bezk_host_pack_record_floats": (C.c_int, [C.c_int, C.POINTER(BezkTaskCfg)]),
-    "bezk_host_pack_begin": (_I64, [C.c_int, _P, _P, _P, _P, C.POINTER(BezkTaskCfg), _P, _I64, _I64]),
+    "bezk_host_pack_begin": (_I64, [C.c_int, _P, _P, _P, _P, _P, C.POINTER(BezkTaskCfg), _P, _I64, _I64]),
     "bezk_post_physics_packed": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U64, _U64, _P, _P, _P, _P,
-                                           C.POINTER(BezkTaskCfg), _P, _P, _P, C.c_int, _I64, _I64, _P, _P, _P]),
+                                           C.POINTER(BezkTaskCfg), _P, _P, _P, C.c_int, _I64, _I64, _P, _P,
+                                           C.POINTER(BezkRolloutCfg), _P, _P, _P, _P]),
     "bezk_host_pack_wait": (C.c_int, [_I64]),
     "bezk_post_physics_staged": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U64, _U64, _P, _P, _P, _P,
-                                           C.POINTER(BezkTaskCfg), _P, _P, _P, C.c_int, _I64, _I64, _P, _P, _P]),
+                                           C.POINTER(BezkTaskCfg), _P, _P, _P, C.c_int, _I64, _I64, _P, _P,
+                                           C.POINTER(BezkRolloutCfg), _P, _P, _P, _P]),
     "bezk_philox_uniforms": (C.c_int, [_U64, _U64, _P, _I64, _P]),
     "bezk_gae": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double, C.c_double, _P, _P, C.c_int32, _I64, _P]),
     "bezk_rms_scratch_doubles": (_I64, [C.c_int32]),

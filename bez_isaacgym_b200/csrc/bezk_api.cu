@@ -52,6 +52,16 @@ int bezk_pre_physics(const float* actions, float* actions_out, float* targets, c
     return cuda_rc(bezk::launch_pre_physics(actions, actions_out, targets, *cfg, n, (cudaStream_t)stream), "bezk_pre_physics");
 }
 
+// rl_games play_steps reward path in the fused step's epilogue (bezk_post_physics_rollout and the host-pipeline entries)
+static void set_rollout(bezk::TaskArgs& a, const BezkRolloutCfg* rollout, const float* values, float* shaped_rewards, uint8_t* dones_u8) {
+    a.shaped_rew = shaped_rewards; a.dones_u8 = dones_u8;
+    if (shaped_rewards) {
+        a.shp_scale = rollout->scale_value; a.shp_shift = rollout->shift_value; a.shp_gamma = rollout->gamma;
+        a.shp_bootstrap = rollout->value_bootstrap != 0;
+        a.values = a.shp_bootstrap ? values : nullptr;
+    }
+}
+
 static int run_task(int parts, bezk::TaskArgs& a, const BezkTaskCfg* cfg, void* stream, const char* where, int task = BEZK_TASK_KICK) {
     if (int rc = check_cfg(cfg)) return rc;
     REQUIRE(a.n >= 0, "n < 0");
@@ -195,14 +205,15 @@ int bezk_host_pack_record_floats(int task, const BezkTaskCfg* cfg) {
 }
 
 int64_t bezk_host_pack_begin(int task, const float* rigid_body_host, const float* net_contact_host, const float* root_states_host,
-                             const float* dof_state_host, const BezkTaskCfg* cfg, float* dst, int64_t env0, int64_t n) {
+                             const float* dof_state_host, const float* values_host, const BezkTaskCfg* cfg, float* dst, int64_t env0,
+                             int64_t n) {
     if (!(task == BEZK_TASK_KICK || task == BEZK_TASK_WALK || task == BEZK_TASK_ORIENT)) return -(int64_t)fail(BEZK_E_BADARG, "unknown task");
     if (int rc = check_cfg(cfg)) return -(int64_t)rc;
     if (env0 < 0 || n < 0) return -(int64_t)fail(BEZK_E_BADARG, "env0 / n < 0");
     if (n == 0) return 0;
     if (!(rigid_body_host && net_contact_host && root_states_host && dst)) return -(int64_t)fail(BEZK_E_BADARG, "pack buffers NULL");
     if (!ALIGNED(dst, 16)) return -(int64_t)fail(BEZK_E_ALIGN, "dst must be 16-byte aligned");
-    return bezk::host_pack_begin(task, rigid_body_host, net_contact_host, root_states_host, dof_state_host, *cfg, dst, env0, n);
+    return bezk::host_pack_begin(task, rigid_body_host, net_contact_host, root_states_host, dof_state_host, values_host, *cfg, dst, env0, n);
 }
 
 int bezk_host_pack_wait(int64_t ticket) {
@@ -215,12 +226,16 @@ int bezk_post_physics_staged(int task, float* dof_state, const float* imu_stage,
                              const float* initial_root_states, const float* uniforms, const float* goal_uniforms, uint64_t seed,
                              uint64_t step, int64_t* reset_buf, int64_t* progress_buf, int64_t* timeout_buf, int64_t* randomize_buf,
                              const BezkTaskCfg* cfg, float* obs, float* obs_clipped, float* rew, int parts, int64_t n,
-                             int64_t env_base, float* dof_state_wb, float* root_states_wb, void* stream) {
+                             int64_t env_base, float* dof_state_wb, float* root_states_wb, const BezkRolloutCfg* rollout,
+                             const float* values, float* shaped_rewards, uint8_t* dones_u8, void* stream) {
     REQUIRE(task == BEZK_TASK_KICK || task == BEZK_TASK_WALK || task == BEZK_TASK_ORIENT, "unknown task");
     REQUIRE(parts >= 1 && parts <= 7, "parts must be a non-empty subset of {1,2,4}");
     REQUIRE(env_base >= 0, "env_base < 0");
     REQUIRE(cfg, "cfg is NULL");
     REQUIRE(!(cfg->flags & BEZK_F_WRITE_CONTACT_FILTER), "the contact-filter write-back would land in the staging buffer: clear BEZK_F_WRITE_CONTACT_FILTER");
+    REQUIRE(!(shaped_rewards || dones_u8) || parts == 7, "the reward epilogue rides in the fused step (parts = 7)");
+    REQUIRE(!shaped_rewards || rollout, "shaped_rewards requested without a BezkRolloutCfg");
+    REQUIRE(!(shaped_rewards && rollout && rollout->value_bootstrap) || values, "value_bootstrap needs values");
     bezk::TaskArgs a;
     memset(&a, 0, sizeof(a));
     a.dof_state = dof_state; a.rigid_body = imu_stage; a.root_states = root_states; a.net_contact = feet_stage;
@@ -234,6 +249,7 @@ int bezk_post_physics_staged(int task, float* dof_state, const float* imu_stage,
     const bool cleats = (cfg->flags & BEZK_F_CLEATS) != 0;
     a.rb_stride = 10; a.rb_off = 0;
     a.cf_stride = cleats ? 24 : 8; a.cf_l_off = 0; a.cf_r_off = cleats ? 12 : 4;
+    set_rollout(a, rollout, values, shaped_rewards, dones_u8);
     return run_task(parts, a, cfg, stream, "bezk_post_physics_staged", task);
 }
 
@@ -242,10 +258,13 @@ int bezk_post_physics_packed(int task, float* dof_state, const float* records, f
                              const float* goal_uniforms, uint64_t seed, uint64_t step, int64_t* reset_buf, int64_t* progress_buf,
                              int64_t* timeout_buf, int64_t* randomize_buf, const BezkTaskCfg* cfg, float* obs, float* obs_clipped,
                              float* rew, int parts, int64_t n, int64_t env_base, float* dof_state_wb, float* root_states_wb,
+                             const BezkRolloutCfg* rollout, const float* values, float* shaped_rewards, uint8_t* dones_u8,
                              void* stream) {
     REQUIRE(task == BEZK_TASK_KICK || task == BEZK_TASK_WALK || task == BEZK_TASK_ORIENT, "unknown task");
     REQUIRE(parts >= 1 && parts <= 7, "parts must be a non-empty subset of {1,2,4}");
     REQUIRE(env_base >= 0 && n >= 0, "env_base / n < 0");
+    REQUIRE(!(shaped_rewards || dones_u8) || parts == 7, "the reward epilogue rides in the fused step (parts = 7)");
+    REQUIRE(!shaped_rewards || rollout, "shaped_rewards requested without a BezkRolloutCfg");
     if (int rc = check_cfg(cfg)) return rc;
     if (n == 0) return 0;
     REQUIRE(records && root_states, "records / root_states NULL");
@@ -265,6 +284,10 @@ int bezk_post_physics_packed(int task, float* dof_state, const float* records, f
     a.obs = obs; a.obs_clipped = obs_clipped; a.rew = rew; a.n = n;
     a.rb_stride = L.stride; a.rb_off = 0;
     a.cf_stride = L.stride; a.cf_l_off = L.l_off; a.cf_r_off = L.r_off;
+    // values == NULL with value_bootstrap: the critic values ride in the records' last float (bezk_host_pack_begin's values_host)
+    const bool in_records = shaped_rewards && rollout->value_bootstrap && values == nullptr;
+    set_rollout(a, rollout, in_records ? records + (L.stride - 1) : values, shaped_rewards, dones_u8);
+    if (in_records) a.values_stride = L.stride;
     return run_task(parts, a, cfg, stream, "bezk_post_physics_packed", task);
 }
 
@@ -305,12 +328,7 @@ int bezk_post_physics_rollout(int task, float* dof_state, const float* rigid_bod
     a.reset_in = reset_buf; a.reset_out = reset_buf; a.progress_in = progress_buf; a.progress_out = progress_buf;
     a.timeout_buf = timeout_buf; a.randomize_buf = randomize_buf;
     a.obs = obs; a.obs_clipped = obs_clipped; a.rew = rew; a.n = n;
-    a.shaped_rew = shaped_rewards; a.dones_u8 = dones_u8;
-    if (shaped_rewards) {
-        a.shp_scale = rollout->scale_value; a.shp_shift = rollout->shift_value; a.shp_gamma = rollout->gamma;
-        a.shp_bootstrap = rollout->value_bootstrap != 0;
-        a.values = a.shp_bootstrap ? values : nullptr;
-    }
+    set_rollout(a, rollout, values, shaped_rewards, dones_u8);
     return run_task(BEZK_PART_BOOKKEEP | BEZK_PART_OBS | BEZK_PART_REWARD, a, cfg, stream, "bezk_post_physics_rollout", task);
 }
 

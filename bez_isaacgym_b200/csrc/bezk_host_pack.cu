@@ -36,6 +36,7 @@ constexpr int kPrefetchAhead = 12;    // envs; the AoS rows are 1144 / 264 B apa
 struct Job {
     const float* rb; const float* cf; const float* root; float* rec;        // rec: record of env env0 (the job's own destination)
     const float* dof; float* dof_dst;                                       // optional: dense dof_state rows copied along
+    const float* values;                                                    // optional: (N,) critic values -> the record's last float
     int64_t rb_stride, rb_off, cf_stride, cf_l, cf_r, root_stride;       // floats
     PackLayout L;
     int64_t env0, n;
@@ -60,6 +61,7 @@ inline void pack_one(const Job& j, const PackLayout& L, const float* rb, const f
     int used = 10 + 2 * fw + 3;
     if (STRIDE == 24 || L.root_n == 7) { q[3] = r[13]; q[4] = r[14]; q[5] = r[20]; q[6] = r[21]; used += 4; }
     for (int k = used; k < stride; ++k) t[k] = 0.0f;
+    if (j.values) t[stride - 1] = j.values[e];               // the pad slot (always >= 1 float): value bootstrap of the reward epilogue
     float* d = j.rec + (e - j.env0) * stride;
 #if defined(__x86_64__)
     for (int k = 0; k < stride; k += 4) _mm_stream_ps(d + k, _mm_load_ps(t + k));
@@ -134,6 +136,7 @@ public:
         // out of range while the fields change, open it (release) only when the job is complete
         j.next.store(INT64_MAX / 2, std::memory_order_relaxed);
         j.rb = proto.rb; j.cf = proto.cf; j.root = proto.root; j.rec = proto.rec; j.dof = proto.dof; j.dof_dst = proto.dof_dst;
+        j.values = proto.values;
         j.rb_stride = proto.rb_stride; j.rb_off = proto.rb_off; j.cf_stride = proto.cf_stride; j.cf_l = proto.cf_l; j.cf_r = proto.cf_r;
         j.root_stride = proto.root_stride; j.L = proto.L;
         j.env0 = proto.env0; j.n = proto.n;
@@ -274,18 +277,19 @@ PackLayout pack_layout(int task, const BezkTaskCfg& cfg) {
     L.r_off = L.l_off + L.feet_w;
     L.root_off = L.r_off + L.feet_w;
     L.root_n = task == BEZK_TASK_KICK ? 7 : 3;
-    L.stride = (L.root_off + L.root_n + 3) / 4 * 4;
+    L.stride = (L.root_off + L.root_n + 1 + 3) / 4 * 4;       // >= 1 pad float: the critic value's slot
     return L;
 }
 
 int64_t host_pack_begin(int task, const float* rigid_body, const float* net_contact, const float* root_states, const float* dof_state,
-                        const BezkTaskCfg& cfg, float* dst, int64_t env0, int64_t n) {
+                        const float* values, const BezkTaskCfg& cfg, float* dst, int64_t env0, int64_t n) {
     if (n <= 0) return 0;
     Pool& p = Pool::get();
     p.ensure_threads(0);
     Job j;
     j.rb = rigid_body; j.cf = net_contact; j.root = root_states;
     j.dof = dof_state; j.dof_dst = dof_state ? dst : nullptr;
+    j.values = values;
     j.rec = dof_state ? dst + n * 36 : dst;                  // [n x 36 dof rows |] n records
     j.rb_stride = (int64_t)cfg.num_bodies * 13; j.rb_off = (int64_t)cfg.imu_body * 13 + 3;
     j.cf_stride = (int64_t)cfg.num_bodies * 3; j.cf_l = (int64_t)cfg.left_foot_body * 3; j.cf_r = (int64_t)cfg.right_foot_body * 3;

@@ -32,6 +32,7 @@ struct TaskArgs {
     float* rew;
     // rl_games play_steps reward path folded into the reward epilogue (bezk_post_physics_rollout); all optional
     const float* values;         // (n,) un-normalised critic values of this step (value bootstrap)
+    int values_stride;           // floats between two envs' values (0 = 1; the host pipeline's records carry them in their last float)
     float* shaped_rew;           // (n,) out: (rew + shift) * scale [+ gamma * value * timeout]
     uint8_t* dones_u8;           // (n,) out: reset mask as uint8 (the experience buffer's `dones` slot of the NEXT step)
     float shp_scale, shp_shift, shp_gamma;
@@ -72,7 +73,8 @@ cudaError_t stage_sparse_rows(const float*, const float*, const BezkTaskCfg&, fl
 struct PackLayout { int stride, l_off, r_off, feet_w, root_off, root_n; };
 PackLayout pack_layout(int task, const BezkTaskCfg& cfg);
 int host_pack_config(int threads, int spin_us, int pin);
-int64_t host_pack_begin(int task, const float*, const float*, const float*, const float*, const BezkTaskCfg&, float*, int64_t, int64_t);
+int64_t host_pack_begin(int task, const float*, const float*, const float*, const float*, const float*, const BezkTaskCfg&, float*, int64_t,
+                        int64_t);
 cudaError_t launch_unpack_root(int task, const float* records, PackLayout L, float* root_states, int64_t n, cudaStream_t st);
 int host_pack_wait(int64_t ticket);
 cudaError_t launch_pre_physics(const float*, float*, float*, const BezkTaskCfg&, int64_t, cudaStream_t);

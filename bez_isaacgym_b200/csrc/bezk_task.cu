@@ -219,7 +219,7 @@ __device__ __forceinline__ void gather_env(const TaskArgs& a, const BezkTaskCfg&
         if (BOOKREW) {
             g.reset_prev = ld_i64(a.reset_in + e);
             g.progress = ld_i64(a.progress_in + e);
-            if (a.values) g.value = ld_f32(a.values + e);
+            if (a.values) g.value = ld_f32(a.values + e * a.values_stride);
         }
     }
 }
@@ -682,6 +682,7 @@ cudaError_t launch_goal_uniforms(uint64_t seed, uint64_t step, float* out2, cuda
 void fill_alignment(TaskArgs& a, const BezkTaskCfg& cfg) {
     if (a.dof_state_wb == nullptr) a.dof_state_wb = a.dof_state;
     if (a.root_states_wb == nullptr) a.root_states_wb = a.root_states;
+    if (a.values_stride <= 0) a.values_stride = 1;
     a.use_tma = aligned16(a.dof_state) && aligned16(a.root_states) && aligned16(a.dof_state_wb) && (a.obs == nullptr || aligned16(a.obs)) &&
                 (a.obs_clipped == nullptr || aligned16(a.obs_clipped));
     if (a.rb_stride == 0) { a.rb_stride = cfg.num_bodies * 13; a.rb_off = cfg.imu_body * 13 + 3; }

@@ -189,6 +189,7 @@ class KickEnv(VecTask):
         self._rng_step = 0
         self._ce_copy_out = False
         self._rollout = None                # (BezkRolloutCfg, values, shaped_rewards, dones_u8) set by set_rollout_targets
+        self._d_values = None               # staged_ce host pipeline: device image of host-resident critic values
         self._lib = _lib.load()
         if self.host_staged:
             pin = dict(pin_memory=True)
@@ -318,6 +319,12 @@ class KickEnv(VecTask):
         rw, ow = 13 * self._actors, self._obs_width
         off = lambda t, k: None if t is None else _P(t.data_ptr() + k * t.element_size())      # noqa: E731
         clip = self.obs_clipped_buf
+        ro = self._rollout if parts == _lib.PART_ALL else None       # (cfg, values, shaped_rewards, dones_u8): reward epilogue
+        if ro is None:
+            tail = [None, None, None, None]
+        else:                            # values: a device tensor, or None when they ride in the packed records
+            dv = ro[1] if (ro[1] is not None and ro[1].is_cuda) else (None if self._pack else self._d_values)
+            tail = [C.byref(ro[0]), off(dv, lo), off(ro[2], lo), off(ro[3], lo)]
         if self._pack:
             # chunk (lo, hi) of the pack buffer: [dof rows (hi - lo) x 36 |] records (hi - lo) x rs
             d_dof = off(self._d_pack, lo * self._pw) if (self._pack_dof and not whole_dof) else off(self._d_dof, lo * 36)
@@ -328,7 +335,7 @@ class KickEnv(VecTask):
                 off(self.goal, lo * 2), off(self.goal_angle, lo), off(self.ball_init, lo * 2), off(self.initial_root_states, lo * rw),
                 None, None, self._seed, self._rng_step, off(self.reset_buf, lo), off(self.progress_buf, lo), off(self.timeout_buf, lo),
                 None, C.byref(self._kcfg), off(self.obs_buf, lo * ow), off(clip, lo * ow), off(self.rew_buf, lo), parts, hi - lo,
-                self.env_base + lo, off(self.dof_state, lo * 36), off(self.root_states, lo * rw), self._stream())
+                self.env_base + lo, off(self.dof_state, lo * 36), off(self.root_states, lo * rw), *tail, self._stream())
             if rc:
                 _lib.check(rc, "bezk_post_physics_packed")
             return
@@ -338,7 +345,7 @@ class KickEnv(VecTask):
             off(self.goal, lo * 2), off(self.goal_angle, lo), off(self.ball_init, lo * 2), off(self.initial_root_states, lo * rw),
             None, None, self._seed, self._rng_step, off(self.reset_buf, lo), off(self.progress_buf, lo), off(self.timeout_buf, lo),
             None, C.byref(self._kcfg), off(self.obs_buf, lo * ow), off(clip, lo * ow), off(self.rew_buf, lo), parts, hi - lo,
-            self.env_base + lo, off(self.dof_state, lo * 36), off(self.root_states, lo * rw), self._stream())
+            self.env_base + lo, off(self.dof_state, lo * 36), off(self.root_states, lo * rw), *tail, self._stream())
         if rc:
             _lib.check(rc, "bezk_post_physics_staged")
 
@@ -362,6 +369,10 @@ class KickEnv(VecTask):
         tickets = self._pack_begin(self._ce_chunks) if self._pack else None
         if tl:
             self._host_stamps.append(("pack_issued", time.perf_counter()))
+        ro = self._rollout
+        if ro is not None and ro[1] is not None and not ro[1].is_cuda and not self._pack:
+            with torch.cuda.stream(self._s_in):          # copy-engine pipeline: the step's critic values, one dense copy
+                self._d_values.copy_(ro[1].view(-1), non_blocking=True)
         for c, (lo, hi) in enumerate(self._ce_chunks):
             with torch.cuda.stream(self._s_in):
                 if self._pack:           # records gathered by the host workers while the engine moved the previous chunk
@@ -422,11 +433,13 @@ class KickEnv(VecTask):
         self._ev_pack.synchronize()                       # the previous step's copies out of the pack buffer are done
         kc = C.byref(self._kcfg)
         with_dof = self._pack_dof if with_dof is None else with_dof
+        ro = self._rollout
+        hv = _ptr(ro[1]) if (ro is not None and ro[1] is not None and not ro[1].is_cuda) else None    # host values -> records
         tickets = []
         for lo, hi in chunks:
             dst = _P(self._h_pack.data_ptr() + 4 * (lo * self._pw + (0 if with_dof or not self._pack_dof else (hi - lo) * 36)))
             t = self._lib.bezk_host_pack_begin(ops._TASK_ID[self.TASK], _ptr(self.rigid_body), _ptr(self.net_contact),
-                                               _ptr(self.root_states), _ptr(self.dof_state) if with_dof else None, kc, dst,
+                                               _ptr(self.root_states), _ptr(self.dof_state) if with_dof else None, hv, kc, dst,
                                                lo, hi - lo)
             if t < 0:
                 _lib.check(int(-t), "bezk_host_pack_begin")
@@ -728,23 +741,33 @@ class KickEnv(VecTask):
         ``shaped_rewards = (rew + shift) * scale + gamma * values * time_outs`` (e.g. ``mb_rewards[t]``) and the uint8 reset
         mask ``dones_u8`` (e.g. the experience buffer's ``dones`` slot ``t + 1``).  ``values``: the (N,)/(N,1) un-normalised
         critic values of the step (what ``policy_head`` wrote).  Call with no arguments to disarm."""
-        if self.host_staged or self.fusion != "fused":
-            raise NotImplementedError("the reward epilogue rides in the fused GPU-pipeline step")
+        if self.fusion != "fused":
+            raise NotImplementedError("the reward epilogue rides in the fused step (fusion='fused')")
         if shaped_rewards is None and dones_u8 is None:
             self._rollout = None
             return
         n, dev = self.num_envs, self.compute_device
 
-        def chk(t, dtype, name):
+        def chk(t, dtype, name, host_ok=False):
             if t is None:
                 return None
-            if t.dtype != dtype or t.numel() != n or not t.is_contiguous() or t.device != dev:
-                raise ValueError(f"{name} must be a contiguous {dtype} tensor with {n} elements on {dev}")
+            on_host = host_ok and self.host_staged and t.device.type == "cpu"
+            if on_host and not t.is_pinned():
+                raise ValueError(f"{name} on the host must be pinned")
+            if t.dtype != dtype or t.numel() != n or not t.is_contiguous() or (t.device != dev and not on_host):
+                raise ValueError(f"{name} must be a contiguous {dtype} tensor with {n} elements on {dev}"
+                                 + (" (or pinned host memory)" if host_ok and self.host_staged else ""))
             return t
 
         if shaped_rewards is not None and value_bootstrap and values is None:
             raise ValueError("value_bootstrap needs the step's critic values")
-        self._rollout = (ops.make_rollout_cfg(gamma, scale_value, shift_value, value_bootstrap), chk(values, torch.float32, "values"),
+        # host pipelines: `values` may live in pinned HOST memory (the policy ran there) -- staged_pack carries them in the
+        # records' pad float, staged_ce uploads them with one dense copy, zero_copy / staged let the kernel read them in place;
+        # the outputs stay DEVICE tensors (the rollout storage GAE reads)
+        values = chk(values, torch.float32, "values", host_ok=True)
+        if values is not None and not values.is_cuda and self.host_mode == "staged_ce" and not self._pack and self._d_values is None:
+            self._d_values = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._rollout = (ops.make_rollout_cfg(gamma, scale_value, shift_value, value_bootstrap), values,
                          chk(shaped_rewards, torch.float32, "shaped_rewards"), chk(dones_u8, torch.uint8, "dones_u8"))
 
     def step_precomputed_targets(self, env_actions=None):

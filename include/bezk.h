@@ -139,6 +139,14 @@ int bezk_post_physics_chunk(float* dof_state, const float* rigid_body, float* ro
                             float* rew, int parts, int64_t n, int64_t env_base, float* dof_state_wb,
                             float* root_states_wb, void* stream);
 
+/* Parameters of the reward epilogue (documented at bezk_post_physics_rollout below). */
+typedef struct BezkRolloutCfg {
+    float scale_value;        /* 0.01 */
+    float shift_value;        /* 0    */
+    float gamma;              /* (float)0.99 -- torch multiplies the fp32 tensor by the Python double cast to fp32 */
+    int32_t value_bootstrap;  /* 1 */
+} BezkRolloutCfg;
+
 /* Host pipeline (sim_device=cpu / use_gpu_pipeline: False; ref: tasks/base/vec_task.py:51-98 device selection): the simulator
  * tensors live in PINNED HOST memory.  bezk_stage_sparse_rows pulls the few bytes per env the step needs out of the two sparse
  * AoS tensors with strided copy-engine transfers (cudaMemcpy2DAsync) into compact DEVICE staging, for envs [env0, env0 + n):
@@ -178,12 +186,16 @@ int bezk_stage_sparse_rows_split(const float* rigid_body_host, const float* net_
  * bezk_post_physics_packed is bezk_post_physics_chunk for a chunk whose records are on the DEVICE (pointer already offset to the
  * chunk's first record, like every other argument): it scatters the root subset into the chunk's rows of root_states (a device
  * image of the simulator tensor; its other columns are never read) and runs the step reading the IMU slice and the foot rows
- * straight out of the records.  BEZK_F_WRITE_CONTACT_FILTER must be clear. */
+ * straight out of the records.  BEZK_F_WRITE_CONTACT_FILTER must be clear.
+ * Both bezk_post_physics_staged and bezk_post_physics_packed take the reward-epilogue arguments of bezk_post_physics_rollout
+ * (rollout, values, shaped_rewards, dones_u8: DEVICE pointers offset to the chunk; all NULL = off; parts must be 7).  With the
+ * packed records the critic values can travel in the record's last (pad) float instead: pass values_host (N,) to
+ * bezk_host_pack_begin and values = NULL to bezk_post_physics_packed. */
 int bezk_host_pack_config(int32_t threads, int32_t spin_us, int32_t pin);
 int bezk_host_pack_record_floats(int task, const BezkTaskCfg* cfg);
 int64_t bezk_host_pack_begin(int task, const float* rigid_body_host, const float* net_contact_host,
-                             const float* root_states_host, const float* dof_state_host, const BezkTaskCfg* cfg,
-                             float* dst, int64_t env0, int64_t n);
+                             const float* root_states_host, const float* dof_state_host, const float* values_host,
+                             const BezkTaskCfg* cfg, float* dst, int64_t env0, int64_t n);
 int bezk_host_pack_wait(int64_t ticket);
 int bezk_post_physics_packed(int task, float* dof_state, const float* records, float* root_states, float* prev_lin_vel,
                              float* goal, const float* goal_angle, const float* ball_init,
@@ -191,14 +203,16 @@ int bezk_post_physics_packed(int task, float* dof_state, const float* records, f
                              uint64_t seed, uint64_t step, int64_t* reset_buf, int64_t* progress_buf,
                              int64_t* timeout_buf, int64_t* randomize_buf, const BezkTaskCfg* cfg, float* obs,
                              float* obs_clipped, float* rew, int parts, int64_t n, int64_t env_base,
-                             float* dof_state_wb, float* root_states_wb, void* stream);
+                             float* dof_state_wb, float* root_states_wb, const BezkRolloutCfg* rollout,
+                             const float* values, float* shaped_rewards, uint8_t* dones_u8, void* stream);
 int bezk_post_physics_staged(int task, float* dof_state, const float* imu_stage, float* root_states, float* feet_stage,
                              float* prev_lin_vel, float* goal, const float* goal_angle, const float* ball_init,
                              const float* initial_root_states, const float* uniforms, const float* goal_uniforms,
                              uint64_t seed, uint64_t step, int64_t* reset_buf, int64_t* progress_buf,
                              int64_t* timeout_buf, int64_t* randomize_buf, const BezkTaskCfg* cfg, float* obs,
                              float* obs_clipped, float* rew, int parts, int64_t n, int64_t env_base,
-                             float* dof_state_wb, float* root_states_wb, void* stream);
+                             float* dof_state_wb, float* root_states_wb, const BezkRolloutCfg* rollout,
+                             const float* values, float* shaped_rewards, uint8_t* dones_u8, void* stream);
 
 /* The dense (n,36) uniforms the Philox path of bezk_post_physics / bezk_reset_idx consumes for
  * (seed, step): lets a checker feed the identical draws to the reference's reset_idx. */
@@ -328,12 +342,6 @@ int bezk_post_physics_task(int task, float* dof_state, const float* rigid_body, 
  * Each of shaped_rewards / dones_u8 may be NULL.  rew / reset_buf / timeout_buf are written as by bezk_post_physics_task.
  * Always the whole step (parts = 7).  env_base: global id of env 0 of this launch (Philox key of the reset noise; 0 for an
  * un-sharded task) -- env-sharded ranks pass their shard offset so that the noise does not depend on the sharding. */
-typedef struct BezkRolloutCfg {
-    float scale_value;        /* 0.01 */
-    float shift_value;        /* 0    */
-    float gamma;              /* (float)0.99 -- torch multiplies the fp32 tensor by the Python double cast to fp32 */
-    int32_t value_bootstrap;  /* 1 */
-} BezkRolloutCfg;
 int bezk_post_physics_rollout(int task, float* dof_state, const float* rigid_body, float* root_states,
                               float* net_contact, float* prev_lin_vel, float* goal, const float* goal_angle,
                               const float* ball_init, const float* initial_root_states,

@@ -342,7 +342,7 @@ def test_host_pack_gathers_the_sparse_rows(task, cleats):
     fw = 12 if cleats else 3
     nroot = 7 if task == "kick" else 3
     rs = lib.bezk_host_pack_record_floats(tid, ctypes.byref(cfg))
-    assert rs == -(-(10 + 2 * fw + nroot) // 4) * 4 and (rs, task, cleats) != (24, "kick", True)
+    assert rs == -(-(10 + 2 * fw + nroot + 1) // 4) * 4 and (rs, task, cleats) != (24, "kick", True)   # always >= 1 pad float
     if task == "kick" and not cleats:
         assert rs == 24                                          # 96 B per env
     n = 70_001
@@ -356,7 +356,7 @@ def test_host_pack_gathers_the_sparse_rows(task, cleats):
     P = lambda a, off=0: ctypes.c_void_p(a.ctypes.data + 4 * off)           # noqa: E731
     # 97 ragged jobs (> 64 ring slots) issued before any wait, covering [0, n) in order
     edges = sorted(set([0, n] + [int(x) for x in rng.integers(1, n, size=96)]))
-    tickets = [lib.bezk_host_pack_begin(tid, P(rb), P(cf), P(root), None, ctypes.byref(cfg), P(rec, lo * rs), lo, hi - lo)
+    tickets = [lib.bezk_host_pack_begin(tid, P(rb), P(cf), P(root), None, None, ctypes.byref(cfg), P(rec, lo * rs), lo, hi - lo)
                for lo, hi in zip(edges[:-1], edges[1:])]
     assert all(t > 0 for t in tickets) and tickets == sorted(tickets)
     for t in reversed(tickets):
@@ -378,14 +378,17 @@ def test_host_pack_gathers_the_sparse_rows(task, cleats):
     # chunk layout with the dense dof_state rows copied along: dst = [k x 36 dof floats | k records]
     lo, k = 4099, 30_001
     buf = np.full(k * (36 + rs), -7.0, dtype=np.float32)
-    assert lib.bezk_host_pack_wait(lib.bezk_host_pack_begin(tid, P(rb), P(cf), P(root), P(dof), ctypes.byref(cfg), P(buf), lo, k)) == 0
+    vals = rng.standard_normal(n, dtype=np.float32)            # critic values ride in the record's last (pad) float
+    assert lib.bezk_host_pack_wait(lib.bezk_host_pack_begin(tid, P(rb), P(cf), P(root), P(dof), P(vals), ctypes.byref(cfg), P(buf), lo,
+                                                            k)) == 0
     assert np.array_equal(bits(buf[:k * 36].reshape(k, 36)), bits(dof[lo:lo + k]))
-    assert np.array_equal(bits(buf[k * 36:].reshape(k, rs)), bits(rec[lo:lo + k]))
-    assert lib.bezk_host_pack_begin(tid, P(rb), P(cf), P(root), None, ctypes.byref(cfg), P(rec), 5, 0) == 0
+    got = buf[k * 36:].reshape(k, rs)
+    assert np.array_equal(bits(got[:, :rs - 1]), bits(rec[lo:lo + k, :rs - 1])) and np.array_equal(bits(got[:, rs - 1]), bits(vals[lo:lo + k]))
+    assert lib.bezk_host_pack_begin(tid, P(rb), P(cf), P(root), None, None, ctypes.byref(cfg), P(rec), 5, 0) == 0
     assert lib.bezk_host_pack_wait(0) == 0
-    assert lib.bezk_host_pack_begin(tid, None, P(cf), P(root), None, ctypes.byref(cfg), P(rec), 0, 4) == -10001
-    assert lib.bezk_host_pack_begin(9, P(rb), P(cf), P(root), None, ctypes.byref(cfg), P(rec), 0, 4) == -10001
-    assert lib.bezk_host_pack_begin(tid, P(rb), P(cf), P(root), None, ctypes.byref(cfg), P(rec, 1), 0, 4) == -10002
+    assert lib.bezk_host_pack_begin(tid, None, P(cf), P(root), None, None, ctypes.byref(cfg), P(rec), 0, 4) == -10001
+    assert lib.bezk_host_pack_begin(9, P(rb), P(cf), P(root), None, None, ctypes.byref(cfg), P(rec), 0, 4) == -10001
+    assert lib.bezk_host_pack_begin(tid, P(rb), P(cf), P(root), None, None, ctypes.byref(cfg), P(rec, 1), 0, 4) == -10002
     assert lib.bezk_host_pack_wait(1 << 40) == 10001
     assert lib.bezk_post_physics_packed(tid, *([None] * 10), 0, 0, *([None] * 4), ctypes.byref(cfg), None, None, None, 7, 4, 0, None, None,
-                                        None) == 10001
+                                        None, None, None, None, None) == 10001

@@ -438,8 +438,18 @@ def test_host_pipeline_equals_gpu_pipeline(host_mode, task):
         sim = SyntheticGym(n, device="cuda:0", cleats=cleats, state=st.clone(), host=(kind == "host"), task=task)
         envs[kind] = cls(cfg, "cuda:0", 0, True, sim=sim)
         envs[kind].progress_buf.copy_(torch.arange(n, device="cuda") % envs[kind].max_episode_length)
+    # rl_games' per-step reward path in the step's epilogue (a16): also served by the copy-engine / packed host pipelines, with
+    # the critic values arriving from pinned HOST memory (the outputs are device rollout slots on both sides)
+    epilogue = True
+    sh = {k: torch.zeros(n, device="cuda") for k in envs}
+    dn = {k: torch.zeros(n, dtype=torch.uint8, device="cuda") for k in envs}
     for step in range(4):
         a = sg.make_actions(n, seed=step)
+        if epilogue:
+            vals = torch.randn(n, generator=torch.Generator().manual_seed(step))
+            envs["gpu"].set_rollout_targets(values=vals.cuda(), shaped_rewards=sh["gpu"], dones_u8=dn["gpu"])
+            envs["host"].set_rollout_targets(values=vals.pin_memory() if step != 2 else vals.cuda(), shaped_rewards=sh["host"],
+                                             dones_u8=dn["host"])
         o_g, r_g, d_g, e_g = envs["gpu"].step(a.cuda())
         o_h, r_h, d_h, e_h = envs["host"].step(a.pin_memory() if step % 2 else a)
         assert o_h["obs"].device.type == "cpu" and r_h.device.type == "cpu"
@@ -447,6 +457,9 @@ def test_host_pipeline_equals_gpu_pipeline(host_mode, task):
         og, oh = o_g["obs"].cpu(), o_h["obs"]
         assert bool(((og == oh) | (og.isnan() & oh.isnan())).all()) and torch.equal(r_g.cpu(), r_h)
         assert torch.equal(d_g.cpu(), d_h) and torch.equal(e_g["time_outs"].cpu(), e_h["time_outs"])
+        if epilogue:
+            assert torch.equal(sh["gpu"], sh["host"]) and torch.equal(dn["gpu"], dn["host"]) and torch.equal(dn["host"].cpu().long(), d_h)
+            assert float(sh["host"].abs().sum()) > 0
         assert torch.equal(envs["gpu"].dof_state.cpu(), envs["host"].dof_state), "resets written into the host dof_state"
         assert torch.equal(envs["gpu"].net_contact.cpu(), envs["host"].net_contact), "contact filter written back (or left alone)"
         assert torch.equal(envs["gpu"].root_states.cpu(), envs["host"].root_states)

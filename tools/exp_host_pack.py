@@ -50,7 +50,7 @@ def main():
         t0 = time.perf_counter()
         tickets, begins, waits = [], [], []
         for lo in range(0, n, c):
-            tickets.append(lib.bezk_host_pack_begin(0, P(rb), P(cf), P(root), P(dof) if args.dof else None, ctypes.byref(cfg),
+            tickets.append(lib.bezk_host_pack_begin(0, P(rb), P(cf), P(root), P(dof) if args.dof else None, None, ctypes.byref(cfg),
                                                     ctypes.c_void_p(rec.ctypes.data + 4 * lo * pw), lo, min(c, n - lo)))
             begins.append(round(1e3 * (time.perf_counter() - t0), 3))
         for t in tickets:
