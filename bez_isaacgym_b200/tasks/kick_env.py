@@ -94,13 +94,14 @@ class KickEnv(VecTask):
         # simulator tensors (borrowed) and their device images
         self.root_states, self.dof_state = self.sim.root_states, self.sim.dof_state
         self.rigid_body, self.net_contact = self.sim.rigid_body, self.sim.net_contact
-        # host pipelines (every task): "zero_copy" (default) hands the PINNED host tensors straight to the kernels -- they gather
-        # the few bytes they need over PCIe and write resets back in place; "staged" copies all four tensors to HBM first;
+        # host pipelines (every task; default "auto", resolved below): "zero_copy" hands the PINNED host tensors straight to the
+        # kernels -- they gather the few bytes they need over PCIe and write resets back in place; "staged" copies all four
+        # tensors to HBM first;
         # "staged_ce" moves everything with the copy engines in a chunked three-stream pipeline (dense tensors by
         # cudaMemcpyAsync, the sparse AoS rows by strided cudaMemcpy2DAsync pulls, results back by cudaMemcpyAsync);
         # "staged_pack" is staged_ce with the sparse rows gathered by HOST worker threads into pinned pack buffers
         # (bezk_host_pack_begin / _wait) and moved by dense copies -- the engine is row-rate-bound on strided pulls
-        self.host_mode = env_cfg.get("hostPipeline", "zero_copy") if self.host_staged else None
+        self.host_mode = env_cfg.get("hostPipeline", "auto") if self.host_staged else None
         if self.host_mode == "auto":
             # the fastest pipeline this host can feed: the packed pipeline needs ~8 worker threads per GPU to stay ahead of the
             # link (98 vs 69 M env-steps/s on 16 cores / 1 GPU); with 4 cores per GPU (8 ranks on 32 cores) the gather becomes
