@@ -245,9 +245,11 @@ def test_policy_head_philox_noise_is_standard_normal_and_reproducible():
     col = zc - zc.mean(0)
     corr = (col.T @ col) / n
     assert float((corr - torch.diag(torch.diag(corr))).abs().max()) < 2e-2   # columns uncorrelated
-    # the numpy restatement of Philox + Box-Muller reproduces the device draws (sm_100a logf/cosf vs numpy: ~1e-6)
+    # the numpy restatement of Philox + Box-Muller reproduces the device draws: the STREAM (counters, keys, pairing) is what is
+    # pinned; the device evaluates lg2 / sin / cos / sqrt on the special-function unit (absolute error of a draw up to ~1e-5,
+    # reached next to the zeros of sin / cos where the fast range reduction loses its low bits)
     want = philox_ref.normals18(seed=11, step=5, envs=range(64))
-    U.assert_close(z[:64].cpu(), torch.from_numpy(want).float(), rtol=1e-5, atol=2e-6, what="philox normals")
+    U.assert_close(z[:64].cpu(), torch.from_numpy(want).float(), rtol=1e-5, atol=3e-5, what="philox normals")
     # sampling through the head with noise=None uses exactly these draws
     mu = torch.zeros(n, 18, device="cuda"); logstd = torch.zeros(18, device="cuda")
     act = torch.empty(n, 18, device="cuda")
