@@ -466,18 +466,21 @@ def learner_leg(args, world, rank, dev):
             ops.gae(rewards, values, dones, last_values, last_dones, 0.99, 0.95, advs, rets)
             L.normalize_advantages(rets, values, process_group=group, out=adv_n.view(-1))       # moments -> all-reduce -> normalise
             val_rms(values, out=vals_n); val_rms(rets, out=rets_n)                               # two train-mode updates per epoch
-            for _ in range(mini_epochs):
+            # the obs normaliser's 5 x 4 train-mode updates: the moments of the 4 distinct minibatches ONCE (+ one all-reduce of
+            # all of them), one merge kernel for the whole sequence; each update's normalise pass stays where rl_games has it
+            obs_rms.plan([obses[:, i * E:(i + 1) * E] for i in range(nmb)], list(range(nmb)) * mini_epochs)
+            for me in range(mini_epochs):
                 for i in range(nmb):
                     sl = slice(i * E, (i + 1) * E)
-                    obs_rms(obses[:, sl], out=norm_obs)                                        # moments -> all-reduce -> merge -> normalise
+                    obs_rms.planned(me * nmb + i, obses[:, sl], out=norm_obs)                  # normalise with the stats after this update
                     ops.ppo_loss_slabs(actions[:, sl], mu_net, logstd, old_mu[:, sl], old_sigma[:, sl], val_net, vals_n[:, sl],
                                        rets_n[:, sl], old_neglogp[:, sl], adv_n[:, sl], kc, stats, part, grad_mu=gmu,
                                        grad_values=gv, grad_logstd=gls)
                     if group is not None:
                         dist.all_reduce(bucket, group=group)                                   # PPO gradients (+ KL), one flat bucket
         if group is not None:
-            counters["collectives"] = 3 + 2 * mini_epochs * nmb
-            counters["bytes"] = 8 * (3 + 2 * 3) + mini_epochs * nmb * (8 * 109 + 4 * (POLICY_PARAMS + 1))
+            counters["collectives"] = 3 + 1 + mini_epochs * nmb
+            counters["bytes"] = 8 * (3 + 2 * 3) + 8 * 109 * nmb + mini_epochs * nmb * 4 * (POLICY_PARAMS + 1)
         return epoch, counters
 
     def timed(epoch, iters):

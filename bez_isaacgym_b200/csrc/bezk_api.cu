@@ -385,6 +385,16 @@ int bezk_rms_merge(const double* acc, const double* pivot, double* running_mean,
     return cuda_rc(bezk::launch_rms_merge(acc, pivot, running_mean, running_var, count, c, (cudaStream_t)stream), "bezk_rms_merge");
 }
 
+int bezk_rms_merge_sequence(const double* acc, int32_t n_batches, const int32_t* order, int32_t n_updates, const double* pivot,
+                            double* running_mean, double* running_var, double* count, double* seq, int32_t c, void* stream) {
+    REQUIRE(c > 0 && c <= 1024, "c must be 1 .. 1024");
+    REQUIRE(n_batches > 0 && n_updates >= 0, "n_batches must be positive, n_updates non-negative");
+    if (n_updates == 0) return 0;
+    REQUIRE(acc && order && running_mean && running_var && count && seq, "rms buffers NULL");
+    return cuda_rc(bezk::launch_rms_merge_sequence(acc, order, n_updates, pivot, running_mean, running_var, count, seq, c,
+                                                   (cudaStream_t)stream), "bezk_rms_merge_sequence");
+}
+
 int bezk_rms_normalize(const float* x, const double* running_mean, const double* running_var, float eps, int unnorm, float* y,
                        int64_t m, int32_t c, void* stream) {
     REQUIRE(m >= 0 && c > 0 && c <= 4096, "bad m/c");

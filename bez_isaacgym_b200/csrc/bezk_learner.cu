@@ -337,6 +337,42 @@ __global__ void rms_merge_kernel(const double* __restrict__ acc, const double* _
     if (j == 0 && B > 0.0) count[0] = tot;
 }
 
+// K4c: a whole SEQUENCE of merges in one launch.  The obs normaliser is updated with the same few minibatches again and again
+// (mini_epochs x minibatches per epoch, rl_games calc_gradients) and its batch moments do not depend on the policy, so they are
+// computed ONCE per distinct minibatch (acc rows, all with the pivot taken at plan time) and this kernel replays the reference's
+// update `order[u]`, u = 0 .. nu-1, writing the statistics AFTER update u to seq[u] = [mean(c), var(c)] -- what the u-th train
+// forward normalises with -- and the final state back to running_*.  One thread per column, the updates in order: the same
+// arithmetic as nu calls of rms_merge_kernel (only the pivot of the moments differs, at fp64 rounding level).
+__global__ void rms_merge_sequence_kernel(const double* __restrict__ acc, const int32_t* __restrict__ order, int nu,
+                                          const double* __restrict__ pivot, double* running_mean, double* running_var, double* count,
+                                          double* __restrict__ seq, int c) {
+    const int j = threadIdx.x;
+    double cnt = count[0];
+    const double p = (pivot && j < c) ? pivot[j] : 0.0;
+    double mean = j < c ? running_mean[j] : 0.0, var = j < c ? running_var[j] : 1.0;
+    for (int u = 0; u < nu; ++u) {
+        const double* a = acc + (int64_t)order[u] * (1 + 2 * c);
+        const double B = a[0];
+        if (B > 0.0) {
+            const double tot = cnt + B;
+            if (j < c) {
+                const double S = a[1 + j], SS = a[1 + c + j];
+                const double mean_b = p + S / B;
+                const double var_b = (SS - S * S / B) / (B - 1.0);          // NaN for B == 1, like torch.var
+                const double delta = mean_b - mean;
+                const double new_mean = mean + delta * B / tot;
+                var = (var * cnt + var_b * B + delta * delta * cnt * B / tot) / tot;
+                mean = new_mean;
+            }
+            cnt = tot;
+        }
+        if (j < c) { seq[((int64_t)u * 2 + 0) * c + j] = mean; seq[((int64_t)u * 2 + 1) * c + j] = var; }
+    }
+    __syncthreads();                    // every thread has read count[0]
+    if (j < c) { running_mean[j] = mean; running_var[j] = var; }
+    if (j == 0) count[0] = cnt;
+}
+
 // K5: normalise / un-normalise
 template <bool SLABS>
 __global__ void __launch_bounds__(256, 8) rms_normalize_kernel(const float* __restrict__ x, const double* __restrict__ running_mean,
@@ -545,6 +581,14 @@ cudaError_t launch_rms_merge(const double* acc, const double* pivot, double* run
                              double* count, int c, cudaStream_t st) {
     if (c > 1024) return cudaErrorInvalidValue;
     rms_merge_kernel<<<1, ((c + 31) / 32) * 32, 0, st>>>(acc, pivot, running_mean, running_var, count, c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rms_merge_sequence(const double* acc, const int32_t* order, int nu, const double* pivot, double* running_mean,
+                                      double* running_var, double* count, double* seq, int c, cudaStream_t st) {
+    if (c > 1024) return cudaErrorInvalidValue;
+    if (nu == 0) return cudaSuccess;
+    rms_merge_sequence_kernel<<<1, ((c + 31) / 32) * 32, 0, st>>>(acc, order, nu, pivot, running_mean, running_var, count, seq, c);
     return cudaGetLastError();
 }
 

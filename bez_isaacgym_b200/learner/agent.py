@@ -194,9 +194,22 @@ class A2CAgent:
                                               extra=dict(returns=returns, advantages=self.advantages, old_values=old_values))
 
     # ------------------------------------------------------------------ learner
-    def calc_gradients(self, input_dict):
-        """a2c_continuous.py ``calc_gradients`` on one minibatch (slab views)."""
-        obs = self.running_mean_std(input_dict["obses"]) if self.config["normalize_input"] else input_dict["obses"]
+    def _plan_obs_normaliser(self):
+        """The epoch's mini_epochs x minibatches train-mode updates of the obs normaliser, planned: one moments pass per distinct
+        minibatch (+ one all-reduce), one merge kernel (``RunningMeanStd.plan``); ``calc_gradients`` then normalises update ``u``."""
+        if self.config["normalize_input"]:
+            nmb = len(self.dataset)
+            self.running_mean_std.plan([self.dataset[i]["obses"] for i in range(nmb)], list(range(nmb)) * self.mini_epochs_num)
+
+    def calc_gradients(self, input_dict, update=None):
+        """a2c_continuous.py ``calc_gradients`` on one minibatch (slab views).  ``update``: index of this call in the planned
+        sequence of obs-normaliser updates (None: the per-minibatch train forward)."""
+        if not self.config["normalize_input"]:
+            obs = input_dict["obses"]
+        elif update is None:
+            obs = self.running_mean_std(input_dict["obses"])
+        else:
+            obs = self.running_mean_std.planned(update, input_dict["obses"])
         obs = obs.reshape(-1, obs.shape[-1]).contiguous()        # (T*E, obs): a single-minibatch epoch hands over (T, N, obs)
         mu, value = self._forward(obs, autocast=True)
         loss, info = losses.ppo_loss(mu, value, self.model.sigma, input_dict["actions"], input_dict["mus"], input_dict["sigmas"],
@@ -224,9 +237,10 @@ class A2CAgent:
 
     def _learn_eager(self):
         last = None
-        for _ in range(self.mini_epochs_num):
+        self._plan_obs_normaliser()
+        for me in range(self.mini_epochs_num):
             for i in range(len(self.dataset)):
-                last = self.calc_gradients(self.dataset[i])
+                last = self.calc_gradients(self.dataset[i], me * len(self.dataset) + i)
                 if self.scheduler is not None:
                     kl = self._mean_kl(last["kl"])
                     lr, _ = self.scheduler.update(self.last_lr, self.config["entropy_coef"], self.epoch_num, 0, float(kl))
@@ -238,9 +252,10 @@ class A2CAgent:
         ``torch.where``): no host synchronisation, so the whole learner phase can be captured into one CUDA graph."""
         last = None
         sch = self.scheduler
-        for _ in range(self.mini_epochs_num):
+        self._plan_obs_normaliser()
+        for me in range(self.mini_epochs_num):
             for i in range(len(self.dataset)):
-                last = self.calc_gradients(self.dataset[i])
+                last = self.calc_gradients(self.dataset[i], me * len(self.dataset) + i)
                 if sch is not None:
                     kl = self._mean_kl(last["kl"]).float()
                     lr = self._lr_t

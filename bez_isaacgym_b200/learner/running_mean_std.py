@@ -53,6 +53,51 @@ class RunningMeanStd(nn.Module):
         bdist.allreduce_sum_(self._acc, self.process_group)
         ops.rms_merge(self._acc, self._pivot, self.running_mean, self.running_var, self.count.view(1))
 
+    # ------------------------------------------------------------------ planned updates (one moment pass per distinct batch)
+    def plan(self, batches, order):
+        """rl_games updates the obs normaliser with the SAME minibatches in every mini-epoch (``calc_gradients``:
+        ``obs = self.running_mean_std(obs)`` in train mode), and the batch moments do not depend on the policy.  ``plan`` takes
+        the epoch's distinct ``batches`` (contiguous (m, insize) tensors or slab views) and the update ``order`` (indices into
+        ``batches``, e.g. ``[0, 1, 2, 3] * mini_epochs``): ONE moments pass per distinct batch (pivot = the running mean now), one
+        SUM all-reduce of all of them when distributed, one kernel that replays the reference's merge for every update in
+        order.  Afterwards ``running_*`` hold the state after the last update and ``planned(u, x)`` normalises with the
+        statistics after update ``u`` -- exactly what ``forward`` would have used at that point of the epoch."""
+        if not self.training:
+            raise RuntimeError("plan() replays train-mode updates: call .train() first")
+        dev = batches[0].device
+        self._workspace(dev)
+        c, nb = self.insize, len(batches)
+        key = (tuple(int(o) for o in order), nb, str(dev))
+        if getattr(self, "_plan_key", None) != key:
+            if min(key[0]) < 0 or max(key[0]) >= nb:
+                raise ValueError("order must index into batches")
+            self._plan_order = torch.tensor(key[0], dtype=torch.int32, device=dev)
+            self._plan_acc = torch.empty(nb, 1 + 2 * c, dtype=torch.float64, device=dev)
+            self._plan_seq = torch.empty(len(key[0]), 2, c, dtype=torch.float64, device=dev)
+            self._plan_key = key
+        self._pivot.copy_(self.running_mean)              # replicated on all ranks -> identical pivots
+        for b, x in enumerate(batches):
+            x = x.detach()
+            if x.is_contiguous():
+                ops.rms_moments(x.view(-1, c), self._pivot, self._plan_acc[b], self._scratch)
+            else:
+                ops.rms_moments_slabs(x, self._pivot, self._plan_acc[b], self._scratch)
+        bdist.allreduce_sum_(self._plan_acc, self.process_group)
+        ops.rms_merge_sequence(self._plan_acc, self._plan_order, self._pivot, self.running_mean, self.running_var, self.count.view(1),
+                               self._plan_seq)
+        return self._plan_seq
+
+    def planned(self, u: int, input: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """The train-mode forward of update ``u`` of the last ``plan``: normalise with the statistics after that update."""
+        x = input.detach()
+        mean, var = self._plan_seq[u, 0], self._plan_seq[u, 1]
+        if x.is_contiguous():
+            y = out if out is not None else torch.empty_like(x)
+            return ops.rms_normalize(x, mean, var, y, eps=self.epsilon)
+        y = out if out is not None else torch.empty(x.shape[0] * x.shape[1], self.insize, dtype=torch.float32, device=x.device)
+        ops.rms_normalize_slabs(x, mean, var, y, eps=self.epsilon)
+        return y
+
     def forward(self, input: torch.Tensor, unnorm: bool = False, out: torch.Tensor = None) -> torch.Tensor:
         x = input.detach()
         if x.dtype != torch.float32:

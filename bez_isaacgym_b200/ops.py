@@ -278,6 +278,19 @@ def rms_merge(acc, pivot, running_mean, running_var, count):
                                   _p(count, F64, "count", 1), c, _stream(acc)), "bezk_rms_merge")
 
 
+def rms_merge_sequence(acc, order, pivot, running_mean, running_var, count, seq):
+    """``acc`` (n_batches, 1+2c) moments of the distinct batches (one pivot), ``order`` (n_updates,) int32 device tensor: replays
+    the reference's update for batch ``order[u]``, u in order; ``seq`` (n_updates, 2, c) gets [mean, var] after each update."""
+    c = running_mean.numel()
+    nb, nu = acc.numel() // (1 + 2 * c), order.numel()
+    lib = _lib.load()
+    _lib.check(lib.bezk_rms_merge_sequence(_p(acc, F64, "acc", nb * (1 + 2 * c)), nb, _p(order, torch.int32, "order"), nu,
+                                           _p(pivot, F64, "pivot", c, True), _p(running_mean, F64, "running_mean", c),
+                                           _p(running_var, F64, "running_var", c), _p(count, F64, "count", 1),
+                                           _p(seq, F64, "seq", nu * 2 * c), c, _stream(acc)), "bezk_rms_merge_sequence")
+    return seq
+
+
 def rms_normalize(x, running_mean, running_var, y, eps=1e-5, unnorm=False):
     c = running_mean.numel()
     m = x.numel() // c

@@ -240,6 +240,16 @@ int bezk_rms_moments(const float* x, const double* pivot, double* acc, double* p
  * count () f64 with the reference's parallel-variance update (unbiased batch variance). */
 int bezk_rms_merge(const double* acc, const double* pivot, double* running_mean, double* running_var,
                    double* count, int32_t c, void* stream);
+/* K4c.  A SEQUENCE of those merges in one launch: acc (n_batches, 1+2c) holds the moments of n_batches distinct batches (all taken
+ * with the same pivot, possibly all-reduced over ranks in ONE collective); update u = 0 .. n_updates-1 merges batch order[u]
+ * (device int32, values in [0, n_batches)) exactly as bezk_rms_merge would; seq (n_updates, 2, c) f64 receives [mean, var] AFTER
+ * update u -- the statistics the u-th train-mode forward normalises with (pass seq + u*2*c and seq + (u*2+1)*c to
+ * bezk_rms_normalize[_slabs]) -- and running_mean / running_var / count the final state.  rl_games updates the obs normaliser with
+ * the SAME minibatches in every mini-epoch (calc_gradients: `obs = self.running_mean_std(obs)` in train mode) and the moments do
+ * not depend on the policy: n_batches moment passes per epoch instead of mini_epochs * n_batches, same statistics. */
+int bezk_rms_merge_sequence(const double* acc, int32_t n_batches, const int32_t* order, int32_t n_updates,
+                            const double* pivot, double* running_mean, double* running_var, double* count, double* seq,
+                            int32_t c, void* stream);
 /* K5.  y = clamp((x - mean.float()) / sqrt(var.float() + eps), -5, 5)   (unnorm = 0)
  *      y = sqrt(var.float() + eps) * clamp(x, -5, 5) + mean.float()      (unnorm = 1)
  * x, y (m,c) f32 (y may alias x). */

@@ -168,3 +168,45 @@ def test_a2c_agent_cuda_graph_learner_phase_equals_eager():
         torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-6)
     assert infos[0][-1]["lr"] == pytest.approx(infos[1][-1]["lr"], rel=1e-5)
     assert float(infos[0][-1]["kl"]) == pytest.approx(float(infos[1][-1]["kl"]), rel=1e-3, abs=1e-7)
+
+
+@pytest.mark.parametrize("slabs", [False, True])
+def test_planned_running_mean_std_equals_the_per_minibatch_updates(slabs):
+    """``RunningMeanStd.plan`` / ``planned`` (``bezk_rms_merge_sequence``): ONE moments pass per distinct minibatch and one merge
+    kernel for the epoch's 5 x 4 train-mode updates give the statistics -- after EVERY update -- and the normalised minibatches of
+    the per-minibatch ``forward`` calls rl_games makes (same arithmetic; only the moments' pivot differs, at fp64 rounding level),
+    also against the fp64 oracle, and keep the checkpoint identity count = 1 + 5 * frame."""
+    from bez_isaacgym_b200.learner import RunningMeanStd
+    from oracle import rl_games_oracle as rg
+    T, n, c, nmb, mini_epochs = 32, 1024, 54, 4, 5
+    E = n // nmb
+    g = torch.Generator().manual_seed(3)
+    obses = (torch.randn(T, n, c, generator=g) * torch.linspace(0.5, 3, c) + torch.linspace(-2, 2, c)).cuda()
+    if slabs:
+        batches = [obses[:, i * E:(i + 1) * E] for i in range(nmb)]                 # read in place from time-major storage
+    else:
+        batches = [obses[:, i * E:(i + 1) * E].reshape(-1, c).contiguous() for i in range(nmb)]
+    order = list(range(nmb)) * mini_epochs
+    seq_mod, plan_mod, orc = RunningMeanStd(c).cuda(), RunningMeanStd(c).cuda(), rg.RunningMeanStd(c)
+    for m in (seq_mod, plan_mod):                                                   # a warm state, not the (0, 1, 1) start
+        m.running_mean.copy_(torch.linspace(-1, 1, c)); m.running_var.fill_(2.0); m.count.fill_(1000.0)
+    orc.running_mean.copy_(torch.linspace(-1, 1, c).double()); orc.running_var.fill_(2.0); orc.count.fill_(1000.0)
+    seq = plan_mod.plan(batches, order)
+    assert seq.shape == (len(order), 2, c)
+    for u, b in enumerate(order):
+        want = seq_mod(batches[b])                                                  # the per-minibatch train forward
+        got = plan_mod.planned(u, batches[b])
+        assert torch.allclose(seq[u, 0], seq_mod.running_mean, rtol=1e-12, atol=1e-13), u
+        assert torch.allclose(seq[u, 1], seq_mod.running_var, rtol=1e-11, atol=1e-13), u
+        U.assert_close(got, want, rtol=1e-6, atol=1e-6, what=f"normalised minibatch of update {u}")
+        flat = batches[b].reshape(-1, c).cpu()
+        U.assert_close(got, orc(flat), rtol=1e-4, atol=1e-4, what=f"oracle, update {u}")
+    assert torch.allclose(plan_mod.running_mean, seq_mod.running_mean, rtol=1e-12, atol=1e-13)
+    assert torch.allclose(plan_mod.running_var, seq_mod.running_var, rtol=1e-11, atol=1e-13)
+    assert plan_mod.count.item() == seq_mod.count.item() == 1000 + mini_epochs * T * n
+    # a second epoch reuses the plan's buffers; eval mode refuses to plan
+    plan_mod.plan(batches, order)
+    assert plan_mod.count.item() == 1000 + 2 * mini_epochs * T * n
+    plan_mod.eval()
+    with pytest.raises(RuntimeError):
+        plan_mod.plan(batches, order)
