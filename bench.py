@@ -13,8 +13,9 @@ Legs of the B200 arm (ONE JSON line, rank 0):
                      the critic values of every step in pinned host memory; copies inside the timed region), same envs per GPU,
                      the reward shaping / value bootstrap / uint8 dones written by the step's epilogue as in the device leg
   learner            BASELINE configs[2]/[3]: the PPO epoch math on a 4096 x 32 rollout per GPU -- GAE, advantage moments, value
-                     RunningMeanStd x2, then mini_epochs x minibatches x (obs RunningMeanStd moments -> all-reduce -> merge ->
-                     normalise, fused PPO loss fwd+bwd, flat 124 237-float gradient bucket all-reduce), no MLP; with its own
+                     RunningMeanStd x2, the obs RunningMeanStd's mini_epochs x minibatches updates planned once (moments of the
+                     distinct minibatches -> one all-reduce -> one merge-sequence kernel), then mini_epochs x minibatches x
+                     (normalise, fused PPO loss fwd+bwd, flat 124 237-float gradient bucket all-reduce), no MLP; with its own
                      roofline and the collectives' cost (with-collectives minus without)
   cpu_baseline       the reference torch ops (oracle port) on the host cores, bounded sample of the same workload (N=1 only)
   gpu_torch_baseline the same port with CUDA tensors on the same B200 (the torch-eager op sequence is the bar)
@@ -561,8 +562,10 @@ def learner_leg(args, world, rank, dev):
         k["frac"] = k["gbs"] / peak
     worst = min(kernels, key=lambda k: kernels[k]["frac"])
     return {"workload": f"PPO epoch math per GPU on a {T} x {n} rollout: GAE, advantage moments + normalise, value RunningMeanStd x2, "
-                        f"{mini_epochs} x {nmb} minibatches of {mbs} x (obs RunningMeanStd train forward on slab views, fused PPO loss "
-                        f"fwd+bwd, {POLICY_PARAMS}-float gradient bucket all-reduce); no MLP",
+                        f"the {mini_epochs} x {nmb} train-mode updates of the obs RunningMeanStd planned once (moments of the {nmb} distinct "
+                        f"minibatches on slab views, one all-reduce, one merge-sequence kernel), then {mini_epochs} x {nmb} minibatches of "
+                        f"{mbs} x (normalise with the statistics of that update, fused PPO loss fwd+bwd, {POLICY_PARAMS}-float gradient "
+                        f"bucket all-reduce); no MLP",
             "envs_per_gpu": n, "horizon": T, "minibatch": mbs, "mini_epochs": mini_epochs, "n_gpus": world,
             "ms_per_epoch": best, "launch": best_how,
             "ms_per_epoch_eager": ms_dist, "ms_per_epoch_eager_no_collectives": ms_local,
