@@ -698,7 +698,7 @@ __global__ void __launch_bounds__(PPO_TILE, 4) ppo_loss_kernel(const PpoArgs a, 
     __shared__ __align__(128) float s_osig[PPO_TILE * 18];
     __shared__ __align__(128) float s_gmu[PPO_TILE * 18];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ float s_sigma[18], s_logstd[18], s_isig[18];
+    __shared__ float s_sigma[18], s_logstd[18], s_isig[18], s_ry[18];
     __shared__ double s_red[PPO_TILE / 32][PPO_PART];
 
     const int tid = threadIdx.x;
@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(PPO_TILE, 4) ppo_loss_kernel(const PpoArgs a, 
     // per-column constants.  The FORWARD quantities (neglogp, KL) divide by sigma exactly as the reference does (branch-free IEEE
     // division, Mth); only the hand-derived GRADIENT sweep below multiplies by 1/sigma (it has no reference op order to follow).
     // (the 2 x 18 constants are read from shared memory -- broadcast loads -- instead of living in 36 registers)
-    if (tid < 18) s_isig[tid] = 1.0f / s_sigma[tid];
+    if (tid < 18) { s_isig[tid] = 1.0f / s_sigma[tid]; s_ry[tid] = Mth<true>::rcp_refined(s_sigma[tid]); }
     __syncthreads();
     const float* sig = s_sigma;
     const float* isig = s_isig;
@@ -781,6 +781,10 @@ __global__ void __launch_bounds__(PPO_TILE, 4) ppo_loss_kernel(const PpoArgs a, 
             // ---- neglogp (models.py), bound loss, KL: one sweep over the 18 action dims ----
             float sq = 0.0f, bsum = 0.0f, kl = 0.0f;
             Mth<true> mk;
+            // two of the three quotients per action dim divide by sigma_j, a per-column constant: its refined reciprocal is
+            // formed once per CTA and the divisors are range-checked once per thread (same bits as mk.div, fewer instructions)
+#pragma unroll
+            for (int j = 0; j < 18; ++j) mk.check_divisor(sig[j]);
             const float2* act2 = reinterpret_cast<const float2*>(s_act + tid * 18);
             const float2* mu2 = reinterpret_cast<const float2*>(s_mu + tid * 18);
             const float2* omu2 = reinterpret_cast<const float2*>(s_omu + tid * 18);
@@ -792,7 +796,7 @@ __global__ void __launch_bounds__(PPO_TILE, 4) ppo_loss_kernel(const PpoArgs a, 
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const int j = 2 * h + q;
-                    const float zz = mk.div(av[q] - mv[q], sig[j]);      // the reference DIVIDES by sigma (models.py neglogp): exact
+                    const float zz = mk.div_by(av[q] - mv[q], sig[j], s_ry[j]);   // the reference DIVIDES by sigma (models.py neglogp): exact
                     sq += zz * zz;
                     float hi, lo;
                     if (cfg.bound_form == 0) {          // rl_games 1.1.3 as recalled
@@ -801,7 +805,7 @@ __global__ void __launch_bounds__(PPO_TILE, 4) ppo_loss_kernel(const PpoArgs a, 
                         hi = fmaxf(mv[q] - cfg.soft_bound, 0.0f); lo = fminf(mv[q] + cfg.soft_bound, 0.0f);
                     }
                     bsum += lo * lo + hi * hi;
-                    const float c1 = logf(mk.div(osv[q], sig[j]) + 1e-5f);       // torch_ext.policy_kl: log(p1_sigma / p0_sigma + 1e-5)
+                    const float c1 = logf(mk.div_by(osv[q], sig[j], s_ry[j]) + 1e-5f);   // torch_ext.policy_kl: log(p1_sigma / p0_sigma + 1e-5)
                     const float dm = omv[q] - mv[q];
                     const float c2 = mk.div(sig[j] * sig[j] + dm * dm, 2.0f * (osv[q] * osv[q] + 1e-5f));   // exact, no branch per dim
                     kl += (c1 + c2) + (-0.5f);

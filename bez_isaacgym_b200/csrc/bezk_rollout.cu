@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(PH_TILE) policy_head_kernel(const HeadArgs a, 
     __shared__ __align__(128) float s_act[PH_TILE * 18];
     __shared__ __align__(128) float s_tgt[PH_TILE * 18];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ float s_sigma[18], s_logstd[18];
+    __shared__ float s_sigma[18], s_logstd[18], s_ry[18];
     const int tid = threadIdx.x;
     constexpr uint32_t TILE_BYTES = PH_TILE * 18 * 4;
     const int64_t i0 = (int64_t)blockIdx.x * PH_TILE;
@@ -181,7 +181,11 @@ __global__ void __launch_bounds__(PH_TILE) policy_head_kernel(const HeadArgs a, 
     pdl_launch_dependents();
     if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
     pdl_wait();
-    if (tid < 18) { const float ls = a.logstd[tid]; s_logstd[tid] = ls; s_sigma[tid] = expf(ls); }
+    if (tid < 18) {
+        const float ls = a.logstd[tid];
+        const float sg = expf(ls);
+        s_logstd[tid] = ls; s_sigma[tid] = sg; s_ry[tid] = Mth<true>::rcp_refined(sg);     // the divisor of every row's neglogp
+    }
     __syncthreads();
     if (full) {
         if (tid == 0) {
@@ -208,6 +212,8 @@ __global__ void __launch_bounds__(PH_TILE) policy_head_kernel(const HeadArgs a, 
         for (int j = 0; j < 18; ++j) lsum += s_logstd[j];
         float sq = 0.0f;
         Mth<true> mq;                                                    // exact division without a branch per dimension
+#pragma unroll
+        for (int j = 0; j < 18; ++j) mq.check_divisor(s_sigma[j]);       // per-column constants: range-checked once per thread
         float2* mu2 = reinterpret_cast<float2*>(s_mu + tid * 18);
         float2* eps2 = reinterpret_cast<float2*>(s_eps + tid * 18);
         float2* act2 = reinterpret_cast<float2*>(s_act + tid * 18);
@@ -224,7 +230,7 @@ __global__ void __launch_bounds__(PH_TILE) policy_head_kernel(const HeadArgs a, 
                 const int j = 2 * h + q;
                 const float sg = s_sigma[j];
                 av[q] = mv[q] + sg * ev[q];                              // Normal(mu, sigma).sample()
-                const float zz = mq.div(av[q] - mv[q], sg);              // models.py neglogp: the reference divides by sigma
+                const float zz = mq.div_by(av[q] - mv[q], sg, s_ry[j]);  // models.py neglogp: the reference divides by sigma
                 sq += zz * zz;
                 cv[q] = clamp_nan(av[q], -1.0f, 1.0f) * 1.0f + 0.0f;     // preprocess_actions: clamp, rescale_actions(-1, 1)
                 float stored;
