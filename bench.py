@@ -450,7 +450,7 @@ def learner_leg(args, world, rank, dev):
     advs, rets = torch.empty_like(rewards), torch.empty_like(rewards)
     adv_n = torch.empty(T, n, device=dev)
     vals_n, rets_n = torch.empty_like(values), torch.empty_like(values)
-    norm_obs = torch.empty(mbs, 54, device=dev)
+    norm_obs = torch.empty(nmb, mbs, 54, device=dev)                         # one mini-epoch of network inputs
     bucket = torch.randn(POLICY_PARAMS + 1, generator=g, device=dev)       # flat gradient bucket (+ the KL scalar for the shared LR)
     stats = torch.empty(8, dtype=torch.float64, device=dev)
     part = torch.empty(ops.ppo_scratch_doubles(), dtype=torch.float64, device=dev)
@@ -468,12 +468,14 @@ def learner_leg(args, world, rank, dev):
             L.normalize_advantages(rets, values, process_group=group, out=adv_n.view(-1))       # moments -> all-reduce -> normalise
             val_rms(values, out=vals_n); val_rms(rets, out=rets_n)                               # two train-mode updates per epoch
             # the obs normaliser's 5 x 4 train-mode updates: the moments of the 4 distinct minibatches ONCE (+ one all-reduce of
-            # all of them), one merge kernel for the whole sequence; each update's normalise pass stays where rl_games has it
-            obs_rms.plan([obses[:, i * E:(i + 1) * E] for i in range(nmb)], list(range(nmb)) * mini_epochs)
+            # all of them), one merge kernel for the whole sequence, then ONE normalise launch per mini-epoch (each minibatch
+            # with the statistics after ITS update)
+            views = [obses[:, i * E:(i + 1) * E] for i in range(nmb)]
+            obs_rms.plan(views, list(range(nmb)) * mini_epochs)
             for me in range(mini_epochs):
+                obs_rms.planned_group(me * nmb, views, out=norm_obs)
                 for i in range(nmb):
                     sl = slice(i * E, (i + 1) * E)
-                    obs_rms.planned(me * nmb + i, obses[:, sl], out=norm_obs)                  # normalise with the stats after this update
                     ops.ppo_loss_slabs(actions[:, sl], mu_net, logstd, old_mu[:, sl], old_sigma[:, sl], val_net, vals_n[:, sl],
                                        rets_n[:, sl], old_neglogp[:, sl], adv_n[:, sl], kc, stats, part, grad_mu=gmu,
                                        grad_values=gv, grad_logstd=gls)
@@ -549,7 +551,7 @@ def learner_leg(args, world, rank, dev):
         return a.elapsed_time(b) / (5 * reps)
     rms = L.RunningMeanStd(54).to(dev)
     sl = slice(0, E)
-    k_rms = ktime(lambda: rms(obses[:, sl], out=norm_obs))
+    k_rms = ktime(lambda: rms(obses[:, sl], out=norm_obs[0]))
     k_ppo = ktime(lambda: ops.ppo_loss_slabs(actions[:, sl], mu_net, logstd, old_mu[:, sl], old_sigma[:, sl], val_net, vals_n[:, sl],
                                              rets_n[:, sl], old_neglogp[:, sl], adv_n[:, sl], kc, stats, part, grad_mu=gmu,
                                              grad_values=gv, grad_logstd=gls))

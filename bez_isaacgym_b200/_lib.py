@@ -105,6 +105,7 @@ SIGNATURES = {
                                       _P]),
     "bezk_goal_uniforms": (C.c_int, [_U64, _U64, _P, _P]),
     "bezk_rms_moments_slabs": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _I64, C.c_int32, _P]),
+    "bezk_rms_normalize_slabs_batched": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _I64, C.c_float, _P, _I64, C.c_int32, C.c_int32, _P]),
     "bezk_rms_normalize_slabs": (C.c_int, [_P, _I64, _I64, _P, _P, C.c_float, C.c_int, _P, _I64, C.c_int32, _P]),
     "bezk_ppo_loss_slabs": (C.c_int, [_P] * 10 + [_I64, _I64, C.POINTER(BezkPpoCfg)] + [_P] * 6 + [_I64, _P]),
     "bezk_swap_and_flatten01": (C.c_int, [_P, _P, C.c_int32, _I64, _I64, _I64, C.c_int32, _P]),

@@ -415,6 +415,20 @@ int bezk_rms_normalize_slabs(const float* x, int64_t slab_rows, int64_t slab_str
                                               (cudaStream_t)stream), "bezk_rms_normalize_slabs");
 }
 
+int bezk_rms_normalize_slabs_batched(const float* x, int64_t slab_rows, int64_t slab_stride, int64_t batch_stride,
+                                     const double* mean, const double* var, int64_t stat_stride, float eps, float* y, int64_t m,
+                                     int32_t c, int32_t n_batches, void* stream) {
+    REQUIRE(m >= 0 && c > 0 && c <= 4096 && n_batches >= 0 && n_batches <= 65535, "bad m / c / n_batches");
+    if (m == 0 || n_batches == 0) return 0;
+    REQUIRE(x && y && mean && var, "rms buffers NULL");
+    REQUIRE(batch_stride >= 0 && stat_stride >= 0, "negative stride");
+    if (slab_rows <= 0 || slab_rows > m) { slab_rows = m; slab_stride = m; }
+    if (int rc = check_slabs(slab_rows, slab_stride, m)) return rc;
+    REQUIRE(m / slab_rows <= 65535, "more than 65535 slabs");
+    return cuda_rc(bezk::launch_rms_normalize_batched(x, mean, var, eps, y, m, c, slab_rows, slab_stride, batch_stride, stat_stride,
+                                                      n_batches, (cudaStream_t)stream), "bezk_rms_normalize_slabs_batched");
+}
+
 int bezk_rms_train_forward(const float* x, int64_t slab_rows, int64_t slab_stride, double* running_mean, double* running_var,
                            double* count, float eps, float* y, double* partials, int64_t m, int32_t c, void* stream) {
     REQUIRE(m > 0 && c > 0 && c <= 4096, "bad m/c");

@@ -93,6 +93,8 @@ cudaError_t launch_rms_merge_sequence(const double*, const int32_t*, int, const 
                                       cudaStream_t);
 cudaError_t launch_rms_normalize(const float*, const double*, const double*, float, int, float*, int64_t, int, int64_t, int64_t,
                                  cudaStream_t);
+cudaError_t launch_rms_normalize_batched(const float*, const double*, const double*, float, float*, int64_t, int, int64_t, int64_t,
+                                         int64_t, int64_t, int, cudaStream_t);
 cudaError_t launch_adv_moments(const float*, const float*, double*, double*, int64_t, cudaStream_t);
 cudaError_t launch_adv_normalize(const float*, const float*, const double*, float*, int, int64_t, cudaStream_t);
 cudaError_t launch_swap_flatten(const void*, void*, int, int64_t, int64_t, int64_t, int, cudaStream_t);

@@ -378,12 +378,16 @@ template <bool SLABS>
 __global__ void __launch_bounds__(256, 8) rms_normalize_kernel(const float* __restrict__ x, const double* __restrict__ running_mean,
                                                             const double* __restrict__ running_var, float eps, int unnorm,
                                                             float* __restrict__ y, int64_t total, int c, int vec4,
-                                                            int64_t slab_src_elems) {
+                                                            int64_t slab_src_elems, int64_t x_batch_elems = 0,
+                                                            int64_t y_batch_elems = 0, int64_t stat_batch = 0) {
     // blockIdx.y = slab: `total` elements of THIS slab, read from x + blockIdx.y * slab_src_elems, written to
     // y + blockIdx.y * total (one slab = the whole array in the contiguous case)
+    // blockIdx.z = batch (bezk_rms_normalize_slabs_batched): several minibatches, each with its OWN statistics, in one launch
     if (SLABS) {
-        x += (int64_t)blockIdx.y * slab_src_elems;
-        y += (int64_t)blockIdx.y * total;
+        x += (int64_t)blockIdx.z * x_batch_elems + (int64_t)blockIdx.y * slab_src_elems;
+        y += (int64_t)blockIdx.z * y_batch_elems + (int64_t)blockIdx.y * total;
+        running_mean += (int64_t)blockIdx.z * stat_batch;
+        running_var += (int64_t)blockIdx.z * stat_batch;
     }
     extern __shared__ float s_stat[];       // [2][c]: mean.float(), sqrt(var.float() + eps)
     for (int j = threadIdx.x; j < c; j += blockDim.x) {
@@ -589,6 +593,27 @@ cudaError_t launch_rms_merge_sequence(const double* acc, const int32_t* order, i
     if (c > 1024) return cudaErrorInvalidValue;
     if (nu == 0) return cudaSuccess;
     rms_merge_sequence_kernel<<<1, ((c + 31) / 32) * 32, 0, st>>>(acc, order, nu, pivot, running_mean, running_var, count, seq, c);
+    return cudaGetLastError();
+}
+
+// n_batches minibatches in one launch: batch b is the slab view based at x + b * x_batch_rows * c, normalised with the statistics
+// at running_mean / running_var + b * stat_batch into y + b * m * c
+cudaError_t launch_rms_normalize_batched(const float* x, const double* running_mean, const double* running_var, float eps, float* y,
+                                         int64_t m, int c, int64_t slab_rows, int64_t slab_stride, int64_t x_batch_rows,
+                                         int64_t stat_batch, int n_batches, cudaStream_t st) {
+    if (m * c == 0 || n_batches == 0) return cudaSuccess;
+    if (slab_rows <= 0 || slab_rows > m || m % slab_rows != 0) return cudaErrorInvalidValue;
+    const int64_t nslabs = m / slab_rows;
+    if (nslabs > 65535 || n_batches > 65535) return cudaErrorInvalidValue;
+    const int64_t total = slab_rows * c;
+    const int vec4 = aligned16(x) && aligned16(y) && total % 4 == 0 && (slab_stride * c) % 4 == 0 && (x_batch_rows * c) % 4 == 0 &&
+                     (m * c) % 4 == 0;
+    int blocks = stream_blocks(vec4 ? total / 4 : total, 256, 8);
+    const int cap = (int)((148 * 8 + nslabs * n_batches - 1) / (nslabs * n_batches));
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    rms_normalize_kernel<true><<<dim3((unsigned)blocks, (unsigned)nslabs, (unsigned)n_batches), 256, 2 * c * sizeof(float), st>>>(
+        x, running_mean, running_var, eps, 0, y, total, c, vec4, slab_stride * c, x_batch_rows * c, m * c, stat_batch);
     return cudaGetLastError();
 }
 

@@ -199,7 +199,8 @@ class A2CAgent:
         minibatch (+ one all-reduce), one merge kernel (``RunningMeanStd.plan``); ``calc_gradients`` then normalises update ``u``."""
         if self.config["normalize_input"]:
             nmb = len(self.dataset)
-            self.running_mean_std.plan([self.dataset[i]["obses"] for i in range(nmb)], list(range(nmb)) * self.mini_epochs_num)
+            self._obs_views = [self.dataset[i]["obses"] for i in range(nmb)]
+            self.running_mean_std.plan(self._obs_views, list(range(nmb)) * self.mini_epochs_num)
 
     def calc_gradients(self, input_dict, update=None):
         """a2c_continuous.py ``calc_gradients`` on one minibatch (slab views).  ``update``: index of this call in the planned
@@ -209,7 +210,10 @@ class A2CAgent:
         elif update is None:
             obs = self.running_mean_std(input_dict["obses"])
         else:
-            obs = self.running_mean_std.planned(update, input_dict["obses"])
+            nmb = len(self.dataset)
+            if update % nmb == 0:        # ONE normalise launch per mini-epoch: every minibatch with the statistics of ITS update
+                self._obs_norm = self.running_mean_std.planned_group(update, self._obs_views, out=getattr(self, "_obs_norm", None))
+            obs = self._obs_norm[update % nmb]
         obs = obs.reshape(-1, obs.shape[-1]).contiguous()        # (T*E, obs): a single-minibatch epoch hands over (T, N, obs)
         mu, value = self._forward(obs, autocast=True)
         loss, info = losses.ppo_loss(mu, value, self.model.sigma, input_dict["actions"], input_dict["mus"], input_dict["sigmas"],

@@ -98,6 +98,22 @@ class RunningMeanStd(nn.Module):
         ops.rms_normalize_slabs(x, mean, var, y, eps=self.epsilon)
         return y
 
+    def planned_group(self, u0: int, batches, out: torch.Tensor = None) -> torch.Tensor:
+        """The train-mode forwards of updates ``u0 .. u0 + len(batches) - 1`` of the last ``plan`` in ONE launch (the minibatches
+        of one mini-epoch: equally spaced slab views of one rollout tensor).  Returns (len(batches), m, insize)."""
+        nb, m = len(batches), batches[0].numel() // self.insize
+        if u0 < 0 or u0 + nb > self._plan_seq.shape[0]:
+            raise ValueError("u0 + len(batches) exceeds the planned updates")
+        y = out if out is not None else torch.empty(nb, m, self.insize, dtype=torch.float32, device=batches[0].device)
+        step = batches[1].data_ptr() - batches[0].data_ptr() if nb > 1 else 0
+        spaced = nb == 1 or (step > 0 and all(b.shape == batches[0].shape and b.stride() == batches[0].stride() and
+                                              b.data_ptr() - batches[0].data_ptr() == k * step for k, b in enumerate(batches)))
+        if not spaced:                   # separately allocated minibatches: one launch each
+            for k, b in enumerate(batches):
+                self.planned(u0 + k, b, out=y[k].view(b.shape) if b.is_contiguous() else y[k])
+            return y
+        return ops.rms_normalize_slabs_batched([b.detach() for b in batches], self._plan_seq, u0, y, eps=self.epsilon)
+
     def forward(self, input: torch.Tensor, unnorm: bool = False, out: torch.Tensor = None) -> torch.Tensor:
         x = input.detach()
         if x.dtype != torch.float32:

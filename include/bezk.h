@@ -385,6 +385,13 @@ int bezk_rms_moments_slabs(const float* x, int64_t slab_rows, int64_t slab_strid
 int bezk_rms_normalize_slabs(const float* x, int64_t slab_rows, int64_t slab_stride, const double* running_mean,
                              const double* running_var, float eps, int unnorm, float* y, int64_t m, int32_t c,
                              void* stream);
+/* n_batches minibatches in ONE launch, each with its own statistics (the planned updates of bezk_rms_merge_sequence: the
+ * minibatches of one mini-epoch): batch b is the slab view based at x + b * batch_stride * c (batch_stride in rows: E for the
+ * consecutive env blocks of time-major storage), normalised with mean + b * stat_stride / var + b * stat_stride (doubles; 2c for
+ * consecutive updates of a seq buffer) into y + b * m * c. */
+int bezk_rms_normalize_slabs_batched(const float* x, int64_t slab_rows, int64_t slab_stride, int64_t batch_stride,
+                                     const double* mean, const double* var, int64_t stat_stride, float eps, float* y,
+                                     int64_t m, int32_t c, int32_t n_batches, void* stream);
 /* bezk_ppo_loss with the ROLLOUT-side tensors (actions, old_mu, old_sigma (.,18); old_values, returns, old_neglogp,
  * advantages (.,)) read as slabs; mu, values (network outputs) and all outputs are contiguous batch rows. */
 int bezk_ppo_loss_slabs(const float* actions, const float* mu, const float* logstd, const float* old_mu,

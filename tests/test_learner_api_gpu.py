@@ -204,6 +204,14 @@ def test_planned_running_mean_std_equals_the_per_minibatch_updates(slabs):
     assert torch.allclose(plan_mod.running_mean, seq_mod.running_mean, rtol=1e-12, atol=1e-13)
     assert torch.allclose(plan_mod.running_var, seq_mod.running_var, rtol=1e-11, atol=1e-13)
     assert plan_mod.count.item() == seq_mod.count.item() == 1000 + mini_epochs * T * n
+    # one launch per mini-epoch: the four minibatches of mini-epoch `me`, each with the statistics of ITS update
+    for me in range(mini_epochs):
+        grp = plan_mod.planned_group(me * nmb, batches)
+        assert grp.shape == (nmb, T * E, c)
+        for i in range(nmb):
+            assert torch.equal(grp[i], plan_mod.planned(me * nmb + i, batches[i]).view(T * E, c)), (me, i)
+    with pytest.raises(Exception):
+        plan_mod.planned_group(len(order) - 1, batches)                            # runs past the planned updates
     # a second epoch reuses the plan's buffers; eval mode refuses to plan
     plan_mod.plan(batches, order)
     assert plan_mod.count.item() == 1000 + 2 * mini_epochs * T * n
