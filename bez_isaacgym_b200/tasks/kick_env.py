@@ -106,7 +106,10 @@ class KickEnv(VecTask):
             # the fastest pipeline this host can feed: the packed pipeline needs ~8 worker threads per GPU to stay ahead of the
             # link (98 vs 69 M env-steps/s on 16 cores / 1 GPU); with 4 cores per GPU (8 ranks on 32 cores) the gather becomes
             # the bottleneck and the copy-engine pulls win (176 vs 151 M, profiles/r02_host_pack.md)
-            self.host_mode = "staged_pack" if self._host_core_share() - 1 >= 8 else "staged_ce"
+            if fusion != "fused" or bool(env_cfg.get("writeContactFilter", False)):
+                self.host_mode = "zero_copy"              # the staged pipelines run the fused step and cannot write the filter back
+            else:
+                self.host_mode = "staged_pack" if self._host_core_share() - 1 >= 8 else "staged_ce"
         #: the resolved pipeline name ("staged_pack" runs on the staged_ce machinery: host_mode reads "staged_ce" for both)
         self.host_pipeline = self.host_mode
         self._pack = self.host_mode == "staged_pack"

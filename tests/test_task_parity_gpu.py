@@ -569,3 +569,28 @@ torch.save([t.cpu() for t in (obs, rew, reset, progress, timeout, shaped, dones,
             for a, b in zip(*outs):
                 assert torch.equal(a, b) or bool(((a == b) | (a.isnan() & b.isnan())).all())
             assert int(outs[0][2].sum()) > 0
+
+
+def test_default_host_pipeline_resolves_to_a_mode_that_serves_the_configuration():
+    """``env.hostPipeline`` defaults to ``auto``: a staged pipeline (packed when the process has host cores to gather with) for the
+    fused step, ``zero_copy`` when the caller asks for what only that mode does (the two-kernel split, the in-place contact filter)."""
+    from bez_isaacgym_b200.synthetic_sim import SyntheticGym
+    from bez_isaacgym_b200 import tasks as T
+    n = 1000
+    st = sg.make_state(n, seed=5)
+
+    def make(fusion="fused", **env):
+        cfg = bm.default_task_cfg(n, use_gpu_pipeline=False, rl_device="cpu")
+        cfg["env"].update(env)
+        return T.KickEnv(cfg, "cuda:0", 0, True, sim=SyntheticGym(n, device="cuda:0", state=st.clone(), host=True), fusion=fusion)
+
+    a = sg.make_actions(n, seed=1)
+    e_auto, e_split, e_filter = make(), make("split"), make(writeContactFilter=True)
+    assert e_auto.host_pipeline in ("staged_pack", "staged_ce")
+    assert e_split.host_pipeline == "zero_copy" and e_filter.host_pipeline == "zero_copy"
+    outs = [e.step(a) for e in (e_auto, e_split, e_filter)]
+    torch.cuda.synchronize()
+    for o, r, d, _ in outs[1:]:
+        same = (o["obs"] == outs[0][0]["obs"]) | (o["obs"].isnan() & outs[0][0]["obs"].isnan())
+        assert bool(same.all()) and torch.equal(r, outs[0][1]) and torch.equal(d, outs[0][2])
+    assert not torch.equal(e_filter.net_contact, e_auto.net_contact), "only the zero-copy mode filters the simulator's tensor in place"
