@@ -103,13 +103,19 @@ class KickEnv(VecTask):
         # (bezk_host_pack_begin / _wait) and moved by dense copies -- the engine is row-rate-bound on strided pulls
         self.host_mode = env_cfg.get("hostPipeline", "auto") if self.host_staged else None
         if self.host_mode == "auto":
-            # the fastest pipeline this host can feed: the packed pipeline needs ~8 worker threads per GPU to stay ahead of the
-            # link (98 vs 69 M env-steps/s on 16 cores / 1 GPU); with 4 cores per GPU (8 ranks on 32 cores) the gather becomes
-            # the bottleneck and the copy-engine pulls win (176 vs 151 M, profiles/r02_host_pack.md)
+            # the fastest pipeline for this size on this host (profiles/r02_host_pack.md).  Small tasks: the zero-copy kernels
+            # (two launches, no staging: 0.12 ms per step at the reference's default 4 096 envs vs 0.21-0.57 ms for a staged
+            # pipeline's copies, events and launches).  Large ones: the packed pipeline when the process has ~8 worker threads
+            # to stay ahead of the link (98 vs 69 M env-steps/s at 262 144 envs on 16 cores / 1 GPU); with 4 cores per GPU
+            # (8 ranks on 32 cores) the gather becomes the bottleneck and the copy-engine pulls win (176 vs 151 M).
+            n_envs = int(env_cfg["numEnvs"])
+            pack_ok = self._host_core_share() - 1 >= 8
             if fusion != "fused" or bool(env_cfg.get("writeContactFilter", False)):
                 self.host_mode = "zero_copy"              # the staged pipelines run the fused step and cannot write the filter back
+            elif n_envs < (12288 if pack_ok else 98304):
+                self.host_mode = "zero_copy"
             else:
-                self.host_mode = "staged_pack" if self._host_core_share() - 1 >= 8 else "staged_ce"
+                self.host_mode = "staged_pack" if pack_ok else "staged_ce"
         #: the resolved pipeline name ("staged_pack" runs on the staged_ce machinery: host_mode reads "staged_ce" for both)
         self.host_pipeline = self.host_mode
         self._pack = self.host_mode == "staged_pack"
@@ -209,7 +215,8 @@ class KickEnv(VecTask):
             self._ce_split = bool(env_cfg.get("hostPipelineSplitSparse", True))
             # env.hostPipelineChunks: a count (equal chunks) or a list of relative sizes -- a small first chunk shortens the
             # pipeline's fill (its gather + H2D are exposed), a small last one its drain (its D2H is)
-            chunks = env_cfg.get("hostPipelineChunks", 4)
+            # default: ~32 768+ envs per chunk, at most 4 (1 chunk at 16 384 envs, 2 at 65 536, 4 from 131 072 on: measured)
+            chunks = env_cfg.get("hostPipelineChunks", min(4, max(1, n // 32768)))
             weights = [1.0] * max(1, int(chunks)) if isinstance(chunks, (int, float)) else [float(w) for w in chunks]
             if not weights or min(weights) <= 0:
                 raise ValueError("env.hostPipelineChunks must be a positive count or a list of positive relative sizes")

@@ -470,7 +470,7 @@ def test_host_pipeline_equals_gpu_pipeline(host_mode, task):
     link = envs["host"].link_counters()
     assert link["h2d_bytes"] > 0 and link["d2h_bytes"] > 0
     if host_mode == "auto":
-        assert envs["host"].host_pipeline in ("staged_pack", "staged_ce")
+        assert envs["host"].host_pipeline == "zero_copy"          # a small task: two zero-copy launches beat any staged pipeline
 
 
 def test_chunked_step_equals_one_launch():
@@ -572,21 +572,22 @@ torch.save([t.cpu() for t in (obs, rew, reset, progress, timeout, shaped, dones,
 
 
 def test_default_host_pipeline_resolves_to_a_mode_that_serves_the_configuration():
-    """``env.hostPipeline`` defaults to ``auto``: a staged pipeline (packed when the process has host cores to gather with) for the
-    fused step, ``zero_copy`` when the caller asks for what only that mode does (the two-kernel split, the in-place contact filter)."""
+    """``env.hostPipeline`` defaults to ``auto``: ``zero_copy`` for small tasks (two launches, nothing staged) and when the caller
+    asks for what only that mode does (the two-kernel split, the in-place contact filter); a staged pipeline for the fused step of
+    a large task -- packed when the process has host cores to gather with -- in chunks of >= 32 768 envs."""
     from bez_isaacgym_b200.synthetic_sim import SyntheticGym
     from bez_isaacgym_b200 import tasks as T
-    n = 1000
-    st = sg.make_state(n, seed=5)
 
-    def make(fusion="fused", **env):
+    def make(n, st, fusion="fused", **env):
         cfg = bm.default_task_cfg(n, use_gpu_pipeline=False, rl_device="cpu")
         cfg["env"].update(env)
         return T.KickEnv(cfg, "cuda:0", 0, True, sim=SyntheticGym(n, device="cuda:0", state=st.clone(), host=True), fusion=fusion)
 
+    n = 100352                                                    # >= 98 304: staged whatever the host's core count
+    st = sg.make_state(n, seed=5, filler=False)
     a = sg.make_actions(n, seed=1)
-    e_auto, e_split, e_filter = make(), make("split"), make(writeContactFilter=True)
-    assert e_auto.host_pipeline in ("staged_pack", "staged_ce")
+    e_auto, e_split, e_filter = make(n, st), make(n, st, "split"), make(n, st, writeContactFilter=True)
+    assert e_auto.host_pipeline in ("staged_pack", "staged_ce") and len(e_auto._ce_chunks) == 3
     assert e_split.host_pipeline == "zero_copy" and e_filter.host_pipeline == "zero_copy"
     outs = [e.step(a) for e in (e_auto, e_split, e_filter)]
     torch.cuda.synchronize()
@@ -594,3 +595,5 @@ def test_default_host_pipeline_resolves_to_a_mode_that_serves_the_configuration(
         same = (o["obs"] == outs[0][0]["obs"]) | (o["obs"].isnan() & outs[0][0]["obs"].isnan())
         assert bool(same.all()) and torch.equal(r, outs[0][1]) and torch.equal(d, outs[0][2])
     assert not torch.equal(e_filter.net_contact, e_auto.net_contact), "only the zero-copy mode filters the simulator's tensor in place"
+    small = make(1000, sg.make_state(1000, seed=5))
+    assert small.host_pipeline == "zero_copy"
