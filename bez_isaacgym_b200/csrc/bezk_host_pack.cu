@@ -220,9 +220,11 @@ private:
                 while (help(*j)) {}
                 continue;
             }
-            // Nothing to claim.  Poll for the next job for spin_us_ before blocking: a step issues its jobs every few
-            // milliseconds, and a futex wake costs the ISSUING thread tens of microseconds to milliseconds (the woken thread
-            // tends to start on the waker's core), which would sit on the step's critical path.
+            // Nothing to claim.  Poll for the next job for spin_us_ before blocking: the jobs of one step arrive microseconds
+            // apart.  The default is SHORT (100 us): between steps the workers sleep and leave the cores to the simulator; on
+            // the B200 hosts a futex wake costs the issuing thread ~30 us and polling for 0 / 100 / 2000 us measures the same
+            // (profiles/r02_host_pack.md).  On hosts where a wake is expensive (an overcommitted guest: the woken thread runs
+            // on the waker's core for milliseconds) raise it to the step period with bezk_host_pack_config.
             bool again = false;
             const int spin_us = spin_us_.load(std::memory_order_relaxed);
             if (spin_us > 0) {
@@ -257,7 +259,7 @@ private:
     Job slots_[kSlots];
     std::atomic<int64_t> issued_{0};
     std::atomic<int> sleepers_{0};
-    std::atomic<int> spin_us_{2000};
+    std::atomic<int> spin_us_{100};
     std::atomic<bool> stopping_{false};
     int64_t seq_ = 0;
     bool stop_ = false;

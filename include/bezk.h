@@ -180,8 +180,8 @@ int bezk_stage_sparse_rows_split(const float* rigid_body_host, const float* net_
  * bezk_host_pack_wait(ticket) returns once the job's output is written (the caller's thread packs too while it waits).
  * Jobs are served in issue order.  One thread at a time may issue / wait.  bezk_host_pack_config sizes the pool (threads = 0:
  * hardware threads - 1, at most 16; the pool only grows), sets how long an idle worker polls for the next job before it blocks
- * (spin_us, default 2000; < 0 keeps the current value: a step issues jobs every few milliseconds and a futex wake would sit on its
- * critical path) and whether workers are pinned one per CPU (pin, honoured before the first worker starts; < 0 keeps it); it
+ * (spin_us, default 100; < 0 keeps the current value: between steps the workers sleep and leave the cores to the simulator -- raise
+ * it to the step period on hosts where a futex wake is expensive) and whether workers are pinned one per CPU (pin, honoured before the first worker starts; < 0 keeps it); it
  * returns the worker count (-BEZK_E_BADARG on a bad thread count).  No CUDA call is made by these four.
  * bezk_post_physics_packed is bezk_post_physics_chunk for a chunk whose records are on the DEVICE (pointer already offset to the
  * chunk's first record, like every other argument): it scatters the root subset into the chunk's rows of root_states (a device

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--timeline", action="store_true", help="add the per-chunk device / host timeline of one step (staged_ce / staged_pack)")
     ap.add_argument("--pack-threads", type=int, default=0)
     ap.add_argument("--pack-dof", type=int, default=0)
+    ap.add_argument("--pack-spin-us", type=int, default=-1)
     args = ap.parse_args()
     n = args.envs
     # under torchrun: one process per GPU, a gloo barrier before each timed loop (all ranks load the host link together)
@@ -55,6 +56,7 @@ def main():
         cfg["env"]["hostPipelineTimeline"] = args.timeline and mode in ("staged_ce", "staged_pack")
         cfg["env"]["hostPackThreads"] = args.pack_threads
         cfg["env"]["hostPackDof"] = bool(args.pack_dof)
+        cfg["env"]["hostPackSpinUs"] = args.pack_spin_us
         env = KickEnv(cfg, dev, 0, True, sim=sim)
         for _ in range(5):
             env.step(act)
