@@ -87,6 +87,7 @@ SIGNATURES = {
     "bezk_rms_scratch_doubles": (_I64, [C.c_int32]),
     "bezk_rms_moments": (C.c_int, [_P, _P, _P, _P, _I64, C.c_int32, _P]),
     "bezk_rms_merge": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P]),
+    "bezk_rms_moments_slabs_batched": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _I64, C.c_int32, C.c_int32, _P]),
     "bezk_rms_merge_sequence": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, _P, C.c_int32, _P]),
     "bezk_rms_normalize": (C.c_int, [_P, _P, _P, C.c_float, C.c_int, _P, _I64, C.c_int32, _P]),
     "bezk_rms_train_forward": (C.c_int, [_P, _I64, _I64, _P, _P, _P, C.c_float, _P, _P, _I64, C.c_int32, _P]),

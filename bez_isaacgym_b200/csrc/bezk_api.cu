@@ -378,6 +378,17 @@ int bezk_rms_moments_slabs(const float* x, int64_t slab_rows, int64_t slab_strid
                    "bezk_rms_moments_slabs");
 }
 
+int bezk_rms_moments_slabs_batched(const float* x, int64_t slab_rows, int64_t slab_stride, int64_t batch_stride, const double* pivot,
+                                   double* acc, double* partials, int64_t m, int32_t c, int32_t n_batches, void* stream) {
+    REQUIRE(m > 0 && c > 0 && n_batches >= 0 && n_batches <= 65535 && batch_stride >= 0, "bad m / c / n_batches / batch_stride");
+    if (n_batches == 0) return 0;
+    REQUIRE(x && acc && partials, "rms buffers NULL");
+    if (slab_rows <= 0 || slab_rows > m) { slab_rows = m; slab_stride = m; }
+    if (int rc = check_slabs(slab_rows, slab_stride, m)) return rc;
+    return cuda_rc(bezk::launch_rms_moments_batched(x, pivot, acc, partials, m, c, slab_rows, slab_stride, batch_stride, n_batches,
+                                                    (cudaStream_t)stream), "bezk_rms_moments_slabs_batched");
+}
+
 int bezk_rms_merge(const double* acc, const double* pivot, double* running_mean, double* running_var, double* count, int32_t c,
                    void* stream) {
     REQUIRE(c > 0, "c must be positive");

@@ -89,6 +89,8 @@ cudaError_t launch_rms_moments(const float*, const double*, double*, double*, in
 cudaError_t launch_rms_merge_normalize(const float*, const double*, double*, double*, double*, float, float*, int64_t, int, int64_t,
                                        int64_t, cudaStream_t);
 cudaError_t launch_rms_merge(const double*, const double*, double*, double*, double*, int, cudaStream_t);
+cudaError_t launch_rms_moments_batched(const float*, const double*, double*, double*, int64_t, int, int64_t, int64_t, int64_t, int,
+                                       cudaStream_t);
 cudaError_t launch_rms_merge_sequence(const double*, const int32_t*, int, const double*, double*, double*, double*, double*, int,
                                       cudaStream_t);
 cudaError_t launch_rms_normalize(const float*, const double*, const double*, float, int, float*, int64_t, int, int64_t, int64_t,

@@ -169,7 +169,11 @@ constexpr int RMS_STAGES = 4;
 template <bool SLABS>       // the contiguous instantiation carries no slab arithmetic (32 registers; with it: 44, and 7 % slower)
 __global__ void __launch_bounds__(RMS_THREADS) rms_partials_tma_kernel(const float* __restrict__ x, const double* __restrict__ pivot,
                                                                        double* __restrict__ partials, int64_t m, int c,
-                                                                       int64_t slab_rows, int64_t slab_stride) {
+                                                                       int64_t slab_rows, int64_t slab_stride,
+                                                                       int64_t x_batch_elems) {
+    // blockIdx.y = batch (bezk_rms_moments_slabs_batched): its own rows and its own gridDim.x partial rows
+    x += (int64_t)blockIdx.y * x_batch_elems;
+    partials += (int64_t)blockIdx.y * gridDim.x * 2 * c;
     extern __shared__ __align__(128) unsigned char rms_smem[];
     __shared__ __align__(8) uint64_t s_full[RMS_STAGES];
     float* s_tile = reinterpret_cast<float*>(rms_smem);                       // [RMS_STAGES][RMS_TR * c]
@@ -299,6 +303,9 @@ __global__ void __launch_bounds__(256) moments_finalize_kernel(const double* __r
                                                                const double* __restrict__ snap_count = nullptr) {
     pdl_wait();                 // programmatic dependent launch: everything below may read the previous kernel's output
     pdl_launch_dependents();
+    // blockIdx.y = batch: its nblocks partial rows, its own accumulator row
+    partials += (int64_t)blockIdx.y * nblocks * 2 * c;
+    acc += (int64_t)blockIdx.y * (1 + 2 * c);
     const int lane = threadIdx.x & 31;
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (snap_mean && blockIdx.x == 0) {
@@ -538,9 +545,9 @@ cudaError_t launch_rms_moments(const float* x, const double* pivot, double* acc,
             if (cap > RMS_MAX_BLOCKS) cap = RMS_MAX_BLOCKS;
             nblocks = (int)(ntiles < cap ? ntiles : cap);
             cudaError_t err = slabs ? launch_pdl(learner_pdl(), rms_partials_tma_kernel<true>, dim3((unsigned)nblocks), dim3(RMS_THREADS), smem, st, x, pivot,
-                                                partials, m, c, slab_rows, slab_stride)
+                                                partials, m, c, slab_rows, slab_stride, (int64_t)0)
                                     : launch_pdl(learner_pdl(), rms_partials_tma_kernel<false>, dim3((unsigned)nblocks), dim3(RMS_THREADS), smem, st, x, pivot,
-                                                partials, m, c, m, m);
+                                                partials, m, c, m, m, (int64_t)0);
             if (err != cudaSuccess) return err;
             return launch_pdl(learner_pdl(), moments_finalize_kernel, dim3((unsigned)((2 * c + 7) / 8)), dim3(256), 0, st, partials, nblocks, c, m, acc,
                              snap_mean, snap_var, snap_count);
@@ -560,6 +567,52 @@ cudaError_t launch_rms_moments(const float* x, const double* pivot, double* acc,
     if (err != cudaSuccess) return err;
     return launch_pdl(learner_pdl(), moments_finalize_kernel, dim3((unsigned)((2 * c + 7) / 8)), dim3(256), 0, st, partials, nblocks, c, m, acc, snap_mean,
                      snap_var, snap_count);
+}
+
+// The moments of n_batches equally spaced minibatches in ONE pair of launches (partials + fold, blockIdx.y = batch): batch b is
+// the slab view based at x + b * x_batch_rows * c; acc (n_batches, 1 + 2c).  Only the TMA path is batched; anything else falls
+// back to one launch_rms_moments per batch.
+cudaError_t launch_rms_moments_batched(const float* x, const double* pivot, double* acc, double* partials, int64_t m, int c,
+                                       int64_t slab_rows, int64_t slab_stride, int64_t x_batch_rows, int n_batches, cudaStream_t st) {
+    if (n_batches <= 0) return cudaSuccess;
+    if (slab_rows <= 0 || slab_rows >= m) { slab_rows = m; slab_stride = m; }
+    if (m % slab_rows != 0) return cudaErrorInvalidValue;
+    const bool slabs = slab_rows < m;
+    const bool tma_ok = c > 1 && c <= RMS_MAX_C && n_batches <= 65535 && aligned16(x) && ((RMS_TR * c * 4) % 16 == 0) &&
+                        (((m % RMS_TR) * c * 4) % 16 == 0) && m >= 4 * RMS_TR && ((x_batch_rows * c * 4) % 16 == 0) &&
+                        (!slabs || (slab_rows % RMS_TR == 0 && (slab_stride * c * 4) % 16 == 0)) &&
+                        (size_t)RMS_STAGES * RMS_TR * c * sizeof(float) <= 220 * 1024;
+    if (!tma_ok || n_batches == 1) {
+        for (int b = 0; b < n_batches; ++b)
+            if (cudaError_t e = launch_rms_moments(x + (int64_t)b * x_batch_rows * c, pivot, acc + (int64_t)b * (1 + 2 * c), partials, m, c,
+                                                   slab_rows, slab_stride, st, nullptr, nullptr))
+                return e;
+        return cudaSuccess;
+    }
+    const int64_t ntiles = (m + RMS_TR - 1) / RMS_TR;
+    size_t smem = (size_t)RMS_STAGES * RMS_TR * c * sizeof(float);
+    const size_t red = (size_t)2 * (RMS_THREADS / c) * c * sizeof(double);
+    if (red > smem) smem = red;
+    static SmemOptIn opt_plain, opt_slabs;
+    if (cudaError_t e2 = opt_plain.ensure(rms_partials_tma_kernel<false>, 220 * 1024)) return e2;
+    if (cudaError_t e2 = opt_slabs.ensure(rms_partials_tma_kernel<true>, 220 * 1024)) return e2;
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    int64_t cap = 148LL * per_sm;
+    if (cap > RMS_MAX_BLOCKS) cap = RMS_MAX_BLOCKS;
+    int64_t per_batch = cap / n_batches;                 // the batches share the resident CTAs (and the partials scratch)
+    if (per_batch < 1) per_batch = 1;
+    if ((int64_t)n_batches * per_batch > RMS_MAX_BLOCKS) return cudaErrorInvalidValue;
+    const int nblocks = (int)(ntiles < per_batch ? ntiles : per_batch);
+    const dim3 grid((unsigned)nblocks, (unsigned)n_batches);
+    cudaError_t err = slabs ? launch_pdl(learner_pdl(), rms_partials_tma_kernel<true>, grid, dim3(RMS_THREADS), smem, st, x, pivot, partials, m, c,
+                                        slab_rows, slab_stride, (int64_t)(x_batch_rows * c))
+                            : launch_pdl(learner_pdl(), rms_partials_tma_kernel<false>, grid, dim3(RMS_THREADS), smem, st, x, pivot, partials, m, c,
+                                        m, m, (int64_t)(x_batch_rows * c));
+    if (err != cudaSuccess) return err;
+    return launch_pdl(learner_pdl(), moments_finalize_kernel, dim3((unsigned)((2 * c + 7) / 8), (unsigned)n_batches), dim3(256), 0, st,
+                      (const double*)partials, nblocks, c, m, acc, (const double*)nullptr, (const double*)nullptr, (const double*)nullptr);
 }
 
 cudaError_t launch_rms_merge_normalize(const float* x, const double* acc_ext, double* running_mean, double* running_var, double* count,

@@ -76,16 +76,27 @@ class RunningMeanStd(nn.Module):
             self._plan_seq = torch.empty(len(key[0]), 2, c, dtype=torch.float64, device=dev)
             self._plan_key = key
         self._pivot.copy_(self.running_mean)              # replicated on all ranks -> identical pivots
-        for b, x in enumerate(batches):
-            x = x.detach()
-            if x.is_contiguous():
-                ops.rms_moments(x.view(-1, c), self._pivot, self._plan_acc[b], self._scratch)
-            else:
-                ops.rms_moments_slabs(x, self._pivot, self._plan_acc[b], self._scratch)
+        if self._equally_spaced(batches):                 # minibatches = consecutive env blocks of one rollout tensor: one launch pair
+            ops.rms_moments_slabs_batched([x.detach() for x in batches], self._pivot, self._plan_acc, self._scratch)
+        else:
+            for b, x in enumerate(batches):
+                x = x.detach()
+                if x.is_contiguous():
+                    ops.rms_moments(x.view(-1, c), self._pivot, self._plan_acc[b], self._scratch)
+                else:
+                    ops.rms_moments_slabs(x, self._pivot, self._plan_acc[b], self._scratch)
         bdist.allreduce_sum_(self._plan_acc, self.process_group)
         ops.rms_merge_sequence(self._plan_acc, self._plan_order, self._pivot, self.running_mean, self.running_var, self.count.view(1),
                                self._plan_seq)
         return self._plan_seq
+
+    @staticmethod
+    def _equally_spaced(batches):
+        """Equally spaced views of one tensor with one geometry (what the batched kernels take in a single launch)."""
+        nb = len(batches)
+        step = batches[1].data_ptr() - batches[0].data_ptr() if nb > 1 else 0
+        return nb == 1 or (step > 0 and all(b.shape == batches[0].shape and b.stride() == batches[0].stride() and
+                                            b.data_ptr() - batches[0].data_ptr() == k * step for k, b in enumerate(batches)))
 
     def planned(self, u: int, input: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
         """The train-mode forward of update ``u`` of the last ``plan``: normalise with the statistics after that update."""
@@ -105,10 +116,7 @@ class RunningMeanStd(nn.Module):
         if u0 < 0 or u0 + nb > self._plan_seq.shape[0]:
             raise ValueError("u0 + len(batches) exceeds the planned updates")
         y = out if out is not None else torch.empty(nb, m, self.insize, dtype=torch.float32, device=batches[0].device)
-        step = batches[1].data_ptr() - batches[0].data_ptr() if nb > 1 else 0
-        spaced = nb == 1 or (step > 0 and all(b.shape == batches[0].shape and b.stride() == batches[0].stride() and
-                                              b.data_ptr() - batches[0].data_ptr() == k * step for k, b in enumerate(batches)))
-        if not spaced:                   # separately allocated minibatches: one launch each
+        if not self._equally_spaced(batches):             # separately allocated minibatches: one launch each
             for k, b in enumerate(batches):
                 self.planned(u0 + k, b, out=y[k].view(b.shape) if b.is_contiguous() else y[k])
             return y

@@ -457,18 +457,38 @@ def rms_normalize_slabs(x, running_mean, running_var, y, eps=1e-5, unnorm=False)
     return y
 
 
-def rms_normalize_slabs_batched(batches, seq, u0, y, eps=1e-5):
-    """``batches``: equally spaced slab views (or contiguous (m, c) blocks) of ONE tensor -- the minibatches of a mini-epoch;
-    ``seq`` (n_updates, 2, c) from ``rms_merge_sequence``; batch b is normalised with the statistics of update ``u0 + b`` into
-    ``y[b]`` (``y``: (len(batches), m, c) contiguous).  One launch."""
-    nb, c = len(batches), seq.shape[-1]
+def _spaced_slabs(batches, c):
+    """(ptr, slab_rows, slab_stride, m, batch_stride_rows) of equally spaced slab views / contiguous blocks of ONE tensor."""
+    nb = len(batches)
     ptr, rows, stride, m = _slab_view(batches[0], F32, "batches[0]", c)
     step_bytes = (batches[1].data_ptr() - batches[0].data_ptr()) if nb > 1 else 0
     for b in range(1, nb):
         p2, r2, s2, m2 = _slab_view(batches[b], F32, f"batches[{b}]", c)
         if (r2, s2, m2) != (rows, stride, m) or p2.value - ptr.value != b * step_bytes or step_bytes <= 0 or step_bytes % (4 * c):
             raise BezkError("batches must be equally spaced views of one tensor with the same slab geometry")
-    step = step_bytes // (4 * c)
+    return ptr, rows, stride, m, step_bytes // (4 * c)
+
+
+def rms_moments_slabs_batched(batches, pivot, acc, partials):
+    """The moments of ``len(batches)`` equally spaced minibatches in one pair of launches; ``acc`` (len(batches), 1 + 2c)."""
+    c = acc.shape[-1] // 2
+    nb = len(batches)
+    ptr, rows, stride, m, step = _spaced_slabs(batches, c)
+    if partials.numel() < rms_scratch_doubles(c):
+        raise BezkError("partials scratch too small")
+    lib = _lib.load()
+    _lib.check(lib.bezk_rms_moments_slabs_batched(ptr, rows, stride, step, _p(pivot, F64, "pivot", c, True),
+                                                  _p(acc, F64, "acc", nb * (1 + 2 * c)), _p(partials, F64, "partials"), m, c, nb,
+                                                  _stream(batches[0])), "bezk_rms_moments_slabs_batched")
+    return acc
+
+
+def rms_normalize_slabs_batched(batches, seq, u0, y, eps=1e-5):
+    """``batches``: equally spaced slab views (or contiguous (m, c) blocks) of ONE tensor -- the minibatches of a mini-epoch;
+    ``seq`` (n_updates, 2, c) from ``rms_merge_sequence``; batch b is normalised with the statistics of update ``u0 + b`` into
+    ``y[b]`` (``y``: (len(batches), m, c) contiguous).  One launch."""
+    nb, c = len(batches), seq.shape[-1]
+    ptr, rows, stride, m, step = _spaced_slabs(batches, c)
     if u0 < 0 or u0 + nb > seq.shape[0]:
         raise BezkError("u0 + len(batches) exceeds the planned updates")
     mean = seq[u0, 0]

@@ -240,6 +240,11 @@ int bezk_rms_moments(const float* x, const double* pivot, double* acc, double* p
  * count () f64 with the reference's parallel-variance update (unbiased batch variance). */
 int bezk_rms_merge(const double* acc, const double* pivot, double* running_mean, double* running_var,
                    double* count, int32_t c, void* stream);
+/* bezk_rms_moments_slabs for n_batches equally spaced minibatches in one pair of launches: batch b is the slab view based at
+ * x + b * batch_stride * c (batch_stride in rows), acc (n_batches, 1+2c) receives one row per batch; same pivot, same scratch. */
+int bezk_rms_moments_slabs_batched(const float* x, int64_t slab_rows, int64_t slab_stride, int64_t batch_stride,
+                                   const double* pivot, double* acc, double* partials, int64_t m, int32_t c,
+                                   int32_t n_batches, void* stream);
 /* K4c.  A SEQUENCE of those merges in one launch: acc (n_batches, 1+2c) holds the moments of n_batches distinct batches (all taken
  * with the same pivot, possibly all-reduced over ranks in ONE collective); update u = 0 .. n_updates-1 merges batch order[u]
  * (device int32, values in [0, n_batches)) exactly as bezk_rms_merge would; seq (n_updates, 2, c) f64 receives [mean, var] AFTER
