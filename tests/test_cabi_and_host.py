@@ -392,3 +392,19 @@ def test_host_pack_gathers_the_sparse_rows(task, cleats):
     assert lib.bezk_host_pack_wait(1 << 40) == 10001
     assert lib.bezk_post_physics_packed(tid, *([None] * 10), 0, 0, *([None] * 4), ctypes.byref(cfg), None, None, None, 7, 4, 0, None, None,
                                         None, None, None, None, None) == 10001
+
+
+def test_bench_arms_share_one_workload_config(monkeypatch):
+    """The driver compares the ``config`` objects of ``bench.py`` and ``bench.py --impl reference``: both come from ONE function of
+    the same arguments, name the BASELINE configs[3] shard size by default and carry no model keys."""
+    import importlib
+    import sys
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    bench = importlib.import_module("bench")
+    a = bench.parse()
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--gpus", "1", "--steps", "3", "--warmup", "1"])
+    b = bench.parse()
+    ca, cb = bench.workload_config(a), bench.workload_config(b)
+    assert ca == cb and ca["envs_per_gpu"] == 262144 and ca["horizon"] == 32 and "workload" in ca and "model" not in ca
+    assert a.gpus == 1 and a.warmup >= 3 and a.e2e_mode == "auto"
+    assert bench.METRIC == "task+GAE env-steps/s" and bench.UNIT == "env-steps/s"
