@@ -597,3 +597,39 @@ def test_default_host_pipeline_resolves_to_a_mode_that_serves_the_configuration(
     assert not torch.equal(e_filter.net_contact, e_auto.net_contact), "only the zero-copy mode filters the simulator's tensor in place"
     small = make(1000, sg.make_state(1000, seed=5))
     assert small.host_pipeline == "zero_copy"
+
+
+def test_packed_host_pipeline_at_the_baseline_size_is_bit_identical_to_the_gpu_pipeline():
+    """The configuration ``bench.py``'s e2e leg runs (262 144 envs, ``staged_pack``, 4 chunks, critic values arriving from pinned
+    host memory, reward epilogue in the step): every output of two steps equals the GPU pipeline's bit for bit."""
+    from bez_isaacgym_b200.synthetic_sim import SyntheticGym
+    from bez_isaacgym_b200 import tasks as T
+    n = 262144
+    st = sg.make_state(n, seed=11, filler=False)
+
+    class OwnedRootSim(SyntheticGym):
+        owns_root_reset = True
+
+    envs = {}
+    for kind in ("gpu", "host"):
+        cfg = bm.default_task_cfg(n, use_gpu_pipeline=(kind == "gpu"), rl_device="cuda:0" if kind == "gpu" else "cpu")
+        cfg["env"]["hostPipeline"] = "staged_pack"
+        cfg["env"]["imuPrevVelAliasing"] = False
+        envs[kind] = T.KickEnv(cfg, "cuda:0", 0, True, sim=OwnedRootSim(n, device="cuda:0", state=st.clone(), host=(kind == "host")))
+        envs[kind].progress_buf.copy_(torch.arange(n, device="cuda") % envs[kind].max_episode_length)
+    assert envs["host"].host_pipeline == "staged_pack" and len(envs["host"]._ce_chunks) == 4
+    sh = {k: torch.zeros(n, device="cuda") for k in envs}
+    dn = {k: torch.zeros(n, dtype=torch.uint8, device="cuda") for k in envs}
+    for step in range(2):
+        a = sg.make_actions(n, seed=step)
+        vals = torch.randn(n, generator=torch.Generator().manual_seed(step))
+        envs["gpu"].set_rollout_targets(values=vals.cuda(), shaped_rewards=sh["gpu"], dones_u8=dn["gpu"])
+        envs["host"].set_rollout_targets(values=vals.pin_memory(), shaped_rewards=sh["host"], dones_u8=dn["host"])
+        o_g, r_g, d_g, e_g = envs["gpu"].step(a.cuda())
+        o_h, r_h, d_h, e_h = envs["host"].step(a.pin_memory())
+        torch.cuda.synchronize()
+        og, oh = o_g["obs"].cpu(), o_h["obs"]
+        assert bool(((og == oh) | (og.isnan() & oh.isnan())).all()) and torch.equal(r_g.cpu(), r_h) and torch.equal(d_g.cpu(), d_h)
+        assert torch.equal(e_g["time_outs"].cpu(), e_h["time_outs"]) and torch.equal(sh["gpu"], sh["host"]) and torch.equal(dn["gpu"], dn["host"])
+        assert torch.equal(envs["gpu"].dof_state.cpu(), envs["host"].dof_state) and torch.equal(envs["gpu"].targets.cpu(), envs["host"].targets)
+    assert int(d_g.sum()) > 100
