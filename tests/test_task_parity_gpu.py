@@ -633,3 +633,8 @@ def test_packed_host_pipeline_at_the_baseline_size_is_bit_identical_to_the_gpu_p
         assert torch.equal(e_g["time_outs"].cpu(), e_h["time_outs"]) and torch.equal(sh["gpu"], sh["host"]) and torch.equal(dn["gpu"], dn["host"])
         assert torch.equal(envs["gpu"].dof_state.cpu(), envs["host"].dof_state) and torch.equal(envs["gpu"].targets.cpu(), envs["host"].targets)
     assert int(d_g.sum()) > 100
+    from tests.test_parity_report_gpu import record
+    record("host_pipeline_staged_pack_262144_envs", {
+        "compared_with": "KickEnv.step of the GPU pipeline on the same state, 2 steps", "chunks": 4,
+        "bit_identical": ["obs", "rew", "reset", "time_outs", "shaped_rewards", "dones_u8", "dof_state (reset rows)", "PD targets"],
+        "resets_in_last_step": int(d_g.sum())})
