@@ -469,6 +469,10 @@ def test_host_pipeline_equals_gpu_pipeline(host_mode, task):
     assert int(d_g.sum()) > 0
     link = envs["host"].link_counters()
     assert link["h2d_bytes"] > 0 and link["d2h_bytes"] > 0
+    if host_mode == "staged_pack" and task == "kick" and not cleats and variant == "":
+        # the byte counts bench.py reports are those of the copies issued: per env-step dof_state 144 + record 96 + actions 72 in,
+        # obs 216 + rew 4 + reset 8 + time_outs 8 + PD targets 72 out
+        assert link["h2d_bytes"] == 4 * n * (144 + 96 + 72) and link["d2h_bytes"] == 4 * n * (216 + 4 + 8 + 8 + 72)
     if host_mode == "auto":
         assert envs["host"].host_pipeline == "zero_copy"          # a small task: two zero-copy launches beat any staged pipeline
 
