@@ -103,19 +103,22 @@ class KickEnv(VecTask):
         # (bezk_host_pack_begin / _wait) and moved by dense copies -- the engine is row-rate-bound on strided pulls
         self.host_mode = env_cfg.get("hostPipeline", "auto") if self.host_staged else None
         if self.host_mode == "auto":
-            # the fastest pipeline for this size on this host (profiles/r02_host_pack.md).  Small tasks: the zero-copy kernels
-            # (two launches, no staging: 0.12 ms per step at the reference's default 4 096 envs vs 0.21-0.57 ms for a staged
-            # pipeline's copies, events and launches).  Large ones: the packed pipeline when the process has ~8 worker threads
+            # the fastest pipeline for this size on this host (profiles/r02_host_pack.md).  Small tasks (< 49 152 envs): the
+            # zero-copy kernels (two launches, no staging: 0.12 ms per step at the reference's default 4 096 envs vs 0.21-0.57 ms
+            # for a staged pipeline's copies, events and launches).  Large ones: the packed pipeline when the process has ~8 worker threads
             # to stay ahead of the link (98 vs 69 M env-steps/s at 262 144 envs on 16 cores / 1 GPU); with 4 cores per GPU
             # (8 ranks on 32 cores) the gather becomes the bottleneck and the copy-engine pulls win (176 vs 151 M).
             n_envs = int(env_cfg["numEnvs"])
             pack_ok = self._host_core_share() - 1 >= 8
             if fusion != "fused" or bool(env_cfg.get("writeContactFilter", False)):
                 self.host_mode = "zero_copy"              # the staged pipelines run the fused step and cannot write the filter back
-            elif n_envs < (12288 if pack_ok else 98304):
+            elif n_envs < 49152:                          # 16 384 envs: zero_copy 0.33 ms, packed 0.32; 65 536: 1.23 vs 0.82
                 self.host_mode = "zero_copy"
+            elif pack_ok and self._host_gather_fast_enough():
+                # (a core count says little about an overcommitted guest: the gather itself is timed before it is relied on)
+                self.host_mode = "staged_pack"
             else:
-                self.host_mode = "staged_pack" if pack_ok else "staged_ce"
+                self.host_mode = "staged_ce" if n_envs >= 98304 else "zero_copy"
         #: the resolved pipeline name ("staged_pack" runs on the staged_ce machinery: host_mode reads "staged_ce" for both)
         self.host_pipeline = self.host_mode
         self._pack = self.host_mode == "staged_pack"
@@ -290,6 +293,32 @@ class KickEnv(VecTask):
         except AttributeError:
             cores = os.cpu_count() or 2
         return max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+
+    def _host_gather_fast_enough(self, limit_ns_per_env=7.0):
+        """Calibration for ``hostPipeline: auto``: the packed pipeline only pays when the host threads gather an env faster than the
+        link moves one (~7.6 ns per env-step at 262 144 envs); on the B200 hosts the gather runs at 3-4 ns per env on 15 threads,
+        on an overcommitted guest (this repo's development container: 35 ns) the copy-engine pipeline is the better choice.
+        Three timed gathers of up to 65 536 envs of the simulator's own tensors, best of three."""
+        import time
+        lib = _lib.load()
+        task = ops._TASK_ID[self.TASK]
+        kcfg = ops.make_task_cfg(num_bodies=self.sim.num_bodies, cleats=self.cleats)
+        rs = lib.bezk_host_pack_record_floats(task, C.byref(kcfg))
+        threads = max(1, min(16, self._host_core_share() - 1))
+        if rs <= 0 or lib.bezk_host_pack_config(threads, -1, -1) <= 0:
+            return False
+        m = min(self.num_envs, 65536)
+        rec = torch.empty(m * rs, dtype=torch.float32)
+        best = float("inf")
+        for _ in range(3):
+            t0 = time.perf_counter()
+            t = lib.bezk_host_pack_begin(task, _ptr(self.rigid_body), _ptr(self.net_contact), _ptr(self.root_states), None, None,
+                                         C.byref(kcfg), _ptr(rec), 0, m)
+            if t < 0 or lib.bezk_host_pack_wait(t):
+                return False
+            best = min(best, time.perf_counter() - t0)
+        self.host_gather_ns_per_env = 1e9 * best / m
+        return self.host_gather_ns_per_env <= limit_ns_per_env
 
     # ------------------------------------------------------------------ construction helpers
     def create_sim(self):
