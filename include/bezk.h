@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BEZK_VERSION 120          /* 0.1.2 */
+#define BEZK_VERSION 130          /* 0.1.3: host packer, packed / staged entries with the reward epilogue, planned RunningMeanStd updates */
 #define BEZK_NUM_DOF 18
 #define BEZK_NUM_OBS 54
 

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/bezk.h but not exported by libbezk.so"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in bez_isaacgym_b200/_lib.py"
     assert sorted(_lib.SIGNATURES) == declared, "ctypes table and header disagree"
-    assert lib.bezk_version() == 120
+    assert lib.bezk_version() == 130
 
 
 def test_struct_layout_matches_header():
