@@ -127,7 +127,8 @@ public:
     }
 
     int64_t begin(const Job& proto) {
-        const int64_t t = ++seq_;                       // caller-serialised (one thread issues the step)
+        std::lock_guard<std::mutex> issue(issue_m_);    // issuing threads take turns (uncontended in the one-thread-per-env case)
+        const int64_t t = seq_.fetch_add(1, std::memory_order_relaxed) + 1;
         Job& j = slots_[t % kSlots];
         while (j.ticket.load(std::memory_order_acquire) != 0) {      // the ring wrapped onto a job still in flight: finish it
             if (!help(j)) BEZK_CPU_RELAX();
@@ -155,7 +156,7 @@ public:
     // Blocks until job `t` is packed; the caller packs pieces itself while it waits.
     int wait(int64_t t) {
         if (t == 0) return 0;                            // an empty job
-        if (t < 0 || t > seq_) return -1;
+        if (t < 0 || t > seq_.load(std::memory_order_relaxed)) return -1;
         Job& j = slots_[t % kSlots];
         for (;;) {
             const int64_t cur = j.ticket.load(std::memory_order_acquire);
@@ -261,7 +262,8 @@ private:
     std::atomic<int> sleepers_{0};
     std::atomic<int> spin_us_{100};
     std::atomic<bool> stopping_{false};
-    int64_t seq_ = 0;
+    std::mutex issue_m_;
+    std::atomic<int64_t> seq_{0};
     bool stop_ = false;
     bool pin_ = false;
 };

@@ -178,7 +178,7 @@ int bezk_stage_sparse_rows_split(const float* rigid_body_host, const float* net_
  * the sim_device=cpu pipeline).
  * bezk_host_pack_begin is asynchronous: it returns a ticket > 0 (0 for n == 0, -BEZK_E_* on a bad argument);
  * bezk_host_pack_wait(ticket) returns once the job's output is written (the caller's thread packs too while it waits).
- * Jobs are served in issue order.  One thread at a time may issue / wait.  bezk_host_pack_config sizes the pool (threads = 0:
+ * Jobs are served in issue order; any thread may issue and wait (the pool is process-wide).  bezk_host_pack_config sizes the pool (threads = 0:
  * hardware threads - 1, at most 16; the pool only grows), sets how long an idle worker polls for the next job before it blocks
  * (spin_us, default 100; < 0 keeps the current value: between steps the workers sleep and leave the cores to the simulator -- raise
  * it to the step period on hosts where a futex wake is expensive) and whether workers are pinned one per CPU (pin, honoured before the first worker starts; < 0 keeps it); it

@@ -408,3 +408,40 @@ def test_bench_arms_share_one_workload_config(monkeypatch):
     assert ca == cb and ca["envs_per_gpu"] == 262144 and ca["horizon"] == 32 and "workload" in ca and "model" not in ca
     assert a.gpus == 1 and a.warmup >= 3 and a.e2e_mode == "auto"
     assert bench.METRIC == "task+GAE env-steps/s" and bench.UNIT == "env-steps/s"
+
+
+def test_host_pack_pool_serves_several_issuing_threads():
+    """The pool is process-wide: jobs issued and awaited from several Python threads at once (two envs stepping in two threads)
+    all complete with the right bytes."""
+    import threading
+    import numpy as np
+    from bez_isaacgym_b200 import _lib, ops
+    lib = _lib.load()
+    lib.bezk_host_pack_config(3, 50, -1)
+    cfg = ops.make_task_cfg(num_bodies=22)
+    rs = lib.bezk_host_pack_record_floats(0, ctypes.byref(cfg))
+    n, errors = 20_000, []
+    P = lambda a, off=0: ctypes.c_void_p(a.ctypes.data + 4 * off)           # noqa: E731
+
+    def worker(seed):
+        rng = np.random.default_rng(seed)
+        rb = rng.standard_normal((n, 22, 13), dtype=np.float32)
+        cf = rng.standard_normal((n, 22, 3), dtype=np.float32)
+        root = rng.standard_normal((n, 2, 13), dtype=np.float32)
+        rec = np.zeros((n, rs), np.float32)
+        for it in range(40):
+            cut = int(rng.integers(1, n))
+            ts = [lib.bezk_host_pack_begin(0, P(rb), P(cf), P(root), None, None, ctypes.byref(cfg), P(rec, lo * rs), lo, hi - lo)
+                  for lo, hi in ((0, cut), (cut, n))]
+            if any(lib.bezk_host_pack_wait(t) for t in ts) or not np.array_equal(rec[:, :10], rb[:, cfg.imu_body, 3:13]) \
+                    or not np.array_equal(rec[:, 16:19], root[:, 0, 0:3]):
+                errors.append((seed, it))
+                return
+            rec[:] = 0
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errors and not any(t.is_alive() for t in threads)
